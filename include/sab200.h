@@ -1,0 +1,173 @@
+/*
+ * sab200.h -- C ABI of libsab200.so, the B200 (sm_100a) backend for the per-frame
+ * site-assignment hot path of bjmorgan/site-analysis.
+ *
+ * Plain pointers and sizes only; no torch / pybind types.  Every device pointer is
+ * caller-owned (the Python host allocates through torch); `stream` is a cudaStream_t
+ * passed as void*.  The library allocates device memory only for the small static
+ * site tables uploaded by the sab_set_* calls.  All functions return SAB_OK (0) or
+ * an error code; sab_last_error() gives the message of the calling thread's last
+ * failure.  There is no CPU fallback anywhere behind this interface.
+ *
+ * The reference (pure Python + numba) has no FFI of its own: its only seam is the
+ * SiteCollection ABC (reference site_analysis/site_collection.py:185-245) selected by
+ * the hard-coded map in trajectory.py:86-91.  Each entry point below names the
+ * reference code it replaces; INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add at that seam.
+ *
+ * Conventions
+ *   frac      double[F][N][3]  fractional coordinates of every atom in every frame,
+ *                              exactly `structure.frac_coords` (NOT wrapped)
+ *   lattice   double[3][3] (lattice_stride = 0) or double[F][3][3] (stride = 9),
+ *                              rows are lattice vectors (pymatgen `lattice.matrix`)
+ *   result    int32[F][A]      site LIST POSITION of mobile atom a in frame f,
+ *                              SAB_NONE (-1) = no site, <= SAB_AMBIGUOUS_BASE (-2-k) =
+ *                              several sites contain the atom: spill[k] = n followed by
+ *                              the n candidate positions; sab_resolve() settles these
+ *                              with the reference's priority rules
+ */
+#ifndef SAB200_H
+#define SAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAB_ABI_VERSION 1
+
+enum { SAB_SPHERICAL = 0, SAB_VORONOI = 1, SAB_POLYHEDRAL = 2, SAB_DYNAMIC_VORONOI = 3 };
+enum { SAB_OK = 0, SAB_EINVAL = 1, SAB_ECUDA = 2, SAB_EOVERFLOW = 3, SAB_ESTATE = 4 };
+
+#define SAB_NONE (-1)
+#define SAB_AMBIGUOUS_BASE (-2)
+
+typedef struct sab_engine sab_engine;
+
+int sab_abi_version(void);
+const char *sab_last_error(void);
+
+/* One engine = one SiteCollection (reference site_collection.py:185) bound to one GPU.
+ * mobile_idx[A]: structure indices of the tracked atoms (reference Atom.index, atom.py:25). */
+int sab_engine_create(sab_engine **out, int kind, int device, int n_atoms, int n_mobile,
+                      const int32_t *mobile_idx, int n_sites);
+void sab_engine_destroy(sab_engine *e);
+
+/* ---- static site tables (host pointers; copied to the device) --------------------- */
+
+/* SphericalSite.frac_coords / .rcut (spherical_site.py:40-58), VoronoiSite.frac_coords
+ * (voronoi_site.py:36-49).  rcut_sq_max[s] = largest double q with sqrt(q) <= rcut[s]
+ * (so `q <= rcut_sq_max` == the reference's `sqrt(q) <= rcut`, spherical_site.py:145-146);
+ * both NULL for Voronoi. */
+int sab_set_centres(sab_engine *e, const double *centres, const double *rcut,
+                    const double *rcut_sq_max);
+
+/* PolyhedralSite.vertex_indices (polyhedral_site.py:218-236) padded to vmax, and the
+ * Qhull face topology FaceTopologyCache.face_simplices (polyhedral_site.py:154-155)
+ * padded to fmax (local vertex numbers). */
+int sab_set_polyhedra(sab_engine *e, int vmax, const int32_t *n_vert, const int32_t *vert_idx,
+                      int fmax, const int32_t *n_face, const int32_t *simplices);
+
+/* DynamicVoronoiSite.reference_indices (dynamic_voronoi_site.py:62-78) padded to rmax. */
+int sab_set_reference_atoms(sab_engine *e, int rmax, const int32_t *n_ref, const int32_t *ref_idx);
+
+/* Number M and list of the distinct structure atoms referenced by vertices / reference
+ * slots ("framework atoms"); compact numbering used by the PBC state below. */
+int sab_framework_count(sab_engine *e);
+int sab_framework_atoms(sab_engine *e, int32_t *out);
+
+/* ---- PBC image-shift state ---------------------------------------------------------
+ * Replaces the per-site caches PolyhedralSite._pbc_image_shifts/_pbc_cached_raw_frac
+ * (polyhedral_site.py:377-416) and _CentreGroup.pbc_shifts/cached_raw_frac
+ * (dynamic_voronoi_site_collection.py:38-70).  The engine keeps, per framework atom m,
+ * the last raw coordinate prev_raw[m] and the cumulative wrap count W[m]
+ * (sum of rint(raw_t - raw_{t-1}), pbc_utils.py:210-217); the shift of slot (s, v) at a
+ * frame is slot_shift[s][v] - W[atom(s, v)].
+ *   slot_shift int32[S][vmax|rmax][3], prev_raw double[M][3], wraps int32[M][3],
+ *   excursion double[M][3][2] = running (min, max) of raw - W per atom and dimension. */
+int sab_set_pbc_state(sab_engine *e, const int32_t *slot_shift, const double *prev_raw,
+                      const int32_t *wraps, const double *excursion);
+int sab_get_pbc_state(sab_engine *e, int32_t *slot_shift, double *prev_raw, int32_t *wraps,
+                      double *excursion);
+
+/* Sites whose PBC state was initialised by the legacy spread rule (reference_center is None,
+ * pbc_utils.py:16-41 via correct_pbc :140-145) get NO non-negative offset in the frame of
+ * initialisation; site_flags uint8[S] marks them and frames_from_now is that frame's index
+ * counted from the next frame the engine will process.  NULL clears the marker. */
+int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int64_t frames_from_now);
+
+/* Engine options.  SAB_OPT_SKIP_STEP_CHECK_ONCE: the next batch does not test its first frame
+ * against the 0.3 step bound (used right after the host re-initialised a group at that frame,
+ * dynamic_voronoi_site_collection.py:188-195). */
+#define SAB_OPT_SKIP_STEP_CHECK_ONCE 1
+int sab_set_option(sab_engine *e, int key, int64_t value);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+
+/* Bytes of device workspace sab_assign_device needs for n_frames frames. */
+int64_t sab_workspace_bytes(sab_engine *e, int64_t n_frames);
+
+/* Pass 1 of the PBC state (polyhedral / dynamic Voronoi only): sums the wraps of every
+ * framework atom over the frames and returns them (host int32[M][3]) together with the
+ * raw coordinates of the last frame (host double[M][3]); engine state is NOT modified.
+ * Used by multi-GPU shards to build the exclusive scan of wrap totals across ranks. */
+int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_frames, void *d_workspace,
+                    int64_t workspace_bytes, void *stream, int32_t *totals, double *last_raw);
+
+/* Assign every mobile atom of every frame; replaces <X>SiteCollection.analyse_structure /
+ * assign_site_occupations (polyhedral_site_collection.py:66-107, voronoi_site_collection.py:
+ * 52-99, dynamic_voronoi_site_collection.py:203-244, spherical_site_collection.py:53-92)
+ * for a whole trajectory (trajectory.py:413-432).  All d_* pointers are device memory.
+ *   d_spill / spill_capacity (int32 elements): candidate lists of ambiguous atom-frames.
+ *   info[8] (host, written on return): [0] ambiguous atom-frames, [1] spill elements used,
+ *   [2] spill overflow (0/1), [3] first frame whose step exceeded the 0.3 cache-validity
+ *   bound (pbc_utils.py:216) or -1, [4] frames that took the exhaustive (non-pruned) path,
+ *   [5] kernels launched, [6..7] reserved.
+ * When info[3] < 0 the PBC state advances to the end of the batch.  When info[3] = t >= 0 the
+ * results of frames < t are valid, the PBC state is left untouched, and the caller commits
+ * the valid prefix with sab_commit_pbc(..., n_commit = t) (same workspace, unmodified). */
+int sab_assign_device(sab_engine *e, const double *d_frac, const double *d_lattice,
+                      int lattice_stride, int64_t n_frames, int32_t *d_result,
+                      int32_t *d_spill, int64_t spill_capacity, void *d_workspace,
+                      int64_t workspace_bytes, void *stream, int64_t *info);
+
+int sab_commit_pbc(sab_engine *e, const double *d_frac, int64_t n_frames, int64_t n_commit,
+                   void *d_workspace, int64_t workspace_bytes, void *stream);
+
+/* Same, from HOST buffers (pinned or pageable): chunks the trajectory, overlaps H2D of
+ * chunk k+1 with the kernels of chunk k on two internal streams and copies the result
+ * back.  This is the call a reference-side plugin would make per trajectory. */
+int sab_assign_host(sab_engine *e, const double *h_frac, const double *h_lattice,
+                    int lattice_stride, int64_t n_frames, int32_t *h_result,
+                    int64_t chunk_frames, int64_t *info);
+
+/* ---- priority resolver --------------------------------------------------------------
+ * Replays PriorityAssignmentMixin._get_priority_sites (site_collection.py:113-182),
+ * SiteCollection.update_occupation (:279-310) and Atom.update_recent_site (atom.py:181-192)
+ * over the batch, in frame order and atom order, settling every ambiguous entry of
+ * d_result in place.  Tables (host pointers, may be NULL when absent):
+ *   rank int32[S][S-1]   reference _distance_ranked_sites as list positions
+ *   lookup double[S][3]  centres of _NearestSiteLookup
+ *   neigh_off int32[S+1], neigh int32[*]  face-sharing neighbours (polyhedral_site_
+ *                        collection.py:165-191), used when rank == NULL
+ * History state (host, in/out): recent int32[A][2], prev int32[A] (-2 = empty trajectory,
+ *   -1 = None), and the per-site transition Counters (site.py:68-71) as dense rows in Counter
+ *   insertion order: tr_n int32[S], tr_key int32[S][tr_width], tr_cnt int64[S][tr_width].
+ *   SAB_EOVERFLOW if a site collects more than tr_width distinct destinations. */
+int sab_set_priority_tables(sab_engine *e, const int32_t *rank, const double *lookup,
+                            const int32_t *neigh_off, const int32_t *neigh);
+int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames, int32_t *d_result,
+                const int32_t *d_spill, void *stream, int32_t *recent, int32_t *prev,
+                int32_t *tr_n, int32_t *tr_key, int64_t *tr_cnt, int tr_width);
+
+/* Dynamic-Voronoi centres of one frame range, double[F][S][3] on the device (bitwise
+ * comparable with DynamicVoronoiSite.centre, dynamic_voronoi_site_collection.py:104).
+ * Does not advance engine state. */
+int sab_dynvor_centres(sab_engine *e, const double *d_frac, int64_t n_frames, double *d_centres,
+                       void *d_workspace, int64_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAB200_H */

@@ -1,0 +1,7 @@
+#!/bin/sh
+# Builds libsab200.so in-tree for sm_100a.  -fmad=false is part of the numerical contract.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false \
+    -Xcompiler -fPIC -shared "$@" -o "$HERE/../libsab200.so" "$HERE/sab200.cu" -lcudart

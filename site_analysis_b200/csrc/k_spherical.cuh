@@ -1,0 +1,84 @@
+// k_spherical.cuh -- spherical-cutoff containment for every (frame, atom).
+//
+// Replaces the containment tests of SphericalSiteCollection.assign_site_occupations
+// (spherical_site_collection.py:71-92): SphericalSite.contains_point is
+//     mic_distance(site.frac_coords, x, L) <= rcut          (spherical_site.py:145-146)
+// i.e. sqrt(min over 27 images of |D.L|^2) <= rcut.  The host passes rcut_q[s] = the largest
+// double q with sqrt(q) <= rcut[s], so the test is `q <= rcut_q[s]` with no sqrt on the device.
+//
+// The kernel emits the FULL set of containing sites per atom-frame: none -> SAB_NONE, one ->
+// its list position (any priority order finds it, site_collection.py:113-182 yields every
+// site), several -> a spilled candidate list for the priority resolver (k_resolve.cuh).
+//
+// Exact image pruning: if q(central image) <= rcut_q the site contains the atom (the minimum
+// can only be smaller); otherwise, when rcut < 0.5 hmin (1 - 1e-9), every non-central image is
+// farther than rcut and the site does not contain it.  Sites with larger radii take all 27.
+#pragma once
+#include "sab_device.cuh"
+
+#define SAB_SPH_KEEP 8
+
+__device__ __forceinline__ bool sab_sphere_contains(const double *c, const double *x, double rcut,
+                                                    double rcut_q, const SabLattice &lat)
+{
+    double d0, d1, d2;
+    sab_dbase(c, x, d0, d1, d2);
+    if (sab_image_q(d0, d1, d2, lat.m) <= rcut_q) return true;
+    if (rcut < 0.5 * lat.hmin * (1.0 - SAB_REL_MARGIN)) return false;
+    return sab_mic_q27(d0, d1, d2, lat.m) <= rcut_q;
+}
+
+__global__ void k_spherical_assign(const double *__restrict__ frac, const double *__restrict__ lattice,
+                                   int lattice_stride, int64_t n_frames, int n_atoms, int n_mobile,
+                                   const int32_t *__restrict__ mobile, int n_sites,
+                                   const double *__restrict__ centres, const double *__restrict__ rcut,
+                                   const double *__restrict__ rcut_q, int32_t *__restrict__ result,
+                                   int32_t *__restrict__ spill, long long spill_capacity,
+                                   unsigned long long *__restrict__ counters /* [0] ambiguous [1] spill used [2] overflow */)
+{
+    extern __shared__ double sm[];                   // centres[S*3] | rcut[S] | rcut_q[S]
+    double *sc = sm, *sr = sm + 3 * n_sites, *sq = sr + n_sites;
+    __shared__ SabLattice lat;
+    for (int i = threadIdx.x; i < 3 * n_sites; i += blockDim.x) sc[i] = centres[i];
+    for (int i = threadIdx.x; i < n_sites; i += blockDim.x) { sr[i] = rcut[i]; sq[i] = rcut_q[i]; }
+    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const double *frame = frac + (size_t)f * n_atoms * 3;
+        __syncthreads();
+        if (threadIdx.x == 0) sab_lattice_load(lattice + (size_t)f * lattice_stride, lat);
+        __syncthreads();
+        for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
+            double x[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
+            int cnt = 0;
+            int keep[SAB_SPH_KEEP];
+            for (int s = 0; s < n_sites; s++)
+                if (sab_sphere_contains(sc + 3 * s, x, sr[s], sq[s], lat)) {
+                    if (cnt < SAB_SPH_KEEP) keep[cnt] = s;
+                    cnt++;
+                }
+            int out;
+            if (cnt == 0) out = SAB_NONE;
+            else if (cnt == 1) out = keep[0];
+            else {
+                atomicAdd(&counters[0], 1ULL);
+                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(cnt + 1));
+                if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
+                    counters[2] = 1ULL;
+                    out = SAB_NONE;
+                } else {
+                    spill[off] = cnt;
+                    if (cnt <= SAB_SPH_KEEP) {
+                        for (int i = 0; i < cnt; i++) spill[off + 1 + i] = keep[i];
+                    } else {
+                        int k = 0;
+                        for (int s = 0; s < n_sites; s++)
+                            if (sab_sphere_contains(sc + 3 * s, x, sr[s], sq[s], lat)) spill[off + 1 + k++] = s;
+                    }
+                    out = SAB_AMBIGUOUS_BASE - (int)off;
+                }
+            }
+            result[(size_t)f * n_mobile + a] = out;
+        }
+    }
+}

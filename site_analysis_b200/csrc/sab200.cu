@@ -1,0 +1,600 @@
+// sab200.cu -- engine and C ABI of libsab200.so (see include/sab200.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
+// -fmad=false is part of the numerical contract (no FMA contraction anywhere).
+#include "../../include/sab200.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "k_nearest.cuh"
+#include "k_polyhedral.cuh"
+#include "k_resolve.cuh"
+#include "k_spherical.cuh"
+#include "k_wrap.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(SAB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <class T> static cudaError_t upload(T **dst, const T *src, size_t n)
+{
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+enum { CNT_AMBIGUOUS = 0, CNT_SPILL = 1, CNT_OVERFLOW = 2, CNT_FIRST_BAD = 3, CNT_FULL27 = 4, CNT_N = 8 };
+
+struct sab_engine {
+    int kind = 0, device = 0, N = 0, A = 0, S = 0;
+    int sm_count = 148;
+    int32_t *d_mobile = nullptr;
+    double *d_centres = nullptr, *d_rcut = nullptr, *d_rcut_q = nullptr;
+    // polyhedron vertices / dynamic-Voronoi reference atoms ("slots")
+    int smax = 0, fmax = 0, M = 0;
+    std::vector<int32_t> fw_atoms;
+    int32_t *d_fw_atoms = nullptr, *d_nslot = nullptr, *d_slot_atom = nullptr, *d_slot_fw = nullptr;
+    int32_t *d_nface = nullptr; uint8_t *d_simp = nullptr;
+    // PBC state
+    int32_t *d_slot_shift = nullptr, *d_wraps = nullptr;
+    double *d_prev_raw = nullptr, *d_excursion = nullptr;
+    bool pbc_set = false;
+    uint8_t *d_legacy_init = nullptr; int64_t legacy_init_frame = -1;
+    // priority tables
+    int32_t *d_rank = nullptr, *d_neigh_off = nullptr, *d_neigh = nullptr; double *d_lookup = nullptr;
+    // counters
+    unsigned long long *d_counters = nullptr;
+    // host-path staging
+    void *stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
+    void *ws = nullptr; size_t ws_bytes = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
+};
+
+extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
+extern "C" const char *sab_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sab_engine_create(sab_engine **out, int kind, int device, int n_atoms, int n_mobile,
+                                 const int32_t *mobile_idx, int n_sites)
+{
+    if (!out || kind < 0 || kind > 3 || n_atoms <= 0 || n_mobile <= 0 || n_sites <= 0 || !mobile_idx)
+        return fail(SAB_EINVAL, "sab_engine_create: bad arguments");
+    for (int a = 0; a < n_mobile; a++)
+        if (mobile_idx[a] < 0 || mobile_idx[a] >= n_atoms)
+            return fail(SAB_EINVAL, "mobile atom index %d out of range [0,%d)", mobile_idx[a], n_atoms);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SAB_ECUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    sab_engine *e = new sab_engine();
+    e->kind = kind; e->device = device; e->N = n_atoms; e->A = n_mobile; e->S = n_sites;
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    CU(upload(&e->d_mobile, mobile_idx, (size_t)n_mobile));
+    CU(cudaMalloc((void **)&e->d_counters, CNT_N * sizeof(unsigned long long)));
+    *out = e;
+    return SAB_OK;
+}
+
+extern "C" void sab_engine_destroy(sab_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    void *ptrs[] = {e->d_mobile, e->d_centres, e->d_rcut, e->d_rcut_q, e->d_fw_atoms, e->d_nslot, e->d_slot_atom,
+                    e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
+                    e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
+                    e->stage[0], e->stage[1], e->ws};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (e->streams[i]) cudaStreamDestroy(e->streams[i]);
+        if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
+    }
+    delete e;
+}
+
+extern "C" int sab_set_centres(sab_engine *e, const double *centres, const double *rcut, const double *rcut_sq_max)
+{
+    if (!e || !centres) return fail(SAB_EINVAL, "sab_set_centres: null argument");
+    if (e->kind != SAB_SPHERICAL && e->kind != SAB_VORONOI) return fail(SAB_EINVAL, "sab_set_centres: wrong engine kind");
+    if (e->kind == SAB_SPHERICAL && (!rcut || !rcut_sq_max)) return fail(SAB_EINVAL, "spherical sites need rcut and rcut_sq_max");
+    CU(cudaSetDevice(e->device));
+    CU(upload(&e->d_centres, centres, (size_t)3 * e->S));
+    if (e->kind == SAB_SPHERICAL) {
+        CU(upload(&e->d_rcut, rcut, (size_t)e->S));
+        CU(upload(&e->d_rcut_q, rcut_sq_max, (size_t)e->S));
+    }
+    return SAB_OK;
+}
+
+static int set_slots(sab_engine *e, int smax, const int32_t *n_slot, const int32_t *slot_atom)
+{
+    if (smax <= 0) return fail(SAB_EINVAL, "slot width must be positive");
+    std::vector<int32_t> uniq;
+    for (int s = 0; s < e->S; s++) {
+        if (n_slot[s] <= 0 || n_slot[s] > smax) return fail(SAB_EINVAL, "site %d: bad vertex/reference count %d", s, n_slot[s]);
+        for (int v = 0; v < n_slot[s]; v++) {
+            int32_t at = slot_atom[(size_t)s * smax + v];
+            if (at < 0 || at >= e->N) return fail(SAB_EINVAL, "site %d: atom index %d out of range", s, at);
+            uniq.push_back(at);
+        }
+    }
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    e->fw_atoms = uniq; e->M = (int)uniq.size(); e->smax = smax;
+    std::vector<int32_t> fw((size_t)e->S * smax, 0), at((size_t)e->S * smax, 0);
+    for (int s = 0; s < e->S; s++)
+        for (int v = 0; v < n_slot[s]; v++) {
+            int32_t a = slot_atom[(size_t)s * smax + v];
+            at[(size_t)s * smax + v] = a;
+            fw[(size_t)s * smax + v] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), a) - uniq.begin());
+        }
+    CU(upload(&e->d_fw_atoms, uniq.data(), uniq.size()));
+    CU(upload(&e->d_nslot, n_slot, (size_t)e->S));
+    CU(upload(&e->d_slot_atom, at.data(), at.size()));
+    CU(upload(&e->d_slot_fw, fw.data(), fw.size()));
+    e->pbc_set = false;
+    return SAB_OK;
+}
+
+extern "C" int sab_set_polyhedra(sab_engine *e, int vmax, const int32_t *n_vert, const int32_t *vert_idx,
+                                 int fmax, const int32_t *n_face, const int32_t *simplices)
+{
+    if (!e || !n_vert || !vert_idx || !n_face || !simplices) return fail(SAB_EINVAL, "sab_set_polyhedra: null argument");
+    if (e->kind != SAB_POLYHEDRAL) return fail(SAB_EINVAL, "sab_set_polyhedra: wrong engine kind");
+    if (vmax > SAB_MAX_VERT) return fail(SAB_EINVAL, "polyhedra with more than %d vertices are not supported", SAB_MAX_VERT);
+    if (fmax <= 0) return fail(SAB_EINVAL, "fmax must be positive");
+    CU(cudaSetDevice(e->device));
+    int rc = set_slots(e, vmax, n_vert, vert_idx);
+    if (rc) return rc;
+    std::vector<uint8_t> simp((size_t)e->S * fmax * 3, 0);
+    for (int s = 0; s < e->S; s++) {
+        if (n_face[s] < 4 || n_face[s] > fmax) return fail(SAB_EINVAL, "site %d: bad face count %d", s, n_face[s]);
+        for (int j = 0; j < 3 * n_face[s]; j++) {
+            int v = simplices[(size_t)s * fmax * 3 + j];
+            if (v < 0 || v >= n_vert[s]) return fail(SAB_EINVAL, "site %d: face vertex %d out of range", s, v);
+            simp[(size_t)s * fmax * 3 + j] = (uint8_t)v;
+        }
+    }
+    e->fmax = fmax;
+    CU(upload(&e->d_nface, n_face, (size_t)e->S));
+    CU(upload(&e->d_simp, simp.data(), simp.size()));
+    return SAB_OK;
+}
+
+extern "C" int sab_set_reference_atoms(sab_engine *e, int rmax, const int32_t *n_ref, const int32_t *ref_idx)
+{
+    if (!e || !n_ref || !ref_idx) return fail(SAB_EINVAL, "sab_set_reference_atoms: null argument");
+    if (e->kind != SAB_DYNAMIC_VORONOI) return fail(SAB_EINVAL, "sab_set_reference_atoms: wrong engine kind");
+    CU(cudaSetDevice(e->device));
+    return set_slots(e, rmax, n_ref, ref_idx);
+}
+
+extern "C" int sab_framework_count(sab_engine *e) { return e ? e->M : 0; }
+extern "C" int sab_framework_atoms(sab_engine *e, int32_t *out)
+{
+    if (!e || !out) return fail(SAB_EINVAL, "sab_framework_atoms: null argument");
+    std::copy(e->fw_atoms.begin(), e->fw_atoms.end(), out);
+    return SAB_OK;
+}
+
+extern "C" int sab_set_pbc_state(sab_engine *e, const int32_t *slot_shift, const double *prev_raw,
+                                 const int32_t *wraps, const double *excursion)
+{
+    if (!e || !slot_shift || !prev_raw || !wraps || !excursion) return fail(SAB_EINVAL, "sab_set_pbc_state: null argument");
+    if (e->M == 0) return fail(SAB_ESTATE, "sab_set_pbc_state: no vertex/reference tables set");
+    CU(cudaSetDevice(e->device));
+    CU(upload(&e->d_slot_shift, slot_shift, (size_t)e->S * e->smax * 3));
+    CU(upload(&e->d_prev_raw, prev_raw, (size_t)e->M * 3));
+    CU(upload(&e->d_wraps, wraps, (size_t)e->M * 3));
+    CU(upload(&e->d_excursion, excursion, (size_t)e->M * 6));
+    e->pbc_set = true;
+    return SAB_OK;
+}
+
+extern "C" int sab_get_pbc_state(sab_engine *e, int32_t *slot_shift, double *prev_raw, int32_t *wraps, double *excursion)
+{
+    if (!e || !e->pbc_set) return fail(SAB_ESTATE, "sab_get_pbc_state: PBC state not set");
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    if (slot_shift) CU(cudaMemcpy(slot_shift, e->d_slot_shift, sizeof(int32_t) * (size_t)e->S * e->smax * 3, cudaMemcpyDeviceToHost));
+    if (prev_raw) CU(cudaMemcpy(prev_raw, e->d_prev_raw, sizeof(double) * (size_t)e->M * 3, cudaMemcpyDeviceToHost));
+    if (wraps) CU(cudaMemcpy(wraps, e->d_wraps, sizeof(int32_t) * (size_t)e->M * 3, cudaMemcpyDeviceToHost));
+    if (excursion) CU(cudaMemcpy(excursion, e->d_excursion, sizeof(double) * (size_t)e->M * 6, cudaMemcpyDeviceToHost));
+    return SAB_OK;
+}
+
+extern "C" int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int64_t frames_from_now)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_legacy_init: null engine");
+    CU(cudaSetDevice(e->device));
+    if (!site_flags) { if (e->d_legacy_init) { cudaFree(e->d_legacy_init); e->d_legacy_init = nullptr; } e->legacy_init_frame = -1; return SAB_OK; }
+    CU(upload(&e->d_legacy_init, site_flags, (size_t)e->S));
+    e->legacy_init_frame = frames_from_now;
+    return SAB_OK;
+}
+
+extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_option: null engine");
+    if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
+    return fail(SAB_EINVAL, "unknown option %d", key);
+}
+
+// ---------------------------------------------------------------- workspace layout
+struct Workspace {
+    int n_chunks = 0; int m3 = 0;
+    int32_t *totals = nullptr; double *chunk_exc = nullptr; int32_t *rows = nullptr;
+    size_t bytes = 0;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static Workspace layout(const sab_engine *e, int64_t F, void *base)
+{
+    Workspace w;
+    w.m3 = 3 * e->M;
+    if (w.m3 == 0 || F == 0) { w.bytes = 256; return w; }
+    w.n_chunks = (int)((F + SAB_WRAP_CHUNK - 1) / SAB_WRAP_CHUNK);
+    size_t off = 0;
+    char *b = (char *)base;
+    w.totals = (int32_t *)(b + off); off += align256(sizeof(int32_t) * (size_t)w.n_chunks * w.m3);
+    w.chunk_exc = (double *)(b + off); off += align256(sizeof(double) * 2 * (size_t)w.n_chunks * w.m3);
+    w.rows = (int32_t *)(b + off); off += align256(sizeof(int32_t) * (size_t)F * w.m3);
+    w.bytes = off + 256;
+    return w;
+}
+
+extern "C" int64_t sab_workspace_bytes(sab_engine *e, int64_t n_frames)
+{
+    if (!e || n_frames < 0) return -1;
+    return (int64_t)layout(e, n_frames, nullptr).bytes;
+}
+
+static int run_wrap_pass(sab_engine *e, const double *d_frac, int64_t F, const Workspace &w, cudaStream_t st, bool rows_and_commit)
+{
+    dim3 grid(w.n_chunks, (w.m3 + 127) / 128);
+    k_wrap_totals<<<grid, 128, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, e->d_prev_raw, w.totals,
+                                        e->d_counters + CNT_FIRST_BAD, e->skip_step_check_once ? 1 : 0);
+    e->launches++;
+    if (!rows_and_commit) return SAB_OK;
+    k_wrap_bases<<<(w.m3 + 127) / 128, 128, 0, st>>>(w.totals, w.n_chunks, w.m3, e->d_wraps);
+    k_wrap_rows<<<grid, 128, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, e->d_prev_raw, w.totals, w.rows, w.chunk_exc);
+    e->launches += 2;
+    return SAB_OK;
+}
+
+extern "C" int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_frames, void *d_workspace,
+                               int64_t workspace_bytes, void *stream, int32_t *totals, double *last_raw)
+{
+    if (!e || !d_frac || !totals || !last_raw) return fail(SAB_EINVAL, "sab_wrap_totals: null argument");
+    if (!e->pbc_set) return fail(SAB_ESTATE, "sab_wrap_totals: PBC state not set");
+    if (n_frames <= 0) return fail(SAB_EINVAL, "sab_wrap_totals: no frames");
+    CU(cudaSetDevice(e->device));
+    Workspace w = layout(e, n_frames, d_workspace);
+    if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    run_wrap_pass(e, d_frac, n_frames, w, st, false);
+    CU(cudaGetLastError());
+    std::vector<int32_t> h((size_t)w.n_chunks * w.m3);
+    CU(cudaMemcpyAsync(h.data(), w.totals, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, st));
+    std::vector<double> lastf((size_t)e->N * 3);
+    CU(cudaMemcpyAsync(lastf.data(), d_frac + (size_t)(n_frames - 1) * e->N * 3, sizeof(double) * lastf.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int c = 0; c < w.m3; c++) {
+        int t = 0;
+        for (int k = 0; k < w.n_chunks; k++) t += h[(size_t)k * w.m3 + c];
+        totals[c] = t;
+        last_raw[c] = lastf[(size_t)e->fw_atoms[c / 3] * 3 + c % 3];
+    }
+    return SAB_OK;
+}
+
+static int launch_assign(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride, int64_t F,
+                         int32_t *d_result, int32_t *d_spill, int64_t spill_cap, const Workspace &w, cudaStream_t st,
+                         double *d_centres_out)
+{
+    int grid = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 8);
+    switch (e->kind) {
+    case SAB_VORONOI: {
+        int block = std::min(1024, ((e->A + 31) / 32) * 32);
+        size_t smem = sizeof(double) * 3 * (size_t)e->S;
+        CU(cudaFuncSetAttribute(k_nearest_assign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_nearest_assign<false><<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile,
+            e->S, e->d_centres, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, -1, nullptr, d_result,
+            e->d_counters + CNT_FULL27);
+        break;
+    }
+    case SAB_DYNAMIC_VORONOI: {
+        int block = std::min(1024, ((std::max(e->A, 128) + 31) / 32) * 32);
+        size_t smem = sizeof(double) * 3 * (size_t)e->S;
+        CU(cudaFuncSetAttribute(k_nearest_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_nearest_assign<true><<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile,
+            e->S, nullptr, e->smax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, w.rows, w.m3,
+            e->d_legacy_init, e->legacy_init_frame, d_centres_out, d_result, e->d_counters + CNT_FULL27);
+        break;
+    }
+    case SAB_SPHERICAL: {
+        int block = std::min(1024, ((e->A + 31) / 32) * 32);
+        size_t smem = sizeof(double) * 5 * (size_t)e->S;
+        CU(cudaFuncSetAttribute(k_spherical_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_spherical_assign<<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile, e->S,
+            e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
+        break;
+    }
+    case SAB_POLYHEDRAL: {
+        int block = 256;
+        size_t smem = sizeof(double) * 3 * (size_t)e->A + sizeof(int) * (size_t)e->A * (1 + SAB_POLY_KEEP);
+        CU(cudaFuncSetAttribute(k_polyhedral_assign_exhaustive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
+                        e->d_legacy_init};
+        k_polyhedral_assign_exhaustive<<<grid, block, smem, st>>>(d_frac, F, e->N, e->A, e->d_mobile, e->S, T, w.rows, w.m3,
+            e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters);
+        break;
+    }
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
+
+static int check_ready(sab_engine *e)
+{
+    if ((e->kind == SAB_SPHERICAL || e->kind == SAB_VORONOI) && !e->d_centres) return fail(SAB_ESTATE, "site centres not set");
+    if (e->kind == SAB_POLYHEDRAL && !e->d_simp) return fail(SAB_ESTATE, "polyhedra not set");
+    if (e->kind == SAB_DYNAMIC_VORONOI && !e->d_slot_atom) return fail(SAB_ESTATE, "reference atoms not set");
+    if ((e->kind == SAB_POLYHEDRAL || e->kind == SAB_DYNAMIC_VORONOI) && !e->pbc_set) return fail(SAB_ESTATE, "PBC state not set");
+    return SAB_OK;
+}
+
+extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride,
+                                 int64_t n_frames, int32_t *d_result, int32_t *d_spill, int64_t spill_capacity,
+                                 void *d_workspace, int64_t workspace_bytes, void *stream, int64_t *info)
+{
+    if (!e || !d_frac || !d_lattice || !d_result || !info) return fail(SAB_EINVAL, "sab_assign_device: null argument");
+    if (lattice_stride != 0 && lattice_stride != 9) return fail(SAB_EINVAL, "lattice_stride must be 0 or 9");
+    if (n_frames < 0) return fail(SAB_EINVAL, "negative frame count");
+    int rc = check_ready(e);
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    info[3] = -1;
+    if (n_frames == 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace w = layout(e, n_frames, d_workspace);
+    if (w.m3 && (!d_workspace || (int64_t)w.bytes > workspace_bytes))
+        return fail(SAB_EINVAL, "workspace too small: need %zu bytes, got %lld", w.bytes, (long long)workspace_bytes);
+    int64_t l0 = e->launches;
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    if (w.m3) { run_wrap_pass(e, d_frac, n_frames, w, st, true); CU(cudaGetLastError()); }
+    rc = launch_assign(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, w, st, nullptr);
+    if (rc) return rc;
+    unsigned long long h[CNT_N];
+    CU(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    e->skip_step_check_once = false;
+    info[0] = (int64_t)h[CNT_AMBIGUOUS]; info[1] = (int64_t)h[CNT_SPILL]; info[2] = (int64_t)h[CNT_OVERFLOW];
+    info[3] = (h[CNT_FIRST_BAD] == ~0ULL) ? -1 : (int64_t)h[CNT_FIRST_BAD];
+    info[4] = (int64_t)h[CNT_FULL27];
+    if (h[CNT_OVERFLOW]) {                   // nothing committed: the caller retries with a larger spill buffer
+        info[5] = e->launches - l0;
+        return fail(SAB_EOVERFLOW, "candidate spill buffer overflow (%llu elements needed, capacity %lld)",
+                    h[CNT_SPILL], (long long)spill_capacity);
+    }
+    if (w.m3 && info[3] < 0) {               // no cache-invalidating step: the whole batch is committed
+        k_wrap_commit<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, n_frames, e->N, e->d_fw_atoms, w.m3, w.n_chunks,
+                                                          w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion);
+        e->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        if (e->legacy_init_frame >= 0) e->legacy_init_frame -= n_frames;      // now in the past
+    }
+    info[5] = e->launches - l0;
+    return SAB_OK;
+}
+
+extern "C" int sab_commit_pbc(sab_engine *e, const double *d_frac, int64_t n_frames, int64_t n_commit,
+                              void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    if (!e || !d_frac || n_commit < 0 || n_commit > n_frames) return fail(SAB_EINVAL, "sab_commit_pbc: bad arguments");
+    if (!e->pbc_set) return fail(SAB_ESTATE, "sab_commit_pbc: PBC state not set");
+    if (n_commit == 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace w = layout(e, n_frames, d_workspace);
+    if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
+    k_wrap_commit<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, n_commit, e->N, e->d_fw_atoms, w.m3, w.n_chunks,
+                                                      w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    if (e->legacy_init_frame >= 0) e->legacy_init_frame -= n_commit;
+    return SAB_OK;
+}
+
+extern "C" int sab_dynvor_centres(sab_engine *e, const double *d_frac, int64_t n_frames, double *d_centres,
+                                  void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    if (!e || e->kind != SAB_DYNAMIC_VORONOI || !d_frac || !d_centres) return fail(SAB_EINVAL, "sab_dynvor_centres: bad arguments");
+    int rc = check_ready(e);
+    if (rc) return rc;
+    if (n_frames <= 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace w = layout(e, n_frames, d_workspace);
+    if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    run_wrap_pass(e, d_frac, n_frames, w, st, true);
+    CU(cudaGetLastError());
+    static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double *d_lat = nullptr;
+    CU(cudaMalloc((void **)&d_lat, sizeof ident));
+    CU(cudaMemcpyAsync(d_lat, ident, sizeof ident, cudaMemcpyHostToDevice, st));
+    rc = launch_assign(e, d_frac, d_lat, 0, n_frames, nullptr, nullptr, 0, w, st, d_centres);
+    cudaStreamSynchronize(st);
+    cudaFree(d_lat);
+    return rc;
+}
+
+// ---------------------------------------------------------------- host-buffer path
+extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double *h_lattice, int lattice_stride,
+                               int64_t n_frames, int32_t *h_result, int64_t chunk_frames, int64_t *info)
+{
+    if (!e || !h_frac || !h_lattice || !h_result || !info) return fail(SAB_EINVAL, "sab_assign_host: null argument");
+    if (lattice_stride != 0 && lattice_stride != 9) return fail(SAB_EINVAL, "lattice_stride must be 0 or 9");
+    int rc = check_ready(e);
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    info[3] = -1;
+    if (n_frames <= 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    if (chunk_frames <= 0) chunk_frames = 8192;
+    chunk_frames = std::min(chunk_frames, n_frames);
+    const size_t frame_b = sizeof(double) * 3 * (size_t)e->N, res_b = sizeof(int32_t) * (size_t)e->A;
+    const size_t spill_elems = (size_t)chunk_frames * e->A * 2 + 1024;
+    const size_t ws_b = layout(e, chunk_frames, nullptr).bytes;
+    // per-buffer staging: frames | lattices | result | spill | workspace
+    size_t o_lat = align256(frame_b * chunk_frames), o_res = o_lat + align256(sizeof(double) * 9 * chunk_frames);
+    size_t o_spill = o_res + align256(res_b * chunk_frames), o_ws = o_spill + align256(sizeof(int32_t) * spill_elems);
+    size_t need = o_ws + align256(ws_b);
+    if (need > e->stage_bytes) {
+        for (int i = 0; i < 2; i++) { if (e->stage[i]) cudaFree(e->stage[i]); e->stage[i] = nullptr; }
+        for (int i = 0; i < 2; i++) CU(cudaMalloc(&e->stage[i], need));
+        e->stage_bytes = need;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (!e->streams[i]) CU(cudaStreamCreateWithFlags(&e->streams[i], cudaStreamNonBlocking));
+        if (!e->ev_free[i]) CU(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming));
+    }
+    // The wrap scan carries state from chunk to chunk through the engine (stream-ordered):
+    // chunk k+1's kernels must follow chunk k's commit, so compute is serialised on stream 0
+    // while the H2D copy of the next chunk runs on stream 1 (and vice versa).
+    cudaEvent_t ev_copied[2], ev_done[2];
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    }
+    cudaStream_t s_copy = e->streams[1], s_comp = e->streams[0];
+    int64_t tot_info[8] = {0, 0, 0, -1, 0, 0, 0, 0};
+    int status = SAB_OK;
+    int64_t n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    auto issue_copy = [&](int64_t k) -> cudaError_t {
+        int b = (int)(k & 1);
+        int64_t f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
+        char *base = (char *)e->stage[b];
+        cudaError_t er = cudaStreamWaitEvent(s_copy, ev_done[b], 0);     // buffer b free again
+        if (er != cudaSuccess) return er;
+        er = cudaMemcpyAsync(base, h_frac + (size_t)f0 * e->N * 3, frame_b * nf, cudaMemcpyHostToDevice, s_copy);
+        if (er != cudaSuccess) return er;
+        if (lattice_stride)
+            er = cudaMemcpyAsync(base + o_lat, h_lattice + (size_t)f0 * 9, sizeof(double) * 9 * nf, cudaMemcpyHostToDevice, s_copy);
+        else
+            er = cudaMemcpyAsync(base + o_lat, h_lattice, sizeof(double) * 9, cudaMemcpyHostToDevice, s_copy);
+        if (er != cudaSuccess) return er;
+        return cudaEventRecord(ev_copied[b], s_copy);
+    };
+    CU(issue_copy(0));
+    for (int64_t k = 0; k < n_chunks && status == SAB_OK; k++) {
+        int b = (int)(k & 1);
+        int64_t f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
+        char *base = (char *)e->stage[b];
+        if (k + 1 < n_chunks) CU(issue_copy(k + 1));
+        CU(cudaStreamWaitEvent(s_comp, ev_copied[b], 0));
+        int64_t ci[8];
+        status = sab_assign_device(e, (const double *)base, (const double *)(base + o_lat), lattice_stride, nf,
+                                   (int32_t *)(base + o_res), (int32_t *)(base + o_spill), (int64_t)spill_elems,
+                                   base + o_ws, (int64_t)align256(ws_b), s_comp, ci);
+        if (status != SAB_OK) break;
+        if (ci[0] > 0) { status = fail(SAB_ESTATE, "sab_assign_host: %lld atom-frames are contained by several sites; "
+                                       "use sab_assign_device + sab_resolve", (long long)ci[0]); break; }
+        CU(cudaMemcpyAsync(h_result + (size_t)f0 * e->A, base + o_res, res_b * nf, cudaMemcpyDeviceToHost, s_comp));
+        CU(cudaEventRecord(ev_done[b], s_comp));
+        tot_info[0] += ci[0]; tot_info[1] += ci[1]; tot_info[4] += ci[4]; tot_info[5] += ci[5];
+        if (ci[3] >= 0 && tot_info[3] < 0) tot_info[3] = f0 + ci[3];
+    }
+    cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_copy);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_copied[i]); cudaEventDestroy(ev_done[i]); }
+    for (int i = 0; i < 8; i++) info[i] = tot_info[i];
+    return status;
+}
+
+// ---------------------------------------------------------------- priority resolver
+extern "C" int sab_set_priority_tables(sab_engine *e, const int32_t *rank, const double *lookup,
+                                       const int32_t *neigh_off, const int32_t *neigh)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_priority_tables: null engine");
+    CU(cudaSetDevice(e->device));
+    if (rank) CU(upload(&e->d_rank, rank, (size_t)e->S * (size_t)std::max(e->S - 1, 1)));
+    if (lookup) CU(upload(&e->d_lookup, lookup, (size_t)3 * e->S));
+    if (neigh_off) {
+        CU(upload(&e->d_neigh_off, neigh_off, (size_t)e->S + 1));
+        CU(upload(&e->d_neigh, neigh, (size_t)std::max(neigh_off[e->S], 1)));
+    }
+    return SAB_OK;
+}
+
+extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames, int32_t *d_result,
+                           const int32_t *d_spill, void *stream, int32_t *recent, int32_t *prev,
+                           int32_t *tr_n, int32_t *tr_key, int64_t *tr_cnt, int tr_width)
+{
+    if (!e || !d_frac || !d_result || !recent || !prev || !tr_n || !tr_key || !tr_cnt || tr_width <= 0)
+        return fail(SAB_EINVAL, "sab_resolve: null argument");
+    if (n_frames <= 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SabHistory H{};
+    H.K = tr_width;
+    int *d_over = nullptr;
+    size_t nk = (size_t)e->S * tr_width;
+    CU(cudaMalloc((void **)&H.recent, sizeof(int32_t) * 2 * e->A));
+    CU(cudaMalloc((void **)&H.prev, sizeof(int32_t) * e->A));
+    CU(cudaMalloc((void **)&H.tr_n, sizeof(int32_t) * e->S));
+    CU(cudaMalloc((void **)&H.tr_key, sizeof(int32_t) * nk));
+    CU(cudaMalloc((void **)&H.tr_cnt, sizeof(long long) * nk));
+    CU(cudaMalloc((void **)&d_over, sizeof(int)));
+    CU(cudaMemcpyAsync(H.recent, recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.prev, prev, sizeof(int32_t) * e->A, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.tr_n, tr_n, sizeof(int32_t) * e->S, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.tr_key, tr_key, sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.tr_cnt, tr_cnt, sizeof(long long) * nk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
+    SabPriorityTables P{e->d_rank, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
+    int block = std::min(1024, ((e->A + 31) / 32) * 32);
+    size_t smem = sizeof(int) * (size_t)e->A;
+    CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_resolve<<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, d_over);
+    e->launches++;
+    CU(cudaGetLastError());
+    int over = 0;
+    CU(cudaMemcpyAsync(recent, H.recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(prev, H.prev, sizeof(int32_t) * e->A, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tr_n, H.tr_n, sizeof(int32_t) * e->S, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tr_key, H.tr_key, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tr_cnt, H.tr_cnt, sizeof(long long) * nk, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(H.recent); cudaFree(H.prev); cudaFree(H.tr_n); cudaFree(H.tr_key); cudaFree(H.tr_cnt); cudaFree(d_over);
+    if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);
+    return SAB_OK;
+}

@@ -1,0 +1,509 @@
+"""Array-level host driver of the CUDA backend: one ``AssignmentEngine`` per site collection.
+
+This is the layer between the reference-shaped Python objects (``Trajectory``,
+``*SiteCollection``) and the C ABI in ``include/sab200.h``.  It owns
+
+* the static site tables uploaded to the device,
+* the PBC image-shift state (reference ``polyhedral_site.py:377-416``,
+  ``dynamic_voronoi_site_collection.py:38-105``) in its per-atom prefix-scan form,
+* the sequential history the reference keeps in Python objects -- ``Atom._recent_sites``
+  (``atom.py:55``), the previous trajectory entry, ``Site.transitions`` (``site.py:71``) --
+  which only the priority resolver and the user-visible attributes need.
+
+PyTorch is used for device memory, pinned staging and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _native as nat
+from . import _tables as tab
+
+EXCURSION_LIMIT = 0.3 - 1e-6     # guard of the scan formulation (pbc_utils.py:216)
+
+
+class GuardError(RuntimeError):
+    """The trajectory violates a precondition under which the frame-parallel formulation is
+    provably identical to the reference's sequential caches ("Guards")."""
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise nat.NativeError("site_analysis_b200 needs a CUDA device: there is no CPU fallback")
+    return torch
+
+
+def fold_history(recent: np.ndarray, prev: np.ndarray, transitions: list, rows: np.ndarray, append: bool) -> None:
+    """Advance (recent, prev, transitions) over finished result rows, in place.
+
+    Vectorised restatement of what the reference does per atom per frame in
+    ``SiteCollection.update_occupation`` (site_collection.py:300-310) and
+    ``Atom.update_recent_site`` (atom.py:190-192), followed by ``atom.trajectory.append``
+    (trajectory.py:357) when ``append``.  ``rows`` is (F, A) of list positions, -1 = None.
+    """
+    rows = np.asarray(rows)
+    F, A = rows.shape
+    if F == 0:
+        return
+    if not append and F != 1:
+        raise ValueError("analyse-without-append is defined for one frame at a time")
+    before = np.vstack([prev[None, :], rows[:-1]]) if append else prev[None, :]
+    moved = (before >= 0) & (rows >= 0) & (before != rows)
+    if moved.any():
+        f_idx, a_idx = np.nonzero(moved)              # row-major == (frame, atom) order
+        src = before[f_idx, a_idx].astype(np.int64)
+        dst = rows[f_idx, a_idx].astype(np.int64)
+        key = src * (int(rows.max()) + 2) + dst
+        _, first, counts = np.unique(key, return_index=True, return_counts=True)
+        for i in np.argsort(first, kind="stable"):    # Counter insertion order = first occurrence
+            d = transitions[int(src[first[i]])]
+            k = int(dst[first[i]])
+            d[k] = d.get(k, 0) + int(counts[i])
+    # two most recent distinct assigned sites per atom
+    assigned = rows >= 0
+    any_assigned = assigned.any(axis=0)
+    if any_assigned.any():
+        last_f = F - 1 - np.argmax(assigned[::-1], axis=0)
+        cols = np.arange(A)
+        last_v = rows[last_f, cols]
+        other = assigned & (rows != last_v[None, :])
+        has_other = other.any(axis=0)
+        other_f = F - 1 - np.argmax(other[::-1], axis=0)
+        other_v = rows[other_f, cols]
+        old0, old1 = recent[:, 0].copy(), recent[:, 1].copy()
+        new1 = np.where(has_other, other_v, np.where(old0 == last_v, old1, old0))
+        recent[:, 0] = np.where(any_assigned, last_v, old0)
+        recent[:, 1] = np.where(any_assigned, new1, old1)
+    if append:
+        prev[:] = rows[-1]
+
+
+class AssignmentEngine:
+    """GPU assignment of every mobile atom in every frame to a site (list positions).
+
+    Args:
+        kind: ``"spherical" | "voronoi" | "polyhedral" | "dynamic_voronoi"``.
+        n_atoms: atoms per frame N.
+        mobile_idx: structure indices of the tracked atoms (A,).
+        centres, rcut: spherical / Voronoi site tables.
+        slots: per site, the vertex (polyhedral) or reference (dynamic Voronoi) atom indices.
+        reference_centres: per site ``None`` or a (3,) array (PBC unwrapping target).
+        primed: per polyhedral site ``None`` or ``(image_shifts (V,3), cached_raw (V,3))`` as
+            left by the reference's ``SiteFactory`` (site_factory.py:248-257).
+        simplices: per polyhedral site ``None`` or an existing (n_faces, 3) face topology.
+        rank_table: optional precomputed distance-rank table (S, S-1).
+        strict: raise ``GuardError`` when a guard fails (default) instead of warning.
+    """
+
+    KINDS = {"spherical": nat.SPHERICAL, "voronoi": nat.VORONOI, "polyhedral": nat.POLYHEDRAL,
+             "dynamic_voronoi": nat.DYNAMIC_VORONOI}
+
+    def __init__(self, kind: str, n_atoms: int, mobile_idx, *, centres=None, rcut=None,
+                 slots: Sequence[Sequence[int]] | None = None, reference_centres=None, primed=None,
+                 simplices=None, rank_table=None, device: int | None = None, strict: bool = True):
+        torch = _torch()
+        self.L = nat.lib()
+        self.kind = kind
+        self.k = self.KINDS[kind]
+        self.N = int(n_atoms)
+        self.mobile = np.ascontiguousarray(mobile_idx, dtype=np.int32)
+        self.A = len(self.mobile)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.strict = strict
+        self.rank_table = None if rank_table is None else np.ascontiguousarray(rank_table, dtype=np.int32)
+        self._priority_uploaded = False
+        self.slots = None
+        if self.k in (nat.SPHERICAL, nat.VORONOI):
+            self.centres = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 3)
+            self.S = len(self.centres)
+        else:
+            self.slots = [list(map(int, s)) for s in slots]
+            self.S = len(self.slots)
+            self.ref_centres = ([None] * self.S if reference_centres is None else
+                                [None if (c is None or np.any(np.isnan(c))) else np.asarray(c, dtype=np.float64)
+                                 for c in reference_centres])
+            self.primed = [None] * self.S if primed is None else list(primed)
+            self.simplices = [None] * self.S if simplices is None else list(simplices)
+        h = C.c_void_p()
+        nat.check(self.L.sab_engine_create(C.byref(h), self.k, self.device, self.N, self.A,
+                                           nat.ptr(self.mobile), self.S))
+        self.h = h
+        if self.k == nat.SPHERICAL:
+            self.rcut = np.ascontiguousarray(np.broadcast_to(np.asarray(rcut, dtype=np.float64), (self.S,)))
+            self.rcut_q = np.ascontiguousarray(tab.sqrt_threshold(self.rcut))
+            nat.check(self.L.sab_set_centres(self.h, nat.ptr(self.centres), nat.ptr(self.rcut), nat.ptr(self.rcut_q)))
+        elif self.k == nat.VORONOI:
+            nat.check(self.L.sab_set_centres(self.h, nat.ptr(self.centres), None, None))
+        elif self.k == nat.DYNAMIC_VORONOI:
+            n_ref, ref = self._padded(self.slots)
+            self._n_slot, self._slot_atom = n_ref, ref
+            nat.check(self.L.sab_set_reference_atoms(self.h, ref.shape[1], nat.ptr(n_ref), nat.ptr(ref)))
+            self._load_framework()
+            # dynamic_voronoi_site_collection.py:151-164: groups by reference count, first seen first
+            seen: list[int] = []
+            for s in self.slots:
+                if len(s) not in seen:
+                    seen.append(len(s))
+            self.group_of_site = np.array([seen.index(len(s)) for s in self.slots], dtype=np.int32)
+        else:
+            self._n_slot, self._slot_atom = self._padded(self.slots)
+        self._pbc_ready = False
+        self.frames_done = 0
+        self.reset_history()
+        self.last_info: dict = {}
+
+    # ------------------------------------------------------------------ small helpers
+    @staticmethod
+    def _padded(lists):
+        n = np.array([len(x) for x in lists], dtype=np.int32)
+        out = np.zeros((len(lists), int(n.max())), dtype=np.int32)
+        for i, x in enumerate(lists):
+            out[i, :len(x)] = x
+        return n, np.ascontiguousarray(out)
+
+    def _load_framework(self):
+        M = self.L.sab_framework_count(self.h)
+        self.fw_atoms = np.zeros(M, dtype=np.int32)
+        nat.check(self.L.sab_framework_atoms(self.h, nat.ptr(self.fw_atoms)))
+        lut = -np.ones(self.N, dtype=np.int64)
+        lut[self.fw_atoms] = np.arange(M)
+        self.slot_fw = lut[self._slot_atom]           # (S, smax) compact ids (padding maps atom 0)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.sab_engine_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ history (host)
+    def reset_history(self):
+        self.recent = -np.ones((self.A, 2), dtype=np.int32)
+        self.prev = np.full(self.A, -2, dtype=np.int32)
+        self.transitions = [dict() for _ in range(self.S)]
+        self._pending: list[tuple[np.ndarray, bool]] = []
+
+    def reset(self):
+        """Trajectory.reset(): history and PBC caches cleared, face topology kept
+        (trajectory.py:364-373, polyhedral_site.py:264-279, dynamic_voronoi_site_collection.py:197-201)."""
+        self.reset_history()
+        self._pbc_ready = False
+        if self.slots is not None:
+            self.primed = [None] * self.S
+        self.frames_done = 0
+
+    def sync_history(self):
+        """Fold every finished batch into (recent, prev, transitions)."""
+        for rows, append in self._pending:
+            if not isinstance(rows, np.ndarray):
+                rows = rows.cpu().numpy()
+            fold_history(self.recent, self.prev, self.transitions, rows, append)
+        self._pending = []
+
+    # ------------------------------------------------------------------ PBC state initialisation
+    def _init_pbc(self, raw0: np.ndarray, lat0: np.ndarray):
+        """Build slot shifts relative to prev_raw = the first frame (W = 0).
+
+        Polyhedral sites primed by the builder carry (shift, cached raw) from the build
+        structure; they are advanced to the first frame exactly as ``update_pbc_shifts``
+        would (pbc_utils.py:210-217).  Unprimed sites (hand-made, or after reset) get the
+        reference's full correction on the first frame (polyhedral_site.py:410-416;
+        dynamic_voronoi_site_collection.py:188-195).
+        """
+        S = self.S
+        smax = self._slot_atom.shape[1]
+        slot_shift = np.zeros((S, smax, 3), dtype=np.int32)
+        legacy = np.zeros(S, dtype=np.uint8)
+        lo = {}
+        for s in range(S):
+            atoms = self.slots[s]
+            r = raw0[atoms]
+            pr = self.primed[s] if self.k == nat.POLYHEDRAL else None
+            done = False
+            if pr is not None:
+                sh, cached = np.asarray(pr[0], dtype=np.int64), np.asarray(pr[1], dtype=np.float64)
+                diff = r - cached
+                w = np.round(diff)
+                if np.all(np.abs(diff - w) < 0.3):
+                    slot_shift[s, :len(atoms)] = sh - w.astype(np.int64)
+                    for a, c in zip(atoms, cached + w):      # cached point in the unwrapped frame
+                        lo.setdefault(a, []).append(c)
+                    done = True
+            if not done:
+                rc = self.ref_centres[s]
+                slot_shift[s, :len(atoms)] = tab.full_pbc_unwrap(r, rc, lat0)
+                if rc is None:
+                    legacy[s] = 1
+        if self.k == nat.POLYHEDRAL:
+            n_face = np.zeros(S, dtype=np.int32)
+            faces = []
+            for s in range(S):
+                if self.simplices[s] is None:
+                    atoms = self.slots[s]
+                    vc = tab.unwrapped_vertices(raw0[atoms], slot_shift[s, :len(atoms)], non_negative=not legacy[s])
+                    self.simplices[s] = tab.hull_simplices(vc, s)
+                faces.append(np.asarray(self.simplices[s], dtype=np.int32))
+                n_face[s] = len(faces[-1])
+            fmax = int(n_face.max())
+            simp = np.zeros((S, fmax, 3), dtype=np.int32)
+            for s, f in enumerate(faces):
+                simp[s, :len(f)] = f
+            nat.check(self.L.sab_set_polyhedra(self.h, smax, nat.ptr(self._n_slot), nat.ptr(self._slot_atom),
+                                               fmax, nat.ptr(n_face), nat.ptr(np.ascontiguousarray(simp))))
+            self._load_framework()
+        M = len(self.fw_atoms)
+        prev_raw = np.ascontiguousarray(raw0[self.fw_atoms], dtype=np.float64)
+        wraps = np.zeros((M, 3), dtype=np.int32)
+        exc = np.stack([prev_raw, prev_raw], axis=-1)           # (M, 3, 2) min, max
+        pos = {int(a): i for i, a in enumerate(self.fw_atoms)}
+        for a, pts in lo.items():
+            p = np.array(pts)
+            exc[pos[a], :, 0] = np.minimum(exc[pos[a], :, 0], p.min(axis=0))
+            exc[pos[a], :, 1] = np.maximum(exc[pos[a], :, 1], p.max(axis=0))
+        self.slot_shift = np.ascontiguousarray(slot_shift)
+        nat.check(self.L.sab_set_pbc_state(self.h, nat.ptr(self.slot_shift), nat.ptr(prev_raw), nat.ptr(wraps),
+                                           nat.ptr(np.ascontiguousarray(exc))))
+        if legacy.any():
+            nat.check(self.L.sab_set_legacy_init(self.h, nat.ptr(legacy), 0))
+        else:
+            nat.check(self.L.sab_set_legacy_init(self.h, None, 0))
+        self._pbc_ready = True
+
+    def _reinit_groups(self, raw_t, lat_t):
+        """Dynamic Voronoi: a step >= 0.3 at this frame re-initialises every group that contains a
+        jumping reference slot (dynamic_voronoi_site_collection.py:94-95, 188-195)."""
+        M = len(self.fw_atoms)
+        sh = np.zeros((self.S,) + self.slot_shift.shape[1:], dtype=np.int32)
+        prev_raw = np.zeros((M, 3)); wraps = np.zeros((M, 3), dtype=np.int32); exc = np.zeros((M, 3, 2))
+        nat.check(self.L.sab_get_pbc_state(self.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
+        diff = raw_t[self.fw_atoms] - prev_raw
+        w = np.round(diff)
+        bad_atom = np.any(np.abs(diff - w) >= 0.3, axis=1)                     # (M,)
+        w_t = wraps + w.astype(np.int32)                                       # W after this frame
+        legacy = np.zeros(self.S, dtype=np.uint8)
+        bad_groups = set()
+        for s in range(self.S):
+            if bad_atom[self.slot_fw[s, :len(self.slots[s])]].any():
+                bad_groups.add(int(self.group_of_site[s]))
+        for s in range(self.S):
+            if int(self.group_of_site[s]) not in bad_groups:
+                continue
+            atoms = self.slots[s]
+            rc = self.ref_centres[s]
+            image = tab.full_pbc_unwrap(raw_t[atoms], rc, lat_t)
+            sh[s, :len(atoms)] = image + w_t[self.slot_fw[s, :len(atoms)]]
+            if rc is None:
+                legacy[s] = 1
+        # the jumping atoms start a fresh excursion record at this frame
+        u_t = raw_t[self.fw_atoms] - w_t
+        exc[bad_atom, :, 0] = u_t[bad_atom]
+        exc[bad_atom, :, 1] = u_t[bad_atom]
+        self.slot_shift = np.ascontiguousarray(sh)
+        nat.check(self.L.sab_set_pbc_state(self.h, nat.ptr(self.slot_shift), nat.ptr(np.ascontiguousarray(prev_raw)),
+                                           nat.ptr(np.ascontiguousarray(wraps)), nat.ptr(np.ascontiguousarray(exc))))
+        nat.check(self.L.sab_set_legacy_init(self.h, nat.ptr(legacy) if legacy.any() else None, 0))
+        nat.check(self.L.sab_set_option(self.h, nat.OPT_SKIP_STEP_CHECK_ONCE, 1))
+
+    def _check_excursion(self):
+        if self.k != nat.POLYHEDRAL:
+            return
+        M = len(self.fw_atoms)
+        exc = np.zeros((M, 3, 2))
+        nat.check(self.L.sab_get_pbc_state(self.h, None, None, None, nat.ptr(exc)))
+        span = exc[:, :, 1] - exc[:, :, 0]
+        if span.max() >= EXCURSION_LIMIT:
+            m, d = np.unravel_index(np.argmax(span), span.shape)
+            msg = (f"framework atom {int(self.fw_atoms[m])} moved over {span.max():.3f} fractional units along "
+                   f"axis {d}; beyond {EXCURSION_LIMIT:.3f} the reference's lazily updated PBC caches "
+                   "(polyhedral_site.py:398-416) are no longer equivalent to the frame-parallel scan")
+            if self.strict:
+                raise GuardError(msg)
+            import warnings
+            warnings.warn(msg)
+
+    # ------------------------------------------------------------------ priority tables
+    def _upload_priority_tables(self):
+        if self._priority_uploaded:
+            return
+        rank = lookup = off = flat = None
+        if self.k == nat.SPHERICAL:
+            lookup = self.centres
+        elif self.k == nat.POLYHEDRAL and all(c is not None for c in self.ref_centres):
+            lookup = np.ascontiguousarray(np.array(self.ref_centres, dtype=np.float64))
+        if lookup is not None:
+            rank = self.rank_table if self.rank_table is not None else tab.distance_rank_table(lookup)
+            self.rank_table = np.ascontiguousarray(rank, dtype=np.int32)
+        elif self.k == nat.POLYHEDRAL:
+            off, flat = tab.face_sharing_neighbours(self.slots)
+        nat.check(self.L.sab_set_priority_tables(self.h, nat.ptr(self.rank_table) if lookup is not None else None,
+                                                 nat.ptr(lookup), nat.ptr(off), nat.ptr(flat)))
+        self._priority_uploaded = True
+
+    def _resolve(self, d_frac, F, d_result, d_spill, stream, append):
+        self.sync_history()
+        self._upload_priority_tables()
+        width = max(32, 2 * max((len(t) for t in self.transitions), default=0))
+        while True:
+            tr_n = np.zeros(self.S, dtype=np.int32)
+            tr_key = np.zeros((self.S, width), dtype=np.int32)
+            tr_cnt = np.zeros((self.S, width), dtype=np.int64)
+            for s, t in enumerate(self.transitions):
+                tr_n[s] = len(t)
+                if t:
+                    tr_key[s, :len(t)] = list(t.keys())
+                    tr_cnt[s, :len(t)] = list(t.values())
+            recent, prev = self.recent.copy(), self.prev.copy()
+            d_backup = d_result.clone()
+            code = self.L.sab_resolve(self.h, d_frac.data_ptr(), F, d_result.data_ptr(), d_spill.data_ptr(), stream,
+                                      nat.ptr(recent), nat.ptr(prev), nat.ptr(tr_n), nat.ptr(tr_key), nat.ptr(tr_cnt), width)
+            if code == 3 and width < 4 * self.S:         # SAB_EOVERFLOW: widen the counter rows, redo
+                d_result.copy_(d_backup)
+                width *= 4
+                continue
+            nat.check(code)
+            break
+        self.recent = recent
+        if append:
+            self.prev = prev
+        self.transitions = [dict(zip(map(int, tr_key[s, :tr_n[s]]), map(int, tr_cnt[s, :tr_n[s]])))
+                            for s in range(self.S)]
+
+    # ------------------------------------------------------------------ the hot path
+    def assign_device(self, d_frac, d_lattice, *, append: bool = True):
+        """Assign a device-resident batch.  ``d_frac`` (F, N, 3) float64 cuda tensor, ``d_lattice`` (3, 3)
+        or (F, 3, 3).  Returns an (F, A) int32 cuda tensor of site list positions (-1 = None)."""
+        torch = _torch()
+        assert d_frac.is_cuda and d_frac.dtype == torch.float64 and d_frac.is_contiguous()
+        F = int(d_frac.shape[0])
+        assert tuple(d_frac.shape[1:]) == (self.N, 3), f"expected (F, {self.N}, 3), got {tuple(d_frac.shape)}"
+        if not append and F != 1:
+            raise ValueError("analyse-without-append is defined for one frame at a time")
+        d_lattice = d_lattice.contiguous()
+        stride = 9 if d_lattice.dim() == 3 else 0
+        if stride:
+            assert d_lattice.shape[0] == F
+        dev = d_frac.device
+        d_result = torch.empty((F, self.A), dtype=torch.int32, device=dev)
+        self._last_pending = []
+        if F == 0:
+            return d_result
+        if self.slots is not None and not self._pbc_ready:
+            lat0 = (d_lattice[0] if stride else d_lattice).cpu().numpy()
+            self._init_pbc(d_frac[0].cpu().numpy(), lat0)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        f0 = 0
+        total = dict(ambiguous=0, full27=0, launches=0, reinits=0)
+        while f0 < F:
+            nf = F - f0
+            sub = d_frac[f0:]
+            sub_lat = d_lattice[f0:] if stride else d_lattice
+            sub_res = d_result[f0:]
+            ws_bytes = int(self.L.sab_workspace_bytes(self.h, nf))
+            d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            cap = self._spill_capacity(nf)
+            info = np.zeros(8, dtype=np.int64)
+            while True:
+                d_spill = torch.empty(cap, dtype=torch.int32, device=dev)
+                code = self.L.sab_assign_device(self.h, sub.data_ptr(), sub_lat.data_ptr(), stride, nf,
+                                                sub_res.data_ptr(), d_spill.data_ptr(), cap, d_ws.data_ptr(), ws_bytes,
+                                                stream, nat.ptr(info))
+                if code == 3:                             # spill overflow (nothing committed): grow and redo
+                    cap = int(info[1]) * 2 + 1024
+                    continue
+                nat.check(code)
+                break
+            n_ok = nf if info[3] < 0 else int(info[3])
+            total["full27"] += int(info[4]); total["launches"] += int(info[5])
+            if info[3] >= 0:
+                if self.k == nat.POLYHEDRAL:
+                    raise GuardError(
+                        f"frame {self.frames_done + f0 + n_ok}: a polyhedron vertex moved >= 0.3 fractional units in "
+                        "one step (pbc_utils.py:216 invalidates the site's cache and the reference re-derives "
+                        "it lazily, which is inherently sequential)")
+                nat.check(self.L.sab_commit_pbc(self.h, sub.data_ptr(), nf, n_ok, d_ws.data_ptr(), ws_bytes, stream))
+            if n_ok:
+                ambiguous = bool(info[0]) and bool((sub_res[:n_ok] <= nat.AMBIGUOUS_BASE).any().item())
+                if ambiguous:
+                    self._resolve(sub, n_ok, sub_res, d_spill, stream, append)
+                    total["ambiguous"] += int(info[0])
+                else:
+                    self._pending.append((sub_res[:n_ok], append))
+                    self._last_pending.append((len(self._pending) - 1, f0, n_ok))
+            f0 += n_ok
+            if info[3] >= 0:
+                raw_t = d_frac[f0].cpu().numpy()
+                lat_t = (d_lattice[f0] if stride else d_lattice).cpu().numpy()
+                self._reinit_groups(raw_t, lat_t)
+                total["reinits"] += 1
+        self.frames_done += F
+        self._check_excursion()
+        self.last_info = total
+        return d_result
+
+    def _spill_capacity(self, nf: int) -> int:
+        if self.k == nat.SPHERICAL:
+            return int(nf * self.A * 4 + 1024)
+        if self.k == nat.POLYHEDRAL:
+            return int(max(nf * self.A // 8, 1) + 1024)
+        return 16
+
+    def assign(self, frac: np.ndarray, lattice: np.ndarray, *, append: bool = True, chunk_frames: int = 32768) -> np.ndarray:
+        """Assign a host trajectory (F, N, 3): staging -> device -> (F, A) int32 numpy."""
+        torch = _torch()
+        frac = np.ascontiguousarray(frac, dtype=np.float64)
+        lattice = np.ascontiguousarray(lattice, dtype=np.float64)
+        F = frac.shape[0]
+        out = np.empty((F, self.A), dtype=np.int32)
+        dev = torch.device("cuda", self.device)
+        for f0 in range(0, F, chunk_frames):
+            f1 = min(F, f0 + chunk_frames)
+            d_frac = torch.from_numpy(frac[f0:f1]).to(dev)
+            lat = lattice if lattice.ndim == 2 else lattice[f0:f1]
+            d_lat = torch.from_numpy(np.ascontiguousarray(lat)).to(dev)
+            out[f0:f1] = self.assign_device(d_frac, d_lat, append=append).cpu().numpy()
+            for idx, start, n in self._last_pending:      # history folds lazily from the host copy
+                self._pending[idx] = (out[f0 + start:f0 + start + n], self._pending[idx][1])
+        return out
+
+    def assign_host_pipelined(self, frac: np.ndarray, lattice: np.ndarray, out: np.ndarray | None = None,
+                              chunk_frames: int = 8192) -> np.ndarray:
+        """The C-ABI host-buffer call (``sab_assign_host``): chunked, copy/compute overlapped.
+
+        Frames whose atoms sit in several sites at once need the resolver and are not handled by
+        this entry point (it raises); use :meth:`assign` for such trajectories."""
+        assert frac.dtype == np.float64 and frac.flags["C_CONTIGUOUS"]
+        lattice = np.ascontiguousarray(lattice, dtype=np.float64)
+        F = frac.shape[0]
+        if out is None:
+            out = np.empty((F, self.A), dtype=np.int32)
+        if self.slots is not None and not self._pbc_ready and F:
+            self._init_pbc(frac[0], lattice if lattice.ndim == 2 else lattice[0])
+        info = np.zeros(8, dtype=np.int64)
+        nat.check(self.L.sab_assign_host(self.h, frac.ctypes.data, nat.ptr(lattice), 9 if lattice.ndim == 3 else 0,
+                                         F, out.ctypes.data, chunk_frames, nat.ptr(info)))
+        if info[3] >= 0:
+            raise GuardError(f"frame {int(info[3])}: a framework step >= 0.3 fractional units needs the re-initialising "
+                             "path; use AssignmentEngine.assign")
+        self._check_excursion()
+        self._pending.append((out, True))
+        self.frames_done += F
+        self.last_info = dict(ambiguous=0, full27=int(info[4]), launches=int(info[5]), reinits=0)
+        return out
+
+    def dynvor_centres(self, d_frac):
+        """(F, S, 3) float64 cuda tensor of dynamic-Voronoi centres for a batch (state not advanced)."""
+        torch = _torch()
+        F = int(d_frac.shape[0])
+        if not self._pbc_ready:
+            raise nat.NativeError("dynvor_centres needs an initialised PBC state (assign a frame first)")
+        ws_bytes = int(self.L.sab_workspace_bytes(self.h, F))
+        d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d_frac.device)
+        d_c = torch.empty((F, self.S, 3), dtype=torch.float64, device=d_frac.device)
+        nat.check(self.L.sab_dynvor_centres(self.h, d_frac.data_ptr(), F, d_c.data_ptr(), d_ws.data_ptr(), ws_bytes,
+                                            torch.cuda.current_stream(d_frac.device).cuda_stream))
+        return d_c

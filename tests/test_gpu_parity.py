@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA path (through the reference-shaped Python API and the C ABI) against
+(a) the committed golden outputs of the unmodified reference and (b) the CPU oracle run on
+the same inputs.  Bit-exact: every (frame, atom) site index incl. None, transition Counters
+incl. insertion order, recent-site history, dynamic-Voronoi centres as float64 bit patterns."""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+from helpers import has_jump, trajectory_from_case, transitions_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_batch(case):
+    t = trajectory_from_case(case)
+    rows = t.trajectory_from_arrays(case["frac"], case["lattice"])
+    return t, rows
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_batch_matches_reference_golden(oracle_mod, name):
+    import site_analysis_b200 as sab
+    case = oracle_mod.load_case(name)
+    if str(case["kind"]) == "PolyhedralSite" and has_jump(case):
+        with pytest.raises(sab.GuardError):
+            _run_batch(case)
+        return
+    t, rows = _run_batch(case)
+    want = case["atoms_traj"]
+    assert rows.shape == want.shape
+    assert int((rows != want).sum()) == 0
+    # the oracle on the same inputs says the same (it is pinned to the reference separately)
+    o = oracle_mod.SiteOracle.from_case(case)
+    assert np.array_equal(o.run(case["frac"], case["lattice"]), rows)
+    want_tr = oracle_mod.transitions_from_case(case)
+    got_tr = transitions_of(t)
+    assert got_tr == want_tr
+    for k in got_tr:
+        assert list(got_tr[k]) == list(want_tr[k])
+    got_recent = np.array([[-1 if r is None else r for r in a._recent_sites] for a in t.atoms])
+    assert np.array_equal(got_recent, case["recent"])
+    assert len(t) == rows.shape[0] and t.timesteps[:3] == [1, 2, 3][:len(t)]
+    assert [(-1 if v is None else v) for v in t.atoms[0].trajectory] == want[:, 0].tolist()
+    assert t.atom_sites == [None if v < 0 else int(v) for v in want[-1]]
+
+
+@pytest.mark.parametrize("name", ["readme_spherical", "simple_cubic_polyhedral", "fuzz_spherical_1", "fuzz_voronoi_0",
+                                  "fuzz_polyhedral_1", "fuzz_polyhedral_6", "fuzz_dynvor_1", "fuzz_dynvor_2"])
+def test_per_frame_api_matches_reference_golden(oracle_mod, name):
+    """append_timestep one structure at a time == the reference's own loop (trajectory.py:413-432)."""
+    import site_analysis_b200 as sab
+    case = oracle_mod.load_case(name)
+    t = trajectory_from_case(case)
+    lat = case["lattice"]
+    species = [str(s) for s in case["species"]]
+    for f in range(case["frac"].shape[0]):
+        st = sab.SimpleStructure(lat if lat.ndim == 2 else lat[f], species, case["frac"][f])
+        t.append_timestep(st, t=f + 1)
+    got = np.array([[(-1 if v is None else v) for v in a.trajectory] for a in t.atoms]).T
+    assert np.array_equal(got, case["atoms_traj"])
+    assert transitions_of(t) == oracle_mod.transitions_from_case(case)
+    # sites_trajectory: atoms listed in atom order per site per frame
+    st_last = t.sites_trajectory[-1]
+    for s, site in enumerate(t.sites):
+        assert st_last[s] == [a.index for a in t.atoms if a.in_site == site.index]
+
+
+@pytest.mark.parametrize("name", ["fuzz_voronoi_1", "fuzz_polyhedral_0", "fuzz_dynvor_0", "fuzz_spherical_2"])
+def test_ragged_batches_equal_one_batch(oracle_mod, name):
+    """State carried between calls (PBC wrap counters, history) makes any split equivalent."""
+    case = oracle_mod.load_case(name)
+    t = trajectory_from_case(case)
+    F = case["frac"].shape[0]
+    lat = case["lattice"]
+    parts = []
+    for a, b in [(0, 1), (1, 2), (2, 31), (31, 31), (31, F)]:
+        parts.append(t.trajectory_from_arrays(case["frac"][a:b], lat if lat.ndim == 2 else lat[a:b]))
+    assert np.array_equal(np.vstack(parts), case["atoms_traj"])
+    assert transitions_of(t) == oracle_mod.transitions_from_case(case)
+
+
+@pytest.mark.parametrize("name", golden_names("fuzz_dynvor") + ["argyrodite_0p_dynvor"])
+def test_dynamic_voronoi_centres_bitwise(oracle_mod, name):
+    import torch
+    case = oracle_mod.load_case(name)
+    t = trajectory_from_case(case)
+    lat = case["lattice"]
+    frames = list(case["centre_frames"])
+    for f in range(case["frac"].shape[0]):
+        t.trajectory_from_arrays(case["frac"][f:f + 1], lat if lat.ndim == 2 else lat[f:f + 1])
+        if f in frames:
+            got = np.array([s.centre for s in t.sites])
+            want = case["centres_at"][frames.index(f)]
+            assert np.array_equal(got.view(np.int64), want.view(np.int64)), f
+    assert torch.cuda.is_available()
+
+
+def test_reset_and_replay(oracle_mod):
+    """Trajectory.reset(): history and PBC caches cleared, topology kept, same answers again."""
+    case = oracle_mod.load_case("fuzz_polyhedral_1")
+    t = trajectory_from_case(case)
+    a = t.trajectory_from_arrays(case["frac"], case["lattice"])
+    assert all(s._face_topology_cache is not None for s in t.sites)
+    t.reset()
+    assert len(t) == 0 and all(not s.transitions for s in t.sites) and t.atoms[0].trajectory == []
+    assert all(s._pbc_image_shifts is None for s in t.sites)
+    b = t.trajectory_from_arrays(case["frac"], case["lattice"])
+    o = oracle_mod.SiteOracle.from_case(case)
+    o.run(case["frac"], case["lattice"]); o.reset()
+    assert np.array_equal(b, o.run(case["frac"], case["lattice"]))
+    assert np.array_equal(a, case["atoms_traj"])
+
+
+def test_empty_and_single_frame_inputs(oracle_mod):
+    case = oracle_mod.load_case("fuzz_voronoi_0")
+    t = trajectory_from_case(case)
+    out = t.trajectory_from_arrays(case["frac"][:0], case["lattice"])
+    assert out.shape == (0, len(t.atoms)) and len(t) == 0
+    out = t.trajectory_from_arrays(case["frac"][:1], case["lattice"])
+    assert np.array_equal(out, case["atoms_traj"][:1])
+
+
+def test_c_abi_host_call_matches_device_call(oracle_mod):
+    """sab_assign_host (pageable host buffers, chunked, overlapped) == sab_assign_device."""
+    from site_analysis_b200 import AssignmentEngine
+    case = oracle_mod.load_case("argyrodite_0p_voronoi")
+    frac = np.ascontiguousarray(np.tile(case["frac"], (3, 1, 1)))
+    eng = AssignmentEngine("voronoi", frac.shape[1], case["atom_idx"], centres=case["centres"])
+    a = eng.assign_host_pipelined(frac, case["lattice"], chunk_frames=100)
+    eng2 = AssignmentEngine("voronoi", frac.shape[1], case["atom_idx"], centres=case["centres"])
+    b = eng2.assign(frac, case["lattice"])
+    assert np.array_equal(a, b)
+    pos = {int(v): i for i, v in enumerate(case["site_index"])}
+    want = np.vectorize(lambda v: pos[int(v)])(case["atoms_traj"])
+    assert np.array_equal(a[:140], want) and np.array_equal(a[280:], want)
+    assert eng.last_info["launches"] > 0

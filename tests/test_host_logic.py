@@ -1,0 +1,161 @@
+"""CPU-only tests of the host-side logic of site_analysis_b200 (no kernel calls):
+C-ABI library loads and exports every declared symbol; the one-off tables; the vectorised
+history fold; the reference-shaped object model."""
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import ctypes
+    from site_analysis_b200 import _native as nat
+    header = (ROOT / "include" / "sab200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(sab_[a-z0-9_]+)\s*\(", header)) - {"sab_resolve() settles"})
+    declared = [d for d in declared if d != "sab_engine"]
+    assert sorted(nat.SYMBOLS) == declared
+    lib = ctypes.CDLL(str(nat.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert nat.lib().sab_abi_version() == nat.ABI_VERSION
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from site_analysis_b200 import AssignmentEngine, _native as nat
+    with pytest.raises(nat.NativeError):
+        AssignmentEngine("voronoi", 4, [0], centres=np.zeros((1, 3)))
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "site_analysis_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "site_oracle" not in src and "from oracle" not in src, p
+
+
+@pytest.mark.parametrize("name", ["argyrodite_0p_spherical", "fuzz_spherical_0", "fuzz_polyhedral_0", "readme_spherical"])
+def test_distance_rank_table_matches_reference(oracle_mod, name):
+    from site_analysis_b200 import _tables as tab
+    case = oracle_mod.load_case(name)
+    centres = case["centres"] if "centres" in case else case["ref_center"]
+    assert np.array_equal(tab.distance_rank_table(centres), case["rank_table"].astype(np.int32))
+
+
+def test_sqrt_threshold_is_exactly_equivalent():
+    from site_analysis_b200 import _tables as tab
+    rng = np.random.default_rng(3)
+    rcut = np.concatenate([rng.uniform(0.1, 9.0, 2000), [1.5, 2.0, 3.0, 1e-3, 50.0]])
+    T = tab.sqrt_threshold(rcut)
+    assert np.all(np.sqrt(T) <= rcut)
+    assert np.all(np.sqrt(np.nextafter(T, np.inf)) > rcut)
+
+
+@pytest.mark.parametrize("tag", ["0p", "50p"])
+def test_full_pbc_unwrap_reproduces_the_builder_primed_shifts(oracle_mod, tag):
+    """SiteFactory primes every argyrodite tetrahedron from the build structure (= frame 0):
+    the product's restatement must give the same integer image shifts."""
+    from site_analysis_b200 import _tables as tab
+    case = oracle_mod.load_case(f"argyrodite_{tag}_polyhedral")
+    raw0 = case["frac"][0]
+    assert case["primed"].all()
+    for s in range(len(case["site_index"])):
+        v = case["vert_idx"][s, :case["n_vert"][s]]
+        assert np.array_equal(case["cached_raw0"][s], raw0[v])
+        got = tab.full_pbc_unwrap(raw0[v], case["ref_center"][s], case["lattice"])
+        assert np.array_equal(got, case["shift0"][s])
+
+
+def test_full_pbc_unwrap_legacy_rule():
+    from site_analysis_b200 import _tables as tab
+    raw = np.array([[0.98, 0.1, 0.5], [0.02, 0.2, 0.4], [0.95, 0.15, 0.45], [0.05, 0.12, 0.55]])
+    sh = tab.full_pbc_unwrap(raw, None, np.eye(3))
+    assert sh.tolist() == [[0, 0, 0], [1, 0, 0], [0, 0, 0], [1, 0, 0]]
+
+
+@pytest.mark.parametrize("name", golden_names("fuzz") + ["argyrodite_0p_spherical", "argyrodite_50p_polyhedral"])
+def test_history_fold_matches_reference_bookkeeping(oracle_mod, name):
+    """fold_history over the golden rows reproduces the reference's transition Counters
+    (incl. insertion order) and recent-site pairs, in one batch and in ragged pieces."""
+    from site_analysis_b200.engine import fold_history
+    case = oracle_mod.load_case(name)
+    idx = case["site_index"]
+    pos = {int(v): i for i, v in enumerate(idx)}
+    rows = np.vectorize(lambda v: -1 if v < 0 else pos[int(v)])(case["atoms_traj"]).astype(np.int32)
+    F, A = rows.shape
+    want_tr = oracle_mod.transitions_from_case(case)
+    for cuts in ([0, F], [0, 1, 2, F // 3, F // 3, F - 1, F]):
+        recent = -np.ones((A, 2), dtype=np.int32)
+        prev = np.full(A, -2, dtype=np.int32)
+        tr = [dict() for _ in idx]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            fold_history(recent, prev, tr, rows[a:b], True)
+        got_tr = {int(idx[s]): {int(idx[k]): v for k, v in t.items()} for s, t in enumerate(tr) if t}
+        assert got_tr == want_tr
+        for k in got_tr:
+            assert list(got_tr[k]) == list(want_tr[k])
+        got_recent = np.where(recent >= 0, idx[np.clip(recent, 0, None)], -1)
+        assert np.array_equal(got_recent, case["recent"])
+        assert np.array_equal(prev, rows[-1])
+
+
+def test_trajectory_constructor_errors():
+    """trajectory.py:74-98."""
+    import site_analysis_b200 as sab
+    with pytest.raises(ValueError):
+        sab.Trajectory(sites=[], atoms=[sab.Atom(0)])
+    with pytest.raises(ValueError):
+        sab.Trajectory(sites=[sab.VoronoiSite(np.zeros(3))], atoms=[])
+    with pytest.raises(TypeError):
+        sab.Trajectory(sites=[sab.VoronoiSite(np.zeros(3)), sab.SphericalSite(np.zeros(3), 1.0)], atoms=[sab.Atom(0)])
+    with pytest.raises(TypeError):
+        sab.SphericalSiteCollection([sab.VoronoiSite(np.zeros(3))])
+    a, b = sab.VoronoiSite(np.zeros(3)), sab.VoronoiSite(np.ones(3) * 0.5)
+    b.index = a.index
+    with pytest.raises(ValueError):
+        sab.VoronoiSiteCollection([a, b])
+    c = sab.VoronoiSiteCollection([a])
+    with pytest.raises(ValueError):
+        c.site_by_index(12345)
+
+
+def test_builder_validation_and_index_reset():
+    """builders.py:734-800: errors, Site index counter restarts at 0, builder resets itself."""
+    import site_analysis_b200 as sab
+    st = sab.SimpleStructure(np.eye(3) * 8, ["O", "Li"], [[0, 0, 0], [0.5, 0.5, 0.5]])
+    with pytest.raises(ValueError):
+        sab.TrajectoryBuilder().build()
+    with pytest.raises(ValueError):
+        sab.TrajectoryBuilder().with_structure(st).build()
+    with pytest.raises(ValueError):
+        sab.TrajectoryBuilder().with_structure(st).with_voronoi_sites([[0, 0, 0]]).build()
+    with pytest.raises(ValueError):
+        sab.TrajectoryBuilder().with_structure(st).with_mobile_species("Na").with_voronoi_sites([[0, 0, 0]]).build()
+    with pytest.raises(ValueError):
+        sab.TrajectoryBuilder().with_spherical_sites([[0, 0, 0]], [1.0, 2.0])
+    with pytest.raises(TypeError):
+        (sab.TrajectoryBuilder().with_structure(st).with_mobile_species("Li")
+         .with_voronoi_sites([[0, 0, 0]]).with_spherical_sites([[0, 0, 0]], 1.0).build())
+    sab.Site._newid = 17
+    b = sab.TrajectoryBuilder().with_structure(st).with_mobile_species("Li").with_spherical_sites([[0, 0, 0], [.5, .5, .5]], 1.5, "x")
+    t = b.build()
+    assert [s.index for s in t.sites] == [0, 1] and [s.label for s in t.sites] == ["x", "x"]
+    assert [a.index for a in t.atoms] == [1]
+    assert b._structure is None and b._site_generators == []
+
+
+def test_lazy_trajectories_materialise_like_lists():
+    import site_analysis_b200 as sab
+    atom = sab.Atom(3)
+    atom.trajectory.append(5)
+    atom._lazy_blocks.append(np.array([5, -1, 7], dtype=np.int32))
+    assert atom._last_trajectory_entry() == 7
+    assert atom.trajectory == [5, 5, None, 7]
+    site = sab.VoronoiSite(np.zeros(3)); site.index = 7
+    rows = np.array([[7, 1], [2, 7], [7, 7]], dtype=np.int32)
+    site._lazy_blocks.append((rows, np.array([10, 11])))
+    assert site.trajectory == [[10], [11], [10, 11]]
+    assert site.average_occupation == 1.0
