@@ -102,18 +102,21 @@ __global__ void k_polyhedral_assign_exhaustive(const double *__restrict__ frac, 
                                                int32_t *__restrict__ spill, long long spill_capacity,
                                                unsigned long long *__restrict__ counters)
 {
-    extern __shared__ double smp[];                  // xs[A*3] | cnt[A] | hits[A*KEEP]
+    extern __shared__ double smp[];                  // xs[A*3] | cnt[A] | big[A] | hits[A*KEEP]
     double *xs = smp;
     int *cnt = (int *)(smp + 3 * n_mobile);
-    int *hits = cnt + n_mobile;
+    int *big = cnt + n_mobile;                       // spill offset of atoms in more than KEEP sites, else -1
+    int *hits = big + n_mobile;
+    __shared__ int any_big;
     for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
         const double *frame = frac + (size_t)f * n_atoms * 3;
         const int32_t *wrow = wrows + (size_t)f * m3;
         __syncthreads();
+        if (threadIdx.x == 0) any_big = 0;
         for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
 #pragma unroll
             for (int d = 0; d < 3; d++) xs[3 * a + d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
-            cnt[a] = 0;
+            cnt[a] = 0; big[a] = -1;
         }
         __syncthreads();
         for (int s = threadIdx.x; s < n_sites; s += blockDim.x) {
@@ -139,21 +142,50 @@ __global__ void k_polyhedral_assign_exhaustive(const double *__restrict__ frac, 
             else {
                 atomicAdd(&counters[0], 1ULL);
                 unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
-                if (c > SAB_POLY_KEEP || (long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) {
+                if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) {
                     counters[2] = 1ULL;
                     out = SAB_NONE;
                 } else {
-                    for (int i = 1; i < c; i++) {          // ascending list positions
-                        int v = h[i], j = i;
-                        while (j > 0 && h[j - 1] > v) { h[j] = h[j - 1]; j--; }
-                        h[j] = v;
-                    }
                     spill[off] = c;
-                    for (int i = 0; i < c; i++) spill[off + 1 + i] = h[i];
+                    if (c <= SAB_POLY_KEEP) {
+                        for (int i = 1; i < c; i++) {          // ascending list positions
+                            int v = h[i], j = i;
+                            while (j > 0 && h[j - 1] > v) { h[j] = h[j - 1]; j--; }
+                            h[j] = v;
+                        }
+                        for (int i = 0; i < c; i++) spill[off + 1 + i] = h[i];
+                    } else {                                   // rare: atom on a shared vertex / edge
+                        big[a] = (int)off; cnt[a] = 0; any_big = 1;
+                    }
                     out = SAB_AMBIGUOUS_BASE - (int)off;
                 }
             }
             result[(size_t)f * n_mobile + a] = out;
+        }
+        __syncthreads();
+        if (any_big) {                                         // second sweep fills the long lists
+            for (int s = threadIdx.x; s < n_sites; s += blockDim.x) {
+                double vc[SAB_MAX_VERT][3], lo[3], hi[3], cen[3];
+                int nv;
+                bool legacy_now = T.legacy_init && T.legacy_init[s] && f == legacy_init_frame;
+                sab_poly_vertices(frame, T, s, wrow, legacy_now, vc, nv, lo, hi, cen);
+                const uint8_t *simp = T.simp + (size_t)s * T.fmax * 3;
+                int nf = T.n_face[s];
+                for (int a = 0; a < n_mobile; a++)
+                    if (big[a] >= 0 && sab_poly_contains_atom(vc, cen, simp, nf, lo, hi, xs + 3 * a))
+                        spill[big[a] + 1 + atomicAdd(&cnt[a], 1)] = s;
+            }
+            __syncthreads();
+            for (int a = threadIdx.x; a < n_mobile; a += blockDim.x)
+                if (big[a] >= 0) {
+                    int32_t *l = spill + big[a] + 1;
+                    int c = cnt[a];
+                    for (int i = 1; i < c; i++) {
+                        int v = l[i], j = i;
+                        while (j > 0 && l[j - 1] > v) { l[j] = l[j - 1]; j--; }
+                        l[j] = v;
+                    }
+                }
         }
     }
 }

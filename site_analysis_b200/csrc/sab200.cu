@@ -343,7 +343,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
     }
     case SAB_POLYHEDRAL: {
         int block = 256;
-        size_t smem = sizeof(double) * 3 * (size_t)e->A + sizeof(int) * (size_t)e->A * (1 + SAB_POLY_KEEP);
+        size_t smem = sizeof(double) * 3 * (size_t)e->A + sizeof(int) * (size_t)e->A * (2 + SAB_POLY_KEEP);
         CU(cudaFuncSetAttribute(k_polyhedral_assign_exhaustive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};

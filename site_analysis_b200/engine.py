@@ -412,8 +412,8 @@ class AssignmentEngine:
                 code = self.L.sab_assign_device(self.h, sub.data_ptr(), sub_lat.data_ptr(), stride, nf,
                                                 sub_res.data_ptr(), d_spill.data_ptr(), cap, d_ws.data_ptr(), ws_bytes,
                                                 stream, nat.ptr(info))
-                if code == 3:                             # spill overflow (nothing committed): grow and redo
-                    cap = int(info[1]) * 2 + 1024
+                if code == 3 and int(info[1]) > cap:      # spill overflow (nothing committed): grow and redo
+                    cap = int(info[1]) + int(info[1]) // 4 + 1024
                     continue
                 nat.check(code)
                 break

@@ -4,7 +4,12 @@ from __future__ import annotations
 import numpy as np
 
 
-def sites_and_atoms_from_case(case):
+def sites_and_atoms_from_case(case, seed_topology=True):
+    """``seed_topology``: give polyhedral sites the Qhull face triangles the reference ended up with
+    (the fixture's ``simplices``), i.e. sites that already own a face-topology cache.  For
+    non-simplicial polyhedra (cubes) Qhull's choice of quad diagonals depends on the geometry of
+    the frame in which the reference happened to query the site first; seeding removes that
+    history dependence from the comparison (guard G3)."""
     import site_analysis_b200 as sab
     kind = str(case["kind"])
     labels = [str(l) or None for l in case["labels"]]
@@ -23,6 +28,8 @@ def sites_and_atoms_from_case(case):
             if case["primed"][s]:
                 site._pbc_image_shifts = case["shift0"][s, :nv].copy()
                 site._pbc_cached_raw_frac = case["cached_raw0"][s, :nv].copy()
+            if seed_topology and "n_face" in case and case["n_face"][s] > 0:
+                site._face_topology_cache = sab.polyhedral_site.FaceTopology(case["simplices"][s, :case["n_face"][s]])
         else:
             nr = int(case["n_ref"][s])
             rc = case["ref_center"][s].copy() if case["has_ref_center"][s] else None
@@ -33,9 +40,9 @@ def sites_and_atoms_from_case(case):
     return sites, atoms
 
 
-def trajectory_from_case(case, use_case_rank=True):
+def trajectory_from_case(case, use_case_rank=True, seed_topology=True):
     import site_analysis_b200 as sab
-    sites, atoms = sites_and_atoms_from_case(case)
+    sites, atoms = sites_and_atoms_from_case(case, seed_topology)
     t = sab.Trajectory(sites=sites, atoms=atoms)
     if use_case_rank and "rank_table" in case:
         t.site_collection.rank_table = np.asarray(case["rank_table"], dtype=np.int32)

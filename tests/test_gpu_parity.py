@@ -8,7 +8,7 @@ import pytest
 from conftest import golden_names
 from helpers import has_jump, trajectory_from_case, transitions_of
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
 def _run_batch(case):
@@ -93,6 +93,15 @@ def test_dynamic_voronoi_centres_bitwise(oracle_mod, name):
             want = case["centres_at"][frames.index(f)]
             assert np.array_equal(got.view(np.int64), want.view(np.int64)), f
     assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("name", ["argyrodite_0p_polyhedral", "fuzz_polyhedral_1", "fuzz_polyhedral_5", "fuzz_polyhedral_7"])
+def test_tetrahedra_need_no_seeded_topology(oracle_mod, name):
+    """Simplicial polyhedra: every vertex triple is a face, so the topology hulled from the first
+    frame gives the reference's answers without knowing when the reference queried each site."""
+    case = oracle_mod.load_case(name)
+    t = trajectory_from_case(case, seed_topology=False)
+    assert np.array_equal(t.trajectory_from_arrays(case["frac"], case["lattice"]), case["atoms_traj"])
 
 
 def test_reset_and_replay(oracle_mod):
