@@ -111,6 +111,8 @@ class Trajectory:
         frac_coords = np.asarray(frac_coords)
         rows = self.site_collection.analyse_trajectory(self.atoms, frac_coords, lattice)
         F = rows.shape[0]
+        if F == 0:
+            return rows
         atom_index = np.array([a.index for a in self.atoms])
         for a, atom in enumerate(self.atoms):
             atom._lazy_blocks.append(rows[:, a])
