@@ -68,6 +68,7 @@ struct sab_engine {
     cudaEvent_t ev_free[2] = {nullptr, nullptr};
     int64_t launches = 0;
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
+    cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -103,6 +104,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
         if (e->streams[i]) cudaStreamDestroy(e->streams[i]);
         if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
@@ -386,9 +388,13 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     int64_t l0 = e->launches;
     unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
+    CU(cudaEventRecord(e->ev_t[0], st));
     if (w.m3) { run_wrap_pass(e, d_frac, n_frames, w, st, true); CU(cudaGetLastError()); }
+    CU(cudaEventRecord(e->ev_t[1], st));
     rc = launch_assign(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, w, st, nullptr);
     if (rc) return rc;
+    CU(cudaEventRecord(e->ev_t[2], st));
     unsigned long long h[CNT_N];
     CU(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -396,6 +402,13 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     info[0] = (int64_t)h[CNT_AMBIGUOUS]; info[1] = (int64_t)h[CNT_SPILL]; info[2] = (int64_t)h[CNT_OVERFLOW];
     info[3] = (h[CNT_FIRST_BAD] == ~0ULL) ? -1 : (int64_t)h[CNT_FIRST_BAD];
     info[4] = (int64_t)h[CNT_FULL27];
+    {
+        float ms_wrap = 0.f, ms_main = 0.f;          // CUDA events on the launching stream
+        cudaEventElapsedTime(&ms_wrap, e->ev_t[0], e->ev_t[1]);
+        cudaEventElapsedTime(&ms_main, e->ev_t[1], e->ev_t[2]);
+        info[6] = (int64_t)((double)ms_main * 1e6);
+        info[7] = (int64_t)((double)ms_wrap * 1e6);
+    }
     if (h[CNT_OVERFLOW]) {                   // nothing committed: the caller retries with a larger spill buffer
         info[5] = e->launches - l0;
         return fail(SAB_EOVERFLOW, "candidate spill buffer overflow (%llu elements needed, capacity %lld)",
@@ -531,6 +544,7 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         CU(cudaMemcpyAsync(h_result + (size_t)f0 * e->A, base + o_res, res_b * nf, cudaMemcpyDeviceToHost, s_comp));
         CU(cudaEventRecord(ev_done[b], s_comp));
         tot_info[0] += ci[0]; tot_info[1] += ci[1]; tot_info[4] += ci[4]; tot_info[5] += ci[5];
+        tot_info[6] += ci[6]; tot_info[7] += ci[7];
         if (ci[3] >= 0 && tot_info[3] < 0) tot_info[3] = f0 + ci[3];
     }
     cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_copy);

@@ -397,7 +397,7 @@ class AssignmentEngine:
             self._init_pbc(d_frac[0].cpu().numpy(), lat0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
-        total = dict(ambiguous=0, full27=0, launches=0, reinits=0)
+        total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0)
         while f0 < F:
             nf = F - f0
             sub = d_frac[f0:]
@@ -419,6 +419,7 @@ class AssignmentEngine:
                 break
             n_ok = nf if info[3] < 0 else int(info[3])
             total["full27"] += int(info[4]); total["launches"] += int(info[5])
+            total["assign_ns"] += int(info[6]); total["wrap_ns"] += int(info[7])
             if info[3] >= 0:
                 if self.k == nat.POLYHEDRAL:
                     raise GuardError(
@@ -492,7 +493,8 @@ class AssignmentEngine:
         self._check_excursion()
         self._pending.append((out, True))
         self.frames_done += F
-        self.last_info = dict(ambiguous=0, full27=int(info[4]), launches=int(info[5]), reinits=0)
+        self.last_info = dict(ambiguous=0, full27=int(info[4]), launches=int(info[5]), reinits=0,
+                              assign_ns=int(info[6]), wrap_ns=int(info[7]))
         return out
 
     def dynvor_centres(self, d_frac):
