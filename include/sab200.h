@@ -97,6 +97,20 @@ int sab_get_pbc_state(sab_engine *e, int32_t *slot_shift, double *prev_raw, int3
  * counted from the next frame the engine will process.  NULL clears the marker. */
 int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int64_t frames_from_now);
 
+/* Exact-pruning tables of the tetrahedral kernel (csrc/k_polyhedral_cells.cuh), built once on
+ * the host: a G^3 cell list (CSR) of the tetrahedra that can reach each cell while every
+ * framework coordinate stays within `delta` of anchor[3M] (anchor of raw - W); per-site records
+ * of shared-memory offsets (uint16[S][56]); kmin/nk = range of slot-shift values.  Frames that
+ * leave the delta tube take the exhaustive kernel path, so the tables never decide a result on
+ * their own.  anchor == NULL clears the tables. */
+int sab_set_cell_lists(sab_engine *e, int G, double delta, const double *anchor, int kmin, int nk,
+                       const uint16_t *records, const int32_t *cell_off, const uint16_t *cell_sites);
+
+/* Range (min, max) of raw - W per framework coordinate over the frames, double[M][3][2] (host),
+ * continuing from the engine's wrap state without modifying it; used to place the anchors. */
+int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, void *d_workspace,
+                       int64_t workspace_bytes, void *stream, double *excursion);
+
 /* Engine options.  SAB_OPT_SKIP_STEP_CHECK_ONCE: the next batch does not test its first frame
  * against the 0.3 step bound (used right after the host re-initialised a group at that frame,
  * dynamic_voronoi_site_collection.py:188-195). */

@@ -107,3 +107,84 @@ def sqrt_threshold(rcut: np.ndarray) -> np.ndarray:
         q = np.where(shrink, np.nextafter(q, -np.inf), q)
     assert np.all(np.sqrt(q) <= rcut) and np.all(np.sqrt(np.nextafter(q, np.inf)) > rcut)
     return q
+
+
+# ---------------------------------------------------------------------------------------------
+# exact-pruning tables for the tetrahedral kernel (csrc/k_polyhedral_cells.cuh)
+# ---------------------------------------------------------------------------------------------
+
+_TET_FACES = ((1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2))
+_TET_EDGES = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+
+
+def _box_tet_separated(V: np.ndarray, h: float) -> np.ndarray:
+    """Separating-axis test between the cube [-h, h]^3 and tetrahedra V (n, 4, 3) given relative to
+    the cube centre.  True = certainly disjoint.  Slack makes every verdict conservative
+    (a touching or nearly touching pair counts as intersecting)."""
+    tol = 1e-12
+    sep = (V.min(axis=1) > h + tol).any(axis=1) | (V.max(axis=1) < -h - tol).any(axis=1)
+
+    def axis_test(ax):
+        proj = np.einsum("nvk,nk->nv", V, ax)
+        r = h * np.abs(ax).sum(axis=1)
+        slack = tol * (1.0 + np.abs(proj).max(axis=1) + r)
+        return (proj.min(axis=1) > r + slack) | (proj.max(axis=1) < -r - slack)
+
+    for a, b, c in _TET_FACES:
+        sep |= axis_test(np.cross(V[:, b] - V[:, a], V[:, c] - V[:, a]))
+    eye = np.eye(3)
+    for a, b in _TET_EDGES:
+        e = V[:, b] - V[:, a]
+        for i in range(3):
+            sep |= axis_test(np.cross(e, eye[i][None, :]))
+    return sep
+
+
+def tet_cell_lists(anchor_vertices: np.ndarray, delta: float, G: int, eps: float = 1e-9):
+    """CSR cell lists over the unit cube: for each of the G^3 cells the tetrahedra whose hull,
+    with every vertex free to move by +-delta per axis (=> hull (+) [-delta, delta]^3), can reach
+    the cell for some periodic image.  ``anchor_vertices`` (S, 4, 3) are unwrapped anchor
+    positions (any integer offset per site).  Returns (offsets int32 [G^3 + 1], entries uint16)."""
+    P = np.asarray(anchor_vertices, dtype=np.float64)
+    S = len(P)
+    grow = delta + eps
+    lo = np.floor((P.min(axis=1) - grow) * G).astype(np.int64)
+    hi = np.floor((P.max(axis=1) + grow) * G).astype(np.int64)
+    span = np.minimum(hi - lo + 1, G)                            # cells touched per axis (periodic)
+    nmax = span.max(axis=0)
+    off = np.stack(np.meshgrid(*[np.arange(n) for n in nmax], indexing="ij"), axis=-1).reshape(-1, 3)   # (K, 3)
+    valid = (off[None, :, :] < span[:, None, :]).all(axis=2)     # (S, K)
+    s_idx, k_idx = np.nonzero(valid)
+    cell_unwrapped = lo[s_idx] + off[k_idx]                      # (n, 3)
+    centre = (cell_unwrapped + 0.5) / G
+    keep = np.ones(len(s_idx), dtype=bool)
+    h = 0.5 / G + grow
+    step = 2_000_000
+    for a in range(0, len(s_idx), step):
+        sl = slice(a, a + step)
+        keep[sl] = ~_box_tet_separated(P[s_idx[sl]] - centre[sl][:, None, :], h)
+    s_idx, cell_unwrapped = s_idx[keep], cell_unwrapped[keep]
+    c = np.mod(cell_unwrapped, G)
+    cell = (c[:, 0] * G + c[:, 1]) * G + c[:, 2]
+    pair = np.unique(cell * S + s_idx)                           # dedupe, sorted by (cell, site)
+    cell, site = pair // S, pair % S
+    offsets = np.zeros(G ** 3 + 1, dtype=np.int32)
+    np.add.at(offsets, cell + 1, 1)
+    offsets = np.cumsum(offsets).astype(np.int32)
+    return offsets, site.astype(np.uint16)
+
+
+def tet_records(slot_shift: np.ndarray, slot_fw: np.ndarray, simplices, kmin: int, m3: int) -> np.ndarray:
+    """(S, 56) uint16 shared-memory offsets: [0..11] vertices in slot order, then 4 faces x (9 + pad).
+    offset(v, d) = (slot_shift[s, v, d] - kmin) * m3 + 3 * slot_fw[s, v] + d."""
+    S = len(slot_fw)
+    off = (slot_shift[:, :4, :].astype(np.int64) - kmin) * m3 + 3 * slot_fw[:, :4, None].astype(np.int64) + np.arange(3)
+    assert off.min() >= 0 and off.max() < 65536
+    rec = np.zeros((S, 56), dtype=np.uint16)
+    rec[:, :12] = off.reshape(S, 12)
+    simp = np.stack([np.asarray(f, dtype=np.int64) for f in simplices])          # (S, 4, 3)
+    rows = np.arange(S)[:, None, None]
+    face_off = off[rows, simp, :]                                                  # (S, 4 faces, 3 verts, 3 dims)
+    for j in range(4):
+        rec[:, 12 + 10 * j:12 + 10 * j + 9] = face_off[:, j].reshape(S, 9)
+    return rec

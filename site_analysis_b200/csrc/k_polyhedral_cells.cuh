@@ -1,0 +1,180 @@
+// k_polyhedral_cells.cuh -- polyhedral (tetrahedral) containment with exact spatial pruning.
+//
+// Same outputs as k_polyhedral_assign_exhaustive (k_polyhedral.cuh), same arithmetic per
+// accepted test (reference polyhedral_site.py:26-123, pbc_utils.py:218-229), ~100x less work:
+//
+//  * ATOM-major: one thread per mobile atom, one CTA per frame (grid-stride, several CTAs
+//    resident per SM).
+//  * Per frame the CTA stages, for every referenced framework atom, the nk possible unwrapped
+//    coordinates  raw + (double)(k - W)  (k = slot-shift value, W = cumulative wrap count of the
+//    atom in this frame) into shared memory: one rounding, exactly the reference's
+//    `frac_coords + new_shifts` (pbc_utils.py:220).  A vertex coordinate is then ONE LDS.
+//  * A static cell list over the unit cube (built on the host from anchor positions and a
+//    margin delta that covers the framework's thermal motion) gives each atom the few
+//    tetrahedra whose inflated hull meets its cell.  While staging, the CTA checks that every
+//    framework atom is within delta of its anchor; a frame that violates this takes the
+//    exhaustive path, so pruning never decides anything by itself.
+//  * "Small" sites (extent + 2 delta < 0.45 per axis, checked on the host): only the image
+//    o = rint(centroid - x) of the 8 images x + {0,1}^3 (tools.py:246-253) can lie inside the
+//    vertices' bounding box, so it is the only one tested (others are outside the hull by
+//    > 0.05 fractional units).
+//  * Face data are computed lazily, face by face, with early exit (polyhedral_site.py:109-123);
+//    each site record holds the shared-memory offsets of every face's vertices in Qhull's own
+//    vertex order, so normals and reference points round exactly as in the reference.
+#pragma once
+#include "k_polyhedral.cuh"
+
+#define SAB_TET_REC 56          // uint16 per site record (112 bytes)
+
+struct SabTetTables {
+    int M, m3;                  // referenced framework atoms, 3 M
+    int kmin, nk;               // slot-shift values kmin .. kmin + nk - 1
+    const int32_t *fw_atoms;    // [M]
+    // [S][56] shared-memory offsets into `var`: [0..11] the 4 vertices in SLOT order (x y z each),
+    // then 4 faces x 10: v0 v1 v2 of the face in Qhull's vertex order (9 offsets + 1 pad)
+    const uint16_t *rec;
+    int G;                      // cells per axis
+    const int32_t *cell_off;    // [G^3 + 1]
+    const uint16_t *cell_sites; // CSR entries (site list positions, ascending)
+    const double *anchor;       // [3 M] anchor of raw - W per framework coordinate
+    double delta;               // validity radius of the cell lists
+};
+
+// One tetrahedron against one wrapped atom position.  `var` = staged unwrapped coordinates.
+__device__ __forceinline__ bool sab_tet_contains(const double *__restrict__ var, const uint16_t *__restrict__ rec,
+                                                 const double *x)
+{
+    double v[4][3];
+    {
+        const uint2 *r2 = reinterpret_cast<const uint2 *>(rec);      // 24 bytes = 3 x 8
+        uint2 a = __ldg(r2), b = __ldg(r2 + 1), c2 = __ldg(r2 + 2);
+        v[0][0] = var[a.x & 0xffff]; v[0][1] = var[a.x >> 16]; v[0][2] = var[a.y & 0xffff];
+        v[1][0] = var[a.y >> 16];    v[1][1] = var[b.x & 0xffff]; v[1][2] = var[b.x >> 16];
+        v[2][0] = var[b.y & 0xffff]; v[2][1] = var[b.y >> 16];    v[2][2] = var[c2.x & 0xffff];
+        v[3][0] = var[c2.x >> 16];   v[3][1] = var[c2.y & 0xffff]; v[3][2] = var[c2.y >> 16];
+    }
+    double u[3], c[3], p[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        // non-negative offset: u = ceil(-min) when min < 0 (pbc_utils.py:221-229)
+        u[d] = 0.0;
+        if ((__double2hiint(v[0][d]) | __double2hiint(v[1][d]) | __double2hiint(v[2][d]) | __double2hiint(v[3][d])) < 0) {
+            double mn = fmin(fmin(v[0][d], v[1][d]), fmin(v[2][d], v[3][d]));
+            if (mn < 0.0) u[d] = ceil(-mn);
+        }
+        // centroid, vertices in slot order (polyhedral_site.py:46-51): ((((0 + v0) + v1) + v2) + v3) / 4
+        double s = (v[0][d] + u[d]) + (v[1][d] + u[d]);
+        s += v[2][d] + u[d];
+        s += v[3][d] + u[d];
+        c[d] = s * 0.25;                                        // == s / 4 exactly
+        double o_d = rint(c[d] - x[d]);
+        if (o_d != 0.0 && o_d != 1.0) return false;             // no image of x within reach of this site
+        p[d] = (o_d == 1.0) ? 1.0 + x[d] : x[d];
+    }
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        const unsigned *r = reinterpret_cast<const unsigned *>(rec + 12 + 10 * j);
+        unsigned w0 = __ldg(r), w1 = __ldg(r + 1), w2 = __ldg(r + 2), w3 = __ldg(r + 3), w4 = __ldg(r + 4);
+        double v0[3], v1[3], v2[3];
+        v0[0] = var[w0 & 0xffff] + u[0]; v0[1] = var[w0 >> 16] + u[1]; v0[2] = var[w1 & 0xffff] + u[2];
+        v1[0] = var[w1 >> 16] + u[0];    v1[1] = var[w2 & 0xffff] + u[1]; v1[2] = var[w2 >> 16] + u[2];
+        v2[0] = var[w3 & 0xffff] + u[0]; v2[1] = var[w3 >> 16] + u[1];    v2[2] = var[w4 & 0xffff] + u[2];
+        if (!sab_face_accepts(v0, v1, v2, c, p[0], p[1], p[2])) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_polyhedral_assign_cells(const double *__restrict__ frac, int64_t n_frames, int n_atoms, int n_mobile,
+                          const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabTetTables C,
+                          const int32_t *__restrict__ wrows, int64_t legacy_init_frame,
+                          int32_t *__restrict__ result, int32_t *__restrict__ spill, long long spill_capacity,
+                          unsigned long long *__restrict__ counters, unsigned long long *__restrict__ n_fallback)
+{
+    extern __shared__ double var[];                  // [nk][3 M]
+    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const double *frame = frac + (size_t)f * n_atoms * 3;
+        const int32_t *wrow = wrows + (size_t)f * C.m3;
+        __syncthreads();                             // previous frame's readers are done
+        int bad = 0;
+        for (int i = threadIdx.x; i < C.m3; i += blockDim.x) {
+            int m = i / 3, d = i - 3 * m;
+            double raw = frame[(size_t)C.fw_atoms[m] * 3 + d];
+            int W = wrow[i];
+            if (fabs((raw - (double)W) - C.anchor[i]) > C.delta) bad = 1;
+            for (int k = 0; k < C.nk; k++) var[k * C.m3 + i] = raw + (double)(C.kmin + k - W);
+        }
+        bad = __syncthreads_or(bad);
+        if (T.legacy_init && f == legacy_init_frame) bad = 1;     // first-frame legacy rule: generic path
+        if (threadIdx.x == 0 && bad) atomicAdd(n_fallback, 1ULL);
+        for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
+            double x[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
+            int cnt = 0, keep[SAB_POLY_KEEP];
+            if (!bad) {
+                int ci[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) ci[d] = min(C.G - 1, (int)(x[d] * (double)C.G));
+                int cell = (ci[0] * C.G + ci[1]) * C.G + ci[2];
+                int b = __ldg(C.cell_off + cell), e = __ldg(C.cell_off + cell + 1);
+                for (int i = b; i < e; i++) {
+                    int s = __ldg(C.cell_sites + i);
+                    if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, x)) {
+                        if (cnt < SAB_POLY_KEEP) keep[cnt] = s;
+                        cnt++;
+                    }
+                }
+            } else {                                    // exhaustive, fully general (rare)
+                for (int s = 0; s < n_sites; s++) {
+                    double vc[SAB_MAX_VERT][3], lo[3], hi[3], cen[3];
+                    int nv;
+                    bool legacy_now = T.legacy_init && T.legacy_init[s] && f == legacy_init_frame;
+                    sab_poly_vertices(frame, T, s, wrow, legacy_now, vc, nv, lo, hi, cen);
+                    if (sab_poly_contains_atom(vc, cen, T.simp + (size_t)s * T.fmax * 3, T.n_face[s], lo, hi, x)) {
+                        if (cnt < SAB_POLY_KEEP) keep[cnt] = s;
+                        cnt++;
+                    }
+                }
+            }
+            int out;
+            if (cnt == 0) out = SAB_NONE;
+            else if (cnt == 1) out = keep[0];
+            else {
+                atomicAdd(&counters[0], 1ULL);
+                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(cnt + 1));
+                if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
+                    counters[2] = 1ULL;
+                    out = SAB_NONE;
+                } else {
+                    spill[off] = cnt;
+                    if (cnt <= SAB_POLY_KEEP) {
+                        for (int i = 0; i < cnt; i++) spill[off + 1 + i] = keep[i];   // ascending already
+                    } else {                               // atom on a shared vertex / edge: redo, write all
+                        int k = 0;
+                        if (!bad) {
+                            int ci[3];
+                            for (int d = 0; d < 3; d++) ci[d] = min(C.G - 1, (int)(x[d] * (double)C.G));
+                            int cell = (ci[0] * C.G + ci[1]) * C.G + ci[2];
+                            for (int i = C.cell_off[cell]; i < C.cell_off[cell + 1]; i++) {
+                                int s = C.cell_sites[i];
+                                if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, x)) spill[off + 1 + k++] = s;
+                            }
+                        } else {
+                            for (int s = 0; s < n_sites; s++) {
+                                double vc[SAB_MAX_VERT][3], lo[3], hi[3], cen[3];
+                                int nv;
+                                bool legacy_now = T.legacy_init && T.legacy_init[s] && f == legacy_init_frame;
+                                sab_poly_vertices(frame, T, s, wrow, legacy_now, vc, nv, lo, hi, cen);
+                                if (sab_poly_contains_atom(vc, cen, T.simp + (size_t)s * T.fmax * 3, T.n_face[s], lo, hi, x))
+                                    spill[off + 1 + k++] = s;
+                            }
+                        }
+                    }
+                    out = SAB_AMBIGUOUS_BASE - (int)off;
+                }
+            }
+            result[(size_t)f * n_mobile + a] = out;
+        }
+    }
+}

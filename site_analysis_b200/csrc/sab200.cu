@@ -14,6 +14,7 @@
 
 #include "k_nearest.cuh"
 #include "k_polyhedral.cuh"
+#include "k_polyhedral_cells.cuh"
 #include "k_resolve.cuh"
 #include "k_spherical.cuh"
 #include "k_wrap.cuh"
@@ -69,6 +70,9 @@ struct sab_engine {
     int64_t launches = 0;
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
+    // exact-pruning tables of the tetrahedral kernel
+    bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
+    uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -102,7 +106,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
     void *ptrs[] = {e->d_mobile, e->d_centres, e->d_rcut, e->d_rcut_q, e->d_fw_atoms, e->d_nslot, e->d_slot_atom,
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
-                    e->stage[0], e->stage[1], e->ws};
+                    e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
@@ -153,6 +157,7 @@ static int set_slots(sab_engine *e, int smax, const int32_t *n_slot, const int32
     CU(upload(&e->d_slot_atom, at.data(), at.size()));
     CU(upload(&e->d_slot_fw, fw.data(), fw.size()));
     e->pbc_set = false;
+    e->cells_set = false;
     return SAB_OK;
 }
 
@@ -230,6 +235,26 @@ extern "C" int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int
     if (!site_flags) { if (e->d_legacy_init) { cudaFree(e->d_legacy_init); e->d_legacy_init = nullptr; } e->legacy_init_frame = -1; return SAB_OK; }
     CU(upload(&e->d_legacy_init, site_flags, (size_t)e->S));
     e->legacy_init_frame = frames_from_now;
+    return SAB_OK;
+}
+
+extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const double *anchor, int kmin, int nk,
+                                  const uint16_t *records, const int32_t *cell_off, const uint16_t *cell_sites)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_cell_lists: null engine");
+    CU(cudaSetDevice(e->device));
+    if (!anchor) { e->cells_set = false; return SAB_OK; }           // NULL clears the tables
+    if (e->kind != SAB_POLYHEDRAL || !e->d_simp) return fail(SAB_ESTATE, "sab_set_cell_lists: polyhedra not set");
+    if (e->smax != 4 || e->fmax != 4) return fail(SAB_EINVAL, "cell lists are implemented for tetrahedral sites");
+    if (G < 1 || G > 256 || nk < 1 || nk > 8 || !records || !cell_off || !cell_sites || !(delta > 0.0))
+        return fail(SAB_EINVAL, "sab_set_cell_lists: bad arguments");
+    if ((size_t)nk * 3 * e->M > 65535 || e->S > 65535) return fail(SAB_EINVAL, "cell lists: too many framework atoms or sites for 16-bit offsets");
+    size_t ncell = (size_t)G * G * G;
+    CU(upload(&e->d_anchor, anchor, (size_t)3 * e->M));
+    CU(upload(&e->d_rec, records, (size_t)e->S * SAB_TET_REC));
+    CU(upload(&e->d_cell_off, cell_off, ncell + 1));
+    CU(upload(&e->d_cell_sites, cell_sites, (size_t)std::max(cell_off[ncell], 1)));
+    e->G = G; e->delta = delta; e->kmin = kmin; e->nk = nk; e->cells_set = true;
     return SAB_OK;
 }
 
@@ -311,6 +336,35 @@ extern "C" int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_fr
     return SAB_OK;
 }
 
+extern "C" int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, void *d_workspace,
+                                  int64_t workspace_bytes, void *stream, double *excursion)
+{
+    if (!e || !d_frac || !excursion || n_frames <= 0) return fail(SAB_EINVAL, "sab_scan_excursion: bad arguments");
+    if (!e->pbc_set) return fail(SAB_ESTATE, "sab_scan_excursion: PBC state not set");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace w = layout(e, n_frames, d_workspace);
+    if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    bool skip = e->skip_step_check_once;
+    run_wrap_pass(e, d_frac, n_frames, w, st, true);
+    e->skip_step_check_once = skip;
+    CU(cudaGetLastError());
+    std::vector<double> h((size_t)w.n_chunks * w.m3 * 2);
+    CU(cudaMemcpyAsync(h.data(), w.chunk_exc, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int c = 0; c < w.m3; c++) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int k = 0; k < w.n_chunks; k++) {
+            lo = std::min(lo, h[((size_t)k * w.m3 + c) * 2]);
+            hi = std::max(hi, h[((size_t)k * w.m3 + c) * 2 + 1]);
+        }
+        excursion[2 * c] = lo; excursion[2 * c + 1] = hi;
+    }
+    return SAB_OK;
+}
+
 static int launch_assign(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride, int64_t F,
                          int32_t *d_result, int32_t *d_spill, int64_t spill_cap, const Workspace &w, cudaStream_t st,
                          double *d_centres_out)
@@ -343,7 +397,19 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: {
+    case SAB_POLYHEDRAL: if (e->cells_set) {
+        int block = std::min(256, ((e->A + 31) / 32) * 32);
+        size_t smem = sizeof(double) * (size_t)e->nk * 3 * e->M;
+        CU(cudaFuncSetAttribute(k_polyhedral_assign_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
+                        e->d_legacy_init};
+        SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
+                       e->d_anchor, e->delta};
+        int grid2 = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 16);
+        k_polyhedral_assign_cells<<<grid2, block, smem, st>>>(d_frac, F, e->N, e->A, e->d_mobile, e->S, T, C, w.rows,
+            e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+        break;
+    } else {
         int block = 256;
         size_t smem = sizeof(double) * 3 * (size_t)e->A + sizeof(int) * (size_t)e->A * (2 + SAB_POLY_KEEP);
         CU(cudaFuncSetAttribute(k_polyhedral_assign_exhaustive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -155,6 +155,12 @@ class AssignmentEngine:
         self.frames_done = 0
         self.reset_history()
         self.last_info: dict = {}
+        # exact-pruning tables of the tetrahedral kernel (built lazily from the first sizeable batch)
+        self.use_cells = True
+        self.cells_min_frames = 64
+        self._cells = None              # dict(G, delta, n_entries) once uploaded
+        self._cells_stale = False
+        self._seen_exc = None
 
     # ------------------------------------------------------------------ small helpers
     @staticmethod
@@ -193,6 +199,8 @@ class AssignmentEngine:
         (trajectory.py:364-373, polyhedral_site.py:264-279, dynamic_voronoi_site_collection.py:197-201)."""
         self.reset_history()
         self._pbc_ready = False
+        self._cells = None
+        self._seen_exc = None
         if self.slots is not None:
             self.primed = [None] * self.S
         self.frames_done = 0
@@ -266,6 +274,7 @@ class AssignmentEngine:
             exc[pos[a], :, 0] = np.minimum(exc[pos[a], :, 0], p.min(axis=0))
             exc[pos[a], :, 1] = np.maximum(exc[pos[a], :, 1], p.max(axis=0))
         self.slot_shift = np.ascontiguousarray(slot_shift)
+        self._lat0 = np.asarray(lat0, dtype=np.float64)
         nat.check(self.L.sab_set_pbc_state(self.h, nat.ptr(self.slot_shift), nat.ptr(prev_raw), nat.ptr(wraps),
                                            nat.ptr(np.ascontiguousarray(exc))))
         if legacy.any():
@@ -273,6 +282,48 @@ class AssignmentEngine:
         else:
             nat.check(self.L.sab_set_legacy_init(self.h, None, 0))
         self._pbc_ready = True
+
+    # ------------------------------------------------------------------ exact-pruning tables
+    def _maybe_build_cells(self, d_frac, nf, d_ws, ws_bytes, stream, margin=0.55):
+        """Tetrahedral sites: place anchors at the middle of each framework coordinate's observed
+        range, size the validity tube ``delta`` from the widest range, and build the cell lists
+        (``_tables.tet_cell_lists``).  Purely an accelerator: frames outside the tube fall back to
+        the exhaustive path inside the kernel."""
+        if self.k != nat.POLYHEDRAL or not self.use_cells:
+            return
+        if self._cells is not None and not self._cells_stale:
+            return
+        if nf < self.cells_min_frames:
+            return
+        if any(len(s) != 4 for s in self.slots) or any(len(f) != 4 for f in self.simplices) or self.S > 65535:
+            return
+        M = len(self.fw_atoms)
+        exc = np.zeros((M, 3, 2))
+        nat.check(self.L.sab_scan_excursion(self.h, d_frac.data_ptr(), nf, d_ws.data_ptr(), ws_bytes, stream, nat.ptr(exc)))
+        if self._seen_exc is not None:
+            exc[..., 0] = np.minimum(exc[..., 0], self._seen_exc[..., 0])
+            exc[..., 1] = np.maximum(exc[..., 1], self._seen_exc[..., 1])
+        self._seen_exc = exc
+        anchor = np.ascontiguousarray(0.5 * (exc[..., 0] + exc[..., 1]))
+        delta = float(max(margin * (exc[..., 1] - exc[..., 0]).max() + 1e-6, 5e-3))
+        ss = self.slot_shift[:, :4, :].astype(np.int64)
+        kmin, kmax = int(ss.min()), int(ss.max())
+        nk = kmax - kmin + 1
+        P = anchor[self.slot_fw[:, :4]] + ss                        # (S, 4, 3) anchor vertices, unwrapped
+        extent = (P.max(axis=1) - P.min(axis=1)).max()
+        if nk > 8 or nk * 3 * M > 65535 or delta > 0.12 or extent + 2 * delta + 1e-6 >= 0.45:
+            self._cells, self._cells_stale = None, False
+            nat.check(self.L.sab_set_cell_lists(self.h, 1, 1.0, None, 0, 1, None, None, None))
+            return
+        length = float(np.mean(np.linalg.norm(self._lat0, axis=1)))
+        G = int(min(64, max(4, round(length / 0.65 / 4) * 4)))
+        off, ent = tab.tet_cell_lists(P, delta, G)
+        rec = np.ascontiguousarray(tab.tet_records(self.slot_shift, self.slot_fw, self.simplices, kmin, 3 * M))
+        ent = np.ascontiguousarray(ent if len(ent) else np.zeros(1, dtype=np.uint16))
+        nat.check(self.L.sab_set_cell_lists(self.h, G, delta * (1.0 - 1e-9), nat.ptr(anchor), kmin, nk, nat.ptr(rec),
+                                            nat.ptr(np.ascontiguousarray(off)), nat.ptr(ent)))
+        self._cells = dict(G=G, delta=delta, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3)
+        self._cells_stale = False
 
     def _reinit_groups(self, raw_t, lat_t):
         """Dynamic Voronoi: a step >= 0.3 at this frame re-initialises every group that contains a
@@ -407,6 +458,7 @@ class AssignmentEngine:
             d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             cap = self._spill_capacity(nf)
             info = np.zeros(8, dtype=np.int64)
+            self._maybe_build_cells(sub, nf, d_ws, ws_bytes, stream)
             while True:
                 d_spill = torch.empty(cap, dtype=torch.int32, device=dev)
                 code = self.L.sab_assign_device(self.h, sub.data_ptr(), sub_lat.data_ptr(), stride, nf,
@@ -418,6 +470,8 @@ class AssignmentEngine:
                 nat.check(code)
                 break
             n_ok = nf if info[3] < 0 else int(info[3])
+            if self._cells is not None and info[4] > max(1, nf // 50):
+                self._cells_stale = True                 # too many frames left the tube: re-anchor next batch
             total["full27"] += int(info[4]); total["launches"] += int(info[5])
             total["assign_ns"] += int(info[6]); total["wrap_ns"] += int(info[7])
             if info[3] >= 0:
@@ -484,6 +538,16 @@ class AssignmentEngine:
             out = np.empty((F, self.A), dtype=np.int32)
         if self.slots is not None and not self._pbc_ready and F:
             self._init_pbc(frac[0], lattice if lattice.ndim == 2 else lattice[0])
+        if self.k == nat.POLYHEDRAL and self.use_cells and (self._cells is None or self._cells_stale) and F >= self.cells_min_frames:
+            torch = _torch()                              # anchors from a strided sample spanning the trajectory
+            stride = max(1, F // 8192)
+            dev = torch.device("cuda", self.device)
+            d_s = torch.from_numpy(np.ascontiguousarray(frac[::stride][:8192])).to(dev)
+            ws_bytes = int(self.L.sab_workspace_bytes(self.h, d_s.shape[0]))
+            d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            self._maybe_build_cells(d_s, int(d_s.shape[0]), d_ws, ws_bytes, torch.cuda.current_stream(dev).cuda_stream,
+                                    margin=0.65)
+            del d_s, d_ws
         info = np.zeros(8, dtype=np.int64)
         nat.check(self.L.sab_assign_host(self.h, frac.ctypes.data, nat.ptr(lattice), 9 if lattice.ndim == 3 else 0,
                                          F, out.ctypes.data, chunk_frames, nat.ptr(info)))
@@ -491,6 +555,8 @@ class AssignmentEngine:
             raise GuardError(f"frame {int(info[3])}: a framework step >= 0.3 fractional units needs the re-initialising "
                              "path; use AssignmentEngine.assign")
         self._check_excursion()
+        if self._cells is not None and info[4] > max(1, F // 50):
+            self._cells_stale = True
         self._pending.append((out, True))
         self.frames_done += F
         self.last_info = dict(ambiguous=0, full27=int(info[4]), launches=int(info[5]), reinits=0,

@@ -51,6 +51,7 @@ class SiteCollection:
         self._engine_key = None
         self._current = None            # (frac (N,3), lattice (3,3)) of the last analysed structure
         self.strict = True
+        self.use_cells = True           # exact spatial pruning (False: exhaustive kernels only; for cross-checks)
         self.rank_table = None          # optional override of the distance-rank table (testing)
 
     # -- reference API ---------------------------------------------------------------------
@@ -133,6 +134,7 @@ class SiteCollection:
         if self._engine is None or self._engine_key != key:
             self._engine = AssignmentEngine(self._kind, n_atoms, [a.index for a in atoms], strict=self.strict,
                                             rank_table=self.rank_table, **self._engine_kwargs())
+            self._engine.use_cells = self.use_cells
             self._engine_key = key
         return self._engine
 

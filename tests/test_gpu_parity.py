@@ -104,6 +104,35 @@ def test_tetrahedra_need_no_seeded_topology(oracle_mod, name):
     assert np.array_equal(t.trajectory_from_arrays(case["frac"], case["lattice"]), case["atoms_traj"])
 
 
+@pytest.mark.parametrize("name", ["argyrodite_0p_polyhedral", "argyrodite_100p_polyhedral", "fuzz_polyhedral_1",
+                                  "fuzz_polyhedral_3", "fuzz_polyhedral_5", "fuzz_polyhedral_7"])
+def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
+    """Cell-list kernel (k_polyhedral_cells.cuh) vs exhaustive kernel (k_polyhedral.cuh), both vs golden."""
+    case = oracle_mod.load_case(name)
+    outs = []
+    for use_cells in (True, False):
+        t = trajectory_from_case(case)
+        t.site_collection.use_cells = use_cells
+        outs.append(t.trajectory_from_arrays(case["frac"], case["lattice"]))
+        eng = t.site_collection._engine
+        assert (eng._cells is not None) == use_cells, (name, use_cells, eng._cells)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], case["atoms_traj"])
+
+
+def test_frames_outside_the_validity_tube_fall_back_exactly(oracle_mod):
+    """Anchors from the first 70 frames; the next 70 frames (a different vibration sample, some
+    outside the tube) must still come out identical to the oracle."""
+    case = oracle_mod.load_case("argyrodite_0p_polyhedral")
+    t = trajectory_from_case(case)
+    a = t.trajectory_from_arrays(case["frac"][:70], case["lattice"])
+    eng = t.site_collection._engine
+    assert eng._cells is not None
+    b = t.trajectory_from_arrays(case["frac"][70:], case["lattice"])
+    assert np.array_equal(np.vstack([a, b]), case["atoms_traj"])
+    assert eng.last_info["full27"] >= 0
+
+
 def test_reset_and_replay(oracle_mod):
     """Trajectory.reset(): history and PBC caches cleared, topology kept, same answers again."""
     case = oracle_mod.load_case("fuzz_polyhedral_1")
