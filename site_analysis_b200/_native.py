@@ -20,6 +20,8 @@ SPHERICAL, VORONOI, POLYHEDRAL, DYNAMIC_VORONOI = 0, 1, 2, 3
 NONE = -1
 AMBIGUOUS_BASE = -2
 OPT_SKIP_STEP_CHECK_ONCE = 1
+OPT_POLY_KERNEL = 2
+OPT_SEQ_CHUNK = 3
 
 # every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = [

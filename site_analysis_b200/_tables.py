@@ -175,10 +175,10 @@ def tet_cell_lists(anchor_vertices: np.ndarray, delta: float, G: int, eps: float
 
 
 def tet_records(slot_shift: np.ndarray, slot_fw: np.ndarray, simplices, kmin: int, m3: int) -> np.ndarray:
-    """(S, 56) uint16 shared-memory offsets: [0..11] vertices in slot order, then 4 faces x (9 + pad).
-    offset(v, d) = (slot_shift[s, v, d] - kmin) * m3 + 3 * slot_fw[s, v] + d."""
+    """(S, 56) uint16 shared-memory BYTE offsets: [0..11] vertices in slot order, then 4 faces x (9 + pad).
+    offset(v, d) = 8 * ((slot_shift[s, v, d] - kmin) * m3 + 3 * slot_fw[s, v] + d)."""
     S = len(slot_fw)
-    off = (slot_shift[:, :4, :].astype(np.int64) - kmin) * m3 + 3 * slot_fw[:, :4, None].astype(np.int64) + np.arange(3)
+    off = 8 * ((slot_shift[:, :4, :].astype(np.int64) - kmin) * m3 + 3 * slot_fw[:, :4, None].astype(np.int64) + np.arange(3))
     assert off.min() >= 0 and off.max() < 65536
     rec = np.zeros((S, 56), dtype=np.uint16)
     rec[:, :12] = off.reshape(S, 12)

@@ -40,6 +40,12 @@ struct SabTetTables {
     double delta;               // validity radius of the cell lists
 };
 
+// record offsets are BYTE offsets into `var` (pre-multiplied by 8; var is < 64 KB)
+__device__ __forceinline__ double sab_ldvar(const double *var, unsigned byte_off)
+{
+    return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(var) + byte_off);
+}
+
 // One tetrahedron against one wrapped atom position.  `var` = staged unwrapped coordinates.
 __device__ __forceinline__ bool sab_tet_contains(const double *__restrict__ var, const uint16_t *__restrict__ rec,
                                                  const double *x)
@@ -48,10 +54,10 @@ __device__ __forceinline__ bool sab_tet_contains(const double *__restrict__ var,
     {
         const uint2 *r2 = reinterpret_cast<const uint2 *>(rec);      // 24 bytes = 3 x 8
         uint2 a = __ldg(r2), b = __ldg(r2 + 1), c2 = __ldg(r2 + 2);
-        v[0][0] = var[a.x & 0xffff]; v[0][1] = var[a.x >> 16]; v[0][2] = var[a.y & 0xffff];
-        v[1][0] = var[a.y >> 16];    v[1][1] = var[b.x & 0xffff]; v[1][2] = var[b.x >> 16];
-        v[2][0] = var[b.y & 0xffff]; v[2][1] = var[b.y >> 16];    v[2][2] = var[c2.x & 0xffff];
-        v[3][0] = var[c2.x >> 16];   v[3][1] = var[c2.y & 0xffff]; v[3][2] = var[c2.y >> 16];
+        v[0][0] = sab_ldvar(var, a.x & 0xffff); v[0][1] = sab_ldvar(var, a.x >> 16); v[0][2] = sab_ldvar(var, a.y & 0xffff);
+        v[1][0] = sab_ldvar(var, a.y >> 16);    v[1][1] = sab_ldvar(var, b.x & 0xffff); v[1][2] = sab_ldvar(var, b.x >> 16);
+        v[2][0] = sab_ldvar(var, b.y & 0xffff); v[2][1] = sab_ldvar(var, b.y >> 16);    v[2][2] = sab_ldvar(var, c2.x & 0xffff);
+        v[3][0] = sab_ldvar(var, c2.x >> 16);   v[3][1] = sab_ldvar(var, c2.y & 0xffff); v[3][2] = sab_ldvar(var, c2.y >> 16);
     }
     double u[3], c[3], p[3];
 #pragma unroll
@@ -76,9 +82,9 @@ __device__ __forceinline__ bool sab_tet_contains(const double *__restrict__ var,
         const unsigned *r = reinterpret_cast<const unsigned *>(rec + 12 + 10 * j);
         unsigned w0 = __ldg(r), w1 = __ldg(r + 1), w2 = __ldg(r + 2), w3 = __ldg(r + 3), w4 = __ldg(r + 4);
         double v0[3], v1[3], v2[3];
-        v0[0] = var[w0 & 0xffff] + u[0]; v0[1] = var[w0 >> 16] + u[1]; v0[2] = var[w1 & 0xffff] + u[2];
-        v1[0] = var[w1 >> 16] + u[0];    v1[1] = var[w2 & 0xffff] + u[1]; v1[2] = var[w2 >> 16] + u[2];
-        v2[0] = var[w3 & 0xffff] + u[0]; v2[1] = var[w3 >> 16] + u[1];    v2[2] = var[w4 & 0xffff] + u[2];
+        v0[0] = sab_ldvar(var, w0 & 0xffff) + u[0]; v0[1] = sab_ldvar(var, w0 >> 16) + u[1]; v0[2] = sab_ldvar(var, w1 & 0xffff) + u[2];
+        v1[0] = sab_ldvar(var, w1 >> 16) + u[0];    v1[1] = sab_ldvar(var, w2 & 0xffff) + u[1]; v1[2] = sab_ldvar(var, w2 >> 16) + u[2];
+        v2[0] = sab_ldvar(var, w3 & 0xffff) + u[0]; v2[1] = sab_ldvar(var, w3 >> 16) + u[1];    v2[2] = sab_ldvar(var, w4 & 0xffff) + u[2];
         if (!sab_face_accepts(v0, v1, v2, c, p[0], p[1], p[2])) return false;
     }
     return true;

@@ -15,6 +15,7 @@
 #include "k_nearest.cuh"
 #include "k_polyhedral.cuh"
 #include "k_polyhedral_cells.cuh"
+#include "k_polyhedral_seq.cuh"
 #include "k_resolve.cuh"
 #include "k_spherical.cuh"
 #include "k_wrap.cuh"
@@ -69,6 +70,8 @@ struct sab_engine {
     cudaEvent_t ev_free[2] = {nullptr, nullptr};
     int64_t launches = 0;
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
+    int poly_kernel = 0;                   // SAB_OPT_POLY_KERNEL: 0 auto (chunk-sequential), 1 frame-parallel cells
+    int seq_chunk = 64;                    // SAB_OPT_SEQ_CHUNK
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
     // exact-pruning tables of the tetrahedral kernel
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
@@ -248,7 +251,7 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
     if (e->smax != 4 || e->fmax != 4) return fail(SAB_EINVAL, "cell lists are implemented for tetrahedral sites");
     if (G < 1 || G > 256 || nk < 1 || nk > 8 || !records || !cell_off || !cell_sites || !(delta > 0.0))
         return fail(SAB_EINVAL, "sab_set_cell_lists: bad arguments");
-    if ((size_t)nk * 3 * e->M > 65535 || e->S > 65535) return fail(SAB_EINVAL, "cell lists: too many framework atoms or sites for 16-bit offsets");
+    if ((size_t)nk * 3 * e->M * 8 > 65535 || e->S > 65535) return fail(SAB_EINVAL, "cell lists: too many framework atoms or sites for 16-bit offsets");
     size_t ncell = (size_t)G * G * G;
     CU(upload(&e->d_anchor, anchor, (size_t)3 * e->M));
     CU(upload(&e->d_rec, records, (size_t)e->S * SAB_TET_REC));
@@ -262,6 +265,8 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
 {
     if (!e) return fail(SAB_EINVAL, "sab_set_option: null engine");
     if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
+    if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
     return fail(SAB_EINVAL, "unknown option %d", key);
 }
 
@@ -397,7 +402,20 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set) {
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ_THREADS * SAB_SEQ_MAX_OWN) {
+        size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
+                      sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
+        CU(cudaFuncSetAttribute(k_polyhedral_assign_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
+                        e->d_legacy_init};
+        SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
+                       e->d_anchor, e->delta};
+        int64_t n_chunks = (F + e->seq_chunk - 1) / e->seq_chunk;
+        int grid2 = (int)std::min<int64_t>(n_chunks, (int64_t)e->sm_count * 8);
+        k_polyhedral_assign_seq<<<grid2, SAB_SEQ_THREADS, smem, st>>>(d_frac, F, e->seq_chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+            w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+        break;
+    } else if (e->cells_set) {
         int block = std::min(256, ((e->A + 31) / 32) * 32);
         size_t smem = sizeof(double) * (size_t)e->nk * 3 * e->M;
         CU(cudaFuncSetAttribute(k_polyhedral_assign_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -187,6 +187,9 @@ class AssignmentEngine:
         except Exception:
             pass
 
+    def set_option(self, key: int, value: int) -> None:
+        nat.check(self.L.sab_set_option(self.h, int(key), int(value)))
+
     # ------------------------------------------------------------------ history (host)
     def reset_history(self):
         self.recent = -np.ones((self.A, 2), dtype=np.int32)
@@ -311,7 +314,7 @@ class AssignmentEngine:
         nk = kmax - kmin + 1
         P = anchor[self.slot_fw[:, :4]] + ss                        # (S, 4, 3) anchor vertices, unwrapped
         extent = (P.max(axis=1) - P.min(axis=1)).max()
-        if nk > 8 or nk * 3 * M > 65535 or delta > 0.12 or extent + 2 * delta + 1e-6 >= 0.45:
+        if nk > 8 or nk * 3 * M * 8 > 65535 or delta > 0.12 or extent + 2 * delta + 1e-6 >= 0.45:
             self._cells, self._cells_stale = None, False
             nat.check(self.L.sab_set_cell_lists(self.h, 1, 1.0, None, 0, 1, None, None, None))
             return

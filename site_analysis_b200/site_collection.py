@@ -53,6 +53,7 @@ class SiteCollection:
         self.strict = True
         self.use_cells = True           # exact spatial pruning (False: exhaustive kernels only; for cross-checks)
         self.rank_table = None          # optional override of the distance-rank table (testing)
+        self.engine_options: dict[int, int] = {}   # sab_set_option(key, value) pairs applied to the engine
 
     # -- reference API ---------------------------------------------------------------------
     def site_by_index(self, index):
@@ -135,6 +136,8 @@ class SiteCollection:
             self._engine = AssignmentEngine(self._kind, n_atoms, [a.index for a in atoms], strict=self.strict,
                                             rank_table=self.rank_table, **self._engine_kwargs())
             self._engine.use_cells = self.use_cells
+            for k, v in self.engine_options.items():
+                self._engine.set_option(k, v)
             self._engine_key = key
         return self._engine
 

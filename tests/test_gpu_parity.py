@@ -108,16 +108,18 @@ def test_tetrahedra_need_no_seeded_topology(oracle_mod, name):
                                   "fuzz_polyhedral_3", "fuzz_polyhedral_5", "fuzz_polyhedral_7"])
 def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
     """Cell-list kernel (k_polyhedral_cells.cuh) vs exhaustive kernel (k_polyhedral.cuh), both vs golden."""
+    from site_analysis_b200 import _native as nat
     case = oracle_mod.load_case(name)
     outs = []
-    for use_cells in (True, False):
+    for use_cells, opts in ((True, {}), (True, {nat.OPT_SEQ_CHUNK: 7}), (True, {nat.OPT_POLY_KERNEL: 1}), (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
+        t.site_collection.engine_options = opts          # chunk-sequential (default) / odd chunk / frame-parallel
         outs.append(t.trajectory_from_arrays(case["frac"], case["lattice"]))
         eng = t.site_collection._engine
         assert (eng._cells is not None) == use_cells, (name, use_cells, eng._cells)
-    assert np.array_equal(outs[0], outs[1])
-    assert np.array_equal(outs[0], case["atoms_traj"])
+    for o in outs:
+        assert np.array_equal(o, case["atoms_traj"])
 
 
 def test_frames_outside_the_validity_tube_fall_back_exactly(oracle_mod):
