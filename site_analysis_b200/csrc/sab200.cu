@@ -402,9 +402,11 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ_THREADS * SAB_SEQ_MAX_OWN) {
-        size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
-                      sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && 3 * e->M <= SAB_SEQ_STAGE * 64) {
+        // chunk-sequential kernel: block = one warp per 32 mobile atoms (<= 256 threads), staging fits registers
+        int block = std::max(64, std::min(SAB_SEQ_THREADS, ((e->A + 31) / 32) * 32));
+        while (3 * e->M > SAB_SEQ_STAGE * block) block += 32;
+        size_t smem = sizeof(double) * 2 * (size_t)e->nk * 3 * e->M + sizeof(int) * (size_t)e->A;
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
@@ -412,7 +414,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
                        e->d_anchor, e->delta};
         int64_t n_chunks = (F + e->seq_chunk - 1) / e->seq_chunk;
         int grid2 = (int)std::min<int64_t>(n_chunks, (int64_t)e->sm_count * 8);
-        k_polyhedral_assign_seq<<<grid2, SAB_SEQ_THREADS, smem, st>>>(d_frac, F, e->seq_chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+        k_polyhedral_assign_seq<<<grid2, block, smem, st>>>(d_frac, F, e->seq_chunk, e->N, e->A, e->d_mobile, e->S, T, C,
             w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
         break;
     } else if (e->cells_set) {
