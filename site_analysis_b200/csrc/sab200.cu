@@ -402,10 +402,10 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && 3 * e->M <= SAB_SEQ_STAGE * 64) {
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && 3 * e->M <= SAB_SEQ_STAGE * SAB_SEQ_THREADS) {
         // chunk-sequential kernel: block = one warp per 32 mobile atoms (<= 256 threads), staging fits registers
         int block = std::max(64, std::min(SAB_SEQ_THREADS, ((e->A + 31) / 32) * 32));
-        while (3 * e->M > SAB_SEQ_STAGE * block) block += 32;
+        while (3 * e->M > SAB_SEQ_STAGE * block && block < SAB_SEQ_THREADS) block += 32;
         size_t smem = sizeof(double) * 2 * (size_t)e->nk * 3 * e->M + sizeof(int) * (size_t)e->A;
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
