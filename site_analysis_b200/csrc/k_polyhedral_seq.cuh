@@ -95,29 +95,36 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
 {
     extern __shared__ double sm_seq[];
     const int nvar = C.nk * C.m3;
-    double *var0 = sm_seq;                                       // [2][nk][3M] double-buffered
-    int *last = reinterpret_cast<int *>(var0 + 2 * (size_t)nvar); // [A] certain most-recent site or -1
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
-    const unsigned FULL = 0xffffffffu;
+    double *var0 = sm_seq;                                       // [2][nk][3M] double-buffered staging
+    double *xs = var0 + 2 * (size_t)nvar;                        // [A][3] wrapped mobile coordinates of this frame
+    int *last = reinterpret_cast<int *>(xs + 3 * (size_t)n_mobile);   // [A] certain most-recent site or -1
+    int *slot = last + n_mobile;                                 // [A] miss-list slot of the atom in this frame or -1
+    int *miss_atom = slot + n_mobile;                            // [A]
+    int *miss_b = miss_atom + n_mobile;                          // [A] first candidate of the atom's cell list
+    int *miss_len = miss_b + n_mobile;                           // [A] length of that list
+    int *cnt = miss_len + n_mobile;                              // [A] containing sites found
+    int *hits = cnt + n_mobile;                                  // [A][KEEP]
+    __shared__ int n_miss;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const int64_t f0 = ch * chunk, f1 = min(f0 + (int64_t)chunk, n_frames);
-        for (int a = tid; a < n_mobile; a += nthr) last[a] = -1;   // owner-private
-        // prologue: stage the chunk's first frame
-        int bad = 0;
         __syncthreads();                                         // previous chunk fully consumed
-        {
+        for (int a = tid; a < n_mobile; a += nthr) last[a] = -1;
+        if (tid == 0) n_miss = 0;
+        int bad = 0;
+        {                                                        // prologue: stage the chunk's first frame
             const double *frame = frac + (size_t)f0 * n_atoms * 3;
             const int32_t *wrow = wrows + (size_t)f0 * C.m3;
             for (int i = tid; i < C.m3; i += nthr)
-                bad |= sab_stage_write(var0, C, i, frame[(size_t)C.fw_atoms[i / 3] * 3 + (i % 3)], wrow[i]);
+                bad |= sab_stage_write(var0, C, i, __ldcs(frame + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3)), wrow[i]);
         }
         bad = __syncthreads_or(bad);
         for (int64_t f = f0; f < f1; f++) {
             const double *frame = frac + (size_t)f * n_atoms * 3;
             const int32_t *wrow = wrows + (size_t)f * C.m3;
             double *var = var0 + (size_t)((f - f0) & 1) * nvar, *var_next = var0 + (size_t)(((f - f0) & 1) ^ 1) * nvar;
-            // ---- prefetch the next frame's framework coordinates (consumed after this frame's work) ----
+            // ---- prefetch the next frame's framework coordinates (consumed at the end of this frame) ----
             double nraw[SAB_SEQ_STAGE]; int nW[SAB_SEQ_STAGE];
             const bool have_next = f + 1 < f1;
             if (have_next) {
@@ -126,7 +133,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
 #pragma unroll
                 for (int q = 0; q < SAB_SEQ_STAGE; q++) {
                     int i = tid + q * nthr;
-                    if (i < C.m3) { nraw[q] = fr2[(size_t)C.fw_atoms[i / 3] * 3 + (i % 3)]; nW[q] = w2[i]; }
+                    if (i < C.m3) { nraw[q] = __ldcs(fr2 + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3)); nW[q] = __ldcs(w2 + i); }
                 }
             }
             if (T.legacy_init && f == legacy_init_frame) bad = 1;
@@ -143,67 +150,69 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
                     result[(size_t)f * n_mobile + a] = out;
                 }
             } else {
+                // ---- phase 1: the most recent site first (site_collection.py:147-152) -----------------
 #pragma unroll 1
-                for (int a0 = tid - lane; a0 < n_mobile; a0 += nthr) {       // warp-uniform trip count
-                    const int a = a0 + lane;
-                    const bool active = a < n_mobile;
-                    double x[3] = {0.0, 0.0, 0.0};
-                    int la = -1;
-                    if (active) {
+                for (int a = tid; a < n_mobile; a += nthr) {
+                    double x[3];
 #pragma unroll
-                        for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);   // atom.py:104
-                        la = last[a];
-                    }
-                    // ---- phase 1: the most recent site first (site_collection.py:147-152) -------------
-                    bool hit = la >= 0 && sab_tet_contains(var, C.rec + (size_t)la * SAB_TET_REC, x);
-                    int out = la;
-                    // ---- phase 2: atoms that missed, one at a time, 32 candidates per round ----------
-                    unsigned todo = __ballot_sync(FULL, active && !hit);
-                    int cb = 0, ce = 0;
-                    if (active && !hit) {
+                    for (int d = 0; d < 3; d++) { x[d] = sab_pymod1(__ldcs(frame + (size_t)mobile[a] * 3 + d)); xs[3 * a + d] = x[d]; }
+                    const int la = last[a];
+                    if (la >= 0 && sab_tet_contains(var, C.rec + (size_t)la * SAB_TET_REC, x)) {
+                        slot[a] = -1;
+                        result[(size_t)f * n_mobile + a] = la;
+                    } else {
+                        int j = atomicAdd(&n_miss, 1);
                         int cell = sab_cell_of(x, C.G);
-                        cb = __ldg(C.cell_off + cell); ce = __ldg(C.cell_off + cell + 1);
+                        int b = __ldg(C.cell_off + cell);
+                        slot[a] = j; miss_atom[j] = a; miss_b[j] = b; miss_len[j] = __ldg(C.cell_off + cell + 1) - b; cnt[j] = 0;
                     }
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        double bx[3];
-                        bx[0] = __shfl_sync(FULL, x[0], src); bx[1] = __shfl_sync(FULL, x[1], src); bx[2] = __shfl_sync(FULL, x[2], src);
-                        const int b = __shfl_sync(FULL, cb, src), e = __shfl_sync(FULL, ce, src);
-                        int c = 0, first = -1;
-                        for (int base = b; base < e; base += 32) {
-                            const int i = base + lane;
-                            int s = -1;
-                            bool h = false;
-                            if (i < e) { s = __ldg(C.cell_sites + i); h = sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, bx); }
-                            const unsigned hm = __ballot_sync(FULL, h);
-                            if (hm) {
-                                const int s0 = __shfl_sync(FULL, s, __ffs(hm) - 1);
-                                if (c == 0) first = s0;
-                                c += __popc(hm);
+                }
+                __syncthreads();                                  // B1: miss list complete
+                const int nm = n_miss;
+                if (nm) {
+                    // ---- phase 2: (atom, candidate) pairs spread over all threads.  Each thread walks the
+                    // short miss list once (monotone in p), so no prefix array and no extra barrier. --------
+                    {
+                        int j = 0, acc = 0;
+#pragma unroll 1
+                        for (int p = tid;; p += nthr) {
+                            while (j < nm && acc + miss_len[j] <= p) { acc += miss_len[j]; j++; }
+                            if (j >= nm) break;
+                            const int s = __ldg(C.cell_sites + miss_b[j] + (p - acc));
+                            if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * miss_atom[j])) {
+                                int k = atomicAdd(&cnt[j], 1);
+                                if (k < SAB_POLY_KEEP) hits[j * SAB_POLY_KEEP + k] = s;
                             }
                         }
-                        if (lane == src) {
-                            if (c == 0) out = SAB_NONE;                       // recent sites unchanged
-                            else if (c == 1) { out = first; last[a] = first; }
-                            else {                                            // several sites: resolver decides
-                                last[a] = -1;
-                                atomicAdd(&counters[0], 1ULL);
-                                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
-                                if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; out = SAB_NONE; }
-                                else {
-                                    spill[off] = c;
-                                    int k = 0;                                // ascending: the cell list is sorted
-                                    for (int i = b; i < e; i++) {
-                                        int s = C.cell_sites[i];
-                                        if (sab_tet_contains_cold(var, C.rec + (size_t)s * SAB_TET_REC, bx)) spill[off + 1 + k++] = s;
-                                    }
-                                    out = SAB_AMBIGUOUS_BASE - (int)off;
+                    }
+                    __syncthreads();                              // B2: verdicts complete
+                    if (tid == 0) n_miss = 0;
+                    // ---- phase 3: owners collect --------------------------------------------------------
+#pragma unroll 1
+                    for (int a = tid; a < n_mobile; a += nthr) {
+                        const int j = slot[a];
+                        if (j < 0) continue;
+                        const int c = cnt[j];
+                        int out;
+                        if (c == 0) out = SAB_NONE;                   // recent sites unchanged (atom.py:190-192)
+                        else if (c == 1) { out = hits[j * SAB_POLY_KEEP]; last[a] = out; }
+                        else {
+                            last[a] = -1;                             // several sites: the resolver decides
+                            atomicAdd(&counters[0], 1ULL);
+                            unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+                            if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; out = SAB_NONE; }
+                            else {
+                                spill[off] = c;
+                                int k = 0;                            // ascending: the cell list is sorted
+                                for (int i = 0; i < miss_len[j]; i++) {
+                                    int s = C.cell_sites[miss_b[j] + i];
+                                    if (sab_tet_contains_cold(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * a)) spill[off + 1 + k++] = s;
                                 }
+                                out = SAB_AMBIGUOUS_BASE - (int)off;
                             }
                         }
+                        result[(size_t)f * n_mobile + a] = out;
                     }
-                    if (active) result[(size_t)f * n_mobile + a] = out;
                 }
             }
             // ---- stage the next frame from the prefetched registers ----------------------------------
@@ -215,7 +224,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
                     if (i < C.m3) bad_next |= sab_stage_write(var_next, C, i, nraw[q], nW[q]);
                 }
             }
-            bad = __syncthreads_or(bad_next);                    // one barrier per frame
+            bad = __syncthreads_or(bad_next);                    // B3: next frame staged, this frame consumed
         }
     }
 }

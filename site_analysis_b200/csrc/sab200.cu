@@ -406,7 +406,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         // chunk-sequential kernel: block = one warp per 32 mobile atoms (<= 256 threads), staging fits registers
         int block = std::max(64, std::min(SAB_SEQ_THREADS, ((e->A + 31) / 32) * 32));
         while (3 * e->M > SAB_SEQ_STAGE * block && block < SAB_SEQ_THREADS) block += 32;
-        size_t smem = sizeof(double) * 2 * (size_t)e->nk * 3 * e->M + sizeof(int) * (size_t)e->A;
+        size_t smem = sizeof(double) * (2 * (size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) + sizeof(int) * (size_t)e->A * (6 + SAB_POLY_KEEP);
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
