@@ -86,6 +86,20 @@ __device__ __forceinline__ int sab_stage_write(double *__restrict__ var, const S
     return fabs((raw - (double)W) - C.anchor[i]) > C.delta;
 }
 
+__device__ __forceinline__ void sab_cp_async8(void *smem_dst, const void *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sab_cp_async4(void *smem_dst, const void *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sab_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
+// Shared-memory layout (byte offsets from the dynamic base), one atom per thread (A <= blockDim):
+//   var[2][nk][3M] f64 | raw[3M] f64 | xraw[A][3] f64 | xs[A][3] f64 | rawW[3M] i32 | miss_atom/miss_b/miss_len/cnt[A] i32 | hits[A][KEEP] i32
 __global__ void __launch_bounds__(SAB_SEQ_THREADS, SAB_SEQ_MINBLOCKS)
 k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int chunk, int n_atoms, int n_mobile,
                         const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabTetTables C,
@@ -95,136 +109,127 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
 {
     extern __shared__ double sm_seq[];
     const int nvar = C.nk * C.m3;
-    double *var0 = sm_seq;                                       // [2][nk][3M] double-buffered staging
-    double *xs = var0 + 2 * (size_t)nvar;                        // [A][3] wrapped mobile coordinates of this frame
-    int *last = reinterpret_cast<int *>(xs + 3 * (size_t)n_mobile);   // [A] certain most-recent site or -1
-    int *slot = last + n_mobile;                                 // [A] miss-list slot of the atom in this frame or -1
-    int *miss_atom = slot + n_mobile;                            // [A]
-    int *miss_b = miss_atom + n_mobile;                          // [A] first candidate of the atom's cell list
-    int *miss_len = miss_b + n_mobile;                           // [A] length of that list
-    int *cnt = miss_len + n_mobile;                              // [A] containing sites found
-    int *hits = cnt + n_mobile;                                  // [A][KEEP]
+    double *const var0 = sm_seq;
+    double *const raw = var0 + 2 * nvar;
+    double *const xraw = raw + C.m3;
+    double *const xs = xraw + 3 * n_mobile;
+    int *const rawW = reinterpret_cast<int *>(xs + 3 * n_mobile);
+    int *const miss_atom = rawW + C.m3;
+    int *const miss_b = miss_atom + n_mobile;
+    int *const miss_len = miss_b + n_mobile;
+    int *const cnt = miss_len + n_mobile;
+    int *const hits = cnt + n_mobile;
     __shared__ int n_miss;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const bool owner = tid < n_mobile;
+    const int my_atom = owner ? mobile[tid] : 0;
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const int64_t f0 = ch * chunk, f1 = min(f0 + (int64_t)chunk, n_frames);
+        int la = -1;                                             // certain most-recent site of my atom, or -1
         __syncthreads();                                         // previous chunk fully consumed
-        for (int a = tid; a < n_mobile; a += nthr) last[a] = -1;
         if (tid == 0) n_miss = 0;
-        int bad = 0;
-        {                                                        // prologue: stage the chunk's first frame
+        {                                                        // prologue: fetch the chunk's first frame
             const double *frame = frac + (size_t)f0 * n_atoms * 3;
             const int32_t *wrow = wrows + (size_t)f0 * C.m3;
-            for (int i = tid; i < C.m3; i += nthr)
-                bad |= sab_stage_write(var0, C, i, __ldcs(frame + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3)), wrow[i]);
+            for (int i = tid; i < C.m3; i += nthr) {
+                sab_cp_async8(raw + i, frame + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3));
+                sab_cp_async4(rawW + i, wrow + i);
+            }
+            if (owner) for (int d = 0; d < 3; d++) sab_cp_async8(xraw + 3 * tid + d, frame + (size_t)my_atom * 3 + d);
         }
-        bad = __syncthreads_or(bad);
         for (int64_t f = f0; f < f1; f++) {
             const double *frame = frac + (size_t)f * n_atoms * 3;
             const int32_t *wrow = wrows + (size_t)f * C.m3;
-            double *var = var0 + (size_t)((f - f0) & 1) * nvar, *var_next = var0 + (size_t)(((f - f0) & 1) ^ 1) * nvar;
-            // ---- prefetch the next frame's framework coordinates (consumed at the end of this frame) ----
-            double nraw[SAB_SEQ_STAGE]; int nW[SAB_SEQ_STAGE];
-            const bool have_next = f + 1 < f1;
-            if (have_next) {
+            double *const var = var0 + (int)((f - f0) & 1) * nvar;
+            // ---- stage this frame from the prefetched raw values (each thread reads back only what it
+            // copied itself, so waiting on its own cp.async group is enough) ------------------------
+            sab_cp_async_wait_all();
+            int bad = 0;
+            for (int i = tid; i < C.m3; i += nthr) bad |= sab_stage_write(var, C, i, raw[i], rawW[i]);
+            double x[3] = {0.0, 0.0, 0.0};
+            if (owner) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) { x[d] = sab_pymod1(xraw[3 * tid + d]); xs[3 * tid + d] = x[d]; }   // atom.py:104
+            }
+            bad = __syncthreads_or(bad);                         // B0: var + xs complete
+            if (f + 1 < f1) {                                    // prefetch the next frame (lands during this frame's work)
                 const double *fr2 = frame + (size_t)n_atoms * 3;
                 const int32_t *w2 = wrow + C.m3;
-#pragma unroll
-                for (int q = 0; q < SAB_SEQ_STAGE; q++) {
-                    int i = tid + q * nthr;
-                    if (i < C.m3) { nraw[q] = __ldcs(fr2 + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3)); nW[q] = __ldcs(w2 + i); }
+                for (int i = tid; i < C.m3; i += nthr) {
+                    sab_cp_async8(raw + i, fr2 + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3));
+                    sab_cp_async4(rawW + i, w2 + i);
                 }
+                if (owner) for (int d = 0; d < 3; d++) sab_cp_async8(xraw + 3 * tid + d, fr2 + (size_t)my_atom * 3 + d);
             }
             if (T.legacy_init && f == legacy_init_frame) bad = 1;
             if (bad) {
                 // ---- exhaustive generic path for this frame (outside the validity tube) -------
                 if (tid == 0) atomicAdd(n_fallback, 1ULL);
-#pragma unroll 1
-                for (int a = tid; a < n_mobile; a += nthr) {
+                if (owner) {
                     int c = 0;
-                    int out = sab_exhaustive_atom(frame, wrow, f, legacy_init_frame, mobile[a], n_sites, T, spill,
+                    int out = sab_exhaustive_atom(frame, wrow, f, legacy_init_frame, my_atom, n_sites, T, spill,
                                                   spill_capacity, counters, &c);
-                    if (c == 1) last[a] = out;
-                    else if (c > 1) last[a] = -1;
-                    result[(size_t)f * n_mobile + a] = out;
+                    if (c == 1) la = out;
+                    else if (c > 1) la = -1;
+                    result[(size_t)f * n_mobile + tid] = out;
                 }
-            } else {
-                // ---- phase 1: the most recent site first (site_collection.py:147-152) -----------------
-#pragma unroll 1
-                for (int a = tid; a < n_mobile; a += nthr) {
-                    double x[3];
-#pragma unroll
-                    for (int d = 0; d < 3; d++) { x[d] = sab_pymod1(__ldcs(frame + (size_t)mobile[a] * 3 + d)); xs[3 * a + d] = x[d]; }
-                    const int la = last[a];
-                    if (la >= 0 && sab_tet_contains(var, C.rec + (size_t)la * SAB_TET_REC, x)) {
-                        slot[a] = -1;
-                        result[(size_t)f * n_mobile + a] = la;
-                    } else {
-                        int j = atomicAdd(&n_miss, 1);
-                        int cell = sab_cell_of(x, C.G);
-                        int b = __ldg(C.cell_off + cell);
-                        slot[a] = j; miss_atom[j] = a; miss_b[j] = b; miss_len[j] = __ldg(C.cell_off + cell + 1) - b; cnt[j] = 0;
-                    }
+                continue;                                        // uniform
+            }
+            // ---- phase 1: the most recent site first (site_collection.py:147-152) ---------------------
+            int myslot = -1;
+            if (owner) {
+                if (la >= 0 && sab_tet_contains(var, C.rec + (size_t)la * SAB_TET_REC, x)) {
+                    result[(size_t)f * n_mobile + tid] = la;
+                } else {
+                    myslot = atomicAdd(&n_miss, 1);
+                    const int cell = sab_cell_of(x, C.G);
+                    const int b = __ldg(C.cell_off + cell);
+                    miss_atom[myslot] = tid; miss_b[myslot] = b; miss_len[myslot] = __ldg(C.cell_off + cell + 1) - b; cnt[myslot] = 0;
                 }
-                __syncthreads();                                  // B1: miss list complete
-                const int nm = n_miss;
-                if (nm) {
-                    // ---- phase 2: (atom, candidate) pairs spread over all threads.  Each thread walks the
-                    // short miss list once (monotone in p), so no prefix array and no extra barrier. --------
-                    {
-                        int j = 0, acc = 0;
+            }
+            __syncthreads();                                     // B1: miss list complete
+            const int nm = n_miss;
+            if (nm == 0) continue;                               // uniform
+            // ---- phase 2: (atom, candidate) pairs spread over all threads -----------------------------
+            {
+                int j = 0, acc = 0;
 #pragma unroll 1
-                        for (int p = tid;; p += nthr) {
-                            while (j < nm && acc + miss_len[j] <= p) { acc += miss_len[j]; j++; }
-                            if (j >= nm) break;
-                            const int s = __ldg(C.cell_sites + miss_b[j] + (p - acc));
-                            if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * miss_atom[j])) {
-                                int k = atomicAdd(&cnt[j], 1);
-                                if (k < SAB_POLY_KEEP) hits[j * SAB_POLY_KEEP + k] = s;
-                            }
-                        }
-                    }
-                    __syncthreads();                              // B2: verdicts complete
-                    if (tid == 0) n_miss = 0;
-                    // ---- phase 3: owners collect --------------------------------------------------------
-#pragma unroll 1
-                    for (int a = tid; a < n_mobile; a += nthr) {
-                        const int j = slot[a];
-                        if (j < 0) continue;
-                        const int c = cnt[j];
-                        int out;
-                        if (c == 0) out = SAB_NONE;                   // recent sites unchanged (atom.py:190-192)
-                        else if (c == 1) { out = hits[j * SAB_POLY_KEEP]; last[a] = out; }
-                        else {
-                            last[a] = -1;                             // several sites: the resolver decides
-                            atomicAdd(&counters[0], 1ULL);
-                            unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
-                            if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; out = SAB_NONE; }
-                            else {
-                                spill[off] = c;
-                                int k = 0;                            // ascending: the cell list is sorted
-                                for (int i = 0; i < miss_len[j]; i++) {
-                                    int s = C.cell_sites[miss_b[j] + i];
-                                    if (sab_tet_contains_cold(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * a)) spill[off + 1 + k++] = s;
-                                }
-                                out = SAB_AMBIGUOUS_BASE - (int)off;
-                            }
-                        }
-                        result[(size_t)f * n_mobile + a] = out;
+                for (int p = tid;; p += nthr) {
+                    while (j < nm && acc + miss_len[j] <= p) { acc += miss_len[j]; j++; }
+                    if (j >= nm) break;
+                    const int s = __ldg(C.cell_sites + miss_b[j] + (p - acc));
+                    if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * miss_atom[j])) {
+                        int k = atomicAdd(&cnt[j], 1);
+                        if (k < SAB_POLY_KEEP) hits[j * SAB_POLY_KEEP + k] = s;
                     }
                 }
             }
-            // ---- stage the next frame from the prefetched registers ----------------------------------
-            int bad_next = 0;
-            if (have_next) {
-#pragma unroll
-                for (int q = 0; q < SAB_SEQ_STAGE; q++) {
-                    int i = tid + q * nthr;
-                    if (i < C.m3) bad_next |= sab_stage_write(var_next, C, i, nraw[q], nW[q]);
+            __syncthreads();                                     // B2: verdicts complete
+            if (tid == 0) { n_miss = 0; atomicAdd(&counters[5], (unsigned long long)nm); }
+            // ---- phase 3: owners collect -----------------------------------------------------------------
+            if (myslot >= 0) {
+                const int c = cnt[myslot];
+                int out;
+                if (c == 0) out = SAB_NONE;                       // recent sites unchanged (atom.py:190-192)
+                else if (c == 1) { out = hits[myslot * SAB_POLY_KEEP]; la = out; }
+                else {
+                    la = -1;                                      // several sites: the resolver decides
+                    atomicAdd(&counters[0], 1ULL);
+                    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+                    if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; out = SAB_NONE; }
+                    else {
+                        spill[off] = c;
+                        int k = 0;                                // ascending: the cell list is sorted
+                        for (int i = 0; i < miss_len[myslot]; i++) {
+                            int s = C.cell_sites[miss_b[myslot] + i];
+                            if (sab_tet_contains_cold(var, C.rec + (size_t)s * SAB_TET_REC, x)) spill[off + 1 + k++] = s;
+                        }
+                        out = SAB_AMBIGUOUS_BASE - (int)off;
+                    }
                 }
+                result[(size_t)f * n_mobile + tid] = out;
             }
-            bad = __syncthreads_or(bad_next);                    // B3: next frame staged, this frame consumed
         }
     }
 }

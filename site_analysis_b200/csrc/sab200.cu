@@ -8,6 +8,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -402,19 +403,22 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && 3 * e->M <= SAB_SEQ_STAGE * SAB_SEQ_THREADS) {
-        // chunk-sequential kernel: block = one warp per 32 mobile atoms (<= 256 threads), staging fits registers
-        int block = std::max(64, std::min(SAB_SEQ_THREADS, ((e->A + 31) / 32) * 32));
-        while (3 * e->M > SAB_SEQ_STAGE * block && block < SAB_SEQ_THREADS) block += 32;
-        size_t smem = sizeof(double) * (2 * (size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) + sizeof(int) * (size_t)e->A * (6 + SAB_POLY_KEEP);
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ_THREADS) {
+        // chunk-sequential kernel: one thread per mobile atom
+        int block = std::max(64, ((e->A + 31) / 32) * 32);
+        size_t m3 = 3 * (size_t)e->M;
+        size_t smem = sizeof(double) * (2 * (size_t)e->nk * m3 + m3 + 6 * (size_t)e->A) +
+                      sizeof(int) * (m3 + (size_t)e->A * (4 + SAB_POLY_KEEP));
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
         SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
                        e->d_anchor, e->delta};
-        int64_t n_chunks = (F + e->seq_chunk - 1) / e->seq_chunk;
+        // chunk: long enough to amortise the history-free first frame, short enough to fill the GPU
+        int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk, F / ((int64_t)e->sm_count * 8)));
+        int64_t n_chunks = (F + chunk - 1) / chunk;
         int grid2 = (int)std::min<int64_t>(n_chunks, (int64_t)e->sm_count * 8);
-        k_polyhedral_assign_seq<<<grid2, block, smem, st>>>(d_frac, F, e->seq_chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+        k_polyhedral_assign_seq<<<grid2, block, smem, st>>>(d_frac, F, chunk, e->N, e->A, e->d_mobile, e->S, T, C,
             w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
         break;
     } else if (e->cells_set) {
@@ -494,6 +498,9 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
         cudaEventElapsedTime(&ms_main, e->ev_t[1], e->ev_t[2]);
         info[6] = (int64_t)((double)ms_main * 1e6);
         info[7] = (int64_t)((double)ms_wrap * 1e6);
+        if (const char *dbg = getenv("SAB_DEBUG")) if (dbg[0] == '1')
+            fprintf(stderr, "[sab] frames=%lld full-search atom-frames=%llu (%.3f per frame) fallback frames=%llu assign=%.3f ms wrap=%.3f ms\n",
+                    (long long)n_frames, h[5], (double)h[5] / (double)n_frames, h[CNT_FULL27], ms_main, ms_wrap);
     }
     if (h[CNT_OVERFLOW]) {                   // nothing committed: the caller retries with a larger spill buffer
         info[5] = e->launches - l0;
