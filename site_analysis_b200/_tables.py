@@ -175,16 +175,15 @@ def tet_cell_lists(anchor_vertices: np.ndarray, delta: float, G: int, eps: float
 
 
 def tet_records(slot_shift: np.ndarray, slot_fw: np.ndarray, simplices, kmin: int, m3: int) -> np.ndarray:
-    """(S, 56) uint16 shared-memory BYTE offsets: [0..11] vertices in slot order, then 4 faces x (9 + pad).
-    offset(v, d) = 8 * ((slot_shift[s, v, d] - kmin) * m3 + 3 * slot_fw[s, v] + d)."""
+    """(S, 20) uint16 site records of the tetrahedral kernels: [0..11] BYTE offsets into the staged
+    coordinate table of the 4 vertices in slot order, offset(v, d) = 8 * ((slot_shift[s, v, d] - kmin) * m3
+    + 3 * slot_fw[s, v] + d); [12..17] twelve bytes = local vertex number of (face j, corner k) in Qhull's
+    own order; [18..19] padding."""
     S = len(slot_fw)
     off = 8 * ((slot_shift[:, :4, :].astype(np.int64) - kmin) * m3 + 3 * slot_fw[:, :4, None].astype(np.int64) + np.arange(3))
     assert off.min() >= 0 and off.max() < 65536
-    rec = np.zeros((S, 56), dtype=np.uint16)
+    rec = np.zeros((S, 20), dtype=np.uint16)
     rec[:, :12] = off.reshape(S, 12)
-    simp = np.stack([np.asarray(f, dtype=np.int64) for f in simplices])          # (S, 4, 3)
-    rows = np.arange(S)[:, None, None]
-    face_off = off[rows, simp, :]                                                  # (S, 4 faces, 3 verts, 3 dims)
-    for j in range(4):
-        rec[:, 12 + 10 * j:12 + 10 * j + 9] = face_off[:, j].reshape(S, 9)
+    simp = np.stack([np.asarray(f, dtype=np.uint8) for f in simplices]).reshape(S, 12)     # (S, 4 faces x 3 corners)
+    rec[:, 12:18] = np.ascontiguousarray(simp).view(np.uint16)
     return rec

@@ -24,14 +24,15 @@
 #pragma once
 #include "k_polyhedral.cuh"
 
-#define SAB_TET_REC 56          // uint16 per site record (112 bytes)
+#define SAB_TET_REC 20          // uint16 per site record (40 bytes)
 
 struct SabTetTables {
     int M, m3;                  // referenced framework atoms, 3 M
     int kmin, nk;               // slot-shift values kmin .. kmin + nk - 1
     const int32_t *fw_atoms;    // [M]
-    // [S][56] shared-memory offsets into `var`: [0..11] the 4 vertices in SLOT order (x y z each),
-    // then 4 faces x 10: v0 v1 v2 of the face in Qhull's vertex order (9 offsets + 1 pad)
+    // [S][20] uint16: [0..11] byte offsets into `var` of the 4 vertices in SLOT order (x y z each);
+    // [12..17] = 12 bytes: local vertex number of (face j, corner k) in Qhull's order; [18..19] pad.
+    // 40 bytes per site keep the whole table L1-resident (1056 sites = 42 KB).
     const uint16_t *rec;
     int G;                      // cells per axis
     const int32_t *cell_off;    // [G^3 + 1]
@@ -77,14 +78,24 @@ __device__ __forceinline__ bool sab_tet_contains(const double *__restrict__ var,
         if (o_d != 0.0 && o_d != 1.0) return false;             // no image of x within reach of this site
         p[d] = (o_d == 1.0) ? 1.0 + x[d] : x[d];
     }
+    const unsigned fv0 = __ldg(reinterpret_cast<const unsigned *>(rec + 12));      // faces 0, 1(first corner)
+    const unsigned fv1 = __ldg(reinterpret_cast<const unsigned *>(rec + 14));
+    const unsigned fv2 = __ldg(reinterpret_cast<const unsigned *>(rec + 16));
 #pragma unroll 1
     for (int j = 0; j < 4; j++) {
-        const unsigned *r = reinterpret_cast<const unsigned *>(rec + 12 + 10 * j);
-        unsigned w0 = __ldg(r), w1 = __ldg(r + 1), w2 = __ldg(r + 2), w3 = __ldg(r + 3), w4 = __ldg(r + 4);
+        // corners of face j: bytes 3j, 3j+1, 3j+2 of the 12-byte string fv0|fv1|fv2
+        unsigned long long lo = ((unsigned long long)fv1 << 32) | fv0;
+        unsigned c3;
+        if (j < 2) c3 = (unsigned)(lo >> (24 * j));
+        else c3 = (unsigned)((((unsigned long long)fv2 << 32) | fv1) >> (24 * j - 32));
+        const int i0 = c3 & 0xff, i1 = (c3 >> 8) & 0xff, i2 = (c3 >> 16) & 0xff;
         double v0[3], v1[3], v2[3];
-        v0[0] = sab_ldvar(var, w0 & 0xffff) + u[0]; v0[1] = sab_ldvar(var, w0 >> 16) + u[1]; v0[2] = sab_ldvar(var, w1 & 0xffff) + u[2];
-        v1[0] = sab_ldvar(var, w1 >> 16) + u[0];    v1[1] = sab_ldvar(var, w2 & 0xffff) + u[1]; v1[2] = sab_ldvar(var, w2 >> 16) + u[2];
-        v2[0] = sab_ldvar(var, w3 & 0xffff) + u[0]; v2[1] = sab_ldvar(var, w3 >> 16) + u[1];    v2[2] = sab_ldvar(var, w4 & 0xffff) + u[2];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            v0[d] = sab_ldvar(var, __ldg(rec + 3 * i0 + d)) + u[d];
+            v1[d] = sab_ldvar(var, __ldg(rec + 3 * i1 + d)) + u[d];
+            v2[d] = sab_ldvar(var, __ldg(rec + 3 * i2 + d)) + u[d];
+        }
         if (!sab_face_accepts(v0, v1, v2, c, p[0], p[1], p[2])) return false;
     }
     return true;

@@ -99,7 +99,7 @@ __device__ __forceinline__ void sab_cp_async4(void *smem_dst, const void *gmem_s
 __device__ __forceinline__ void sab_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
 // Shared-memory layout (byte offsets from the dynamic base), one atom per thread (A <= blockDim):
-//   var[2][nk][3M] f64 | raw[3M] f64 | xraw[A][3] f64 | xs[A][3] f64 | rawW[3M] i32 | miss_atom/miss_b/miss_len/cnt[A] i32 | hits[A][KEEP] i32
+//   var[nk][3M] f64 | raw[3M] f64 | xraw[A][3] f64 | xs[A][3] f64 | rawW[3M] i32 | miss_atom/miss_b/miss_len/cnt[A] i32 | hits[A][KEEP] i32
 __global__ void __launch_bounds__(SAB_SEQ_THREADS, SAB_SEQ_MINBLOCKS)
 k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int chunk, int n_atoms, int n_mobile,
                         const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabTetTables C,
@@ -109,8 +109,8 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
 {
     extern __shared__ double sm_seq[];
     const int nvar = C.nk * C.m3;
-    double *const var0 = sm_seq;
-    double *const raw = var0 + 2 * nvar;
+    double *const var = sm_seq;
+    double *const raw = var + nvar;
     double *const xraw = raw + C.m3;
     double *const xs = xraw + 3 * n_mobile;
     int *const rawW = reinterpret_cast<int *>(xs + 3 * n_mobile);
@@ -127,6 +127,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const int64_t f0 = ch * chunk, f1 = min(f0 + (int64_t)chunk, n_frames);
         int la = -1;                                             // certain most-recent site of my atom, or -1
+        int prev_nm = 0;
         __syncthreads();                                         // previous chunk fully consumed
         if (tid == 0) n_miss = 0;
         {                                                        // prologue: fetch the chunk's first frame
@@ -141,7 +142,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
         for (int64_t f = f0; f < f1; f++) {
             const double *frame = frac + (size_t)f * n_atoms * 3;
             const int32_t *wrow = wrows + (size_t)f * C.m3;
-            double *const var = var0 + (int)((f - f0) & 1) * nvar;
+            if (prev_nm) __syncthreads();                        // phase 3 of the previous frame may still read var
             // ---- stage this frame from the prefetched raw values (each thread reads back only what it
             // copied itself, so waiting on its own cp.async group is enough) ------------------------
             sab_cp_async_wait_all();
@@ -174,6 +175,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
                     else if (c > 1) la = -1;
                     result[(size_t)f * n_mobile + tid] = out;
                 }
+                prev_nm = 0;
                 continue;                                        // uniform
             }
             // ---- phase 1: the most recent site first (site_collection.py:147-152) ---------------------
@@ -190,6 +192,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
             }
             __syncthreads();                                     // B1: miss list complete
             const int nm = n_miss;
+            prev_nm = nm;
             if (nm == 0) continue;                               // uniform
             // ---- phase 2: (atom, candidate) pairs spread over all threads -----------------------------
             {

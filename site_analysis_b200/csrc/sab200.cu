@@ -407,7 +407,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         // chunk-sequential kernel: one thread per mobile atom
         int block = std::max(64, ((e->A + 31) / 32) * 32);
         size_t m3 = 3 * (size_t)e->M;
-        size_t smem = sizeof(double) * (2 * (size_t)e->nk * m3 + m3 + 6 * (size_t)e->A) +
+        size_t smem = sizeof(double) * ((size_t)e->nk * m3 + m3 + 6 * (size_t)e->A) +
                       sizeof(int) * (m3 + (size_t)e->A * (4 + SAB_POLY_KEEP));
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
