@@ -1,0 +1,29 @@
+"""A/B timing of the polyhedral kernel variants on identical device-resident data.
+usage (GPU box): python profiles/ab_kernels.py [frames]"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from site_analysis_b200 import AssignmentEngine, _native as nat, synthetic as syn
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 125000
+g = syn.argyrodite_geometry(2)
+d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
+kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
+ref = None
+for label, opts in [("seq (default)", {}), ("seq chunk=32", {nat.OPT_SEQ_CHUNK: 32}), ("seq chunk=128", {nat.OPT_SEQ_CHUNK: 128}),
+                    ("seq1 (256 thr, 5 barriers)", {nat.OPT_POLY_KERNEL: 2}), ("seq1 chunk=128", {nat.OPT_POLY_KERNEL: 2, nat.OPT_SEQ_CHUNK: 128}),
+                    ("frame-parallel cells", {nat.OPT_POLY_KERNEL: 1})]:
+    e = AssignmentEngine("polyhedral", g.n_atoms, g.mobile_idx, **kw)
+    for k, v in opts.items():
+        e.set_option(k, v)
+    ts = []
+    for i in range(5):
+        r = e.assign_device(d_frac, d_lat)
+        e._pending = []
+        ts.append(e.last_info["assign_ns"] * 1e-6)
+    r = r.cpu().numpy()
+    if ref is None:
+        ref = r
+    print(f"{label:32s} assign kernel ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}", flush=True)

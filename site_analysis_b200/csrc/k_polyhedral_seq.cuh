@@ -197,16 +197,25 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
             // ---- phase 2: (atom, candidate) pairs spread over all threads -----------------------------
             {
                 int j = 0, acc = 0;
+#ifdef SAB_SEQ_STATS
+                int ntests = 0;
+#endif
 #pragma unroll 1
                 for (int p = tid;; p += nthr) {
                     while (j < nm && acc + miss_len[j] <= p) { acc += miss_len[j]; j++; }
                     if (j >= nm) break;
+#ifdef SAB_SEQ_STATS
+                    ntests++;
+#endif
                     const int s = __ldg(C.cell_sites + miss_b[j] + (p - acc));
                     if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * miss_atom[j])) {
                         int k = atomicAdd(&cnt[j], 1);
                         if (k < SAB_POLY_KEEP) hits[j * SAB_POLY_KEEP + k] = s;
                     }
                 }
+#ifdef SAB_SEQ_STATS
+                if (ntests) atomicAdd(&counters[6], (unsigned long long)ntests);
+#endif
             }
             __syncthreads();                                     // B2: verdicts complete
             if (tid == 0) { n_miss = 0; atomicAdd(&counters[5], (unsigned long long)nm); }

@@ -17,6 +17,7 @@
 #include "k_polyhedral.cuh"
 #include "k_polyhedral_cells.cuh"
 #include "k_polyhedral_seq.cuh"
+#include "k_polyhedral_seq1.cuh"
 #include "k_resolve.cuh"
 #include "k_spherical.cuh"
 #include "k_wrap.cuh"
@@ -403,7 +404,20 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ_THREADS) {
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 2 && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
+        size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
+                      sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
+        CU(cudaFuncSetAttribute(k_polyhedral_assign_seq1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
+                        e->d_legacy_init};
+        SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
+                       e->d_anchor, e->delta};
+        int64_t n_chunks = (F + e->seq_chunk - 1) / e->seq_chunk;
+        int grid2 = (int)std::min<int64_t>(n_chunks, (int64_t)e->sm_count * 8);
+        k_polyhedral_assign_seq1<<<grid2, SAB_SEQ1_THREADS, smem, st>>>(d_frac, F, e->seq_chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+            w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+        break;
+    } else if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ_THREADS) {
         // chunk-sequential kernel: one thread per mobile atom
         int block = std::max(64, ((e->A + 31) / 32) * 32);
         size_t m3 = 3 * (size_t)e->M;
@@ -499,8 +513,8 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
         info[6] = (int64_t)((double)ms_main * 1e6);
         info[7] = (int64_t)((double)ms_wrap * 1e6);
         if (const char *dbg = getenv("SAB_DEBUG")) if (dbg[0] == '1')
-            fprintf(stderr, "[sab] frames=%lld full-search atom-frames=%llu (%.3f per frame) fallback frames=%llu assign=%.3f ms wrap=%.3f ms\n",
-                    (long long)n_frames, h[5], (double)h[5] / (double)n_frames, h[CNT_FULL27], ms_main, ms_wrap);
+            fprintf(stderr, "[sab] frames=%lld full-search atom-frames=%llu (%.3f per frame) pair tests=%llu (%.1f per frame) fallback frames=%llu assign=%.3f ms wrap=%.3f ms\n",
+                    (long long)n_frames, h[5], (double)h[5] / (double)n_frames, h[6], (double)h[6] / (double)n_frames, h[CNT_FULL27], ms_main, ms_wrap);
     }
     if (h[CNT_OVERFLOW]) {                   // nothing committed: the caller retries with a larger spill buffer
         info[5] = e->launches - l0;
