@@ -12,9 +12,9 @@ g = syn.argyrodite_geometry(2)
 d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
-for label, opts in [("seq (default)", {}), ("seq chunk=32", {nat.OPT_SEQ_CHUNK: 32}), ("seq chunk=128", {nat.OPT_SEQ_CHUNK: 128}),
-                    ("seq1 (256 thr, 5 barriers)", {nat.OPT_POLY_KERNEL: 2}), ("seq1 chunk=128", {nat.OPT_POLY_KERNEL: 2, nat.OPT_SEQ_CHUNK: 128}),
-                    ("frame-parallel cells", {nat.OPT_POLY_KERNEL: 1})]:
+VARIANTS = [("seq1 dynamic (default)", {}), ("seq1 chunk=32", {nat.OPT_SEQ_CHUNK: 32}), ("seq1 chunk=128", {nat.OPT_SEQ_CHUNK: 128}),
+            ("seq cp.async variant", {nat.OPT_POLY_KERNEL: 3}), ("frame-parallel cells", {nat.OPT_POLY_KERNEL: 1})]
+for label, opts in VARIANTS:
     e = AssignmentEngine("polyhedral", g.n_atoms, g.mobile_idx, **kw)
     for k, v in opts.items():
         e.set_option(k, v)

@@ -22,6 +22,7 @@ AMBIGUOUS_BASE = -2
 OPT_SKIP_STEP_CHECK_ONCE = 1
 OPT_POLY_KERNEL = 2
 OPT_SEQ_CHUNK = 3
+OPT_SEQ_BLOCK = 4
 
 # every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = [

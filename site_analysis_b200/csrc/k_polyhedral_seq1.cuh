@@ -23,9 +23,15 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
     int *last = hits + (size_t)n_mobile * SAB_POLY_KEEP;         // [A] certain most-recent site or -1
     int *slot = last + n_mobile;                                 // [A] miss-list slot of the atom in this frame
     __shared__ int n_miss;
+    __shared__ long long next_chunk;
     const int tid = threadIdx.x;
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
-    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    for (;;) {                                                   // persistent CTAs pull chunks from a global counter
+        __syncthreads();
+        if (tid == 0) next_chunk = (long long)atomicAdd(&counters[7], 1ULL);
+        __syncthreads();
+        const int64_t ch = next_chunk;
+        if (ch >= n_chunks) break;
         const int64_t f0 = ch * chunk, f1 = min(f0 + (int64_t)chunk, n_frames);
         for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS) last[a] = -1;     // owner-private: no sync needed
         for (int64_t f = f0; f < f1; f++) {

@@ -74,6 +74,7 @@ struct sab_engine {
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
     int poly_kernel = 0;                   // SAB_OPT_POLY_KERNEL: 0 auto (chunk-sequential), 1 frame-parallel cells
     int seq_chunk = 64;                    // SAB_OPT_SEQ_CHUNK
+    int seq_block = 0;                     // SAB_OPT_SEQ_BLOCK (0 = one warp per 32 mobile atoms)
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
     // exact-pruning tables of the tetrahedral kernel
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
@@ -268,6 +269,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (!e) return fail(SAB_EINVAL, "sab_set_option: null engine");
     if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
     if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
     return fail(SAB_EINVAL, "unknown option %d", key);
 }
@@ -404,7 +406,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 2 && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
         size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
                       sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -412,14 +414,20 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
                         e->d_legacy_init};
         SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
                        e->d_anchor, e->delta};
-        int64_t n_chunks = (F + e->seq_chunk - 1) / e->seq_chunk;
-        int grid2 = (int)std::min<int64_t>(n_chunks, (int64_t)e->sm_count * 8);
-        k_polyhedral_assign_seq1<<<grid2, SAB_SEQ1_THREADS, smem, st>>>(d_frac, F, e->seq_chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+        int per_sm = 3;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_seq1, SAB_SEQ1_THREADS, smem);
+        int resident = std::max(1, per_sm) * e->sm_count;
+        // chunk: long enough to amortise the history-free first frame, short enough to balance the CTAs
+        int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk, F / ((int64_t)resident * 4)));
+        int64_t n_chunks = (F + chunk - 1) / chunk;
+        int grid2 = (int)std::min<int64_t>(n_chunks, resident);
+        k_polyhedral_assign_seq1<<<grid2, SAB_SEQ1_THREADS, smem, st>>>(d_frac, F, chunk, e->N, e->A, e->d_mobile, e->S, T, C,
             w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
         break;
-    } else if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ_THREADS) {
+    } else if (e->cells_set && e->poly_kernel == 3 && e->A <= SAB_SEQ_THREADS) {
         // chunk-sequential kernel: one thread per mobile atom
         int block = std::max(64, ((e->A + 31) / 32) * 32);
+        if (e->seq_block >= block && e->seq_block <= SAB_SEQ_THREADS) block = e->seq_block;
         size_t m3 = 3 * (size_t)e->M;
         size_t smem = sizeof(double) * ((size_t)e->nk * m3 + m3 + 6 * (size_t)e->A) +
                       sizeof(int) * (m3 + (size_t)e->A * (4 + SAB_POLY_KEEP));

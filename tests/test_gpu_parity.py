@@ -111,7 +111,8 @@ def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
     from site_analysis_b200 import _native as nat
     case = oracle_mod.load_case(name)
     outs = []
-    for use_cells, opts in ((True, {}), (True, {nat.OPT_SEQ_CHUNK: 7}), (True, {nat.OPT_POLY_KERNEL: 1}), (False, {})):
+    for use_cells, opts in ((True, {}), (True, {nat.OPT_SEQ_CHUNK: 7}), (True, {nat.OPT_POLY_KERNEL: 1}),
+                            (True, {nat.OPT_POLY_KERNEL: 3}), (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
         t.site_collection.engine_options = opts          # chunk-sequential (default) / odd chunk / frame-parallel
