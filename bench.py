@@ -189,13 +189,23 @@ def main():
     frame0, lat0 = d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy()
     eng = AssignmentEngine("polyhedral", N, geom.mobile_idx, device=local,
                            **syn.polyhedral_engine_kwargs(geom, frame0, lat0))
-    gathered = torch.empty((world * F, A), dtype=torch.int32, device=dev) if world > 1 else None
+    if world > 1:
+        # every rank primes its site tables from the trajectory's first frame (rank 0's frame 0)
+        first = [torch.empty_like(d_frac[0]), torch.empty_like(d_lat[0])]
+        if rank == 0:
+            first = [d_frac[0].clone(), d_lat[0].clone()]
+        dist.broadcast(first[0], 0); dist.broadcast(first[1], 0)
+        frame0, lat0 = first[0].cpu().numpy(), first[1].cpu().numpy()
+        eng = AssignmentEngine("polyhedral", N, geom.mobile_idx, device=local,
+                               **syn.polyhedral_engine_kwargs(geom, frame0, lat0))
+        from site_analysis_b200 import distributed as sd
 
     def step():
+        if world > 1:       # shard carry (two tiny all-gathers) + local kernels + the one result all-gather
+            full = sd.assign_sharded(eng, d_frac, d_lat, frame0, lat0, dist.group.WORLD)
+            return full[rank * F:(rank + 1) * F]
         res = eng.assign_device(d_frac, d_lat)
         eng._pending = []                                  # array path: no Python-object history to maintain
-        if world > 1:                                      # the one collective: reassemble atoms_trajectory
-            dist.all_gather_into_tensor(gathered, res)
         return res
 
     for _ in range(max(args.warmup, 0)):
@@ -211,7 +221,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         res = step()
-        launches += eng.last_info["launches"] + (1 if world > 1 else 0)
+        launches += eng.last_info["launches"] + (2 if world > 1 else 0)
         assign_ns += eng.last_info["assign_ns"]; wrap_ns += eng.last_info["wrap_ns"]
     ev1.record()
     torch.cuda.synchronize()

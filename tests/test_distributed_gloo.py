@@ -1,0 +1,75 @@
+"""world_size-2 `gloo` tests (CPU) of the multi-GPU host logic in site_analysis_b200.distributed:
+contiguous sharding, the wrap-carry exchange (halo + exclusive scan of per-shard wrap totals) and
+the all-gather that reassembles atoms_trajectory."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from site_analysis_b200 import distributed as sd
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _wrap_totals(raw, prev):
+    """numpy statement of the per-shard wrap total: sum_t rint(raw_t - raw_{t-1}) (pbc_utils.py:210-217)."""
+    chain = np.concatenate([prev[None], raw], axis=0)
+    return np.rint(chain[1:] - chain[:-1]).sum(axis=0).astype(np.int32)
+
+
+def _worker(rank, world, port, F, seed, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)                       # same data on every rank
+        M, A = 11, 5
+        walk = 0.2 + np.cumsum(rng.normal(scale=0.02, size=(F, M, 3)), axis=0)     # drifts across cell faces
+        raw = walk % 1.0
+        init_prev = raw[0].copy()
+        f0, f1 = sd.shard_bounds(F, world, rank)
+        mine = raw[f0:f1]
+        halos = sd.exchange_halo(mine[-1], dist.group.WORLD)
+        prev = init_prev if rank == 0 else halos[rank - 1]
+        assert rank == 0 or np.array_equal(prev, raw[f0 - 1])
+        totals = _wrap_totals(mine, prev)
+        base, parts = sd.exchange_wrap_totals(totals, dist.group.WORLD)
+        # the carry equals the wrap count of the full, unsharded scan up to the shard start
+        full = np.rint(np.diff(np.concatenate([init_prev[None], raw]), axis=0)).cumsum(axis=0).astype(np.int32)
+        want = full[f0 - 1] if f0 > 0 else np.zeros_like(full[0])
+        assert np.array_equal(base, want), (rank, base, want)
+        # unwrapped coordinates raw - W are continuous across the shard boundary
+        W_first = base + np.rint(mine[0] - prev).astype(np.int32)
+        assert np.abs((mine[0] - W_first) - (prev - base)).max() < 0.3
+        # result all-gather (ragged shards)
+        rows = torch.arange(f0, f1, dtype=torch.int32)[:, None].repeat(1, A) * 10 + torch.arange(A, dtype=torch.int32)
+        full_rows = sd.gather_assignments(rows, dist.group.WORLD)
+        want_rows = torch.arange(F, dtype=torch.int32)[:, None].repeat(1, A) * 10 + torch.arange(A, dtype=torch.int32)
+        assert torch.equal(full_rows, want_rows)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("F", [64, 37])
+def test_wrap_carry_and_gather_world2(tmp_path, F):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, F, 123, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_shard_bounds_cover_all_frames():
+    for F in (0, 1, 7, 8, 125000, 1000003):
+        for world in (1, 2, 4, 8):
+            spans = [sd.shard_bounds(F, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == F
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
