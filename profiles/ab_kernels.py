@@ -12,8 +12,10 @@ g = syn.argyrodite_geometry(2)
 d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
-VARIANTS = [("seq1 dynamic (default)", {}), ("seq1 chunk=32", {nat.OPT_SEQ_CHUNK: 32}), ("seq1 chunk=128", {nat.OPT_SEQ_CHUNK: 128}),
-            ("seq cp.async variant", {nat.OPT_POLY_KERNEL: 3}), ("frame-parallel cells", {nat.OPT_POLY_KERNEL: 1})]
+VARIANTS = [("seq1 chunk=64", {nat.OPT_SEQ_CHUNK: 64}), ("seq1 chunk=32", {nat.OPT_SEQ_CHUNK: 32}), ("seq1 chunk=24", {nat.OPT_SEQ_CHUNK: 24}),
+            ("seq1 chunk=48", {nat.OPT_SEQ_CHUNK: 48})]
+if len(sys.argv) > 2:
+    VARIANTS = VARIANTS[:int(sys.argv[2])]
 for label, opts in VARIANTS:
     e = AssignmentEngine("polyhedral", g.n_atoms, g.mobile_idx, **kw)
     for k, v in opts.items():

@@ -3,9 +3,12 @@
 #pragma once
 #include "k_polyhedral_seq.cuh"
 #define SAB_SEQ1_THREADS 256
+#ifndef SAB_SEQ1_MINBLOCKS
+#define SAB_SEQ1_MINBLOCKS 3
+#endif
 #define SAB_SEQ1_MAX_OWN 16
 
-__global__ void __launch_bounds__(SAB_SEQ1_THREADS, 3)
+__global__ void __launch_bounds__(SAB_SEQ1_THREADS, SAB_SEQ1_MINBLOCKS)
 k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int chunk, int n_atoms, int n_mobile,
                         const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabTetTables C,
                         const int32_t *__restrict__ wrows, int64_t legacy_init_frame,
@@ -22,6 +25,13 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
     int *hits = cnt + n_mobile;                                  // [A][KEEP]
     int *last = hits + (size_t)n_mobile * SAB_POLY_KEEP;         // [A] certain most-recent site or -1
     int *slot = last + n_mobile;                                 // [A] miss-list slot of the atom in this frame
+#ifdef SAB_SEQ1_PREFETCH
+    // next frame's raw data, fetched with cp.async while this frame is processed; every thread reads
+    // back only the entries it copied itself, so its own wait_group is the only synchronisation
+    int *rawW = slot + n_mobile;                                 // [3M]
+    double *rawbuf = reinterpret_cast<double *>(rawW + C.m3 + (C.m3 & 1));   // [3M]
+    double *xraw = rawbuf + C.m3;                                // [A][3]
+#endif
     __shared__ int n_miss;
     __shared__ long long next_chunk;
     const int tid = threadIdx.x;
@@ -34,20 +44,57 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
         if (ch >= n_chunks) break;
         const int64_t f0 = ch * chunk, f1 = min(f0 + (int64_t)chunk, n_frames);
         for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS) last[a] = -1;     // owner-private: no sync needed
+#ifdef SAB_SEQ1_PREFETCH
+        {
+            const double *fr0 = frac + (size_t)f0 * n_atoms * 3;
+            const int32_t *w0 = wrows + (size_t)f0 * C.m3;
+            for (int i = tid; i < C.m3; i += SAB_SEQ1_THREADS) {
+                sab_cp_async8(rawbuf + i, fr0 + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3));
+                sab_cp_async4(rawW + i, w0 + i);
+            }
+            for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS)
+                for (int d = 0; d < 3; d++) sab_cp_async8(xraw + 3 * a + d, fr0 + (size_t)mobile[a] * 3 + d);
+        }
+#endif
         for (int64_t f = f0; f < f1; f++) {
             const double *frame = frac + (size_t)f * n_atoms * 3;
             const int32_t *wrow = wrows + (size_t)f * C.m3;
             __syncthreads();                                     // previous frame fully consumed
             if (tid == 0) n_miss = 0;
             int bad = 0;
+#ifdef SAB_SEQ1_PREFETCH
+            sab_cp_async_wait_all();
+#endif
             for (int i = tid; i < C.m3; i += SAB_SEQ1_THREADS) {
                 int m = i / 3, d = i - 3 * m;
+#ifdef SAB_SEQ1_PREFETCH
+                double raw = rawbuf[i];
+                int W = rawW[i];
+                (void)m; (void)d;
+#else
                 double raw = frame[(size_t)C.fw_atoms[m] * 3 + d];
                 int W = wrow[i];
+#endif
                 if (fabs((raw - (double)W) - C.anchor[i]) > C.delta) bad = 1;
                 for (int k = 0; k < C.nk; k++) var[k * C.m3 + i] = raw + (double)(C.kmin + k - W);
             }
+#ifdef SAB_SEQ1_PREFETCH
+            for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS)
+                for (int d = 0; d < 3; d++) xs[3 * a + d] = sab_pymod1(xraw[3 * a + d]);       // atom.py:104
+#endif
             bad = __syncthreads_or(bad);
+#ifdef SAB_SEQ1_PREFETCH
+            if (f + 1 < f1) {                                    // lands while this frame is being processed
+                const double *fr2 = frame + (size_t)n_atoms * 3;
+                const int32_t *w2 = wrow + C.m3;
+                for (int i = tid; i < C.m3; i += SAB_SEQ1_THREADS) {
+                    sab_cp_async8(rawbuf + i, fr2 + (size_t)C.fw_atoms[i / 3] * 3 + (i % 3));
+                    sab_cp_async4(rawW + i, w2 + i);
+                }
+                for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS)
+                    for (int d = 0; d < 3; d++) sab_cp_async8(xraw + 3 * a + d, fr2 + (size_t)mobile[a] * 3 + d);
+            }
+#endif
             if (T.legacy_init && f == legacy_init_frame) bad = 1;
             if (bad) {
                 // ---- exhaustive generic path for this frame (outside the validity tube) -------
@@ -68,7 +115,11 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
             for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS) {
                 double x[3];
 #pragma unroll
+#ifdef SAB_SEQ1_PREFETCH
+                for (int d = 0; d < 3; d++) x[d] = xs[3 * a + d];
+#else
                 for (int d = 0; d < 3; d++) { x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]); xs[3 * a + d] = x[d]; }
+#endif
                 const int la = last[a];
                 slot[a] = -1;
                 if (la >= 0 && sab_tet_contains(var, C.rec + (size_t)la * SAB_TET_REC, x)) {

@@ -409,6 +409,9 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
     case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
         size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
                       sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
+#ifdef SAB_SEQ1_PREFETCH
+        smem += sizeof(int) * (3 * (size_t)e->M + 2) + sizeof(double) * (3 * (size_t)e->M + 3 * (size_t)e->A) + 8;
+#endif
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
