@@ -116,7 +116,7 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
  * dynamic_voronoi_site_collection.py:188-195). */
 #define SAB_OPT_SKIP_STEP_CHECK_ONCE 1
 /* SAB_OPT_POLY_KERNEL: 0 = chunk-sequential "previous site first" kernel (default when cell lists
- * are set), 1 = frame-parallel cell-list kernel, 3 = experimental cp.async-prefetch variant.  SAB_OPT_SEQ_CHUNK: frames per chunk (default 64). */
+ * are set), 1 = frame-parallel cell-list kernel, 3 = experimental cp.async-prefetch variant.  SAB_OPT_SEQ_CHUNK: frames per chunk (default 32). */
 #define SAB_OPT_POLY_KERNEL 2
 #define SAB_OPT_SEQ_CHUNK 3
 #define SAB_OPT_SEQ_BLOCK 4   /* threads per CTA of the chunk-sequential kernel (tuning) */

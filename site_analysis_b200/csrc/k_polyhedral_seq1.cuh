@@ -1,10 +1,15 @@
-// k_polyhedral_seq1.cuh -- first chunk-sequential variant (256 threads, five barriers, binary-searched pairs);
-// kept selectable (SAB_OPT_POLY_KERNEL = 2) for A/B measurements against k_polyhedral_seq.cuh.
+// k_polyhedral_seq1.cuh -- the production chunk-sequential tetrahedral kernel ("previous site first"):
+// persistent 256-thread CTAs pull chunks of consecutive frames from a global counter; the next frame's
+// raw coordinates are prefetched with cp.async while the current one is processed.  See
+// k_polyhedral_seq.cuh for the phase structure (that file keeps an experimental variant, kernel id 3).
 #pragma once
 #include "k_polyhedral_seq.cuh"
 #define SAB_SEQ1_THREADS 256
 #ifndef SAB_SEQ1_MINBLOCKS
-#define SAB_SEQ1_MINBLOCKS 3
+#define SAB_SEQ1_MINBLOCKS 4      // 64 registers: 4 CTAs (32 warps) per SM measured fastest (profiles/README.md)
+#endif
+#ifndef SAB_SEQ1_NO_PREFETCH
+#define SAB_SEQ1_PREFETCH 1
 #endif
 #define SAB_SEQ1_MAX_OWN 16
 
@@ -29,7 +34,7 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
     // next frame's raw data, fetched with cp.async while this frame is processed; every thread reads
     // back only the entries it copied itself, so its own wait_group is the only synchronisation
     int *rawW = slot + n_mobile;                                 // [3M]
-    double *rawbuf = reinterpret_cast<double *>(rawW + C.m3 + (C.m3 & 1));   // [3M]
+    double *rawbuf = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(rawW + C.m3) + 7) & ~(uintptr_t)7);   // [3M], 8-byte aligned
     double *xraw = rawbuf + C.m3;                                // [A][3]
 #endif
     __shared__ int n_miss;

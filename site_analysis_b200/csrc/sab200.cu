@@ -73,7 +73,7 @@ struct sab_engine {
     int64_t launches = 0;
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
     int poly_kernel = 0;                   // SAB_OPT_POLY_KERNEL: 0 auto (chunk-sequential), 1 frame-parallel cells
-    int seq_chunk = 64;                    // SAB_OPT_SEQ_CHUNK
+    int seq_chunk = 32;                    // SAB_OPT_SEQ_CHUNK
     int seq_block = 0;                     // SAB_OPT_SEQ_BLOCK (0 = one warp per 32 mobile atoms)
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
     // exact-pruning tables of the tetrahedral kernel
@@ -410,7 +410,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
                       sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
 #ifdef SAB_SEQ1_PREFETCH
-        smem += sizeof(int) * (3 * (size_t)e->M + 2) + sizeof(double) * (3 * (size_t)e->M + 3 * (size_t)e->A) + 8;
+        smem += sizeof(int) * (3 * (size_t)e->M + 4) + sizeof(double) * (3 * (size_t)e->M + 3 * (size_t)e->A) + 16;
 #endif
         CU(cudaFuncSetAttribute(k_polyhedral_assign_seq1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
