@@ -1,0 +1,54 @@
+"""Multi-GPU parity check (run under torchrun on >= 2 GPUs; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py [frames]
+
+Every rank generates the same synthetic argyrodite trajectory, takes its contiguous shard, runs
+site_analysis_b200.distributed.assign_sharded (wrap-carry exchange + NCCL all-gather) and rank 0
+compares the reassembled (F, A) result with the CPU oracle run sequentially over all frames."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
+from site_analysis_b200 import AssignmentEngine, distributed as sd, synthetic as syn  # noqa: E402
+
+
+def main():
+    F = int(sys.argv[1]) if len(sys.argv) > 1 else 6000
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    geom = syn.argyrodite_geometry(2)
+    # framework atoms drift across the cell faces so that the wrap carry between shards is non-trivial
+    frac, lat = syn.argyrodite_trajectory(geom, F, seed=4242, device=dev, sigma_framework=0.12)
+    frame0, lat0 = frac[0].cpu().numpy(), lat[0].cpu().numpy()
+    f0, f1 = sd.shard_bounds(F, world, rank)
+    eng = AssignmentEngine("polyhedral", geom.n_atoms, geom.mobile_idx, device=local,
+                           **syn.polyhedral_engine_kwargs(geom, frame0, lat0))
+    full = sd.assign_sharded(eng, frac[f0:f1].contiguous(), lat[f0:f1].contiguous(), frame0, lat0, dist.group.WORLD)
+    again = sd.assign_sharded(eng, frac[f0:f1].contiguous(), lat[f0:f1].contiguous(), frame0, lat0, dist.group.WORLD)
+    assert torch.equal(full, again), "a second sharded pass over the same trajectory differs"
+    ok = True
+    if rank == 0:
+        import bench
+        want = bench.oracle_for(geom, frame0, lat0)().run(frac.cpu().numpy(), lat.cpu().numpy(), positions=True)
+        got = full.cpu().numpy()
+        mism = int((got != want).sum())
+        wraps = int((np.abs(np.rint(np.diff(frac[:, geom.n_mobile:].cpu().numpy(), axis=0))) > 0).sum())
+        print(f"multigpu_check: world={world} frames={F} framework wrap events={wraps} mismatches vs oracle={mism}")
+        ok = mism == 0
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
