@@ -202,7 +202,7 @@ def main():
 
     def step():
         if world > 1:       # shard carry (two tiny all-gathers) + local kernels + the one result all-gather
-            full = sd.assign_sharded(eng, d_frac, d_lat, frame0, lat0, dist.group.WORLD)
+            full = sd.assign_sharded(eng, d_frac, d_lat, frame0, lat0, dist.group.WORLD, equal_shards=True)
             return full[rank * F:(rank + 1) * F]
         res = eng.assign_device(d_frac, d_lat)
         eng._pending = []                                  # array path: no Python-object history to maintain

@@ -114,3 +114,18 @@ __global__ void k_wrap_commit(const double *__restrict__ frac, int64_t n_frames,
     wraps[col] = rows[(size_t)(n_commit - 1) * m3 + col];
     prev_raw[col] = sab_fw_raw(frac, n_commit - 1, n_atoms, fw_atoms, col);
 }
+
+// 1 thread per column: total wraps over all chunks and the raw coordinate of the last frame
+// (the halo the next GPU shard needs), packed for one small D2H copy.
+__global__ void k_wrap_reduce(const double *__restrict__ frac, int64_t n_frames, int n_atoms,
+                              const int32_t *__restrict__ fw_atoms, int m3, int n_chunks,
+                              const int32_t *__restrict__ totals, int32_t *__restrict__ out_tot,
+                              double *__restrict__ out_last)
+{
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= m3) return;
+    int t = 0;
+    for (int c = 0; c < n_chunks; c++) t += totals[(size_t)c * m3 + col];
+    out_tot[col] = t;
+    out_last[col] = sab_fw_raw(frac, n_frames - 1, n_atoms, fw_atoms, col);
+}

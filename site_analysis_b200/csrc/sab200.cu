@@ -35,13 +35,25 @@ static int fail(int code, const char *fmt, ...)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(SAB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// Host -> device copy into *dst, (re)allocating only when the size changes (sizes are tracked per
+// pointer so that repeated state uploads -- e.g. once per shard pass -- cost one memcpy each).
+#include <unordered_map>
+static std::unordered_map<void *, size_t> g_alloc_bytes;
 template <class T> static cudaError_t upload(T **dst, const T *src, size_t n)
 {
-    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    size_t bytes = n * sizeof(T);
+    auto it = *dst ? g_alloc_bytes.find((void *)*dst) : g_alloc_bytes.end();
+    if (*dst && (it == g_alloc_bytes.end() || it->second != bytes)) {
+        if (it != g_alloc_bytes.end()) g_alloc_bytes.erase(it);
+        cudaFree(*dst); *dst = nullptr;
+    }
     if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T));
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    if (!*dst) {
+        cudaError_t e = cudaMalloc((void **)dst, bytes);
+        if (e != cudaSuccess) return e;
+        g_alloc_bytes[(void *)*dst] = bytes;
+    }
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
 }
 
 enum { CNT_AMBIGUOUS = 0, CNT_SPILL = 1, CNT_OVERFLOW = 2, CNT_FIRST_BAD = 3, CNT_FULL27 = 4, CNT_N = 8 };
@@ -113,7 +125,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
         if (e->streams[i]) cudaStreamDestroy(e->streams[i]);
@@ -331,17 +343,15 @@ extern "C" int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_fr
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     run_wrap_pass(e, d_frac, n_frames, w, st, false);
     CU(cudaGetLastError());
-    std::vector<int32_t> h((size_t)w.n_chunks * w.m3);
-    CU(cudaMemcpyAsync(h.data(), w.totals, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, st));
-    std::vector<double> lastf((size_t)e->N * 3);
-    CU(cudaMemcpyAsync(lastf.data(), d_frac + (size_t)(n_frames - 1) * e->N * 3, sizeof(double) * lastf.size(), cudaMemcpyDeviceToHost, st));
+    // reduce on the device; the chunk-excursion area of the workspace is free scratch here
+    double *d_last = w.chunk_exc;
+    int32_t *d_tot = reinterpret_cast<int32_t *>(w.chunk_exc + w.m3);
+    k_wrap_reduce<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, e->N, e->d_fw_atoms, w.m3, w.n_chunks, w.totals, d_tot, d_last);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(totals, d_tot, sizeof(int32_t) * w.m3, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(last_raw, d_last, sizeof(double) * w.m3, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    for (int c = 0; c < w.m3; c++) {
-        int t = 0;
-        for (int k = 0; k < w.n_chunks; k++) t += h[(size_t)k * w.m3 + c];
-        totals[c] = t;
-        last_raw[c] = lastf[(size_t)e->fw_atoms[c / 3] * 3 + c % 3];
-    }
     return SAB_OK;
 }
 

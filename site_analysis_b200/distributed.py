@@ -63,12 +63,17 @@ def exchange_wrap_totals(totals, group, device=None):
     return base, parts
 
 
-def gather_assignments(local_rows, group):
+def gather_assignments(local_rows, group, equal_shards: bool = False):
     """All-gather the per-rank (F_local, A) int32 results into (sum F_local, A) on every rank.
-    Shards may differ in length by one frame; they are padded for the collective and trimmed."""
+    Shards may differ in length by one frame; they are padded for the collective and trimmed
+    (``equal_shards=True`` skips the length exchange when the caller knows all shards are equal)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    if equal_shards:
+        out = torch.empty((world * local_rows.shape[0], local_rows.shape[1]), dtype=local_rows.dtype, device=local_rows.device)
+        dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
+        return out
     n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
     counts = [int(x.item()) for x in _all_gather(n_local, group)]
     fmax = max(counts)
@@ -83,7 +88,8 @@ def gather_assignments(local_rows, group):
     return torch.cat([out[r * fmax:r * fmax + c] for r, c in enumerate(counts)], dim=0)
 
 
-def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group):
+def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group,
+                   equal_shards: bool = False):
     """Assign this rank's contiguous shard with the correct PBC carry and return the FULL
     (F_total, A) int32 result (device tensor) on every rank.
 
@@ -123,7 +129,7 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
             exc = np.ascontiguousarray(np.stack([u0, u0], axis=-1))
             nat.check(engine.L.sab_set_pbc_state(engine.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
     local = engine.assign_device(d_frac_local, d_lattice_local)
-    if bool((local <= nat.AMBIGUOUS_BASE).any().item()):
+    if engine.last_info.get("ambiguous", 0) > 0:
         raise NotImplementedError("atom-frames contained by several sites in a sharded run need the gathered resolver "
                                   "(run the affected trajectory on one GPU)")
     engine._pending = []
@@ -138,4 +144,4 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
         from .engine import EXCURSION_LIMIT, GuardError
         if float((hi - lo).max().item()) >= EXCURSION_LIMIT and engine.strict:
             raise GuardError("a framework atom moved over >= 0.3 fractional units across the sharded trajectory")
-    return gather_assignments(local, group)
+    return gather_assignments(local, group, equal_shards)
