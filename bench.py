@@ -277,6 +277,11 @@ def main():
         nb = min(F, cores * cb_frames)
         cpu_v, cpu_n, cpu_dt = time_oracle_all_cores(oracle_for(geom, frame0, lat0), d_frac[:nb].cpu().numpy(),
                                                      d_lat[:nb].cpu().numpy(), cb_frames)
+        traffic = None
+        tp = ROOT / "profiles" / "r1_traffic.json"
+        if tp.exists():                                   # one `ncu --set full` capture of this kernel, scaled per frame
+            tj = json.loads(tp.read_text())
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["frames"] * F
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -287,7 +292,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_polyhedral_assign", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": int(bytes_per_launch), "kernel_ms": assign_s * 1e3,
                          "wrap_scan_ms": wrap_ns * 1e-6 / args.steps},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cpu_n, "kind": "port",
