@@ -106,6 +106,14 @@ int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int64_t frames
 int sab_set_cell_lists(sab_engine *e, int G, double delta, const double *anchor, int kmin, int nk,
                        const uint16_t *records, const int32_t *cell_off, const uint16_t *cell_sites);
 
+/* Exact-pruning tables of the nearest-centre (Voronoi) kernel (csrc/k_nearest_cells.cuh): a G^3 cell
+ * list of the centres that can be nearest to a point of each cell, excl[c] = lower bound on the
+ * distance from cell c to any centre not in its list, both in the metric of the lattice whose
+ * INVERSE is passed.  Atoms whose best listed centre is not provably inside that bound in the
+ * frame's own metric are redone against all centres.  cell_off == NULL clears the tables. */
+int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice0_inverse, const int32_t *cell_off,
+                          const uint16_t *cell_sites, const double *excl);
+
 /* Range (min, max) of raw - W per framework coordinate over the frames, double[M][3][2] (host),
  * continuing from the engine's wrap state without modifying it; used to place the anchors. */
 int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, void *d_workspace,

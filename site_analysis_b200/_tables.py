@@ -187,3 +187,65 @@ def tet_records(slot_shift: np.ndarray, slot_fw: np.ndarray, simplices, kmin: in
     simp = np.stack([np.asarray(f, dtype=np.uint8) for f in simplices]).reshape(S, 12)     # (S, 4 faces x 3 corners)
     rec[:, 12:18] = np.ascontiguousarray(simp).view(np.uint16)
     return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# exact-pruning tables for the nearest-centre (Voronoi) kernel (csrc/k_nearest_cells.cuh)
+# ---------------------------------------------------------------------------------------------
+
+def _mic_cartesian(d_frac: np.ndarray, lattice: np.ndarray) -> np.ndarray:
+    """Minimum over the 27 images around the reduced separation of |D . L| (distances.py:175-189)."""
+    d = d_frac - np.round(d_frac)
+    best = np.full(d.shape[:-1], np.inf)
+    for s in _SHIFTS27:
+        best = np.minimum(best, np.linalg.norm((d + s) @ lattice, axis=-1))
+    return best
+
+
+def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: float = 1.06):
+    """For each of the G^3 cells of the unit cube: the sites that can be the nearest centre of some
+    point of the cell, with head-room ``rho`` for lattice strain, and the exclusion radius of the list.
+
+    With R = circumradius of a cell (metric of ``lattice0``), p = cell centre: every point x of the cell
+    has d(x, s) in [d(p, s) - R, d(p, s) + R].  D = min_s (d(p, s) + R) bounds the nearest distance from
+    above; sites with d(p, s) - R > rho * D are left out, and ``excl[c] = rho * D`` is a lower bound on
+    the distance (lattice0 metric) from any point of the cell to any site NOT in its list.  The kernel
+    accepts the best listed site only if it is provably closer than that bound in the frame's own
+    metric, and otherwise searches all sites, so the lists never decide a result on their own.
+
+    Returns (offsets int32 [G^3 + 1], entries uint16 ascending per cell, excl float64 [G^3])."""
+    centres = np.asarray(centres, dtype=np.float64) % 1.0
+    S = len(centres)
+    idx = np.stack(np.meshgrid(*[np.arange(G)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)
+    p = (idx + 0.5) / G
+    corners = np.array([[a, b, c] for a in (-1, 1) for b in (-1, 1) for c in (-1, 1)], dtype=float) * (0.5 / G)
+    R = float(np.linalg.norm(corners @ lattice0, axis=1).max()) * (1.0 + 1e-12)
+    offsets = np.zeros(G ** 3 + 1, dtype=np.int64)
+    entries = []
+    excl = np.empty(G ** 3)
+    # perpendicular heights: |D . L| >= max_i |D_i| h_i for every image, so max_i |d_i| h_i (reduced d)
+    # is a cheap lower bound of the 27-image minimum; the central image is a cheap upper bound
+    a0, a1, a2 = lattice0
+    vol = abs(np.dot(a0, np.cross(a1, a2)))
+    h = vol / np.array([np.linalg.norm(np.cross(a1, a2)), np.linalg.norm(np.cross(a2, a0)), np.linalg.norm(np.cross(a0, a1))])
+    step = max(1, 6_000_000 // max(S, 1))
+    for a in range(0, G ** 3, step):
+        df = centres[None, :, :] - p[a:a + step, None, :]
+        df -= np.round(df)
+        upper = np.linalg.norm(df @ lattice0, axis=-1)                      # central image
+        lower = (np.abs(df) * h).max(axis=-1) * (1.0 - 1e-12)
+        D = (upper + R).min(axis=1)
+        for _ in range(2):                                                  # tighten D with exact distances where needed
+            unsure = (lower - R <= rho * D[:, None]) & (upper > lower * (1 + 1e-9))
+            ci, si = np.nonzero(unsure)
+            if len(ci):
+                exact = _mic_cartesian(df[ci, si], lattice0)
+                upper[ci, si] = exact
+                lower[ci, si] = exact * (1.0 - 1e-12)
+            D = (upper + R).min(axis=1)
+        keep = (lower - R) <= rho * D[:, None]
+        excl[a:a + step] = rho * D
+        offsets[a + 1:a + step + 1] = keep.sum(axis=1)
+        entries.append(np.nonzero(keep)[1])
+    offsets = np.cumsum(offsets).astype(np.int32)
+    return offsets, np.concatenate(entries).astype(np.uint16), excl

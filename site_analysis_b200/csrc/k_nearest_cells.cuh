@@ -1,0 +1,87 @@
+// k_nearest_cells.cuh -- nearest-centre (Voronoi) assignment with exact spatial pruning.
+//
+// Same answers as k_nearest_assign<false> (k_nearest.cuh; reference voronoi_site_collection.py:76-99:
+// argmin over sqrt'd 27-image minimum-image distances, first minimum wins), ~50x less arithmetic:
+// a static cell list gives each atom the few centres that can be nearest to any point of its cell.
+// The list never decides on its own: `excl[c]` is a lower bound (metric of the lattice the list was
+// built with, L0) on the distance from any point of cell c to any centre NOT in the list.  In the
+// frame's own metric that bound is (1 - eta) excl[c] with eta = ||L0^-1 L_t - I||_F.  The best listed
+// centre is accepted only if its squared distance is below ((1 - eta) excl)^2 (1 - 1e-9) -- then no
+// unlisted centre can win or tie, sqrt-merging included -- and below the central-image bound
+// (0.5 hmin)^2 (k_nearest.cuh).  Otherwise the atom is redone against all centres.
+#pragma once
+#include "k_nearest.cuh"
+
+struct SabNearestLists {
+    int G;
+    const int32_t *cell_off;    // [G^3 + 1]
+    const uint16_t *cell_sites; // ascending site list positions
+    const double *excl;         // [G^3]
+    double l0inv[9];            // inverse of the lattice the lists were built with
+};
+
+__global__ void k_nearest_assign_cells(const double *__restrict__ frac, const double *__restrict__ lattice,
+                                       int lattice_stride, int64_t n_frames, int n_atoms, int n_mobile,
+                                       const int32_t *__restrict__ mobile, int n_sites,
+                                       const double *__restrict__ centres, SabNearestLists NL,
+                                       int32_t *__restrict__ result, unsigned long long *__restrict__ n_exhaustive)
+{
+    __shared__ SabLattice lat;
+    __shared__ double shrink;                            // 1 - eta of this frame (<= 0 forces the exhaustive path)
+    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const double *frame = frac + (size_t)f * n_atoms * 3;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sab_lattice_load(lattice + (size_t)f * lattice_stride, lat);
+            double eta2 = 0.0;
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    double m = NL.l0inv[3 * i] * lat.m[j] + NL.l0inv[3 * i + 1] * lat.m[3 + j] + NL.l0inv[3 * i + 2] * lat.m[6 + j];
+                    if (i == j) m -= 1.0;
+                    eta2 += m * m;
+                }
+            shrink = 1.0 - sqrt(eta2) * (1.0 + 1e-9) - 1e-12;
+        }
+        __syncthreads();
+        const double thr = (0.5 * lat.hmin) * (0.5 * lat.hmin) * (1.0 - SAB_REL_MARGIN);
+        for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
+            double x[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);   // atom.py:104
+            int c0 = min(NL.G - 1, (int)(x[0] * (double)NL.G)), c1 = min(NL.G - 1, (int)(x[1] * (double)NL.G)),
+                c2 = min(NL.G - 1, (int)(x[2] * (double)NL.G));
+            const int cell = (c0 * NL.G + c1) * NL.G + c2;
+            const int b = __ldg(NL.cell_off + cell), e = __ldg(NL.cell_off + cell + 1);
+            double best_q = INFINITY, best_s = INFINITY;
+            int best_i = -1;
+            for (int i = b; i < e; i++) {
+                const int s = __ldg(NL.cell_sites + i);
+                double cs[3] = {__ldg(centres + 3 * s), __ldg(centres + 3 * s + 1), __ldg(centres + 3 * s + 2)};
+                double d0, d1, d2;
+                sab_dbase(cs, x, d0, d1, d2);
+                double q = sab_image_q(d0, d1, d2, lat.m);
+                if (q < best_q) {
+                    double r = sqrt(q);
+                    if (r < best_s) { best_s = r; best_q = q; best_i = s; }
+                }
+            }
+            const double lim = shrink * __ldg(NL.excl + cell);
+            const bool safe = best_i >= 0 && shrink > 0.0 && best_q < thr && best_q < lim * lim * (1.0 - SAB_REL_MARGIN);
+            if (!safe) {                                 // rare: strained lattice, sparse sites, tiny cell
+                atomicAdd(n_exhaustive, 1ULL);
+                best_q = INFINITY; best_s = INFINITY; best_i = 0;
+                for (int s = 0; s < n_sites; s++) {
+                    double cs[3] = {__ldg(centres + 3 * s), __ldg(centres + 3 * s + 1), __ldg(centres + 3 * s + 2)};
+                    double d0, d1, d2;
+                    sab_dbase(cs, x, d0, d1, d2);
+                    double q = sab_mic_q27(d0, d1, d2, lat.m);
+                    if (q < best_q) {
+                        double r = sqrt(q);
+                        if (r < best_s) { best_s = r; best_q = q; best_i = s; }
+                    }
+                }
+            }
+            result[(size_t)f * n_mobile + a] = best_i;
+        }
+    }
+}

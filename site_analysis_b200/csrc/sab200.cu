@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "k_nearest.cuh"
+#include "k_nearest_cells.cuh"
 #include "k_polyhedral.cuh"
 #include "k_polyhedral_cells.cuh"
 #include "k_polyhedral_seq.cuh"
@@ -88,6 +89,9 @@ struct sab_engine {
     int seq_chunk = 32;                    // SAB_OPT_SEQ_CHUNK
     int seq_block = 0;                     // SAB_OPT_SEQ_BLOCK (0 = one warp per 32 mobile atoms)
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
+    // exact-pruning tables of the nearest-centre kernel
+    bool nl_set = false; int nl_G = 0; double nl_l0inv[9] = {0};
+    int32_t *d_nl_off = nullptr; uint16_t *d_nl_sites = nullptr; double *d_nl_excl = nullptr;
     // exact-pruning tables of the tetrahedral kernel
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
     uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
@@ -124,7 +128,8 @@ extern "C" void sab_engine_destroy(sab_engine *e)
     void *ptrs[] = {e->d_mobile, e->d_centres, e->d_rcut, e->d_rcut_q, e->d_fw_atoms, e->d_nslot, e->d_slot_atom,
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
-                    e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor};
+                    e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
+                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
@@ -276,6 +281,24 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
     return SAB_OK;
 }
 
+extern "C" int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice0_inverse, const int32_t *cell_off,
+                                     const uint16_t *cell_sites, const double *excl)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_nearest_lists: null engine");
+    CU(cudaSetDevice(e->device));
+    if (!cell_off) { e->nl_set = false; return SAB_OK; }
+    if (e->kind != SAB_VORONOI || !e->d_centres) return fail(SAB_ESTATE, "sab_set_nearest_lists: Voronoi centres not set");
+    if (G < 1 || G > 256 || !lattice0_inverse || !cell_sites || !excl || e->S > 65535)
+        return fail(SAB_EINVAL, "sab_set_nearest_lists: bad arguments");
+    size_t ncell = (size_t)G * G * G;
+    CU(upload(&e->d_nl_off, cell_off, ncell + 1));
+    CU(upload(&e->d_nl_sites, cell_sites, (size_t)std::max(cell_off[ncell], 1)));
+    CU(upload(&e->d_nl_excl, excl, ncell));
+    for (int i = 0; i < 9; i++) e->nl_l0inv[i] = lattice0_inverse[i];
+    e->nl_G = G; e->nl_set = true;
+    return SAB_OK;
+}
+
 extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
 {
     if (!e) return fail(SAB_EINVAL, "sab_set_option: null engine");
@@ -390,7 +413,15 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
 {
     int grid = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 8);
     switch (e->kind) {
-    case SAB_VORONOI: {
+    case SAB_VORONOI: if (e->nl_set) {
+        int block = std::min(256, ((e->A + 31) / 32) * 32);
+        SabNearestLists NL{e->nl_G, e->d_nl_off, e->d_nl_sites, e->d_nl_excl, {0}};
+        for (int i = 0; i < 9; i++) NL.l0inv[i] = e->nl_l0inv[i];
+        int grid2 = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 16);
+        k_nearest_assign_cells<<<grid2, block, 0, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile, e->S,
+            e->d_centres, NL, d_result, e->d_counters + CNT_FULL27);
+        break;
+    } else {
         int block = std::min(1024, ((e->A + 31) / 32) * 32);
         size_t smem = sizeof(double) * 3 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_nearest_assign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

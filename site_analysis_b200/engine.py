@@ -202,7 +202,8 @@ class AssignmentEngine:
         (trajectory.py:364-373, polyhedral_site.py:264-279, dynamic_voronoi_site_collection.py:197-201)."""
         self.reset_history()
         self._pbc_ready = False
-        self._cells = None
+        if self.k == nat.POLYHEDRAL:                 # anchors belong to the PBC state; Voronoi lists are static
+            self._cells = None
         self._seen_exc = None
         if self.slots is not None:
             self.primed = [None] * self.S
@@ -328,6 +329,18 @@ class AssignmentEngine:
         self._cells = dict(G=G, delta=delta, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3)
         self._cells_stale = False
 
+    def _build_nearest_lists(self, lattice0):
+        """Voronoi: cell lists of the centres that can be nearest anywhere in a cell (``_tables.nearest_cell_lists``)."""
+        lattice0 = np.asarray(lattice0, dtype=np.float64)
+        length = float(np.mean(np.linalg.norm(lattice0, axis=1)))
+        spacing = (abs(np.linalg.det(lattice0)) / self.S) ** (1.0 / 3.0)        # mean centre spacing
+        G = int(min(64, max(2, round(length / max(0.6 * spacing, 0.5)))))
+        off, ent, excl = tab.nearest_cell_lists(self.centres, lattice0, G)
+        inv = np.ascontiguousarray(np.linalg.inv(lattice0))
+        nat.check(self.L.sab_set_nearest_lists(self.h, G, nat.ptr(inv), nat.ptr(np.ascontiguousarray(off)),
+                                               nat.ptr(np.ascontiguousarray(ent)), nat.ptr(np.ascontiguousarray(excl))))
+        self._cells = dict(G=G, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3)
+
     def _reinit_groups(self, raw_t, lat_t):
         """Dynamic Voronoi: a step >= 0.3 at this frame re-initialises every group that contains a
         jumping reference slot (dynamic_voronoi_site_collection.py:94-95, 188-195)."""
@@ -449,6 +462,8 @@ class AssignmentEngine:
         if self.slots is not None and not self._pbc_ready:
             lat0 = (d_lattice[0] if stride else d_lattice).cpu().numpy()
             self._init_pbc(d_frac[0].cpu().numpy(), lat0)
+        if self.k == nat.VORONOI and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+            self._build_nearest_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
         total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0)

@@ -136,6 +136,30 @@ def test_frames_outside_the_validity_tube_fall_back_exactly(oracle_mod):
     assert eng.last_info["full27"] >= 0
 
 
+def test_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
+    """k_nearest_assign_cells vs k_nearest_assign (all centres) vs the oracle, with a fluctuating and
+    then a strongly strained lattice (the latter must take the exhaustive path, not a wrong answer)."""
+    import torch
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    frac, lat = syn.argyrodite_trajectory(g, 400, device="cuda")
+    lat[200:] *= 1.09                                   # 9 % strain relative to the lattice the lists were built with
+    outs = []
+    for use_cells in (True, False):
+        eng = AssignmentEngine("voronoi", g.n_atoms, g.mobile_idx, centres=g.site_centres)
+        eng.use_cells = use_cells
+        outs.append(eng.assign_device(frac, lat).cpu().numpy())
+        assert (eng._cells is not None) == use_cells
+        if use_cells:
+            assert eng.last_info["full27"] > 0          # strained frames fell back
+    assert np.array_equal(outs[0], outs[1])
+    o = oracle_mod.SiteOracle("voronoi", g.mobile_idx, centres=g.site_centres)
+    sel = np.r_[0:40, 200:240]
+    want = o.run(frac.cpu().numpy()[sel], lat.cpu().numpy()[sel], positions=True)
+    assert np.array_equal(outs[0][sel], want)
+    assert torch.cuda.is_available()
+
+
 def test_reset_and_replay(oracle_mod):
     """Trajectory.reset(): history and PBC caches cleared, topology kept, same answers again."""
     case = oracle_mod.load_case("fuzz_polyhedral_1")
