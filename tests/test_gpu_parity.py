@@ -144,6 +144,7 @@ def test_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
     g = syn.argyrodite_geometry(2)
     frac, lat = syn.argyrodite_trajectory(g, 400, device="cuda")
     lat[200:] *= 1.09                                   # 9 % strain relative to the lattice the lists were built with
+    lat[300:] *= 2.5                                    # absurd strain: the exclusion bound is void -> exhaustive path
     outs = []
     for use_cells in (True, False):
         eng = AssignmentEngine("voronoi", g.n_atoms, g.mobile_idx, centres=g.site_centres)
@@ -154,7 +155,7 @@ def test_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
             assert eng.last_info["full27"] > 0          # strained frames fell back
     assert np.array_equal(outs[0], outs[1])
     o = oracle_mod.SiteOracle("voronoi", g.mobile_idx, centres=g.site_centres)
-    sel = np.r_[0:40, 200:240]
+    sel = np.r_[0:40, 200:240, 300:320]
     want = o.run(frac.cpu().numpy()[sel], lat.cpu().numpy()[sel], positions=True)
     assert np.array_equal(outs[0][sel], want)
     assert torch.cuda.is_available()
