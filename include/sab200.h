@@ -114,6 +114,13 @@ int sab_set_cell_lists(sab_engine *e, int G, double delta, const double *anchor,
 int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice0_inverse, const int32_t *cell_off,
                           const uint16_t *cell_sites, const double *excl);
 
+/* The same for dynamic-Voronoi sites: lists built around ANCHOR centres double[S][3] with head-room
+ * max_move (metric of lattice0) for the centres' motion; frames in which a centre is farther than
+ * max_move from its anchor take the exhaustive path. */
+int sab_set_dynvor_lists(sab_engine *e, int G, const double *lattice0, const double *lattice0_inverse,
+                         const double *anchors, double max_move, const int32_t *cell_off,
+                         const uint16_t *cell_sites, const double *excl);
+
 /* Range (min, max) of raw - W per framework coordinate over the frames, double[M][3][2] (host),
  * continuing from the engine's wrap state without modifying it; used to place the anchors. */
 int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, void *d_workspace,

@@ -202,7 +202,7 @@ def _mic_cartesian(d_frac: np.ndarray, lattice: np.ndarray) -> np.ndarray:
     return best
 
 
-def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: float = 1.06):
+def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: float = 1.06, move: float = 0.0):
     """For each of the G^3 cells of the unit cube: the sites that can be the nearest centre of some
     point of the cell, with head-room ``rho`` for lattice strain, and the exclusion radius of the list.
 
@@ -212,6 +212,9 @@ def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: f
     the distance (lattice0 metric) from any point of the cell to any site NOT in its list.  The kernel
     accepts the best listed site only if it is provably closer than that bound in the frame's own
     metric, and otherwise searches all sites, so the lists never decide a result on their own.
+
+    ``move`` (dynamic Voronoi): every centre may be up to ``move`` away from the given (anchor)
+    position; then d(x, s_t) is within +-move of d(x, anchor_s), D gains +move, the keep test -move.
 
     Returns (offsets int32 [G^3 + 1], entries uint16 ascending per cell, excl float64 [G^3])."""
     centres = np.asarray(centres, dtype=np.float64) % 1.0
@@ -234,16 +237,16 @@ def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: f
         df -= np.round(df)
         upper = np.linalg.norm(df @ lattice0, axis=-1)                      # central image
         lower = (np.abs(df) * h).max(axis=-1) * (1.0 - 1e-12)
-        D = (upper + R).min(axis=1)
+        D = (upper + R).min(axis=1) + move
         for _ in range(2):                                                  # tighten D with exact distances where needed
-            unsure = (lower - R <= rho * D[:, None]) & (upper > lower * (1 + 1e-9))
+            unsure = (lower - R - move <= rho * D[:, None]) & (upper > lower * (1 + 1e-9))
             ci, si = np.nonzero(unsure)
             if len(ci):
                 exact = _mic_cartesian(df[ci, si], lattice0)
                 upper[ci, si] = exact
                 lower[ci, si] = exact * (1.0 - 1e-12)
-            D = (upper + R).min(axis=1)
-        keep = (lower - R) <= rho * D[:, None]
+            D = (upper + R).min(axis=1) + move
+        keep = (lower - R - move) <= rho * D[:, None]
         excl[a:a + step] = rho * D
         offsets[a + 1:a + step + 1] = keep.sum(axis=1)
         entries.append(np.nonzero(keep)[1])

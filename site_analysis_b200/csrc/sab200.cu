@@ -92,6 +92,7 @@ struct sab_engine {
     // exact-pruning tables of the nearest-centre kernel
     bool nl_set = false; int nl_G = 0; double nl_l0inv[9] = {0};
     int32_t *d_nl_off = nullptr; uint16_t *d_nl_sites = nullptr; double *d_nl_excl = nullptr;
+    double *d_nl_anchor = nullptr, *d_nl_l0 = nullptr; double nl_dmax = 0.0;   // dynamic Voronoi: anchor centres, L0, motion head-room
     // exact-pruning tables of the tetrahedral kernel
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
     uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
@@ -129,7 +130,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
-                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl};
+                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
@@ -287,6 +288,7 @@ extern "C" int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice
     if (!e) return fail(SAB_EINVAL, "sab_set_nearest_lists: null engine");
     CU(cudaSetDevice(e->device));
     if (!cell_off) { e->nl_set = false; return SAB_OK; }
+    if (e->kind == SAB_DYNAMIC_VORONOI) return fail(SAB_EINVAL, "use sab_set_dynvor_lists for dynamic Voronoi sites");
     if (e->kind != SAB_VORONOI || !e->d_centres) return fail(SAB_ESTATE, "sab_set_nearest_lists: Voronoi centres not set");
     if (G < 1 || G > 256 || !lattice0_inverse || !cell_sites || !excl || e->S > 65535)
         return fail(SAB_EINVAL, "sab_set_nearest_lists: bad arguments");
@@ -296,6 +298,27 @@ extern "C" int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice
     CU(upload(&e->d_nl_excl, excl, ncell));
     for (int i = 0; i < 9; i++) e->nl_l0inv[i] = lattice0_inverse[i];
     e->nl_G = G; e->nl_set = true;
+    return SAB_OK;
+}
+
+extern "C" int sab_set_dynvor_lists(sab_engine *e, int G, const double *lattice0, const double *lattice0_inverse,
+                                    const double *anchors, double max_move, const int32_t *cell_off,
+                                    const uint16_t *cell_sites, const double *excl)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_dynvor_lists: null engine");
+    CU(cudaSetDevice(e->device));
+    if (!cell_off) { e->nl_set = false; return SAB_OK; }
+    if (e->kind != SAB_DYNAMIC_VORONOI || !e->d_slot_atom) return fail(SAB_ESTATE, "sab_set_dynvor_lists: reference atoms not set");
+    if (G < 1 || G > 256 || !lattice0 || !lattice0_inverse || !anchors || !cell_sites || !excl || e->S > 65535 || !(max_move >= 0.0))
+        return fail(SAB_EINVAL, "sab_set_dynvor_lists: bad arguments");
+    size_t ncell = (size_t)G * G * G;
+    CU(upload(&e->d_nl_off, cell_off, ncell + 1));
+    CU(upload(&e->d_nl_sites, cell_sites, (size_t)std::max(cell_off[ncell], 1)));
+    CU(upload(&e->d_nl_excl, excl, ncell));
+    CU(upload(&e->d_nl_anchor, anchors, (size_t)3 * e->S));
+    CU(upload(&e->d_nl_l0, lattice0, (size_t)9));
+    for (int i = 0; i < 9; i++) e->nl_l0inv[i] = lattice0_inverse[i];
+    e->nl_G = G; e->nl_dmax = max_move; e->nl_set = true;
     return SAB_OK;
 }
 
@@ -430,7 +453,18 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_counters + CNT_FULL27);
         break;
     }
-    case SAB_DYNAMIC_VORONOI: {
+    case SAB_DYNAMIC_VORONOI: if (e->nl_set && d_result && !d_centres_out) {
+        int block = 256;
+        size_t smem = sizeof(double) * 3 * (size_t)e->S;
+        CU(cudaFuncSetAttribute(k_dynvor_assign_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SabNearestLists NL{e->nl_G, e->d_nl_off, e->d_nl_sites, e->d_nl_excl, {0}};
+        for (int i = 0; i < 9; i++) NL.l0inv[i] = e->nl_l0inv[i];
+        int grid2 = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 8);
+        k_dynvor_assign_cells<<<grid2, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile, e->S,
+            e->smax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, w.rows, w.m3, e->d_legacy_init,
+            e->legacy_init_frame, NL, e->d_nl_anchor, e->d_nl_l0, e->nl_dmax, d_result, e->d_counters + CNT_FULL27);
+        break;
+    } else {
         int block = std::min(1024, ((std::max(e->A, 128) + 31) / 32) * 32);
         size_t smem = sizeof(double) * 3 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_nearest_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

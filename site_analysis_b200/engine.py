@@ -202,8 +202,10 @@ class AssignmentEngine:
         (trajectory.py:364-373, polyhedral_site.py:264-279, dynamic_voronoi_site_collection.py:197-201)."""
         self.reset_history()
         self._pbc_ready = False
-        if self.k == nat.POLYHEDRAL:                 # anchors belong to the PBC state; Voronoi lists are static
+        if self.k in (nat.POLYHEDRAL, nat.DYNAMIC_VORONOI):   # anchors belong to the PBC state; Voronoi lists are static
             self._cells = None
+            if self.k == nat.DYNAMIC_VORONOI:
+                nat.check(self.L.sab_set_dynvor_lists(self.h, 1, None, None, None, 0.0, None, None, None))
         self._seen_exc = None
         if self.slots is not None:
             self.primed = [None] * self.S
@@ -341,6 +343,27 @@ class AssignmentEngine:
                                                nat.ptr(np.ascontiguousarray(ent)), nat.ptr(np.ascontiguousarray(excl))))
         self._cells = dict(G=G, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3)
 
+    def _build_dynvor_lists(self, d_frac, lattice0):
+        """Dynamic Voronoi: anchors = centres of the batch's first frame, head-room from a strided sample."""
+        torch = _torch()
+        lattice0 = np.asarray(lattice0, dtype=np.float64)
+        F = int(d_frac.shape[0])
+        stride = max(1, F // 256)
+        sample = d_frac[::stride][:256].contiguous()
+        cen = self.dynvor_centres(sample).cpu().numpy()                         # (n, S, 3)
+        anchors = np.ascontiguousarray(cen[0])
+        d = tab._mic_cartesian(cen - anchors[None], lattice0)
+        move = float(d.max() * 1.5 + 0.05)
+        length = float(np.mean(np.linalg.norm(lattice0, axis=1)))
+        spacing = (abs(np.linalg.det(lattice0)) / self.S) ** (1.0 / 3.0)
+        G = int(min(64, max(2, round(length / max(0.6 * spacing, 0.5)))))
+        off, ent, excl = tab.nearest_cell_lists(anchors, lattice0, G, move=move)
+        inv = np.ascontiguousarray(np.linalg.inv(lattice0))
+        nat.check(self.L.sab_set_dynvor_lists(self.h, G, nat.ptr(np.ascontiguousarray(lattice0)), nat.ptr(inv), nat.ptr(anchors),
+                                              move, nat.ptr(np.ascontiguousarray(off)), nat.ptr(np.ascontiguousarray(ent)),
+                                              nat.ptr(np.ascontiguousarray(excl))))
+        self._cells = dict(G=G, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3, max_move=move)
+
     def _reinit_groups(self, raw_t, lat_t):
         """Dynamic Voronoi: a step >= 0.3 at this frame re-initialises every group that contains a
         jumping reference slot (dynamic_voronoi_site_collection.py:94-95, 188-195)."""
@@ -464,6 +487,8 @@ class AssignmentEngine:
             self._init_pbc(d_frac[0].cpu().numpy(), lat0)
         if self.k == nat.VORONOI and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
             self._build_nearest_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
+        if self.k == nat.DYNAMIC_VORONOI and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+            self._build_dynvor_lists(d_frac, (d_lattice[0] if stride else d_lattice).cpu().numpy())
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
         total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0)
@@ -566,6 +591,16 @@ class AssignmentEngine:
             self._maybe_build_cells(d_s, int(d_s.shape[0]), d_ws, ws_bytes, torch.cuda.current_stream(dev).cuda_stream,
                                     margin=0.65)
             del d_s, d_ws
+        lat0 = lattice if lattice.ndim == 2 else lattice[0]
+        if self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+            if self.k == nat.VORONOI:
+                self._build_nearest_lists(lat0)
+            elif self.k == nat.DYNAMIC_VORONOI:
+                torch = _torch()
+                stride = max(1, F // 256)
+                d_s = torch.from_numpy(np.ascontiguousarray(frac[::stride][:256])).to(torch.device("cuda", self.device))
+                self._build_dynvor_lists(d_s, lat0)
+                del d_s
         info = np.zeros(8, dtype=np.int64)
         nat.check(self.L.sab_assign_host(self.h, frac.ctypes.data, nat.ptr(lattice), 9 if lattice.ndim == 3 else 0,
                                          F, out.ctypes.data, chunk_frames, nat.ptr(info)))

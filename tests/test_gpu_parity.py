@@ -161,6 +161,26 @@ def test_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
     assert torch.cuda.is_available()
 
 
+def test_dynamic_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
+    """k_dynvor_assign_cells vs the exhaustive kernel vs the oracle on the argyrodite geometry."""
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    frac, lat = syn.argyrodite_trajectory(g, 300, device="cuda", sigma_framework=0.12)
+    slots = [list(map(int, t)) for t in g.tetrahedra]
+    outs = []
+    for use_cells in (True, False):
+        eng = AssignmentEngine("dynamic_voronoi", g.n_atoms, g.mobile_idx, slots=slots, reference_centres=list(g.site_centres))
+        eng.use_cells = use_cells
+        outs.append(eng.assign_device(frac, lat).cpu().numpy())
+        assert (eng._cells is not None) == use_cells
+    assert np.array_equal(outs[0], outs[1])
+    S = len(slots)
+    o = oracle_mod.SiteOracle("dynamic_voronoi", g.mobile_idx, ref_idx=np.array(slots, dtype=np.int32), n_ref=np.full(S, 4, np.int32),
+                              has_ref_center=np.ones(S, np.uint8), ref_center=g.site_centres)
+    want = o.run(frac.cpu().numpy()[:60], lat.cpu().numpy()[:60], positions=True)
+    assert np.array_equal(outs[0][:60], want)
+
+
 def test_reset_and_replay(oracle_mod):
     """Trajectory.reset(): history and PBC caches cleared, topology kept, same answers again."""
     case = oracle_mod.load_case("fuzz_polyhedral_1")
