@@ -129,7 +129,7 @@ __global__ void k_dynvor_assign_cells(const double *__restrict__ frac, const dou
             sm_centres[3 * s] = c[0]; sm_centres[3 * s + 1] = c[1]; sm_centres[3 * s + 2] = c[2];
             double d0, d1, d2;                      // displacement from the anchor, lattice-L0 metric (pruning bound only)
             sab_dbase(c, anchors + 3 * s, d0, d1, d2);
-            if (!(sab_mic_q27(d0, d1, d2, l0) <= dmax * dmax)) moved = 1;
+            if (!(sab_image_q(d0, d1, d2, l0) <= dmax * dmax)) moved = 1;   // central image >= true distance: conservative
         }
         moved = __syncthreads_or(moved);
         if (moved && threadIdx.x == 0) atomicAdd(n_exhaustive, (unsigned long long)n_mobile);
