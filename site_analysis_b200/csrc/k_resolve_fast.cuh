@@ -1,0 +1,227 @@
+// k_resolve_fast.cuh -- the priority resolver with all history in shared memory.
+//
+// Same semantics as k_resolve (k_resolve.cuh): replays PriorityAssignmentMixin._get_priority_sites
+// (site_collection.py:113-182), SiteCollection.update_occupation (:279-310) and
+// Atom.update_recent_site (atom.py:181-192) over the batch in frame order.  Differences:
+//   * recent sites, previous trajectory entry and the per-site transition Counters (insertion-ordered
+//     rows of K keys) live in shared memory;
+//   * a frame needs the ORDERED section (warp 0, ascending atom order) only if (a) some atom has to
+//     consult the Counters (both recent sites miss and several sites contain it), or (b) a transition
+//     inserts a NEW Counter key (insertion order decides later ties, site.py:223).  In all other
+//     frames -- the vast majority -- transitions only increment existing keys, which commutes, so
+//     they are applied with shared-memory atomics in parallel and the frame costs one barrier;
+//   * the next frame's result row is prefetched.
+// A Counter row overflowing K keys sets *overflow; the host then reruns with the global-memory kernel.
+#pragma once
+#include "k_resolve.cuh"
+
+struct SabSmemHistory {
+    int *recent;     // [A][2]
+    int *prev;       // [A]
+    int *tr_n;       // [S]
+    int *tr_key;     // [S][K]
+    int *tr_cnt;     // [S][K]
+    int K;
+};
+
+__device__ __forceinline__ int sab_row_find(const SabSmemHistory &H, int src, int dst)
+{
+    const int n = H.tr_n[src];
+    const int *key = H.tr_key + (size_t)src * H.K;
+    for (int i = 0; i < n; i++) if (key[i] == dst) return i;
+    return -1;
+}
+
+// One warp; mirrors sab_resolve_with_counters with shared-memory Counters.
+__device__ int sab_resolve_with_counters_smem(const int32_t *c, int n, int r0, const double *x, int n_sites,
+                                              const SabPriorityTables &P, const SabSmemHistory &H, int lane)
+{
+    int anchor = r0;
+    if (anchor < 0 && P.lookup) {
+        double bd = INFINITY; int bi = 0;
+        for (int s = lane; s < n_sites; s += 32) {
+            double d0 = P.lookup[3 * s] - x[0], d1 = P.lookup[3 * s + 1] - x[1], d2 = P.lookup[3 * s + 2] - x[2];
+            d0 -= rint(d0); d1 -= rint(d1); d2 -= rint(d2);
+            double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            if (nrm < bd) { bd = nrm; bi = s; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        anchor = bi;
+        if (sab_in_list(c, n, anchor)) return anchor;
+    }
+    if (anchor < 0) {
+        int best = c[0];
+        for (int i = 1; i < n; i++) best = min(best, c[i]);
+        return best;
+    }
+    {
+        const int nk = H.tr_n[anchor];
+        const int *key = H.tr_key + (size_t)anchor * H.K, *cn = H.tr_cnt + (size_t)anchor * H.K;
+        int bc = -1, bi = -1;
+        for (int i = 0; i < nk; i++)
+            if (cn[i] > bc && sab_in_list(c, n, key[i])) { bc = cn[i]; bi = key[i]; }
+        if (bi >= 0) return bi;
+    }
+    if (P.rank) {
+        const int32_t *row = P.rank + (size_t)anchor * (n_sites - 1);
+        int best = INT_MAX;
+        for (int i = lane; i < n_sites - 1; i += 32)
+            if (sab_in_list(c, n, row[i])) { best = i; break; }
+        for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (best != INT_MAX) return row[best];
+    }
+    if (P.neigh_off)
+        for (int i = P.neigh_off[anchor]; i < P.neigh_off[anchor + 1]; i++)
+            if (sab_in_list(c, n, P.neigh[i])) return P.neigh[i];
+    int best = c[0];
+    for (int i = 1; i < n; i++) best = min(best, c[i]);
+    return best;
+}
+
+__global__ void __launch_bounds__(1024)
+k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, int n_mobile,
+               const int32_t *__restrict__ mobile, int n_sites, int32_t *__restrict__ result,
+               const int32_t *__restrict__ spill, SabPriorityTables P, SabHistory G /* global in/out */, int K,
+               int *__restrict__ overflow)
+{
+    extern __shared__ int sm_r[];
+    SabSmemHistory H;
+    H.K = K;
+    H.recent = sm_r;
+    H.prev = H.recent + 2 * n_mobile;
+    H.tr_n = H.prev + n_mobile;
+    H.tr_key = H.tr_n + n_sites;
+    H.tr_cnt = H.tr_key + (size_t)n_sites * K;
+    int *cur_s = H.tr_cnt + (size_t)n_sites * K;     // [A] this frame's (tentative) result
+    int *flag = cur_s + n_mobile;                    // [A] 0 done, 1 existing-key adder, 2 new-key adder, 3 reader
+    __shared__ int need_order, any_reader;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    // load history (global rows may be wider than K: the host guarantees tr_n <= K on entry)
+    for (int a = tid; a < n_mobile; a += nthr) { H.recent[2 * a] = G.recent[2 * a]; H.recent[2 * a + 1] = G.recent[2 * a + 1]; H.prev[a] = G.prev[a]; }
+    for (int s = tid; s < n_sites; s += nthr) {
+        int n = G.tr_n[s];
+        H.tr_n[s] = n;
+        for (int i = 0; i < n && i < K; i++) { H.tr_key[(size_t)s * K + i] = G.tr_key[(size_t)s * G.K + i]; H.tr_cnt[(size_t)s * K + i] = (int)G.tr_cnt[(size_t)s * G.K + i]; }
+    }
+    if (tid == 0) { need_order = 0; any_reader = 0; }
+    __syncthreads();
+    // one atom per thread (the usual case): the next frame's entry and the head of its candidate list
+    // are prefetched into registers so that their global-memory latency is off the per-frame path
+    const bool one_each = n_mobile <= nthr;
+    int pre_r = SAB_NONE, pre_n = 0, pre_c[4] = {0, 0, 0, 0};
+    auto prefetch = [&](int64_t f) {
+        if (!one_each || tid >= n_mobile || f >= n_frames) return;
+        pre_r = result[(size_t)f * n_mobile + tid];
+        if (pre_r <= SAB_AMBIGUOUS_BASE) {
+            const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - pre_r);
+            pre_n = c[0];
+            for (int i = 0; i < 4; i++) pre_c[i] = (i < pre_n) ? c[1 + i] : -1;
+        }
+    };
+    prefetch(0);
+    for (int64_t f = 0; f < n_frames; f++) {
+        // ---- classification (no shared state is modified here except the atom's own recent/prev) ----
+        for (int a = tid; a < n_mobile; a += nthr) {
+            const int r = one_each ? pre_r : result[(size_t)f * n_mobile + a];
+            int cur = r, fl = 0;
+            const int r0 = H.recent[2 * a], r1 = H.recent[2 * a + 1];
+            if (r <= SAB_AMBIGUOUS_BASE) {
+                const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r);
+                int n; bool in0, in1;
+                if (one_each && pre_n <= 4) {
+                    n = pre_n;
+                    in0 = r0 >= 0 && (pre_c[0] == r0 || pre_c[1] == r0 || pre_c[2] == r0 || pre_c[3] == r0);
+                    in1 = r1 >= 0 && (pre_c[0] == r1 || pre_c[1] == r1 || pre_c[2] == r1 || pre_c[3] == r1);
+                } else {
+                    n = c[0]; c++;
+                    in0 = r0 >= 0 && sab_in_list(c, n, r0);
+                    in1 = r1 >= 0 && sab_in_list(c, n, r1);
+                }
+                if (in0) cur = r0;
+                else if (in1) cur = r1;
+                else { fl = 3; any_reader = 1; need_order = 1; }
+            }
+            if (one_each) prefetch(f + 1);
+            if (fl == 0) {
+                const int pv = H.prev[a];
+                if (cur >= 0 && pv >= 0 && pv != cur) {
+                    fl = (sab_row_find(H, pv, cur) >= 0) ? 1 : 2;
+                    if (fl == 2) need_order = 1;
+                } else {
+                    if (cur >= 0 && cur != r0) { H.recent[2 * a + 1] = r0; H.recent[2 * a] = cur; }
+                    H.prev[a] = cur;
+                    if (r <= SAB_AMBIGUOUS_BASE) result[(size_t)f * n_mobile + a] = cur;
+                }
+            }
+            cur_s[a] = cur; flag[a] = fl;
+        }
+        __syncthreads();                                 // B1
+        const bool ordered = need_order != 0, readers = any_reader != 0;
+        if (!readers) {
+            // existing-key increments commute: apply them in parallel
+            for (int a = tid; a < n_mobile; a += nthr) {
+                if (flag[a] != 1) continue;
+                const int cur = cur_s[a], pv = H.prev[a];
+                atomicAdd(&H.tr_cnt[(size_t)pv * K + sab_row_find(H, pv, cur)], 1);
+                const int r0 = H.recent[2 * a];
+                if (cur != r0) { H.recent[2 * a + 1] = r0; H.recent[2 * a] = cur; }
+                H.prev[a] = cur;
+                result[(size_t)f * n_mobile + a] = cur;
+                flag[a] = 0;
+            }
+        }
+        if (!ordered) continue;                          // uniform: the common case costs one barrier
+        __syncthreads();                                 // B2: parallel increments done before the ordered walk
+        if (tid < 32) {
+            for (int a0 = 0; a0 < n_mobile; a0 += 32) {
+                const int a_l = a0 + lane;
+                unsigned todo = __ballot_sync(0xffffffffu, a_l < n_mobile && flag[a_l] != 0);
+                while (todo) {
+                    const int a = a0 + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    int cur = cur_s[a];
+                    if (flag[a] == 3) {
+                        const int r = result[(size_t)f * n_mobile + a];
+                        const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r);
+                        const int n = c[0]; c++;
+                        double x[3];
+                        for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frac[((size_t)f * n_atoms + mobile[a]) * 3 + d]);
+                        cur = sab_resolve_with_counters_smem(c, n, H.recent[2 * a], x, n_sites, P, H, lane);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int pv = H.prev[a];
+                        if (cur >= 0 && pv >= 0 && pv != cur) {          // site_collection.py:300-306
+                            int i = sab_row_find(H, pv, cur);
+                            if (i >= 0) H.tr_cnt[(size_t)pv * K + i]++;
+                            else {
+                                const int nk = H.tr_n[pv];
+                                if (nk < K) { H.tr_key[(size_t)pv * K + nk] = cur; H.tr_cnt[(size_t)pv * K + nk] = 1; H.tr_n[pv] = nk + 1; }
+                                else *overflow = 1;
+                            }
+                        }
+                        const int r0 = H.recent[2 * a];
+                        if (cur >= 0 && cur != r0) { H.recent[2 * a + 1] = r0; H.recent[2 * a] = cur; }
+                        H.prev[a] = cur;
+                        result[(size_t)f * n_mobile + a] = cur;
+                        flag[a] = 0;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) { need_order = 0; any_reader = 0; }
+        }
+        __syncthreads();                                 // B3
+    }
+    __syncthreads();
+    for (int a = tid; a < n_mobile; a += nthr) { G.recent[2 * a] = H.recent[2 * a]; G.recent[2 * a + 1] = H.recent[2 * a + 1]; G.prev[a] = H.prev[a]; }
+    for (int s = tid; s < n_sites; s += nthr) {
+        int n = H.tr_n[s];
+        G.tr_n[s] = n;
+        for (int i = 0; i < n; i++) { G.tr_key[(size_t)s * G.K + i] = H.tr_key[(size_t)s * K + i]; G.tr_cnt[(size_t)s * G.K + i] = H.tr_cnt[(size_t)s * K + i]; }
+    }
+}

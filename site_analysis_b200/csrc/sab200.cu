@@ -20,6 +20,7 @@
 #include "k_polyhedral_seq.cuh"
 #include "k_polyhedral_seq1.cuh"
 #include "k_resolve.cuh"
+#include "k_resolve_fast.cuh"
 #include "k_spherical.cuh"
 #include "k_wrap.cuh"
 
@@ -788,9 +789,25 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
     SabPriorityTables P{e->d_rank, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
     int block = std::min(1024, ((e->A + 31) / 32) * 32);
-    size_t smem = sizeof(int) * (size_t)e->A;
-    CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    k_resolve<<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, d_over);
+    // shared-memory resolver when the Counter rows fit (K keys per site); else the global-memory one
+    int max_n = 0;
+    for (int s2 = 0; s2 < e->S; s2++) max_n = std::max(max_n, (int)tr_n[s2]);
+    int smem_cap = 0;
+    cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+    long long fixed = sizeof(int) * ((long long)e->A * 5 + e->S) + 1024;
+    // rows of tr_width keys must fit in shared memory untruncated; the host starts narrow and widens on
+    // overflow, which eventually selects the global-memory kernel
+    long long fit = ((long long)smem_cap - fixed) / (8LL * e->S);
+    int k_fit = tr_width;
+    if (tr_width <= fit && max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr) {
+        size_t smem = sizeof(int) * ((size_t)e->A * 5 + e->S + 2 * (size_t)e->S * k_fit);
+        CU(cudaFuncSetAttribute(k_resolve_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_resolve_fast<<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
+    } else {
+        size_t smem = sizeof(int) * (size_t)e->A;
+        CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_resolve<<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, d_over);
+    }
     e->launches++;
     CU(cudaGetLastError());
     int over = 0;

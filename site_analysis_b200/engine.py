@@ -437,7 +437,7 @@ class AssignmentEngine:
     def _resolve(self, d_frac, F, d_result, d_spill, stream, append):
         self.sync_history()
         self._upload_priority_tables()
-        width = max(32, 2 * max((len(t) for t in self.transitions), default=0))
+        width = max(12, 2 * max((len(t) for t in self.transitions), default=0))
         while True:
             tr_n = np.zeros(self.S, dtype=np.int32)
             tr_key = np.zeros((self.S, width), dtype=np.int32)
@@ -453,7 +453,7 @@ class AssignmentEngine:
                                       nat.ptr(recent), nat.ptr(prev), nat.ptr(tr_n), nat.ptr(tr_key), nat.ptr(tr_cnt), width)
             if code == 3 and width < 4 * self.S:         # SAB_EOVERFLOW: widen the counter rows, redo
                 d_result.copy_(d_backup)
-                width *= 4
+                width *= 2
                 continue
             nat.check(code)
             break
