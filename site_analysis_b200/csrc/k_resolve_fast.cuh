@@ -66,13 +66,13 @@ __device__ int sab_resolve_with_counters_smem(const int32_t *c, int n, int r0, c
             if (cn[i] > bc && sab_in_list(c, n, key[i])) { bc = cn[i]; bi = key[i]; }
         if (bi >= 0) return bi;
     }
-    if (P.rank) {
-        const int32_t *row = P.rank + (size_t)anchor * (n_sites - 1);
-        int best = INT_MAX;
-        for (int i = lane; i < n_sites - 1; i += 32)
-            if (sab_in_list(c, n, row[i])) { best = i; break; }
-        for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (best != INT_MAX) return row[best];
+    if (P.rank) {                           // site_collection.py:167-171: first member of C in the anchor's ranked row
+        int bestpos = INT_MAX, bests = -1;
+        for (int i = 0; i < n; i++) {
+            const int pos = P.rank_pos[(size_t)anchor * n_sites + c[i]];
+            if (pos < bestpos) { bestpos = pos; bests = c[i]; }
+        }
+        if (bests >= 0) return bests;
     }
     if (P.neigh_off)
         for (int i = P.neigh_off[anchor]; i < P.neigh_off[anchor + 1]; i++)

@@ -76,7 +76,7 @@ struct sab_engine {
     bool pbc_set = false;
     uint8_t *d_legacy_init = nullptr; int64_t legacy_init_frame = -1;
     // priority tables
-    int32_t *d_rank = nullptr, *d_neigh_off = nullptr, *d_neigh = nullptr; double *d_lookup = nullptr;
+    int32_t *d_rank = nullptr, *d_rank_pos = nullptr, *d_neigh_off = nullptr, *d_neigh = nullptr; double *d_lookup = nullptr;
     // counters
     unsigned long long *d_counters = nullptr;
     // host-path staging
@@ -129,7 +129,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
     cudaSetDevice(e->device);
     void *ptrs[] = {e->d_mobile, e->d_centres, e->d_rcut, e->d_rcut_q, e->d_fw_atoms, e->d_nslot, e->d_slot_atom,
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
-                    e->d_legacy_init, e->d_rank, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
+                    e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
@@ -753,7 +753,17 @@ extern "C" int sab_set_priority_tables(sab_engine *e, const int32_t *rank, const
 {
     if (!e) return fail(SAB_EINVAL, "sab_set_priority_tables: null engine");
     CU(cudaSetDevice(e->device));
-    if (rank) CU(upload(&e->d_rank, rank, (size_t)e->S * (size_t)std::max(e->S - 1, 1)));
+    if (rank) {
+        CU(upload(&e->d_rank, rank, (size_t)e->S * (size_t)std::max(e->S - 1, 1)));
+        std::vector<int32_t> pos((size_t)e->S * e->S, INT_MAX);
+        for (int i = 0; i < e->S; i++)
+            for (int j = 0; j < e->S - 1; j++) {
+                int32_t t = rank[(size_t)i * (e->S - 1) + j];
+                if (t < 0 || t >= e->S) return fail(SAB_EINVAL, "rank table entry out of range");
+                pos[(size_t)i * e->S + t] = j;
+            }
+        CU(upload(&e->d_rank_pos, pos.data(), pos.size()));
+    }
     if (lookup) CU(upload(&e->d_lookup, lookup, (size_t)3 * e->S));
     if (neigh_off) {
         CU(upload(&e->d_neigh_off, neigh_off, (size_t)e->S + 1));
@@ -787,7 +797,7 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     CU(cudaMemcpyAsync(H.tr_key, tr_key, sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(H.tr_cnt, tr_cnt, sizeof(long long) * nk, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
-    SabPriorityTables P{e->d_rank, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
+    SabPriorityTables P{e->d_rank, e->d_rank_pos, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
     int block = std::min(1024, ((e->A + 31) / 32) * 32);
     // shared-memory resolver when the Counter rows fit (K keys per site); else the global-memory one
     int max_n = 0;
