@@ -82,7 +82,8 @@ __device__ int sab_resolve_with_counters_smem(const int32_t *c, int n, int r0, c
     return best;
 }
 
-__global__ void __launch_bounds__(1024)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, int n_mobile,
                const int32_t *__restrict__ mobile, int n_sites, int32_t *__restrict__ result,
                const int32_t *__restrict__ spill, SabPriorityTables P, SabHistory G /* global in/out */, int K,
@@ -109,35 +110,41 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     }
     if (tid == 0) { need_order = 0; any_reader = 0; }
     __syncthreads();
-    // one atom per thread (the usual case): the next frame's entry and the head of its candidate list
-    // are prefetched into registers so that their global-memory latency is off the per-frame path
+    // One atom per thread (the usual case): result entries and candidate lists are fetched three / two
+    // frames ahead into registers, so their global-memory latency is off the per-frame critical path.
     const bool one_each = n_mobile <= nthr;
-    int pre_r = SAB_NONE, pre_n = 0, pre_c[4] = {0, 0, 0, 0};
-    auto prefetch = [&](int64_t f) {
-        if (!one_each || tid >= n_mobile || f >= n_frames) return;
-        pre_r = result[(size_t)f * n_mobile + tid];
-        if (pre_r <= SAB_AMBIGUOUS_BASE) {
-            const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - pre_r);
-            pre_n = c[0];
-            for (int i = 0; i < 4; i++) pre_c[i] = (i < pre_n) ? c[1 + i] : -1;
+    const bool mine = one_each && tid < n_mobile;
+    constexpr int PC = 12;                               // candidates kept in registers (longer lists: global)
+    int rq[4] = {SAB_NONE, SAB_NONE, SAB_NONE, SAB_NONE}; // result entries of frames f .. f+3
+    int cn[3] = {0, 0, 0};                               // list lengths of frames f .. f+2
+    int cc[3][PC];
+    auto load_r = [&](int64_t f) -> int { return (mine && f < n_frames) ? result[(size_t)f * n_mobile + tid] : SAB_NONE; };
+    auto load_c = [&](int r, int &n, int *c) {
+        n = 0;
+        if (r <= SAB_AMBIGUOUS_BASE) {
+            const int32_t *p = spill + (SAB_AMBIGUOUS_BASE - r);
+            n = p[0];
+#pragma unroll
+            for (int i = 0; i < PC; i++) c[i] = (i < n) ? p[1 + i] : -1;
         }
     };
-    prefetch(0);
+    rq[0] = load_r(0); rq[1] = load_r(1); rq[2] = load_r(2); rq[3] = load_r(3);
+    load_c(rq[0], cn[0], cc[0]); load_c(rq[1], cn[1], cc[1]); load_c(rq[2], cn[2], cc[2]);
     for (int64_t f = 0; f < n_frames; f++) {
         // ---- classification (no shared state is modified here except the atom's own recent/prev) ----
         for (int a = tid; a < n_mobile; a += nthr) {
-            const int r = one_each ? pre_r : result[(size_t)f * n_mobile + a];
+            const int r = one_each ? rq[0] : result[(size_t)f * n_mobile + a];
             int cur = r, fl = 0;
             const int r0 = H.recent[2 * a], r1 = H.recent[2 * a + 1];
             if (r <= SAB_AMBIGUOUS_BASE) {
-                const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r);
-                int n; bool in0, in1;
-                if (one_each && pre_n <= 4) {
-                    n = pre_n;
-                    in0 = r0 >= 0 && (pre_c[0] == r0 || pre_c[1] == r0 || pre_c[2] == r0 || pre_c[3] == r0);
-                    in1 = r1 >= 0 && (pre_c[0] == r1 || pre_c[1] == r1 || pre_c[2] == r1 || pre_c[3] == r1);
+                bool in0 = false, in1 = false;
+                if (one_each && cn[0] <= PC) {
+#pragma unroll
+                    for (int i = 0; i < PC; i++) { in0 |= cc[0][i] == r0; in1 |= cc[0][i] == r1; }
+                    in0 &= r0 >= 0; in1 &= r1 >= 0;
                 } else {
-                    n = c[0]; c++;
+                    const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r);
+                    const int n = c[0]; c++;
                     in0 = r0 >= 0 && sab_in_list(c, n, r0);
                     in1 = r1 >= 0 && sab_in_list(c, n, r1);
                 }
@@ -145,7 +152,14 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 else if (in1) cur = r1;
                 else { fl = 3; any_reader = 1; need_order = 1; }
             }
-            if (one_each) prefetch(f + 1);
+            if (one_each) {                              // rotate the pipeline and fetch frame f+3's list / f+4's entry
+                rq[0] = rq[1]; rq[1] = rq[2]; rq[2] = rq[3];
+                cn[0] = cn[1]; cn[1] = cn[2];
+#pragma unroll
+                for (int i = 0; i < PC; i++) { cc[0][i] = cc[1][i]; cc[1][i] = cc[2][i]; }
+                load_c(rq[2], cn[2], cc[2]);
+                rq[3] = load_r(f + 4);
+            }
             if (fl == 0) {
                 const int pv = H.prev[a];
                 if (cur >= 0 && pv >= 0 && pv != cur) {

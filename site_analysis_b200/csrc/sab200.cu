@@ -811,8 +811,13 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     int k_fit = tr_width;
     if (tr_width <= fit && max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr) {
         size_t smem = sizeof(int) * ((size_t)e->A * 5 + e->S + 2 * (size_t)e->S * k_fit);
-        CU(cudaFuncSetAttribute(k_resolve_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_resolve_fast<<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
+        if (block <= 256) {
+            CU(cudaFuncSetAttribute(k_resolve_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_resolve_fast<256><<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
+        } else {
+            CU(cudaFuncSetAttribute(k_resolve_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_resolve_fast<1024><<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
+        }
     } else {
         size_t smem = sizeof(int) * (size_t)e->A;
         CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
