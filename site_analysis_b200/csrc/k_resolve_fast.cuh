@@ -98,7 +98,11 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     H.tr_key = H.tr_n + n_sites;
     H.tr_cnt = H.tr_key + (size_t)n_sites * K;
     int *cur_s = H.tr_cnt + (size_t)n_sites * K;     // [A] this frame's (tentative) result
-    int *flag = cur_s + n_mobile;                    // [A] 0 done, 1 existing-key adder, 2 new-key adder, 3 reader
+    int *flag = cur_s + n_mobile;                    // [A] 0 done, 1 existing-key adder, 2 new-key adder, 3 reader, 4 reader (published)
+    constexpr int PC = 12;                           // candidates kept in registers / published per reader
+    int *rd_n = flag + n_mobile;                     // [A] published readers: list length
+    int *rd_c = rd_n + n_mobile;                     // [A][PC] candidates
+    int *rd_p = rd_c + (size_t)n_mobile * PC;        // [A][PC] their positions in the anchor's distance-ranked row
     __shared__ int need_order, any_reader;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     // load history (global rows may be wider than K: the host guarantees tr_n <= K on entry)
@@ -114,7 +118,6 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     // frames ahead into registers, so their global-memory latency is off the per-frame critical path.
     const bool one_each = n_mobile <= nthr;
     const bool mine = one_each && tid < n_mobile;
-    constexpr int PC = 12;                               // candidates kept in registers (longer lists: global)
     int rq[4] = {SAB_NONE, SAB_NONE, SAB_NONE, SAB_NONE}; // result entries of frames f .. f+3
     int cn[3] = {0, 0, 0};                               // list lengths of frames f .. f+2
     int cc[3][PC];
@@ -150,7 +153,20 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 }
                 if (in0) cur = r0;
                 else if (in1) cur = r1;
-                else { fl = 3; any_reader = 1; need_order = 1; }
+                else {
+                    fl = 3; any_reader = 1; need_order = 1;
+                    if (one_each && cn[0] <= PC && r0 >= 0 && P.rank_pos) {
+                        // anchor = recent[0] is known: publish the candidates and their rank positions now
+                        // (one global load each, in parallel over all readers of the frame)
+                        fl = 4;
+                        rd_n[a] = cn[0];
+#pragma unroll
+                        for (int i = 0; i < PC; i++) {
+                            rd_c[a * PC + i] = cc[0][i];
+                            rd_p[a * PC + i] = (i < cn[0]) ? __ldg(P.rank_pos + (size_t)r0 * n_sites + cc[0][i]) : INT_MAX;
+                        }
+                    }
+                }
             }
             if (one_each) {                              // rotate the pipeline and fetch frame f+3's list / f+4's entry
                 rq[0] = rq[1]; rq[1] = rq[2]; rq[2] = rq[3];
@@ -198,7 +214,24 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                     const int a = a0 + __ffs(todo) - 1;
                     todo &= todo - 1;
                     int cur = cur_s[a];
-                    if (flag[a] == 3) {
+                    if (flag[a] == 4) {
+                        // lane i <-> candidate i: learned transitions of the anchor first (highest count, ties by
+                        // Counter insertion order, site.py:216-223), then the distance-ranked row
+                        const int anchor = H.recent[2 * a];
+                        const int n = rd_n[a];
+                        const int ci = (lane < n) ? rd_c[a * PC + lane] : -1;
+                        int cnt = -1, ins = INT_MAX;
+                        if (ci >= 0) { int i = sab_row_find(H, anchor, ci); if (i >= 0) { cnt = H.tr_cnt[(size_t)anchor * K + i]; ins = i; } }
+                        int pos = (lane < n) ? rd_p[a * PC + lane] : INT_MAX;
+                        int bcnt = cnt, bins = ins, bsite = ci, bpos = pos, psite = ci;
+                        for (int o = 16; o; o >>= 1) {
+                            int oc = __shfl_xor_sync(0xffffffffu, bcnt, o), oi = __shfl_xor_sync(0xffffffffu, bins, o), os = __shfl_xor_sync(0xffffffffu, bsite, o);
+                            if (oc > bcnt || (oc == bcnt && oi < bins)) { bcnt = oc; bins = oi; bsite = os; }
+                            int op = __shfl_xor_sync(0xffffffffu, bpos, o), ops = __shfl_xor_sync(0xffffffffu, psite, o);
+                            if (op < bpos) { bpos = op; psite = ops; }
+                        }
+                        cur = (bcnt >= 0) ? bsite : psite;
+                    } else if (flag[a] == 3) {
                         const int r = result[(size_t)f * n_mobile + a];
                         const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r);
                         const int n = c[0]; c++;

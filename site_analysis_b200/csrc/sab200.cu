@@ -799,18 +799,20 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
     SabPriorityTables P{e->d_rank, e->d_rank_pos, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
     int block = std::min(1024, ((e->A + 31) / 32) * 32);
+    for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
+    CU(cudaEventRecord(e->ev_t[0], st));
     // shared-memory resolver when the Counter rows fit (K keys per site); else the global-memory one
     int max_n = 0;
     for (int s2 = 0; s2 < e->S; s2++) max_n = std::max(max_n, (int)tr_n[s2]);
     int smem_cap = 0;
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
-    long long fixed = sizeof(int) * ((long long)e->A * 5 + e->S) + 1024;
+    long long fixed = sizeof(int) * ((long long)e->A * (6 + 2 * 12) + e->S) + 1024;
     // rows of tr_width keys must fit in shared memory untruncated; the host starts narrow and widens on
     // overflow, which eventually selects the global-memory kernel
     long long fit = ((long long)smem_cap - fixed) / (8LL * e->S);
     int k_fit = tr_width;
     if (tr_width <= fit && max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr) {
-        size_t smem = sizeof(int) * ((size_t)e->A * 5 + e->S + 2 * (size_t)e->S * k_fit);
+        size_t smem = sizeof(int) * ((size_t)e->A * (6 + 2 * 12) + e->S + 2 * (size_t)e->S * k_fit);
         if (block <= 256) {
             CU(cudaFuncSetAttribute(k_resolve_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_resolve_fast<256><<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
@@ -825,6 +827,7 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     }
     e->launches++;
     CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev_t[1], st));
     int over = 0;
     CU(cudaMemcpyAsync(recent, H.recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(prev, H.prev, sizeof(int32_t) * e->A, cudaMemcpyDeviceToHost, st));
@@ -833,6 +836,10 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     CU(cudaMemcpyAsync(tr_cnt, H.tr_cnt, sizeof(long long) * nk, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (const char *dbg = getenv("SAB_DEBUG")) if (dbg[0] == '1') {
+        float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_t[0], e->ev_t[1]);
+        fprintf(stderr, "[sab] resolve: frames=%lld kernel=%.3f ms (%.3f us/frame)\n", (long long)n_frames, ms, 1e3 * ms / (double)n_frames);
+    }
     cudaFree(H.recent); cudaFree(H.prev); cudaFree(H.tr_n); cudaFree(H.tr_key); cudaFree(H.tr_cnt); cudaFree(d_over);
     if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);
     return SAB_OK;
