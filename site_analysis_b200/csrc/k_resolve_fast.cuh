@@ -122,14 +122,14 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     int cn[3] = {0, 0, 0};                               // list lengths of frames f .. f+2
     int cc[3][PC];
     auto load_r = [&](int64_t f) -> int { return (mine && f < n_frames) ? result[(size_t)f * n_mobile + tid] : SAB_NONE; };
+    // All PC + 1 loads are issued unconditionally (no load depends on the list length), so a warp never
+    // waits inside the prefetch; entries are masked by the length when they are used.  Reading a few
+    // ints past a short list stays inside the spill buffer (the host allocates >= 1024 ints of slack).
     auto load_c = [&](int r, int &n, int *c) {
-        n = 0;
-        if (r <= SAB_AMBIGUOUS_BASE) {
-            const int32_t *p = spill + (SAB_AMBIGUOUS_BASE - r);
-            n = p[0];
+        const int32_t *p = spill + ((r <= SAB_AMBIGUOUS_BASE) ? (SAB_AMBIGUOUS_BASE - r) : 0);
+        n = p[0];
 #pragma unroll
-            for (int i = 0; i < PC; i++) c[i] = (i < n) ? p[1 + i] : -1;
-        }
+        for (int i = 0; i < PC; i++) c[i] = p[1 + i];
     };
     rq[0] = load_r(0); rq[1] = load_r(1); rq[2] = load_r(2); rq[3] = load_r(3);
     load_c(rq[0], cn[0], cc[0]); load_c(rq[1], cn[1], cc[1]); load_c(rq[2], cn[2], cc[2]);
@@ -143,7 +143,7 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 bool in0 = false, in1 = false;
                 if (one_each && cn[0] <= PC) {
 #pragma unroll
-                    for (int i = 0; i < PC; i++) { in0 |= cc[0][i] == r0; in1 |= cc[0][i] == r1; }
+                    for (int i = 0; i < PC; i++) { in0 |= i < cn[0] && cc[0][i] == r0; in1 |= i < cn[0] && cc[0][i] == r1; }
                     in0 &= r0 >= 0; in1 &= r1 >= 0;
                 } else {
                     const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r);
@@ -162,7 +162,7 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                         rd_n[a] = cn[0];
 #pragma unroll
                         for (int i = 0; i < PC; i++) {
-                            rd_c[a * PC + i] = cc[0][i];
+                            rd_c[a * PC + i] = (i < cn[0]) ? cc[0][i] : -1;
                             rd_p[a * PC + i] = (i < cn[0]) ? __ldg(P.rank_pos + (size_t)r0 * n_sites + cc[0][i]) : INT_MAX;
                         }
                     }
