@@ -103,7 +103,9 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     int *rd_n = flag + n_mobile;                     // [A] published readers: list length
     int *rd_c = rd_n + n_mobile;                     // [A][PC] candidates
     int *rd_p = rd_c + (size_t)n_mobile * PC;        // [A][PC] their positions in the anchor's distance-ranked row
-    __shared__ int need_order, any_reader;
+    int *row_mark = rd_p + (size_t)n_mobile * PC;    // [S] frame stamp: a reader of this frame consults this Counter row
+    int *ord_list = row_mark + n_sites;              // [A] atoms left for the ordered section (unsorted)
+    __shared__ int reader_unknown_row, ord_n;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     // load history (global rows may be wider than K: the host guarantees tr_n <= K on entry)
     for (int a = tid; a < n_mobile; a += nthr) { H.recent[2 * a] = G.recent[2 * a]; H.recent[2 * a + 1] = G.recent[2 * a + 1]; H.prev[a] = G.prev[a]; }
@@ -112,7 +114,8 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
         H.tr_n[s] = n;
         for (int i = 0; i < n && i < K; i++) { H.tr_key[(size_t)s * K + i] = G.tr_key[(size_t)s * G.K + i]; H.tr_cnt[(size_t)s * K + i] = (int)G.tr_cnt[(size_t)s * G.K + i]; }
     }
-    if (tid == 0) { need_order = 0; any_reader = 0; }
+    if (tid == 0) { reader_unknown_row = 0; ord_n = 0; }
+    for (int s2 = tid; s2 < n_sites; s2 += nthr) row_mark[s2] = 0;
     __syncthreads();
     // One atom per thread (the usual case): result entries and candidate lists are fetched three / two
     // frames ahead into registers, so their global-memory latency is off the per-frame critical path.
@@ -135,6 +138,7 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     load_c(rq[0], cn[0], cc[0]); load_c(rq[1], cn[1], cc[1]); load_c(rq[2], cn[2], cc[2]);
     for (int64_t f = 0; f < n_frames; f++) {
         // ---- classification (no shared state is modified here except the atom's own recent/prev) ----
+        int my_need = 0;                                 // this thread has a reader or a new-key adder
         for (int a = tid; a < n_mobile; a += nthr) {
             const int r = one_each ? rq[0] : result[(size_t)f * n_mobile + a];
             int cur = r, fl = 0;
@@ -154,8 +158,10 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 if (in0) cur = r0;
                 else if (in1) cur = r1;
                 else {
-                    fl = 3; any_reader = 1; need_order = 1;
+                    fl = 3; my_need = 1;
+                    if (!(one_each && cn[0] <= PC && r0 >= 0 && P.rank_pos)) reader_unknown_row = 1;
                     if (one_each && cn[0] <= PC && r0 >= 0 && P.rank_pos) {
+                        row_mark[r0] = (int)(f + 1);
                         // anchor = recent[0] is known: publish the candidates and their rank positions now
                         // (one global load each, in parallel over all readers of the frame)
                         fl = 4;
@@ -180,7 +186,7 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 const int pv = H.prev[a];
                 if (cur >= 0 && pv >= 0 && pv != cur) {
                     fl = (sab_row_find(H, pv, cur) >= 0) ? 1 : 2;
-                    if (fl == 2) need_order = 1;
+                    if (fl == 2) my_need = 1;
                 } else {
                     if (cur >= 0 && cur != r0) { H.recent[2 * a + 1] = r0; H.recent[2 * a] = cur; }
                     H.prev[a] = cur;
@@ -189,30 +195,47 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
             }
             cur_s[a] = cur; flag[a] = fl;
         }
-        __syncthreads();                                 // B1
-        const bool ordered = need_order != 0, readers = any_reader != 0;
-        if (!readers) {
-            // existing-key increments commute: apply them in parallel
+        const bool ordered = __syncthreads_or(my_need) != 0;      // B1 (uniform, race-free)
+        {
+            // increments of EXISTING keys commute with everything except a reader of the same Counter row in
+            // this frame: apply those in parallel, leave the rest (and all readers / new keys) to the ordered walk
+            const bool all_ordered = reader_unknown_row != 0;
             for (int a = tid; a < n_mobile; a += nthr) {
-                if (flag[a] != 1) continue;
-                const int cur = cur_s[a], pv = H.prev[a];
-                atomicAdd(&H.tr_cnt[(size_t)pv * K + sab_row_find(H, pv, cur)], 1);
-                const int r0 = H.recent[2 * a];
-                if (cur != r0) { H.recent[2 * a + 1] = r0; H.recent[2 * a] = cur; }
-                H.prev[a] = cur;
-                result[(size_t)f * n_mobile + a] = cur;
-                flag[a] = 0;
+                const int fl = flag[a];
+                if (fl == 0) continue;
+                const int pv = H.prev[a];
+                if (fl == 1 && !all_ordered && row_mark[pv] != (int)(f + 1)) {
+                    const int cur = cur_s[a];
+                    atomicAdd(&H.tr_cnt[(size_t)pv * K + sab_row_find(H, pv, cur)], 1);
+                    const int r0 = H.recent[2 * a];
+                    if (cur != r0) { H.recent[2 * a + 1] = r0; H.recent[2 * a] = cur; }
+                    H.prev[a] = cur;
+                    result[(size_t)f * n_mobile + a] = cur;
+                    flag[a] = 0;
+                } else {
+                    ord_list[atomicAdd(&ord_n, 1)] = a;
+                }
             }
         }
         if (!ordered) continue;                          // uniform: the common case costs one barrier
-        __syncthreads();                                 // B2: parallel increments done before the ordered walk
+        __syncthreads();                                 // B2: parallel increments done, ordered list complete
         if (tid < 32) {
-            for (int a0 = 0; a0 < n_mobile; a0 += 32) {
-                const int a_l = a0 + lane;
-                unsigned todo = __ballot_sync(0xffffffffu, a_l < n_mobile && flag[a_l] != 0);
-                while (todo) {
-                    const int a = a0 + __ffs(todo) - 1;
-                    todo &= todo - 1;
+            const int n_ord = ord_n;
+            // ascending atom order: rank the (few) listed atoms; more than 32 -> walk the flags instead
+            int my_a = (lane < n_ord && n_ord <= 32) ? ord_list[lane] : INT_MAX, my_rank = 0;
+            if (n_ord <= 32)
+                for (int j = 0; j < n_ord; j++) { int aj = __shfl_sync(0xffffffffu, my_a, j); if (aj < my_a) my_rank++; }
+            const int n_items = (n_ord <= 32) ? n_ord : n_mobile;
+            for (int it = 0; it < n_items; it++) {
+                int a;
+                if (n_ord <= 32) {
+                    unsigned who = __ballot_sync(0xffffffffu, lane < n_ord && my_rank == it);
+                    a = __shfl_sync(0xffffffffu, my_a, __ffs(who) - 1);
+                } else {
+                    a = it;
+                    if (flag[a] == 0) continue;
+                }
+                {
                     int cur = cur_s[a];
                     if (flag[a] == 4) {
                         // lane i <-> candidate i: learned transitions of the anchor first (highest count, ties by
@@ -260,7 +283,7 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                     __syncwarp();
                 }
             }
-            if (lane == 0) { need_order = 0; any_reader = 0; }
+            if (lane == 0) { reader_unknown_row = 0; ord_n = 0; }
         }
         __syncthreads();                                 // B3
     }

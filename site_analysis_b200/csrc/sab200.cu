@@ -806,13 +806,13 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     for (int s2 = 0; s2 < e->S; s2++) max_n = std::max(max_n, (int)tr_n[s2]);
     int smem_cap = 0;
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
-    long long fixed = sizeof(int) * ((long long)e->A * (6 + 2 * 12) + e->S) + 1024;
+    long long fixed = sizeof(int) * ((long long)e->A * (7 + 2 * 12) + 2LL * e->S) + 1024;
     // rows of tr_width keys must fit in shared memory untruncated; the host starts narrow and widens on
     // overflow, which eventually selects the global-memory kernel
     long long fit = ((long long)smem_cap - fixed) / (8LL * e->S);
     int k_fit = tr_width;
     if (tr_width <= fit && max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr) {
-        size_t smem = sizeof(int) * ((size_t)e->A * (6 + 2 * 12) + e->S + 2 * (size_t)e->S * k_fit);
+        size_t smem = sizeof(int) * ((size_t)e->A * (7 + 2 * 12) + 2 * (size_t)e->S + 2 * (size_t)e->S * k_fit);
         if (block <= 256) {
             CU(cudaFuncSetAttribute(k_resolve_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_resolve_fast<256><<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);

@@ -503,7 +503,7 @@ class AssignmentEngine:
             info = np.zeros(8, dtype=np.int64)
             self._maybe_build_cells(sub, nf, d_ws, ws_bytes, stream)
             while True:
-                d_spill = torch.empty(cap, dtype=torch.int32, device=dev)
+                d_spill = torch.empty(cap + 64, dtype=torch.int32, device=dev)   # slack: the resolver prefetches whole records
                 code = self.L.sab_assign_device(self.h, sub.data_ptr(), sub_lat.data_ptr(), stride, nf,
                                                 sub_res.data_ptr(), d_spill.data_ptr(), cap, d_ws.data_ptr(), ws_bytes,
                                                 stream, nat.ptr(info))
