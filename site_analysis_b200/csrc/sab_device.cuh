@@ -94,5 +94,8 @@ __device__ __forceinline__ bool sab_face_accepts(const double *v0, const double 
     double dot = (p0 - v0[0]) * n0;
     dot += (p1 - v0[1]) * n1;
     dot += (p2 - v0[2]) * n2;
-    return !(dot != 0.0 && sab_sign(dot) != sab_sign(cd));
+    // reject iff dot != 0 and sign(dot) != sign(cd) (polyhedral_site.py:119-121); sign(cd) == 0 never
+    // matches a non-zero dot.  Sign bits compared as integers (NaN inputs are outside the contract).
+    const bool differ = (__double2hiint(dot) ^ __double2hiint(cd)) < 0;
+    return !(dot != 0.0 && (cd == 0.0 || differ));
 }
