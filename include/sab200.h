@@ -154,11 +154,13 @@ int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_frames, void 
  * 52-99, dynamic_voronoi_site_collection.py:203-244, spherical_site_collection.py:53-92)
  * for a whole trajectory (trajectory.py:413-432).  All d_* pointers are device memory.
  *   d_spill / spill_capacity (int32 elements): candidate lists of ambiguous atom-frames.
- *   info[8] (host, written on return): [0] ambiguous atom-frames, [1] spill elements used,
+ *   info[12] (host, written on return): [0] ambiguous atom-frames, [1] spill elements used,
  *   [2] spill overflow (0/1), [3] first frame whose step exceeded the 0.3 cache-validity
  *   bound (pbc_utils.py:216) or -1, [4] frames that took the exhaustive (non-pruned) path,
  *   [5] kernels launched, [6] device time of the assignment kernel in ns, [7] device time of
- *   the PBC wrap-scan kernels in ns (both from CUDA events on `stream`).
+ *   the PBC wrap-scan kernels in ns (both from CUDA events on `stream`), [8] bit pattern of the
+ *   largest excursion span max(raw - W) - min(raw - W) over all framework coordinates so far (double;
+ *   guard of the scan formulation), [9..11] reserved.
  * When info[3] < 0 the PBC state advances to the end of the batch.  When info[3] = t >= 0 the
  * results of frames < t are valid, the PBC state is left untouched, and the caller commits
  * the valid prefix with sab_commit_pbc(..., n_commit = t) (same workspace, unmodified). */

@@ -94,10 +94,14 @@ __global__ void k_wrap_commit(const double *__restrict__ frac, int64_t n_frames,
                               const int32_t *__restrict__ fw_atoms, int m3, int n_chunks,
                               const int32_t *__restrict__ rows, const double *__restrict__ chunk_exc,
                               double *__restrict__ prev_raw, int32_t *__restrict__ wraps,
-                              double *__restrict__ excursion)
+                              double *__restrict__ excursion, const unsigned long long *__restrict__ veto,
+                              unsigned long long *__restrict__ max_span)
 {
     int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= m3 || n_commit <= 0) return;
+    // automatic commit of a whole batch is skipped when the batch must be re-run or split:
+    // veto[0] = spill overflow flag, veto[1] = first frame with an invalidating step (~0 = none)
+    if (veto && (veto[0] != 0ULL || veto[1] != ~0ULL)) return;
     double lo = excursion[2 * col], hi = excursion[2 * col + 1];
     if (n_commit == n_frames) {
         for (int c = 0; c < n_chunks; c++) {
@@ -111,6 +115,7 @@ __global__ void k_wrap_commit(const double *__restrict__ frac, int64_t n_frames,
         }
     }
     excursion[2 * col] = lo; excursion[2 * col + 1] = hi;
+    if (max_span) atomicMax(max_span, (unsigned long long)__double_as_longlong(fmax(hi - lo, 0.0)));   // guard G1, read by the host
     wraps[col] = rows[(size_t)(n_commit - 1) * m3 + col];
     prev_raw[col] = sab_fw_raw(frac, n_commit - 1, n_atoms, fw_atoms, col);
 }

@@ -58,7 +58,7 @@ template <class T> static cudaError_t upload(T **dst, const T *src, size_t n)
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
 }
 
-enum { CNT_AMBIGUOUS = 0, CNT_SPILL = 1, CNT_OVERFLOW = 2, CNT_FIRST_BAD = 3, CNT_FULL27 = 4, CNT_N = 8 };
+enum { CNT_AMBIGUOUS = 0, CNT_SPILL = 1, CNT_OVERFLOW = 2, CNT_FIRST_BAD = 3, CNT_FULL27 = 4, CNT_SPAN = 8, CNT_N = 12 };
 
 struct sab_engine {
     int kind = 0, device = 0, N = 0, A = 0, S = 0;
@@ -386,7 +386,7 @@ extern "C" int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_fr
     Workspace w = layout(e, n_frames, d_workspace);
     if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     run_wrap_pass(e, d_frac, n_frames, w, st, false);
     CU(cudaGetLastError());
@@ -411,7 +411,7 @@ extern "C" int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n
     cudaStream_t st = (cudaStream_t)stream;
     Workspace w = layout(e, n_frames, d_workspace);
     if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
-    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     bool skip = e->skip_step_check_once;
     run_wrap_pass(e, d_frac, n_frames, w, st, true);
@@ -568,7 +568,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     if (n_frames < 0) return fail(SAB_EINVAL, "negative frame count");
     int rc = check_ready(e);
     if (rc) return rc;
-    for (int i = 0; i < 8; i++) info[i] = 0;
+    for (int i = 0; i < 12; i++) info[i] = 0;
     info[3] = -1;
     if (n_frames == 0) return SAB_OK;
     CU(cudaSetDevice(e->device));
@@ -577,7 +577,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     if (w.m3 && (!d_workspace || (int64_t)w.bytes > workspace_bytes))
         return fail(SAB_EINVAL, "workspace too small: need %zu bytes, got %lld", w.bytes, (long long)workspace_bytes);
     int64_t l0 = e->launches;
-    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
     CU(cudaEventRecord(e->ev_t[0], st));
@@ -586,6 +586,13 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     rc = launch_assign(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, w, st, nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev_t[2], st));
+    if (w.m3) {      // device-side conditional commit: skipped by the kernel itself on overflow / invalidating step
+        k_wrap_commit<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, n_frames, e->N, e->d_fw_atoms, w.m3, w.n_chunks,
+                                                          w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion,
+                                                          e->d_counters + CNT_OVERFLOW, e->d_counters + CNT_SPAN);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
     unsigned long long h[CNT_N];
     CU(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -593,6 +600,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     info[0] = (int64_t)h[CNT_AMBIGUOUS]; info[1] = (int64_t)h[CNT_SPILL]; info[2] = (int64_t)h[CNT_OVERFLOW];
     info[3] = (h[CNT_FIRST_BAD] == ~0ULL) ? -1 : (int64_t)h[CNT_FIRST_BAD];
     info[4] = (int64_t)h[CNT_FULL27];
+    info[8] = (int64_t)h[CNT_SPAN];
     {
         float ms_wrap = 0.f, ms_main = 0.f;          // CUDA events on the launching stream
         cudaEventElapsedTime(&ms_wrap, e->ev_t[0], e->ev_t[1]);
@@ -608,14 +616,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
         return fail(SAB_EOVERFLOW, "candidate spill buffer overflow (%llu elements needed, capacity %lld)",
                     h[CNT_SPILL], (long long)spill_capacity);
     }
-    if (w.m3 && info[3] < 0) {               // no cache-invalidating step: the whole batch is committed
-        k_wrap_commit<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, n_frames, e->N, e->d_fw_atoms, w.m3, w.n_chunks,
-                                                          w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion);
-        e->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(st));
-        if (e->legacy_init_frame >= 0) e->legacy_init_frame -= n_frames;      // now in the past
-    }
+    if (w.m3 && info[3] < 0 && e->legacy_init_frame >= 0) e->legacy_init_frame -= n_frames;      // now in the past
     info[5] = e->launches - l0;
     return SAB_OK;
 }
@@ -631,7 +632,7 @@ extern "C" int sab_commit_pbc(sab_engine *e, const double *d_frac, int64_t n_fra
     Workspace w = layout(e, n_frames, d_workspace);
     if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
     k_wrap_commit<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, n_commit, e->N, e->d_fw_atoms, w.m3, w.n_chunks,
-                                                      w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion);
+                                                      w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion, nullptr, nullptr);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
@@ -650,7 +651,7 @@ extern "C" int sab_dynvor_centres(sab_engine *e, const double *d_frac, int64_t n
     cudaStream_t st = (cudaStream_t)stream;
     Workspace w = layout(e, n_frames, d_workspace);
     if ((int64_t)w.bytes > workspace_bytes) return fail(SAB_EINVAL, "workspace too small: need %zu bytes", w.bytes);
-    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0};
+    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     run_wrap_pass(e, d_frac, n_frames, w, st, true);
     CU(cudaGetLastError());
@@ -672,7 +673,7 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
     if (lattice_stride != 0 && lattice_stride != 9) return fail(SAB_EINVAL, "lattice_stride must be 0 or 9");
     int rc = check_ready(e);
     if (rc) return rc;
-    for (int i = 0; i < 8; i++) info[i] = 0;
+    for (int i = 0; i < 12; i++) info[i] = 0;
     info[3] = -1;
     if (n_frames <= 0) return SAB_OK;
     CU(cudaSetDevice(e->device));
@@ -703,7 +704,7 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         CU(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
     }
     cudaStream_t s_copy = e->streams[1], s_comp = e->streams[0];
-    int64_t tot_info[8] = {0, 0, 0, -1, 0, 0, 0, 0};
+    int64_t tot_info[12] = {0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
     int status = SAB_OK;
     int64_t n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
     auto issue_copy = [&](int64_t k) -> cudaError_t {
@@ -728,7 +729,7 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         char *base = (char *)e->stage[b];
         if (k + 1 < n_chunks) CU(issue_copy(k + 1));
         CU(cudaStreamWaitEvent(s_comp, ev_copied[b], 0));
-        int64_t ci[8];
+        int64_t ci[12];
         status = sab_assign_device(e, (const double *)base, (const double *)(base + o_lat), lattice_stride, nf,
                                    (int32_t *)(base + o_res), (int32_t *)(base + o_spill), (int64_t)spill_elems,
                                    base + o_ws, (int64_t)align256(ws_b), s_comp, ci);
@@ -739,11 +740,12 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         CU(cudaEventRecord(ev_done[b], s_comp));
         tot_info[0] += ci[0]; tot_info[1] += ci[1]; tot_info[4] += ci[4]; tot_info[5] += ci[5];
         tot_info[6] += ci[6]; tot_info[7] += ci[7];
+        tot_info[8] = std::max(tot_info[8], ci[8]);
         if (ci[3] >= 0 && tot_info[3] < 0) tot_info[3] = f0 + ci[3];
     }
     cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_copy);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_copied[i]); cudaEventDestroy(ev_done[i]); }
-    for (int i = 0; i < 8; i++) info[i] = tot_info[i];
+    for (int i = 0; i < 12; i++) info[i] = tot_info[i];
     return status;
 }
 

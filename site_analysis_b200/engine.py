@@ -399,9 +399,11 @@ class AssignmentEngine:
         nat.check(self.L.sab_set_legacy_init(self.h, nat.ptr(legacy) if legacy.any() else None, 0))
         nat.check(self.L.sab_set_option(self.h, nat.OPT_SKIP_STEP_CHECK_ONCE, 1))
 
-    def _check_excursion(self):
+    def _check_excursion(self, span_bits=None):
         if self.k != nat.POLYHEDRAL:
             return
+        if span_bits is not None and float(np.array([span_bits], dtype=np.int64).view(np.float64)[0]) < EXCURSION_LIMIT:
+            return                                        # the device-side maximum already clears guard G1
         M = len(self.fw_atoms)
         exc = np.zeros((M, 3, 2))
         nat.check(self.L.sab_get_pbc_state(self.h, None, None, None, nat.ptr(exc)))
@@ -492,6 +494,7 @@ class AssignmentEngine:
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
         total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0)
+        span_bits = 0
         while f0 < F:
             nf = F - f0
             sub = d_frac[f0:]
@@ -500,7 +503,7 @@ class AssignmentEngine:
             ws_bytes = int(self.L.sab_workspace_bytes(self.h, nf))
             d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             cap = self._spill_capacity(nf)
-            info = np.zeros(8, dtype=np.int64)
+            info = np.zeros(12, dtype=np.int64)
             self._maybe_build_cells(sub, nf, d_ws, ws_bytes, stream)
             while True:
                 d_spill = torch.empty(cap + 64, dtype=torch.int32, device=dev)   # slack: the resolver prefetches whole records
@@ -516,6 +519,7 @@ class AssignmentEngine:
             if self._cells is not None and info[4] > max(1, nf // 50):
                 self._cells_stale = True                 # too many frames left the tube: re-anchor next batch
             total["full27"] += int(info[4]); total["launches"] += int(info[5])
+            span_bits = max(span_bits, int(info[8]))
             total["assign_ns"] += int(info[6]); total["wrap_ns"] += int(info[7])
             if info[3] >= 0:
                 if self.k == nat.POLYHEDRAL:
@@ -539,7 +543,7 @@ class AssignmentEngine:
                 self._reinit_groups(raw_t, lat_t)
                 total["reinits"] += 1
         self.frames_done += F
-        self._check_excursion()
+        self._check_excursion(span_bits)
         self.last_info = total
         return d_result
 
@@ -601,13 +605,13 @@ class AssignmentEngine:
                 d_s = torch.from_numpy(np.ascontiguousarray(frac[::stride][:256])).to(torch.device("cuda", self.device))
                 self._build_dynvor_lists(d_s, lat0)
                 del d_s
-        info = np.zeros(8, dtype=np.int64)
+        info = np.zeros(12, dtype=np.int64)
         nat.check(self.L.sab_assign_host(self.h, frac.ctypes.data, nat.ptr(lattice), 9 if lattice.ndim == 3 else 0,
                                          F, out.ctypes.data, chunk_frames, nat.ptr(info)))
         if info[3] >= 0:
             raise GuardError(f"frame {int(info[3])}: a framework step >= 0.3 fractional units needs the re-initialising "
                              "path; use AssignmentEngine.assign")
-        self._check_excursion()
+        self._check_excursion(int(info[8]))
         if self._cells is not None and info[4] > max(1, F // 50):
             self._cells_stale = True
         self._pending.append((out, True))
