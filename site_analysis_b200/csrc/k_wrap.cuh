@@ -48,17 +48,23 @@ __global__ void k_wrap_totals(const double *__restrict__ frac, int64_t n_frames,
     totals[(size_t)blockIdx.x * m3 + col] = tot;
 }
 
-// 1 thread per column; exclusive scan of the chunk totals starting at the engine's carry.
+// 1 thread per column; exclusive scan of the chunk totals starting at the engine's carry.  The
+// loads are issued 16 at a time (independent) so the walk is not a chain of L2 round trips.
 __global__ void k_wrap_bases(int32_t *__restrict__ totals, int n_chunks, int m3,
                              const int32_t *__restrict__ wraps_carry)
 {
     int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= m3) return;
     int run = wraps_carry[col];
-    for (int c = 0; c < n_chunks; c++) {
-        int t = totals[(size_t)c * m3 + col];
-        totals[(size_t)c * m3 + col] = run;
-        run += t;
+    for (int c0 = 0; c0 < n_chunks; c0 += 16) {
+        int t[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) t[k] = (c0 + k < n_chunks) ? totals[(size_t)(c0 + k) * m3 + col] : 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (c0 + k < n_chunks) totals[(size_t)(c0 + k) * m3 + col] = run;
+            run += t[k];
+        }
     }
 }
 
@@ -104,9 +110,11 @@ __global__ void k_wrap_commit(const double *__restrict__ frac, int64_t n_frames,
     if (veto && (veto[0] != 0ULL || veto[1] != ~0ULL)) return;
     double lo = excursion[2 * col], hi = excursion[2 * col + 1];
     if (n_commit == n_frames) {
+#pragma unroll 8
         for (int c = 0; c < n_chunks; c++) {
-            lo = fmin(lo, chunk_exc[((size_t)c * m3 + col) * 2]);
-            hi = fmax(hi, chunk_exc[((size_t)c * m3 + col) * 2 + 1]);
+            const double2 e2 = *reinterpret_cast<const double2 *>(chunk_exc + ((size_t)c * m3 + col) * 2);
+            lo = fmin(lo, e2.x);
+            hi = fmax(hi, e2.y);
         }
     } else {
         for (int64_t f = 0; f < n_commit; f++) {
