@@ -135,6 +135,9 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
 #define SAB_OPT_POLY_KERNEL 2
 #define SAB_OPT_SEQ_CHUNK 3
 #define SAB_OPT_SEQ_BLOCK 4   /* threads per CTA of the chunk-sequential kernel (tuning) */
+/* 1 (default): tetrahedral tests run an FP32 pre-test first and fall back to the exact float64 test whenever the
+ * point is within the stated error band of a face (results identical either way); 0: float64 only. */
+#define SAB_OPT_FP32_FILTER 5
 int sab_set_option(sab_engine *e, int key, int64_t value);
 
 /* ---- the hot path -------------------------------------------------------------------- */

@@ -12,8 +12,8 @@ g = syn.argyrodite_geometry(2)
 d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
-VARIANTS = [("seq1 chunk=64", {nat.OPT_SEQ_CHUNK: 64}), ("seq1 chunk=32", {nat.OPT_SEQ_CHUNK: 32}), ("seq1 chunk=24", {nat.OPT_SEQ_CHUNK: 24}),
-            ("seq1 chunk=48", {nat.OPT_SEQ_CHUNK: 48})]
+VARIANTS = [("seq1 fp32 pre-test on", {}), ("seq1 fp64 only", {nat.OPT_FP32_FILTER: 0}),
+            ("seq1 fp32 chunk=64", {nat.OPT_SEQ_CHUNK: 64}), ("seq1 fp32 chunk=16", {nat.OPT_SEQ_CHUNK: 16})]
 if len(sys.argv) > 2:
     VARIANTS = VARIANTS[:int(sys.argv[2])]
 for label, opts in VARIANTS:

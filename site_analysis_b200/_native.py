@@ -23,6 +23,7 @@ OPT_SKIP_STEP_CHECK_ONCE = 1
 OPT_POLY_KERNEL = 2
 OPT_SEQ_CHUNK = 3
 OPT_SEQ_BLOCK = 4
+OPT_FP32_FILTER = 5
 
 # every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = [

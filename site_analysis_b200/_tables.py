@@ -185,6 +185,13 @@ def tet_records(slot_shift: np.ndarray, slot_fw: np.ndarray, simplices, kmin: in
     rec = np.zeros((S, 20), dtype=np.uint16)
     rec[:, :12] = off.reshape(S, 12)
     simp = np.stack([np.asarray(f, dtype=np.uint8) for f in simplices]).reshape(S, 12)     # (S, 4 faces x 3 corners)
+    # the FP32 pre-test (csrc/k_polyhedral_cells.cuh) assumes the hull of 4 points: its four faces are
+    # exactly the four vertex triples, in any order and orientation
+    want = {(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)}
+    for s in range(S):
+        got = {tuple(sorted(int(v) for v in simp[s, 3 * j:3 * j + 3])) for j in range(4)}
+        if got != want:
+            raise ValueError(f"site {s}: face list {simp[s].reshape(4, 3).tolist()} is not the hull of a tetrahedron")
     rec[:, 12:18] = np.ascontiguousarray(simp).view(np.uint16)
     return rec
 

@@ -39,6 +39,7 @@ struct SabTetTables {
     const uint16_t *cell_sites; // CSR entries (site list positions, ascending)
     const double *anchor;       // [3 M] anchor of raw - W per framework coordinate
     double delta;               // validity radius of the cell lists
+    int use_f32;                // SAB_OPT_FP32_FILTER: run the FP32 pre-test in front of the exact test
 };
 
 // record offsets are BYTE offsets into `var` (pre-multiplied by 8; var is < 64 KB)
@@ -99,6 +100,90 @@ __device__ __forceinline__ bool sab_tet_contains(const double *__restrict__ var,
         if (!sab_face_accepts(v0, v1, v2, c, p[0], p[1], p[2])) return false;
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 pre-test (the "fp32 fast path re-checked in fp64 within a stated epsilon band").
+//
+// Geometry only: is the image x + k of the atom decisively inside / outside the tetrahedron?
+// It uses the four faces of the simplex in a FIXED vertex order (the verdict does not depend on
+// Qhull's ordering) and single precision with FMA.  Every float coordinate is within
+// delta = 2^-22 of its float64 value (|coordinate| < 4 is checked while staging; the centroid within
+// 2 delta), so with E >= every coordinate difference that enters the test (E < 1 enforced), the
+// computed plane values are within ~60 E^2 delta of their exact values.  A face
+// is DECISIVE only when both |n.(p - v)| and |n.(centroid - v)| exceed T = 256 E^2 delta = 2^-14 E^2
+// -- then the float64
+// reference arithmetic (relative error ~1e-16) has the same signs.  Anything else -- a point within
+// ~1e-4 of a face, a vertex within 1e-5 of a cell face (integer offset u ambiguous), an image choice
+// within 0.05 of a half-integer -- returns MAYBE and the caller runs the exact float64 test.
+// Return: 0 = certainly not contained, 1 = certainly contained, 2 = undecided.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sab_tet_filter32(const float *__restrict__ varf, const uint16_t *__restrict__ rec,
+                                                const double *x)
+{
+    float v[4][3];
+    {
+        const uint2 *r2 = reinterpret_cast<const uint2 *>(rec);
+        uint2 a = __ldg(r2), b = __ldg(r2 + 1), c2 = __ldg(r2 + 2);
+        // record offsets are byte offsets into the float64 table; the float table has the same indexing
+        #define SAB_LDF(o) (*reinterpret_cast<const float *>(reinterpret_cast<const char *>(varf) + ((o) >> 1)))
+        v[0][0] = SAB_LDF(a.x & 0xffff); v[0][1] = SAB_LDF(a.x >> 16); v[0][2] = SAB_LDF(a.y & 0xffff);
+        v[1][0] = SAB_LDF(a.y >> 16);    v[1][1] = SAB_LDF(b.x & 0xffff); v[1][2] = SAB_LDF(b.x >> 16);
+        v[2][0] = SAB_LDF(b.y & 0xffff); v[2][1] = SAB_LDF(b.y >> 16);    v[2][2] = SAB_LDF(c2.x & 0xffff);
+        v[3][0] = SAB_LDF(c2.x >> 16);   v[3][1] = SAB_LDF(c2.y & 0xffff); v[3][2] = SAB_LDF(c2.y >> 16);
+        #undef SAB_LDF
+    }
+    float p[3], c[3], E = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float mn = fminf(fminf(v[0][d], v[1][d]), fminf(v[2][d], v[3][d]));
+        const float mx = fmaxf(fmaxf(v[0][d], v[1][d]), fmaxf(v[2][d], v[3][d]));
+        if (fabsf(mn - rintf(mn)) < 1e-5f) return 2;           // non-negative offset u = ceil(-min) ambiguous in float
+        const float u = (mn < 0.f) ? ceilf(-mn) : 0.f;
+        c[d] = 0.25f * ((v[0][d] + v[1][d]) + (v[2][d] + v[3][d]));
+        const float xf = (float)x[d];
+        const float t = c[d] - xf, k = rintf(t);
+        if (fabsf(t - k) > 0.45f) return 2;                    // image choice not clear-cut (or site not small)
+        const float o = k + u;                                 // == rint(centroid64 + u - x): the only image in reach
+        if (o != 0.f && o != 1.f) return 0;                    // not one of x + {0,1}^3 (tools.py:246-253)
+        p[d] = xf + k;
+        E = fmaxf(E, fmaxf(mx - mn, fmaxf(fabsf(p[d] - mn), fabsf(p[d] - mx))));
+    }
+    E += 1e-6f;
+    if (!(E < 1.0f)) return 2;                                 // error budget below assumes differences < 1
+    const float T = E * E * 6.103515625e-5f;                   // 2^-14 E^2 = 256 E^2 delta
+    bool all_in = true;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {                              // face j = the three vertices other than j
+        const int i0 = (j == 0) ? 1 : 0, i1 = (j <= 1) ? 2 : 1, i2 = (j == 3) ? 2 : 3;
+        const float e0x = v[i0][0] - v[i2][0], e0y = v[i0][1] - v[i2][1], e0z = v[i0][2] - v[i2][2];
+        const float e1x = v[i1][0] - v[i2][0], e1y = v[i1][1] - v[i2][1], e1z = v[i1][2] - v[i2][2];
+        // explicit FMAs (the library is built with -fmad=false for the float64 reference arithmetic)
+        const float n0 = __fmaf_rn(e0y, e1z, -(e0z * e1y));
+        const float n1 = __fmaf_rn(e0z, e1x, -(e0x * e1z));
+        const float n2 = __fmaf_rn(e0x, e1y, -(e0y * e1x));
+        const float cd = __fmaf_rn(n2, c[2] - v[i0][2], __fmaf_rn(n1, c[1] - v[i0][1], n0 * (c[0] - v[i0][0])));
+        const float dt = __fmaf_rn(n2, p[2] - v[i0][2], __fmaf_rn(n1, p[1] - v[i0][1], n0 * (p[0] - v[i0][0])));
+        if (!(fabsf(cd) > T)) return 2;                        // degenerate / needle tetrahedron: exact test decides
+        if (!(fabsf(dt) > T)) { all_in = false; continue; }    // within the band of this face: undecided so far
+        if ((dt > 0.f) != (cd > 0.f)) return 0;                // decisively on the outer side of this face
+    }
+    return all_in ? 1 : 2;
+}
+
+// exact test with the float pre-test in front
+#ifdef SAB_COUNT_F32
+__device__ unsigned long long sab_f32_stats[3];                // verdict histogram (debug builds only)
+#endif
+__device__ __forceinline__ bool sab_tet_contains_f(const double *__restrict__ var, const float *__restrict__ varf,
+                                                   const uint16_t *__restrict__ rec, const double *x, int use_f32)
+{
+    const int f = use_f32 ? sab_tet_filter32(varf, rec, x) : 2;
+#ifdef SAB_COUNT_F32
+    atomicAdd(&sab_f32_stats[f], 1ULL);
+#endif
+    if (f != 2) return f == 1;
+    return sab_tet_contains(var, rec, x);
 }
 
 __global__ void __launch_bounds__(256)

@@ -5,6 +5,12 @@
 #pragma once
 #include "k_polyhedral_seq.cuh"
 #define SAB_SEQ1_THREADS 256
+// SAB_SEQ1_NO_FP32: compile the kernel without the FP32 pre-test (A/B and cross-check builds)
+#ifdef SAB_SEQ1_NO_FP32
+#define SAB_TET_TEST(var, varf, rec, x) sab_tet_contains(var, rec, x)
+#else
+#define SAB_TET_TEST(var, varf, rec, x) sab_tet_contains_f(var, varf, rec, x, C.use_f32)
+#endif
 #ifndef SAB_SEQ1_MINBLOCKS
 #define SAB_SEQ1_MINBLOCKS 4      // 64 registers: 4 CTAs (32 warps) per SM measured fastest (profiles/README.md)
 #endif
@@ -23,7 +29,8 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
     extern __shared__ double sm_seq[];
     double *var = sm_seq;                                        // [nk][3M]
     double *xs = var + (size_t)C.nk * C.m3;                      // [A][3]
-    int *miss_atom = reinterpret_cast<int *>(xs + 3 * (size_t)n_mobile);   // [A]
+    float *varf = reinterpret_cast<float *>(xs + 3 * (size_t)n_mobile);   // [nk][3M] float copy for the FP32 pre-test
+    int *miss_atom = reinterpret_cast<int *>(varf + (size_t)C.nk * C.m3 + ((C.nk * C.m3) & 1));   // [A]
     int *miss_b = miss_atom + n_mobile;                          // [A] first candidate
     int *miss_pref = miss_b + n_mobile;                          // [A+1] exclusive prefix of list lengths
     int *cnt = miss_pref + n_mobile + 1;                         // [A]
@@ -81,7 +88,12 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
                 int W = wrow[i];
 #endif
                 if (fabs((raw - (double)W) - C.anchor[i]) > C.delta) bad = 1;
-                for (int k = 0; k < C.nk; k++) var[k * C.m3 + i] = raw + (double)(C.kmin + k - W);
+                for (int k = 0; k < C.nk; k++) {
+                    const double val = raw + (double)(C.kmin + k - W);       // pbc_utils.py:220, one rounding
+                    var[k * C.m3 + i] = val;
+                    varf[k * C.m3 + i] = (float)val;
+                    if (!(fabs(val) < 3.5)) bad = 1;                         // the FP32 pre-test's error bound assumes |coordinate| < 4
+                }
             }
 #ifdef SAB_SEQ1_PREFETCH
             for (int a = tid; a < n_mobile; a += SAB_SEQ1_THREADS)
@@ -127,7 +139,7 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
 #endif
                 const int la = last[a];
                 slot[a] = -1;
-                if (la >= 0 && sab_tet_contains(var, C.rec + (size_t)la * SAB_TET_REC, x)) {
+                if (la >= 0 && SAB_TET_TEST(var, varf, C.rec + (size_t)la * SAB_TET_REC, x)) {
                     result[(size_t)f * n_mobile + a] = la;
                 } else {
                     int j = atomicAdd(&n_miss, 1);
@@ -162,7 +174,7 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
                 while (hi_j - lo_j > 1) { int mid = (lo_j + hi_j) >> 1; if (miss_pref[mid] <= p) lo_j = mid; else hi_j = mid; }
                 int j = lo_j;
                 int s = __ldg(C.cell_sites + miss_b[j] + (p - miss_pref[j]));
-                if (sab_tet_contains(var, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * miss_atom[j])) {
+                if (SAB_TET_TEST(var, varf, C.rec + (size_t)s * SAB_TET_REC, xs + 3 * miss_atom[j])) {
                     int k = atomicAdd(&cnt[j], 1);
                     if (k < SAB_POLY_KEEP) hits[j * SAB_POLY_KEEP + k] = s;
                 }

@@ -88,6 +88,7 @@ struct sab_engine {
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
     int poly_kernel = 0;                   // SAB_OPT_POLY_KERNEL: 0 auto (chunk-sequential), 1 frame-parallel cells
     int seq_chunk = 32;                    // SAB_OPT_SEQ_CHUNK
+    int fp32_filter = 1;                   // SAB_OPT_FP32_FILTER
     int seq_block = 0;                     // SAB_OPT_SEQ_BLOCK (0 = one warp per 32 mobile atoms)
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
     // exact-pruning tables of the nearest-centre kernel
@@ -328,6 +329,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (!e) return fail(SAB_EINVAL, "sab_set_option: null engine");
     if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
     if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_FP32_FILTER) { e->fp32_filter = value != 0; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
     return fail(SAB_EINVAL, "unknown option %d", key);
@@ -484,6 +486,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
     }
     case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
         size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
+                      sizeof(float) * ((size_t)e->nk * 3 * e->M + 2) +
                       sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
 #ifdef SAB_SEQ1_PREFETCH
         smem += sizeof(int) * (3 * (size_t)e->M + 4) + sizeof(double) * (3 * (size_t)e->M + 3 * (size_t)e->A) + 16;
@@ -492,7 +495,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
         SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
-                       e->d_anchor, e->delta};
+                       e->d_anchor, e->delta, e->fp32_filter};
         int per_sm = 3;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_seq1, SAB_SEQ1_THREADS, smem);
         int resident = std::max(1, per_sm) * e->sm_count;
@@ -514,7 +517,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
         SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
-                       e->d_anchor, e->delta};
+                       e->d_anchor, e->delta, e->fp32_filter};
         // chunk: long enough to amortise the history-free first frame, short enough to fill the GPU
         int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk, F / ((int64_t)e->sm_count * 8)));
         int64_t n_chunks = (F + chunk - 1) / chunk;
@@ -529,7 +532,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                         e->d_legacy_init};
         SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
-                       e->d_anchor, e->delta};
+                       e->d_anchor, e->delta, e->fp32_filter};
         int grid2 = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 16);
         k_polyhedral_assign_cells<<<grid2, block, smem, st>>>(d_frac, F, e->N, e->A, e->d_mobile, e->S, T, C, w.rows,
             e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);

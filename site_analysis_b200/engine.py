@@ -324,7 +324,12 @@ class AssignmentEngine:
         length = float(np.mean(np.linalg.norm(self._lat0, axis=1)))
         G = int(min(64, max(4, round(length / 0.65 / 4) * 4)))
         off, ent = tab.tet_cell_lists(P, delta, G)
-        rec = np.ascontiguousarray(tab.tet_records(self.slot_shift, self.slot_fw, self.simplices, kmin, 3 * M))
+        try:
+            rec = np.ascontiguousarray(tab.tet_records(self.slot_shift, self.slot_fw, self.simplices, kmin, 3 * M))
+        except ValueError:            # face list is not a tetrahedron's hull: the general kernel handles it
+            self._cells, self._cells_stale = None, False
+            nat.check(self.L.sab_set_cell_lists(self.h, 1, 1.0, None, 0, 1, None, None, None))
+            return
         ent = np.ascontiguousarray(ent if len(ent) else np.zeros(1, dtype=np.uint16))
         nat.check(self.L.sab_set_cell_lists(self.h, G, delta * (1.0 - 1e-9), nat.ptr(anchor), kmin, nk, nat.ptr(rec),
                                             nat.ptr(np.ascontiguousarray(off)), nat.ptr(ent)))

@@ -112,7 +112,7 @@ def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
     case = oracle_mod.load_case(name)
     outs = []
     for use_cells, opts in ((True, {}), (True, {nat.OPT_SEQ_CHUNK: 7}), (True, {nat.OPT_POLY_KERNEL: 1}),
-                            (True, {nat.OPT_POLY_KERNEL: 3}), (False, {})):
+                            (True, {nat.OPT_POLY_KERNEL: 3}), (True, {nat.OPT_FP32_FILTER: 0}), (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
         t.site_collection.engine_options = opts          # chunk-sequential (default) / odd chunk / frame-parallel
@@ -220,3 +220,51 @@ def test_c_abi_host_call_matches_device_call(oracle_mod):
     want = np.vectorize(lambda v: pos[int(v)])(case["atoms_traj"])
     assert np.array_equal(a[:140], want) and np.array_equal(a[280:], want)
     assert eng.last_info["launches"] > 0
+
+
+def test_fp32_pretest_never_changes_a_result():
+    """The FP32 pre-test (k_polyhedral_cells.cuh: sab_tet_filter32) may only decide points that are
+    decisively inside / outside; everything within its error band must reach the float64 test.  Mobile
+    ions are put exactly on vertices, edges and faces of the frame's own tetrahedra and 1e-4 .. 1e-16 off
+    them; filter on == filter off == oracle, frame by frame."""
+    import pathlib
+    import sys
+    sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+    import bench
+    from site_analysis_b200 import AssignmentEngine, _native as nat, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    frac, lat = syn.argyrodite_trajectory(g, 260, device="cpu")
+    frac, lat = frac.numpy().copy(), lat.numpy().copy()
+    rng = np.random.default_rng(77)
+    tets = np.asarray(g.tetrahedra)
+    mob = g.mobile_idx
+    n_adv = 0
+    for f in range(20, 260):
+        for a in range(len(mob)):
+            if rng.random() < 0.5:
+                continue
+            v = frac[f, tets[rng.integers(len(tets))]]
+            rel = v - v[0]
+            rel -= np.round(rel)
+            kind = rng.integers(4)
+            w = rng.random(4)
+            if kind == 0:   w[rng.integers(4)] = 0.0                             # on a face
+            elif kind == 1: w[rng.choice(4, 2, replace=False)] = 0.0             # on an edge
+            elif kind == 2: w = np.eye(4)[rng.integers(4)]                       # on a vertex
+            w = w / w.sum()
+            p = v[0] + w @ rel
+            if rng.random() < 0.7:
+                p = p + rng.normal(size=3) * 10.0 ** (-rng.integers(4, 17))
+            frac[f, mob[a]] = p % 1.0
+            n_adv += 1
+    assert n_adv > 10000
+    kw = lambda: syn.polyhedral_engine_kwargs(g, frac[0], lat[0])                # noqa: E731
+    want = bench.oracle_for(g, frac[0], lat[0])().run(frac, lat, positions=True)
+    outs = []
+    for flt in (1, 0):
+        eng = AssignmentEngine("polyhedral", g.n_atoms, mob, device=0, **kw())
+        eng.set_option(nat.OPT_FP32_FILTER, flt)
+        outs.append(eng.assign(frac, lat))
+        assert eng._cells is not None
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], want)
