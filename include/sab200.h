@@ -100,9 +100,11 @@ int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int64_t frames
 /* Exact-pruning tables of the tetrahedral kernel (csrc/k_polyhedral_cells.cuh), built once on
  * the host: a G^3 cell list (CSR) of the tetrahedra that can reach each cell while every
  * framework coordinate stays within `delta` of anchor[3M] (anchor of raw - W); per-site records
- * of shared-memory offsets (uint16[S][56]); kmin/nk = range of slot-shift values.  Frames that
- * leave the delta tube take the exhaustive kernel path, so the tables never decide a result on
- * their own.  anchor == NULL clears the tables. */
+ * of shared-memory offsets (uint16[S][20]: 12 byte offsets 8 * ((shift - kmin) * 3M + 3 fw + d) of the
+ * vertices in slot order, then 12 face-corner bytes in Qhull's order); kmin/nk = range of slot-shift
+ * values.  The lists must be conservative by at least 1e-6 fractional units (the default kernel looks
+ * the cell of an atom up in float32).  Frames that leave the delta tube take the exhaustive kernel
+ * path, so the tables never decide a result on their own.  anchor == NULL clears the tables. */
 int sab_set_cell_lists(sab_engine *e, int G, double delta, const double *anchor, int kmin, int nk,
                        const uint16_t *records, const int32_t *cell_off, const uint16_t *cell_sites);
 
@@ -130,8 +132,10 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
  * against the 0.3 step bound (used right after the host re-initialised a group at that frame,
  * dynamic_voronoi_site_collection.py:188-195). */
 #define SAB_OPT_SKIP_STEP_CHECK_ONCE 1
-/* SAB_OPT_POLY_KERNEL: 0 = chunk-sequential "previous site first" kernel (default when cell lists
- * are set), 1 = frame-parallel cell-list kernel, 3 = experimental cp.async-prefetch variant.  SAB_OPT_SEQ_CHUNK: frames per chunk (default 32). */
+/* SAB_OPT_POLY_KERNEL (tetrahedral sites with cell lists set): 0 = tile kernel, "previous site first" over tiles of
+ * frames with an FP32 pre-test (default); 4 = the per-frame chunk-sequential kernel it replaced; 1 = frame-parallel
+ * cell-list kernel; 3 = experimental prefetch variant.  All give identical results (cross-check twins).
+ * SAB_OPT_SEQ_CHUNK: consecutive frames per CTA chunk (default: automatic). */
 #define SAB_OPT_POLY_KERNEL 2
 #define SAB_OPT_SEQ_CHUNK 3
 #define SAB_OPT_SEQ_BLOCK 4   /* threads per CTA of the chunk-sequential kernel (tuning) */

@@ -12,8 +12,9 @@ g = syn.argyrodite_geometry(2)
 d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
-VARIANTS = [("seq1 fp32 pre-test on", {}), ("seq1 fp64 only", {nat.OPT_FP32_FILTER: 0}),
-            ("seq1 fp32 chunk=64", {nat.OPT_SEQ_CHUNK: 64}), ("seq1 fp32 chunk=16", {nat.OPT_SEQ_CHUNK: 16})]
+VARIANTS = [("tile kernel (default)", {}), ("seq1 (previous default)", {nat.OPT_POLY_KERNEL: 4}),
+            ("tile, 192 threads", {nat.OPT_SEQ_BLOCK: 192}), ("tile, 128 threads", {nat.OPT_SEQ_BLOCK: 128}),
+            ("tile, chunk 64", {nat.OPT_SEQ_CHUNK: 64}), ("tile, fp64 only", {nat.OPT_FP32_FILTER: 0})]
 if len(sys.argv) > 2:
     VARIANTS = VARIANTS[:int(sys.argv[2])]
 for label, opts in VARIANTS:
@@ -28,4 +29,4 @@ for label, opts in VARIANTS:
     r = r.cpu().numpy()
     if ref is None:
         ref = r
-    print(f"{label:32s} assign kernel ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}", flush=True)
+    print(f"{label:32s} assign kernel ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}  fallback frames={e.last_info['full27']}", flush=True)

@@ -19,6 +19,7 @@
 #include "k_polyhedral_cells.cuh"
 #include "k_polyhedral_seq.cuh"
 #include "k_polyhedral_seq1.cuh"
+#include "k_polyhedral_tile.cuh"
 #include "k_resolve.cuh"
 #include "k_resolve_fast.cuh"
 #include "k_spherical.cuh"
@@ -87,7 +88,7 @@ struct sab_engine {
     int64_t launches = 0;
     bool skip_step_check_once = false;     // SAB_OPT_SKIP_STEP_CHECK_ONCE
     int poly_kernel = 0;                   // SAB_OPT_POLY_KERNEL: 0 auto (chunk-sequential), 1 frame-parallel cells
-    int seq_chunk = 32;                    // SAB_OPT_SEQ_CHUNK
+    int seq_chunk = 0;                     // SAB_OPT_SEQ_CHUNK (0 = automatic)
     int fp32_filter = 1;                   // SAB_OPT_FP32_FILTER
     int seq_block = 0;                     // SAB_OPT_SEQ_BLOCK (0 = one warp per 32 mobile atoms)
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // wrap pass start | assign kernel start | assign kernel end
@@ -98,6 +99,8 @@ struct sab_engine {
     // exact-pruning tables of the tetrahedral kernel
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
     uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
+    // tile kernel: compact staging table and float-table site records (derived in sab_set_cell_lists)
+    bool tile_ok = false; int n_used = 0; int2 *d_tile_stage = nullptr; uint16_t *d_tile_rec = nullptr;
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -132,7 +135,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
-                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0};
+                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_stage, e->d_tile_rec};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
@@ -281,6 +284,38 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
     CU(upload(&e->d_cell_off, cell_off, ncell + 1));
     CU(upload(&e->d_cell_sites, cell_sites, (size_t)std::max(cell_off[ncell], 1)));
     e->G = G; e->delta = delta; e->kmin = kmin; e->nk = nk; e->cells_set = true;
+    // ---- tables of the tile kernel (k_polyhedral_tile.cuh): only the (coordinate, shift) pairs in use are staged
+    {
+        const int m3 = 3 * e->M;
+        std::vector<int> slot((size_t)nk * m3, -1);
+        for (int s = 0; s < e->S; s++)
+            for (int v = 0; v < 12; v++) {
+                const int idx = records[(size_t)s * SAB_TET_REC + v] / 8;
+                if (idx >= nk * m3) return fail(SAB_EINVAL, "sab_set_cell_lists: record offset out of range (site %d)", s);
+                slot[idx] = 0;
+            }
+        std::vector<int2> stage;
+        bool ok = m3 < (1 << 20) && e->A <= 4096 && (int64_t)e->N * 3 < INT_MAX && std::abs(kmin) + nk < 512;
+        for (int i = 0; i < m3; i++)
+            for (int k = 0; k < nk; k++)
+                if (slot[(size_t)k * m3 + i] == 0) {
+                    slot[(size_t)k * m3 + i] = (int)stage.size();
+                    stage.push_back(make_int2(e->fw_atoms[i / 3] * 3 + i % 3, i | ((kmin + k + 512) << 20)));
+                    // FP32 pre-test precondition: unwrapped vertex coordinates stay below 2 inside the validity tube
+                    if (!(anchor[i] + (double)(kmin + k) + delta < 2.0 - 1e-6)) ok = false;
+                }
+        if (stage.size() * 4 > 65535) ok = false;
+        e->tile_ok = false;
+        if (ok) {
+            std::vector<uint16_t> rec2((size_t)e->S * 12);
+            for (int s = 0; s < e->S; s++)
+                for (int v = 0; v < 12; v++) rec2[(size_t)s * 12 + v] = (uint16_t)(4 * slot[records[(size_t)s * SAB_TET_REC + v] / 8]);
+            CU(upload(&e->d_tile_stage, stage.data(), stage.size()));
+            CU(upload(&e->d_tile_rec, rec2.data(), rec2.size()));
+            e->n_used = (int)stage.size();
+            e->tile_ok = true;
+        }
+    }
     return SAB_OK;
 }
 
@@ -484,7 +519,36 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
+    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->tile_ok) {
+        // tile kernel: as many frames per tile as keep SAB_TILE_MINBLOCKS CTAs per SM resident
+        const int block = (e->seq_block >= 64 && e->seq_block <= 256 && e->seq_block % 32 == 0) ? e->seq_block : 256;
+        auto smem_for = [&](int t) {
+            return sizeof(float) * (size_t)t * ((size_t)e->n_used + 3 * (size_t)e->A) +
+                   sizeof(int) * ((size_t)SAB_TILE_PAIRS + (size_t)e->A * (3 + SAB_POLY_KEEP));
+        };
+        int tile = SAB_TILE_MAX;
+        while (tile > 1 && smem_for(tile) > (size_t)(220 * 1024 / SAB_TILE_MINBLOCKS)) tile--;
+        if (smem_for(tile) <= 220 * 1024) {
+            const size_t smem = smem_for(tile);
+            CU(cudaFuncSetAttribute(k_polyhedral_assign_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
+                            e->d_legacy_init};
+            SabTileTables C{e->n_used, e->d_tile_stage, e->d_tile_rec, e->G, e->d_cell_off, e->d_cell_sites, e->d_anchor,
+                            e->delta, e->fp32_filter, 3 * e->M};
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_tile, block, smem);
+            const int64_t resident = (int64_t)std::max(1, per_sm) * e->sm_count;
+            // one contiguous chunk per resident CTA (the history-free first frame of a chunk costs a full search)
+            int64_t chunk = e->seq_chunk > 0 ? e->seq_chunk : std::max<int64_t>(tile, (F + resident - 1) / resident);
+            if (e->seq_chunk <= 0) chunk = (chunk + tile - 1) / tile * tile;
+            const int64_t n_chunks = (F + chunk - 1) / chunk;
+            const int grid2 = (int)std::min<int64_t>(n_chunks, resident);
+            k_polyhedral_assign_tile<<<grid2, block, smem, st>>>(d_frac, F, (int)chunk, tile, e->N, e->A, e->d_mobile, e->S, T, C,
+                w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+            break;
+        }
+    }
+    if (e->cells_set && (e->poly_kernel == 0 || e->poly_kernel == 4) && e->A <= SAB_SEQ1_THREADS * SAB_SEQ1_MAX_OWN) {
         size_t smem = sizeof(double) * ((size_t)e->nk * 3 * e->M + 3 * (size_t)e->A) +
                       sizeof(float) * ((size_t)e->nk * 3 * e->M + 2) +
                       sizeof(int) * ((size_t)e->A * (6 + SAB_POLY_KEEP) + 1);
@@ -500,7 +564,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_seq1, SAB_SEQ1_THREADS, smem);
         int resident = std::max(1, per_sm) * e->sm_count;
         // chunk: long enough to amortise the history-free first frame, short enough to balance the CTAs
-        int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk, F / ((int64_t)resident * 4)));
+        int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk > 0 ? e->seq_chunk : 32, F / ((int64_t)resident * 4)));
         int64_t n_chunks = (F + chunk - 1) / chunk;
         int grid2 = (int)std::min<int64_t>(n_chunks, resident);
         k_polyhedral_assign_seq1<<<grid2, SAB_SEQ1_THREADS, smem, st>>>(d_frac, F, chunk, e->N, e->A, e->d_mobile, e->S, T, C,
@@ -519,7 +583,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         SabTetTables C{e->M, 3 * e->M, e->kmin, e->nk, e->d_fw_atoms, e->d_rec, e->G, e->d_cell_off, e->d_cell_sites,
                        e->d_anchor, e->delta, e->fp32_filter};
         // chunk: long enough to amortise the history-free first frame, short enough to fill the GPU
-        int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk, F / ((int64_t)e->sm_count * 8)));
+        int chunk = (int)std::max<int64_t>(8, std::min<int64_t>(e->seq_chunk > 0 ? e->seq_chunk : 32, F / ((int64_t)e->sm_count * 8)));
         int64_t n_chunks = (F + chunk - 1) / chunk;
         int grid2 = (int)std::min<int64_t>(n_chunks, (int64_t)e->sm_count * 8);
         k_polyhedral_assign_seq<<<grid2, block, smem, st>>>(d_frac, F, chunk, e->N, e->A, e->d_mobile, e->S, T, C,

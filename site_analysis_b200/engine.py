@@ -323,7 +323,7 @@ class AssignmentEngine:
             return
         length = float(np.mean(np.linalg.norm(self._lat0, axis=1)))
         G = int(min(64, max(4, round(length / 0.65 / 4) * 4)))
-        off, ent = tab.tet_cell_lists(P, delta, G)
+        off, ent = tab.tet_cell_lists(P, delta, G, eps=2e-6)    # 2e-6: the tile kernel looks cells up in float32
         try:
             rec = np.ascontiguousarray(tab.tet_records(self.slot_shift, self.slot_fw, self.simplices, kmin, 3 * M))
         except ValueError:            # face list is not a tetrahedron's hull: the general kernel handles it

@@ -112,7 +112,8 @@ def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
     case = oracle_mod.load_case(name)
     outs = []
     for use_cells, opts in ((True, {}), (True, {nat.OPT_SEQ_CHUNK: 7}), (True, {nat.OPT_POLY_KERNEL: 1}),
-                            (True, {nat.OPT_POLY_KERNEL: 3}), (True, {nat.OPT_FP32_FILTER: 0}), (False, {})):
+                            (True, {nat.OPT_POLY_KERNEL: 3}), (True, {nat.OPT_POLY_KERNEL: 4}), (True, {nat.OPT_FP32_FILTER: 0}),
+                            (True, {nat.OPT_POLY_KERNEL: 4, nat.OPT_FP32_FILTER: 0}), (True, {nat.OPT_SEQ_CHUNK: 3}), (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
         t.site_collection.engine_options = opts          # chunk-sequential (default) / odd chunk / frame-parallel
@@ -261,10 +262,24 @@ def test_fp32_pretest_never_changes_a_result():
     kw = lambda: syn.polyhedral_engine_kwargs(g, frac[0], lat[0])                # noqa: E731
     want = bench.oracle_for(g, frac[0], lat[0])().run(frac, lat, positions=True)
     outs = []
-    for flt in (1, 0):
+    for kernel, flt in ((0, 1), (0, 0), (4, 1), (4, 0)):          # tile kernel / previous chunk-sequential kernel
         eng = AssignmentEngine("polyhedral", g.n_atoms, mob, device=0, **kw())
+        eng.set_option(nat.OPT_POLY_KERNEL, kernel)
         eng.set_option(nat.OPT_FP32_FILTER, flt)
         outs.append(eng.assign(frac, lat))
         assert eng._cells is not None
-    assert np.array_equal(outs[0], outs[1])
-    assert np.array_equal(outs[0], want)
+    for o in outs:
+        assert np.array_equal(o, want)
+
+
+def test_fast_path_is_the_one_that_runs():
+    """Well-behaved data must not leave the cell lists' validity tube: no frame may take the exhaustive
+    generic path (a silent fallback would still be correct, just ~1000x slower)."""
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    frac, lat = syn.argyrodite_trajectory(g, 2000, device="cuda")
+    eng = AssignmentEngine("polyhedral", g.n_atoms, g.mobile_idx, device=0,
+                           **syn.polyhedral_engine_kwargs(g, frac[0].cpu().numpy(), lat[0].cpu().numpy()))
+    eng.assign_device(frac, lat)
+    assert eng._cells is not None
+    assert eng.last_info["full27"] == 0, eng.last_info
