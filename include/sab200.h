@@ -142,6 +142,7 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
 /* 1 (default): tetrahedral tests run an FP32 pre-test first and fall back to the exact float64 test whenever the
  * point is within the stated error band of a face (results identical either way); 0: float64 only. */
 #define SAB_OPT_FP32_FILTER 5
+#define SAB_OPT_TILE_FRAMES 6 /* frames per tile of the tile kernel, 1..4 (0 = automatic) */
 int sab_set_option(sab_engine *e, int key, int64_t value);
 
 /* ---- the hot path -------------------------------------------------------------------- */

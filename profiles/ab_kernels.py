@@ -13,8 +13,8 @@ d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
 VARIANTS = [("tile kernel (default)", {}), ("seq1 (previous default)", {nat.OPT_POLY_KERNEL: 4}),
-            ("tile, 192 threads", {nat.OPT_SEQ_BLOCK: 192}), ("tile, 128 threads", {nat.OPT_SEQ_BLOCK: 128}),
-            ("tile, chunk 64", {nat.OPT_SEQ_CHUNK: 64}), ("tile, fp64 only", {nat.OPT_FP32_FILTER: 0})]
+            ("tile, 3 frames", {nat.OPT_TILE_FRAMES: 3}), ("tile, 2 frames", {nat.OPT_TILE_FRAMES: 2}),
+            ("tile, chunk 128", {nat.OPT_SEQ_CHUNK: 128}), ("tile, fp64 only", {nat.OPT_FP32_FILTER: 0})]
 if len(sys.argv) > 2:
     VARIANTS = VARIANTS[:int(sys.argv[2])]
 for label, opts in VARIANTS:

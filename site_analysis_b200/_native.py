@@ -24,6 +24,7 @@ OPT_POLY_KERNEL = 2
 OPT_SEQ_CHUNK = 3
 OPT_SEQ_BLOCK = 4
 OPT_FP32_FILTER = 5
+OPT_TILE_FRAMES = 6
 
 # every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = [

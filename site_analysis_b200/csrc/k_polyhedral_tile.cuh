@@ -1,25 +1,30 @@
-// k_polyhedral_tile.cuh -- the production tetrahedral kernel: "previous site first" over TILES of frames.
+// k_polyhedral_tile.cuh -- the production tetrahedral kernel: "previous site first" over TILES of frames,
+// fed by TMA bulk copies.
 //
 // Same contract as k_polyhedral_assign_seq1 (k_polyhedral_seq1.cuh) and bit-identical results, but
-// organised so that a CTA synchronises a few times per TILE of up to 8 frames instead of five times
-// per frame, and so that the common case never touches float64:
+// organised so that (i) global memory is read ONLY by the copy engine: whole frames (and the frames' wrap
+// rows) of the next tile arrive in shared memory through cp.async.bulk + mbarrier while the current tile
+// is processed, (ii) a CTA synchronises a few times per tile instead of five times per frame, and
+// (iii) the common case never touches float64 arithmetic:
 //
 //  * A CTA owns a contiguous range of frames (a "chunk"); thread a owns mobile atom a and carries
 //    `last` = the atom's most recent site as far as it is certain (unknown at the chunk start and
 //    after an atom-frame that several sites contain).
-//  * Per tile the CTA stages, for every (framework coordinate, slot shift) pair that some site uses,
-//    the unwrapped coordinate raw + (double)(shift - W) (pbc_utils.py:220, one float64 rounding)
-//    ROUNDED TO FLOAT, and the wrapped mobile coordinates (atom.py:104) rounded to float, for all
-//    frames of the tile.  The validity tube of the cell lists is checked on the float64 values.
-//  * Round structure (repeat until every owner has finished the tile):
-//      R1  owners walk their frames: FP32 test of `last` (sab_tet_filter32b).  "Certainly inside" is
-//          the reference's answer (it tests the most recent site first and stops at the first hit,
-//          site_collection.py:147-152, polyhedral_site_collection.py:104-107).  Anything else --
-//          outside, undecided, no certain history -- queues the atom-frame's cell-list candidates as
-//          (atom, frame, site) pairs and stops the walk.
+//  * Conversion: from the raw frames in shared memory the CTA writes one ROW per frame:
+//    for every (framework coordinate, slot shift) pair that some site uses the unwrapped coordinate
+//    raw + (double)(shift - W) (pbc_utils.py:220, one float64 rounding) ROUNDED TO FLOAT, followed by the
+//    wrapped mobile coordinates (atom.py:104) rounded to float.  The validity tube of the cell lists
+//    is checked on the float64 values.  Then the raw buffer is free and the next tile's copy is issued.
+//  * Rounds (repeat until every owner has finished the tile):
+//      R1  owners test `last` against all remaining frames of the tile (sab_tet_filter32b, independent
+//          per frame => instruction-level parallelism) and accept the leading run of "certainly inside"
+//          verdicts: that is the reference's answer (it tests the most recent site first and stops at
+//          the first hit, site_collection.py:147-152, polyhedral_site_collection.py:104-107).  The first
+//          frame with any other verdict -- outside, undecided, no certain history -- queues the
+//          atom-frame's cell-list candidates as (atom, frame, site) pairs (warp-cooperative copy).
 //      R2  all threads test the queued pairs: FP32 first, and whenever the point is inside the
 //          stated error band of a face, the exact float64 test with the reference's operation order
-//          (k_polyhedral.cuh: sab_poly_vertices + sab_poly_contains_atom) straight from global memory.
+//          (k_polyhedral.cuh: sab_poly_vertices + sab_poly_contains_atom) from global memory (L2).
 //      R3  owners read the verdict: none -> None, one -> that site (`last` certain again),
 //          several -> spilled list for the priority resolver (`last` unknown); then continue with R1.
 //  * Frames outside the validity tube (and the legacy first-frame rule) take the exhaustive generic
@@ -29,24 +34,27 @@
 #pragma once
 #include "k_polyhedral_seq.cuh"
 
-#define SAB_TILE_MAX 8            // frames per tile (bits of the bad-frame mask / 3-bit frame field of a pair)
-#define SAB_TILE_PAIRS 2048       // queued (atom, frame, site) pairs per round
-#define SAB_TILE_MAX_OWN 16
+#define SAB_TILE_MAX 4            // frames per tile (compile-time unroll bound)
+#define SAB_TILE_PAIRS 1024       // queued (atom, frame, site) pairs per round
+#define SAB_TILE_THREADS 256
 #ifndef SAB_TILE_MINBLOCKS
-#define SAB_TILE_MINBLOCKS 4
+#define SAB_TILE_MINBLOCKS 2
 #endif
 
 struct SabTileTables {
     int n_used;                   // staged (framework coordinate, slot shift) pairs
-    const int2 *stage;            // [n_used] {offset of the coordinate in a frame (3 * atom + d), i | (shift + 512) << 20}
-    const uint16_t *rec;          // [S][12] byte offsets into the staged FLOAT table, vertices in slot order
+    int stride;                   // floats per row: n_used + 3 A, rounded up to a multiple of 4
+    int m3;                       // framework coordinates
+    const int32_t *col_goff;      // [m3] position of the coordinate inside a frame: 3 * atom + d
+    const int32_t *var_off;       // [m3 + 1] CSR over the variants of a coordinate
+    const int2 *vars;             // {slot shift, row position j}
+    const uint16_t *rec;          // [S][12] byte offsets into a row, vertices in slot order
     int G;
     const int32_t *cell_off;      // [G^3 + 1]
     const uint16_t *cell_sites;   // CSR entries, ascending per cell; lists conservative by >= 1e-6 (float cell lookup)
-    const double *anchor;         // [3 M]
+    const double *anchor;         // [m3]
     double delta;
     int use_f32;
-    int m3;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -74,13 +82,19 @@ struct SabTileTables {
 // one half the choice of k is not clear-cut in float: undecided.
 // Return: 0 = certainly not contained, 1 = certainly contained, 2 = undecided.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sab_tet_filter32b(const float *__restrict__ tab, const uint16_t *__restrict__ rec,
+struct SabTetRec { uint2 q0, q1, q2; };                     // 12 uint16 byte offsets into a staged row
+__device__ __forceinline__ SabTetRec sab_tet_rec(const uint16_t *__restrict__ rec)
+{
+    const uint2 *r2 = reinterpret_cast<const uint2 *>(rec);
+    SabTetRec r; r.q0 = __ldg(r2); r.q1 = __ldg(r2 + 1); r.q2 = __ldg(r2 + 2);
+    return r;
+}
+__device__ __forceinline__ int sab_tet_filter32b(const float *__restrict__ tab, const SabTetRec &R,
                                                  const float *__restrict__ xf)
 {
     float a[3], B[3], C[3], D[3], P[3];
     {
-        const uint2 *r2 = reinterpret_cast<const uint2 *>(rec);      // 24 bytes
-        const uint2 q0 = __ldg(r2), q1 = __ldg(r2 + 1), q2 = __ldg(r2 + 2);
+        const uint2 q0 = R.q0, q1 = R.q1, q2 = R.q2;
         #define SAB_LDT(o) (*reinterpret_cast<const float *>(reinterpret_cast<const char *>(tab) + (o)))
         a[0] = SAB_LDT(q0.x & 0xffff); a[1] = SAB_LDT(q0.x >> 16); a[2] = SAB_LDT(q0.y & 0xffff);
         B[0] = SAB_LDT(q0.y >> 16);    B[1] = SAB_LDT(q1.x & 0xffff); B[2] = SAB_LDT(q1.x >> 16);
@@ -145,9 +159,20 @@ __device__ __forceinline__ int sab_cell_of_f(const float *x, int G)
     return (c0 * G + c1) * G + c2;
 }
 
-// write the result of one atom-frame whose containing sites were counted (c) and partly kept (h);
-// `last` follows the certainty rules of the file header.  Lists longer than KEEP are rescanned.
-__device__ __noinline__ int sab_tile_finish(int c, int *h, int &last, const float *__restrict__ tab, const float *xf,
+// full test of one (site, atom-frame): FP32 first, float64 when undecided
+__device__ __forceinline__ bool sab_tile_test(const float *__restrict__ row, const float *__restrict__ xk, int s,
+                                              const double *__restrict__ frame, const int32_t *__restrict__ wrow, int atom,
+                                              const SabPolyTables &T, const SabTileTables &C)
+{
+    int v = 2;
+    if (C.use_f32) v = sab_tet_filter32b(row, sab_tet_rec(C.rec + (size_t)s * 12), xk);
+    if (v == 2) v = sab_tet_exact_global(frame, wrow, T, s, atom);
+    return v != 0;
+}
+
+// result of one atom-frame whose containing sites were counted (c) and partly kept (h); `last` follows
+// the certainty rules of the file header.  Lists longer than KEEP are rescanned in ascending order.
+__device__ __noinline__ int sab_tile_finish(int c, int *h, int &last, const float *__restrict__ row, const float *xk,
                                             const double *__restrict__ frame, const int32_t *__restrict__ wrow, int atom,
                                             const SabPolyTables &T, const SabTileTables &C, int32_t *__restrict__ spill,
                                             long long spill_capacity, unsigned long long *__restrict__ counters)
@@ -163,155 +188,231 @@ __device__ __noinline__ int sab_tile_finish(int c, int *h, int &last, const floa
         for (int i = 1; i < c; i++) { int v = h[i], j = i; while (j > 0 && h[j - 1] > v) { h[j] = h[j - 1]; j--; } h[j] = v; }
         for (int i = 0; i < c; i++) spill[off + 1 + i] = h[i];
     } else {                                          // atom on a vertex / edge shared by many sites: rescan
-        const int cell = sab_cell_of_f(xf, C.G);
+        const int cell = sab_cell_of_f(xk, C.G);
         int k = 0;
         for (int i = C.cell_off[cell]; i < C.cell_off[cell + 1] && k < c; i++) {
             const int s = C.cell_sites[i];
-            int v = C.use_f32 ? sab_tet_filter32b(tab, C.rec + (size_t)s * 12, xf) : 2;
-            if (v == 2) v = sab_tet_exact_global(frame, wrow, T, s, atom);
-            if (v) spill[off + 1 + k++] = s;
+            if (sab_tile_test(row, xk, s, frame, wrow, atom, T, C)) spill[off + 1 + k++] = s;
         }
     }
     return SAB_AMBIGUOUS_BASE - (int)off;
 }
 
-__global__ void __launch_bounds__(256, SAB_TILE_MINBLOCKS)
+// ---- mbarrier / bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP) -------------------------------------
+__device__ __forceinline__ void sab_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sab_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sab_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sab_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(SAB_TILE_THREADS, SAB_TILE_MINBLOCKS)
 k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int chunk, int tile, int n_atoms, int n_mobile,
                          const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabTileTables C,
                          const int32_t *__restrict__ wrows, int64_t legacy_init_frame,
                          int32_t *__restrict__ result, int32_t *__restrict__ spill, long long spill_capacity,
                          unsigned long long *__restrict__ counters, unsigned long long *__restrict__ n_fallback)
 {
-    extern __shared__ float sm_tile[];
-    float *tab = sm_tile;                                         // [tile][n_used]
-    float *xf = tab + (size_t)tile * C.n_used;                    // [tile][A][3]
-    int *pairs = reinterpret_cast<int *>(xf + (size_t)tile * 3 * n_mobile);     // [SAB_TILE_PAIRS]
-    int *cnt = pairs + SAB_TILE_PAIRS;                            // [A] hits of the pending atom-frame
-    int *hits = cnt + n_mobile;                                   // [A][KEEP]
-    int *last = hits + (size_t)n_mobile * SAB_POLY_KEEP;          // [A]
-    int *pos = last + n_mobile;                                   // [A] next frame of the tile; bit 8 = verdict pending
+    extern __shared__ __align__(128) unsigned char sm_tile[];
+    const int n3 = 3 * n_atoms;
+    double *rawd = reinterpret_cast<double *>(sm_tile);                         // [tile][3 N] raw frames (copy engine)
+    int32_t *wbuf = reinterpret_cast<int32_t *>(rawd + (size_t)tile * n3);      // [tile][m3] wrap rows (copy engine)
+    float *tab = reinterpret_cast<float *>(wbuf + (((size_t)tile * C.m3 + 3) & ~(size_t)3));   // [tile][stride] rows
+    int *pairs = reinterpret_cast<int *>(tab + (size_t)tile * C.stride);        // [SAB_TILE_PAIRS]
+    int *cnt = pairs + SAB_TILE_PAIRS;                                          // [A] hits of the pending atom-frame
+    int *hits = cnt + n_mobile;                                                 // [A][KEEP]
+    int *last = hits + (size_t)n_mobile * SAB_POLY_KEEP;                        // [A]
+    int *pos = last + n_mobile;                                                 // [A] next frame of the tile; bit 8 = verdict pending
+    __shared__ __align__(8) uint64_t mbar;
     __shared__ int n_pairs[2];
     __shared__ int bad_mask;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
+    unsigned phase = 0;
+    if (tid == 0) { sab_mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+
+    // the copy engine needs 16-byte aligned addresses and sizes; a tile that does not qualify is copied by the threads
+    auto tma_ok = [&](int64_t f0, int tn) {
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(frac + (size_t)f0 * n3), a1 = reinterpret_cast<uintptr_t>(wrows + (size_t)f0 * C.m3);
+        return ((a0 | a1 | reinterpret_cast<uintptr_t>(wbuf)) & 15) == 0 && (((size_t)tn * n3 * 8) & 15) == 0 &&
+               (((size_t)tn * C.m3 * 4) & 15) == 0;
+    };
+    auto issue = [&](int64_t f0, int tn) {           // thread 0 only
+        const unsigned b0 = (unsigned)((size_t)tn * n3 * 8), b1 = (unsigned)((size_t)tn * C.m3 * 4);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        sab_mbar_expect_tx(&mbar, b0 + b1);
+        sab_bulk_g2s(rawd, frac + (size_t)f0 * n3, b0, &mbar);
+        sab_bulk_g2s(wbuf, wrows + (size_t)f0 * C.m3, b1, &mbar);
+    };
+
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const int64_t c0 = ch * chunk, c1 = min(c0 + (int64_t)chunk, n_frames);
         for (int a = tid; a < n_mobile; a += nthr) last[a] = -1;              // owner-private
+        {
+            const int tn0 = (int)min((int64_t)tile, c1 - c0);
+            if (tid == 0 && tma_ok(c0, tn0)) issue(c0, tn0);                 // buffers are free: see the barrier after conversion
+        }
         for (int64_t f0 = c0; f0 < c1; f0 += tile) {
             const int tn = (int)min((int64_t)tile, c1 - f0);
-            // every thread is past the final barrier A of the previous tile here, i.e. nobody still reads
-            // the staged tables, bad_mask or the queue counters
+            const double *gframe = frac + (size_t)f0 * n3;
+            const int32_t *gwrow = wrows + (size_t)f0 * C.m3;
+            int32_t *res = result + (size_t)f0 * n_mobile;
+            // every thread is past the final barrier A of the previous tile: nobody reads rows, bad_mask or counters
             if (tid == 0) { bad_mask = 0; n_pairs[0] = 0; n_pairs[1] = 0; }
+            if (tma_ok(f0, tn)) {
+                sab_mbar_wait(&mbar, phase);
+                phase ^= 1;
+            } else {
+                for (int q = tid; q < tn * n3; q += nthr) rawd[q] = gframe[q];
+                for (int q = tid; q < tn * C.m3; q += nthr) wbuf[q] = gwrow[q];
+            }
             __syncthreads();
-            // ---- stage the tile ---------------------------------------------------------------------
+            // ---- conversion: raw frames -> float rows -------------------------------------------------
             {
                 int bad = 0;
-                for (int j = tid; j < C.n_used; j += nthr) {
-                    const int2 sj = __ldg(C.stage + j);
-                    const int i = sj.y & 0xfffff, sh = (sj.y >> 20) - 512;
+                for (int i = tid; i < C.m3; i += nthr) {
+                    const int goff = __ldg(C.col_goff + i), vb = __ldg(C.var_off + i), ve = __ldg(C.var_off + i + 1);
                     const double anc = __ldg(C.anchor + i);
-                    for (int k0 = 0; k0 < tn; k0 += 4) {
-                        double r[4]; int w[4];
+                    double r[SAB_TILE_MAX]; int w[SAB_TILE_MAX];
 #pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (k0 + u < tn) {
-                                r[u] = frac[((size_t)(f0 + k0 + u) * n_atoms) * 3 + sj.x];
-                                w[u] = wrows[(size_t)(f0 + k0 + u) * C.m3 + i];
-                            }
+                    for (int k = 0; k < SAB_TILE_MAX; k++)
+                        if (k < tn) {
+                            r[k] = rawd[k * n3 + goff]; w[k] = wbuf[k * C.m3 + i];
+                            if (fabs((r[k] - (double)w[k]) - anc) > C.delta) bad |= 1 << k;
+                        }
+                    for (int v = vb; v < ve; v++) {
+                        const int2 e = __ldg(C.vars + v);
 #pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (k0 + u < tn) {
-                                const double val = r[u] + (double)(sh - w[u]);          // pbc_utils.py:220, one rounding
-                                if (fabs((r[u] - (double)w[u]) - anc) > C.delta || !(fabs(val) < 3.5)) bad |= 1 << (k0 + u);
-                                tab[(size_t)(k0 + u) * C.n_used + j] = (float)val;
+                        for (int k = 0; k < SAB_TILE_MAX; k++)
+                            if (k < tn) {
+                                const double val = r[k] + (double)(e.x - w[k]);            // pbc_utils.py:220, one rounding
+                                if (!(fabs(val) < 3.5)) bad |= 1 << k;                      // FP32 error budget assumes |coordinate| < 4
+                                tab[k * C.stride + e.y] = (float)val;
                             }
                     }
                 }
-                for (int q = tid; q < tn * n_mobile; q += nthr) {
-                    const int k = q / n_mobile, a = q - k * n_mobile;
-                    const double *src = frac + ((size_t)(f0 + k) * n_atoms + mobile[a]) * 3;
+                for (int q = tid; q < 3 * n_mobile; q += nthr) {
+                    const int a = q / 3, goff = __ldg(mobile + a) * 3 + (q - 3 * a);
 #pragma unroll
-                    for (int d = 0; d < 3; d++) xf[(size_t)q * 3 + d] = (float)sab_pymod1(src[d]);        // atom.py:104
+                    for (int k = 0; k < SAB_TILE_MAX; k++)
+                        if (k < tn) tab[k * C.stride + C.n_used + q] = (float)sab_pymod1(rawd[k * n3 + goff]);   // atom.py:104
                 }
                 if (T.legacy_init && legacy_init_frame >= f0 && legacy_init_frame < f0 + tn) bad |= 1 << (int)(legacy_init_frame - f0);
                 if (bad) atomicOr(&bad_mask, bad);
             }
             for (int a = tid; a < n_mobile; a += nthr) pos[a] = 0;
-            __syncthreads();
-            if (tid == 0 && bad_mask) atomicAdd(n_fallback, (unsigned long long)__popc(bad_mask));
+            __syncthreads();                                     // rows complete; raw buffers consumed
+            if (tid == 0) {
+                if (f0 + tile < c1) {                            // next tile of this chunk: lands during the rounds
+                    const int tn2 = (int)min((int64_t)tile, c1 - (f0 + tile));
+                    if (tma_ok(f0 + tile, tn2)) issue(f0 + tile, tn2);
+                }
+                if (bad_mask) atomicAdd(n_fallback, (unsigned long long)__popc(bad_mask));
+            }
+            const int badm = bad_mask;
             // ---- rounds -----------------------------------------------------------------------------
             for (int round = 0;; round++) {
                 int *np = &n_pairs[round & 1];
                 int pending = 0;
-#pragma unroll 1
-                for (int a = tid; a < n_mobile; a += nthr) {
-                    int k = pos[a];
-                    int la = last[a];
-                    if (k & 256) {                               // R3: verdict of the queued atom-frame
-                        k &= 255;
-                        const int out = sab_tile_finish(cnt[a], hits + a * SAB_POLY_KEEP, la, tab + (size_t)k * C.n_used,
-                                                        xf + ((size_t)k * n_mobile + a) * 3,
-                                                        frac + (size_t)(f0 + k) * n_atoms * 3, wrows + (size_t)(f0 + k) * C.m3,
-                                                        mobile[a], T, C, spill, spill_capacity, counters);
-                        result[(size_t)(f0 + k) * n_mobile + a] = out;
-                        k++;
+                for (int a0 = tid - lane; a0 < n_mobile; a0 += nthr) {       // warp-uniform trip count
+                    const int a = a0 + lane;
+                    int m_len = 0, m_b = 0, m_off = 0, m_tag = 0;            // candidate list to queue (this lane)
+                    if (a < n_mobile) {
+                        int k = pos[a], la = last[a];
+                        const float *xa = tab + C.n_used + 3 * a;
+                        if (k & 256) {                               // R3: verdict of the queued atom-frame
+                            k &= 255;
+                            const int out = sab_tile_finish(cnt[a], hits + a * SAB_POLY_KEEP, la, tab + k * C.stride, xa + k * C.stride,
+                                                            gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, mobile[a], T, C,
+                                                            spill, spill_capacity, counters);
+                            res[k * n_mobile + a] = out;
+                            k++;
+                        }
+                        while (k < tn) {                             // R1
+                            if (la >= 0 && C.use_f32) {
+                                const SabTetRec R = sab_tet_rec(C.rec + (size_t)la * 12);
+                                int ok = 0;
+#pragma unroll
+                                for (int kk = 0; kk < SAB_TILE_MAX; kk++)
+                                    if (kk >= k && kk < tn && !((badm >> kk) & 1))
+                                        ok |= (sab_tet_filter32b(tab + kk * C.stride, R, xa + kk * C.stride) == 1) << kk;
+                                while (k < tn && ((ok >> k) & 1)) { res[k * n_mobile + a] = la; k++; }
+                                if (k == tn) break;
+                            }
+                            if ((badm >> k) & 1) {                   // outside the validity tube: generic path
+                                int c = 0;
+                                const int out = sab_exhaustive_atom(gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, f0 + k,
+                                                                    legacy_init_frame, mobile[a], n_sites, T, spill, spill_capacity,
+                                                                    counters, &c);
+                                if (c == 1) la = out; else if (c > 1) la = -1;
+                                res[k * n_mobile + a] = out;
+                                k++;
+                                continue;
+                            }
+                            // full search over the cell list of the atom-frame
+                            const float *xk = xa + k * C.stride;
+                            const int cell = sab_cell_of_f(xk, C.G);
+                            const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
+                            if (len == 0) { res[k * n_mobile + a] = SAB_NONE; k++; continue; }
+                            const int off = atomicAdd(np, len);
+                            if (off + len <= SAB_TILE_PAIRS) {
+                                m_len = len; m_b = b; m_off = off; m_tag = (a << 19) | (k << 16);
+                                cnt[a] = 0;
+                                k |= 256; pending = 1;
+                                break;
+                            }
+                            for (int i = off; i < SAB_TILE_PAIRS; i++) pairs[i] = -1;      // queue full: test the list here
+                            int c = 0, h[SAB_POLY_KEEP];
+                            for (int i = 0; i < len; i++) {
+                                const int s = __ldg(C.cell_sites + b + i);
+                                if (sab_tile_test(tab + k * C.stride, xk, s, gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, mobile[a], T, C)) {
+                                    if (c < SAB_POLY_KEEP) h[c] = s;
+                                    c++;
+                                }
+                            }
+                            const int out = sab_tile_finish(c, h, la, tab + k * C.stride, xk, gframe + (size_t)k * n3,
+                                                            gwrow + (size_t)k * C.m3, mobile[a], T, C, spill, spill_capacity, counters);
+                            res[k * n_mobile + a] = out;
+                            k++;
+                        }
+                        pos[a] = k;
+                        last[a] = la;
                     }
-#pragma unroll 1
-                    for (; k < tn; k++) {                        // R1: walk the frames of the tile
-                        const float *tk = tab + (size_t)k * C.n_used;
-                        const float *xk = xf + ((size_t)k * n_mobile + a) * 3;
-                        if ((bad_mask >> k) & 1) {               // outside the validity tube: generic path
-                            int c = 0;
-                            const int out = sab_exhaustive_atom(frac + (size_t)(f0 + k) * n_atoms * 3, wrows + (size_t)(f0 + k) * C.m3,
-                                                                f0 + k, legacy_init_frame, mobile[a], n_sites, T, spill,
-                                                                spill_capacity, counters, &c);
-                            if (c == 1) la = out; else if (c > 1) la = -1;
-                            result[(size_t)(f0 + k) * n_mobile + a] = out;
-                            continue;
-                        }
-                        if (la >= 0 && C.use_f32 && sab_tet_filter32b(tk, C.rec + (size_t)la * 12, xk) == 1) {
-                            result[(size_t)(f0 + k) * n_mobile + a] = la;
-                            continue;
-                        }
-                        // full search over the cell list of the atom
-                        const int cell = sab_cell_of_f(xk, C.G);
-                        const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
-                        const int off = len > 0 ? atomicAdd(np, len) : 0;
-                        if (off + len <= SAB_TILE_PAIRS) {
-                            for (int i = 0; i < len; i++) pairs[off + i] = (a << 19) | (k << 16) | (int)__ldg(C.cell_sites + b + i);
-                            cnt[a] = 0;
-                            if (len > 0) { k |= 256; pending = 1; break; }
-                            result[(size_t)(f0 + k) * n_mobile + a] = SAB_NONE;          // empty cell: no site
-                            continue;
-                        }
-                        for (int i = off; i < SAB_TILE_PAIRS; i++) pairs[i] = -1;       // queue full: test the list here
-                        int c = 0, h[SAB_POLY_KEEP];
-                        for (int i = 0; i < len; i++) {
-                            const int s = __ldg(C.cell_sites + b + i);
-                            int v = C.use_f32 ? sab_tet_filter32b(tk, C.rec + (size_t)s * 12, xk) : 2;
-                            if (v == 2) v = sab_tet_exact_global(frac + (size_t)(f0 + k) * n_atoms * 3, wrows + (size_t)(f0 + k) * C.m3, T, s, mobile[a]);
-                            if (v) { if (c < SAB_POLY_KEEP) h[c] = s; c++; }
-                        }
-                        const int out = sab_tile_finish(c, h, la, tk, xk, frac + (size_t)(f0 + k) * n_atoms * 3,
-                                                        wrows + (size_t)(f0 + k) * C.m3, mobile[a], T, C, spill, spill_capacity, counters);
-                        result[(size_t)(f0 + k) * n_mobile + a] = out;
+                    // warp-cooperative copy of the queued candidate lists
+                    unsigned m = __ballot_sync(0xffffffffu, m_len > 0);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int len = __shfl_sync(0xffffffffu, m_len, src), b = __shfl_sync(0xffffffffu, m_b, src);
+                        const int off = __shfl_sync(0xffffffffu, m_off, src), tag = __shfl_sync(0xffffffffu, m_tag, src);
+                        for (int i = lane; i < len; i += 32) pairs[off + i] = tag | (int)__ldg(C.cell_sites + b + i);
                     }
-                    pos[a] = k;
-                    last[a] = la;
                 }
                 if (__syncthreads_or(pending) == 0) break;       // barrier A: queue complete / tile finished
                 const int total = min(*np, SAB_TILE_PAIRS);
                 if (tid == 0) n_pairs[(round + 1) & 1] = 0;
                 // ---- R2: queued pairs over all threads ---------------------------------------------
-#pragma unroll 1
                 for (int p = tid; p < total; p += nthr) {
                     const int e = pairs[p];
                     if (e < 0) continue;
                     const int a = e >> 19, k = (e >> 16) & 7, s = e & 0xffff;
-                    int v = C.use_f32 ? sab_tet_filter32b(tab + (size_t)k * C.n_used, C.rec + (size_t)s * 12,
-                                                          xf + ((size_t)k * n_mobile + a) * 3) : 2;
-                    if (v == 2) v = sab_tet_exact_global(frac + (size_t)(f0 + k) * n_atoms * 3, wrows + (size_t)(f0 + k) * C.m3, T, s, mobile[a]);
-                    if (v) {
+                    if (sab_tile_test(tab + k * C.stride, tab + k * C.stride + C.n_used + 3 * a, s, gframe + (size_t)k * n3,
+                                      gwrow + (size_t)k * C.m3, mobile[a], T, C)) {
                         const int c = atomicAdd(&cnt[a], 1);
                         if (c < SAB_POLY_KEEP) hits[a * SAB_POLY_KEEP + c] = s;
                     }
@@ -319,5 +420,6 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
                 __syncthreads();                                 // barrier B: verdicts complete
             }
         }
+        __syncthreads();                                         // chunk done: raw buffers idle before the next chunk's copy
     }
 }

@@ -100,7 +100,8 @@ struct sab_engine {
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
     uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
     // tile kernel: compact staging table and float-table site records (derived in sab_set_cell_lists)
-    bool tile_ok = false; int n_used = 0; int2 *d_tile_stage = nullptr; uint16_t *d_tile_rec = nullptr;
+    bool tile_ok = false; int n_used = 0; int2 *d_tile_vars = nullptr; uint16_t *d_tile_rec = nullptr;
+    int32_t *d_tile_goff = nullptr, *d_tile_voff = nullptr; int tile_frames = 0;   // SAB_OPT_TILE_FRAMES (0 = automatic)
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -135,7 +136,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
-                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_stage, e->d_tile_rec};
+                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec, e->d_tile_goff, e->d_tile_voff};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
@@ -294,25 +295,32 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
                 if (idx >= nk * m3) return fail(SAB_EINVAL, "sab_set_cell_lists: record offset out of range (site %d)", s);
                 slot[idx] = 0;
             }
-        std::vector<int2> stage;
-        bool ok = m3 < (1 << 20) && e->A <= 4096 && (int64_t)e->N * 3 < INT_MAX && std::abs(kmin) + nk < 512;
-        for (int i = 0; i < m3; i++)
+        std::vector<int2> vars;
+        std::vector<int32_t> goff(m3), voff(m3 + 1, 0);
+        bool ok = e->A <= 4096 && (int64_t)e->N * 3 * SAB_TILE_MAX < INT_MAX;
+        for (int i = 0; i < m3; i++) {
+            goff[i] = e->fw_atoms[i / 3] * 3 + i % 3;
             for (int k = 0; k < nk; k++)
                 if (slot[(size_t)k * m3 + i] == 0) {
-                    slot[(size_t)k * m3 + i] = (int)stage.size();
-                    stage.push_back(make_int2(e->fw_atoms[i / 3] * 3 + i % 3, i | ((kmin + k + 512) << 20)));
+                    slot[(size_t)k * m3 + i] = (int)vars.size();
+                    vars.push_back(make_int2(kmin + k, (int)vars.size()));
                     // FP32 pre-test precondition: unwrapped vertex coordinates stay below 2 inside the validity tube
                     if (!(anchor[i] + (double)(kmin + k) + delta < 2.0 - 1e-6)) ok = false;
                 }
-        if (stage.size() * 4 > 65535) ok = false;
+            voff[i + 1] = (int32_t)vars.size();
+        }
+        const size_t stride = (vars.size() + 3 * (size_t)e->A + 3) & ~(size_t)3;
+        if (stride * 4 > 65535 || vars.empty()) ok = false;          // 16-bit byte offsets into a row
         e->tile_ok = false;
         if (ok) {
             std::vector<uint16_t> rec2((size_t)e->S * 12);
             for (int s = 0; s < e->S; s++)
                 for (int v = 0; v < 12; v++) rec2[(size_t)s * 12 + v] = (uint16_t)(4 * slot[records[(size_t)s * SAB_TET_REC + v] / 8]);
-            CU(upload(&e->d_tile_stage, stage.data(), stage.size()));
+            CU(upload(&e->d_tile_vars, vars.data(), vars.size()));
             CU(upload(&e->d_tile_rec, rec2.data(), rec2.size()));
-            e->n_used = (int)stage.size();
+            CU(upload(&e->d_tile_goff, goff.data(), goff.size()));
+            CU(upload(&e->d_tile_voff, voff.data(), voff.size()));
+            e->n_used = (int)vars.size();
             e->tile_ok = true;
         }
     }
@@ -364,6 +372,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (!e) return fail(SAB_EINVAL, "sab_set_option: null engine");
     if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
     if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_TILE_FRAMES) { e->tile_frames = (int)value; return SAB_OK; }
     if (key == SAB_OPT_FP32_FILTER) { e->fp32_filter = value != 0; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
@@ -520,21 +529,23 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         break;
     }
     case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->tile_ok) {
-        // tile kernel: as many frames per tile as keep SAB_TILE_MINBLOCKS CTAs per SM resident
-        const int block = (e->seq_block >= 64 && e->seq_block <= 256 && e->seq_block % 32 == 0) ? e->seq_block : 256;
+        // tile kernel: frames per tile chosen so that SAB_TILE_MINBLOCKS CTAs stay resident per SM
+        const int block = SAB_TILE_THREADS;
+        const size_t stride = ((size_t)e->n_used + 3 * (size_t)e->A + 3) & ~(size_t)3;
         auto smem_for = [&](int t) {
-            return sizeof(float) * (size_t)t * ((size_t)e->n_used + 3 * (size_t)e->A) +
-                   sizeof(int) * ((size_t)SAB_TILE_PAIRS + (size_t)e->A * (3 + SAB_POLY_KEEP));
+            return sizeof(double) * (size_t)t * 3 * e->N + sizeof(int32_t) * (((size_t)t * 3 * e->M + 3) & ~(size_t)3) +
+                   sizeof(float) * (size_t)t * stride + sizeof(int) * ((size_t)SAB_TILE_PAIRS + (size_t)e->A * (3 + SAB_POLY_KEEP)) + 128;
         };
-        int tile = SAB_TILE_MAX;
-        while (tile > 1 && smem_for(tile) > (size_t)(220 * 1024 / SAB_TILE_MINBLOCKS)) tile--;
-        if (smem_for(tile) <= 220 * 1024) {
+        int tile = (e->tile_frames >= 1 && e->tile_frames <= SAB_TILE_MAX) ? e->tile_frames : SAB_TILE_MAX;
+        if (e->tile_frames <= 0)
+            while (tile > 1 && smem_for(tile) > (size_t)(226 * 1024 / SAB_TILE_MINBLOCKS)) tile--;
+        if (smem_for(tile) <= 226 * 1024) {
             const size_t smem = smem_for(tile);
             CU(cudaFuncSetAttribute(k_polyhedral_assign_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                             e->d_legacy_init};
-            SabTileTables C{e->n_used, e->d_tile_stage, e->d_tile_rec, e->G, e->d_cell_off, e->d_cell_sites, e->d_anchor,
-                            e->delta, e->fp32_filter, 3 * e->M};
+            SabTileTables C{e->n_used, (int)stride, 3 * e->M, e->d_tile_goff, e->d_tile_voff, e->d_tile_vars, e->d_tile_rec, e->G,
+                            e->d_cell_off, e->d_cell_sites, e->d_anchor, e->delta, e->fp32_filter};
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_tile, block, smem);
             const int64_t resident = (int64_t)std::max(1, per_sm) * e->sm_count;
