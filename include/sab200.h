@@ -168,7 +168,8 @@ int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_frames, void 
  *   [5] kernels launched, [6] device time of the assignment kernel in ns, [7] device time of
  *   the PBC wrap-scan kernels in ns (both from CUDA events on `stream`), [8] bit pattern of the
  *   largest excursion span max(raw - W) - min(raw - W) over all framework coordinates so far (double;
- *   guard of the scan formulation), [9..11] reserved.
+ *   guard of the scan formulation), [9] atom-frames that the float32 pre-test of the
+ *   tetrahedral kernel could not decide and that were settled by its exact float64 pass, [10..11] reserved.
  * When info[3] < 0 the PBC state advances to the end of the batch.  When info[3] = t >= 0 the
  * results of frames < t are valid, the PBC state is left untouched, and the caller commits
  * the valid prefix with sab_commit_pbc(..., n_commit = t) (same workspace, unmodified). */

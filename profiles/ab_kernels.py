@@ -29,4 +29,4 @@ for label, opts in VARIANTS:
     r = r.cpu().numpy()
     if ref is None:
         ref = r
-    print(f"{label:32s} assign kernel ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}  fallback frames={e.last_info['full27']}", flush=True)
+    print(f"{label:32s} assign kernel ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}  fallback frames={e.last_info['full27']} deferred={e.last_info.get('deferred')}", flush=True)

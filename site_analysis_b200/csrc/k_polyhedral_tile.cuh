@@ -1,60 +1,60 @@
 // k_polyhedral_tile.cuh -- the production tetrahedral kernel: "previous site first" over TILES of frames,
-// fed by TMA bulk copies.
+// fed by TMA bulk copies, float32 in the common case, float64 only where float32 cannot decide.
 //
-// Same contract as k_polyhedral_assign_seq1 (k_polyhedral_seq1.cuh) and bit-identical results, but
-// organised so that (i) global memory is read ONLY by the copy engine: whole frames (and the frames' wrap
-// rows) of the next tile arrive in shared memory through cp.async.bulk + mbarrier while the current tile
-// is processed, (ii) a CTA synchronises a few times per tile instead of five times per frame, and
-// (iii) the common case never touches float64 arithmetic:
+// Same contract as k_polyhedral_assign_seq1 (k_polyhedral_seq1.cuh) and bit-identical results:
 //
+//  * Global memory is read by the copy engine only: the raw frames (and their wrap rows) of the NEXT tile
+//    arrive in shared memory through cp.async.bulk + mbarrier while the current tile is processed.
 //  * A CTA owns a contiguous range of frames (a "chunk"); thread a owns mobile atom a and carries
 //    `last` = the atom's most recent site as far as it is certain (unknown at the chunk start and
-//    after an atom-frame that several sites contain).
-//  * Conversion: from the raw frames in shared memory the CTA writes one ROW per frame:
-//    for every (framework coordinate, slot shift) pair that some site uses the unwrapped coordinate
-//    raw + (double)(shift - W) (pbc_utils.py:220, one float64 rounding) ROUNDED TO FLOAT, followed by the
-//    wrapped mobile coordinates (atom.py:104) rounded to float.  The validity tube of the cell lists
-//    is checked on the float64 values.  Then the raw buffer is free and the next tile's copy is issued.
-//  * Rounds (repeat until every owner has finished the tile):
-//      R1  owners test `last` against all remaining frames of the tile (sab_tet_filter32b, independent
-//          per frame => instruction-level parallelism) and accept the leading run of "certainly inside"
-//          verdicts: that is the reference's answer (it tests the most recent site first and stops at
-//          the first hit, site_collection.py:147-152, polyhedral_site_collection.py:104-107).  The first
-//          frame with any other verdict -- outside, undecided, no certain history -- queues the
-//          atom-frame's cell-list candidates as (atom, frame, site) pairs (warp-cooperative copy).
-//      R2  all threads test the queued pairs: FP32 first, and whenever the point is inside the
-//          stated error band of a face, the exact float64 test with the reference's operation order
-//          (k_polyhedral.cuh: sab_poly_vertices + sab_poly_contains_atom) from global memory (L2).
-//      R3  owners read the verdict: none -> None, one -> that site (`last` certain again),
-//          several -> spilled list for the priority resolver (`last` unknown); then continue with R1.
+//    after an atom-frame that several sites contain or that float32 could not decide).
+//  * Conversion: from the raw frames the CTA writes one float ROW per frame: for every (framework
+//    coordinate, slot shift) pair that some site uses, float(raw - W) + shift (within 2^-22 of the
+//    reference's float64 value raw + (shift - W), pbc_utils.py:220), followed by the wrapped mobile
+//    coordinates (atom.py:104).  The validity tube of the cell lists is checked here (conservatively).
+//  * Rounds.  Owners emit work items, all threads process them, owners read the verdicts:
+//      round 0    every owner tests `last` against all frames of the tile in-thread (independent per frame)
+//                 and accepts the leading run of "certainly inside" verdicts: that is the reference's answer
+//                 (it tests the most recent site first and stops at the first hit, site_collection.py:147-152,
+//                 polyhedral_site_collection.py:104-107).
+//      SEARCH     the first frame with any other verdict (outside, undecided, no certain history) queues the
+//                 atom-frame's cell list as blocks of <= 16 candidates; verdict none -> None, one -> that site
+//                 (`last` certain again), 2..4 -> spilled list for the priority resolver (`last` unknown),
+//                 any candidate undecided in float32 (or more than 4 hits) -> the atom-frame is DEFERRED.
+//      CONTINUE   after a search the remaining frames of the tile are queued as single (atom, frame, site)
+//                 tests of the new `last`, so later rounds stay lane-dense.
+//  * DEFERRED atom-frames are appended to a list and settled after the kernel by k_polyhedral_deferred with
+//    the exact float64 test in the reference's operation order over the whole cell list
+//    (k_polyhedral.cuh: sab_poly_vertices + sab_poly_contains_atom).  The float32 test only ever returns a
+//    verdict that float64 would return identically (see sab_tet_filter32b), so results are bit-identical
+//    to the all-float64 kernels.
 //  * Frames outside the validity tube (and the legacy first-frame rule) take the exhaustive generic
 //    path per atom, as in the other kernels.
-//
-// The FP32 test decides only what float64 would decide identically; see sab_tet_filter32b.
 #pragma once
 #include "k_polyhedral_seq.cuh"
 
 #define SAB_TILE_MAX 4            // frames per tile (compile-time unroll bound)
-#define SAB_TILE_PAIRS 1024       // queued (atom, frame, site) pairs per round
+#define SAB_TILE_BLOCKS 256       // queued candidate blocks (<= 16 candidates each) per round
+#define SAB_TILE_SINGLES 1024     // queued single tests per round
 #define SAB_TILE_THREADS 256
 #ifndef SAB_TILE_MINBLOCKS
 #define SAB_TILE_MINBLOCKS 2
 #endif
+#define SAB_DEFERRED INT_MIN      // result marker, replaced by k_polyhedral_deferred before anything reads it
 
 struct SabTileTables {
     int n_used;                   // staged (framework coordinate, slot shift) pairs
     int stride;                   // floats per row: n_used + 3 A, rounded up to a multiple of 4
     int m3;                       // framework coordinates
-    const int32_t *col_goff;      // [m3] position of the coordinate inside a frame: 3 * atom + d
-    const int32_t *var_off;       // [m3 + 1] CSR over the variants of a coordinate
-    const int2 *vars;             // {slot shift, row position j}
+    const int4 *vars;             // [n_used] {3 * atom + d, framework column i, float bits of the shift, float bits of anchor[i]}
     const uint16_t *rec;          // [S][12] byte offsets into a row, vertices in slot order
     int G;
     const int32_t *cell_off;      // [G^3 + 1]
     const uint16_t *cell_sites;   // CSR entries, ascending per cell; lists conservative by >= 1e-6 (float cell lookup)
-    const double *anchor;         // [m3]
-    double delta;
+    float delta_f;                // validity radius, shrunk by the float error of the check
     int use_f32;
+    long long *defer;             // deferred atom-frames: frame * A + atom
+    long long defer_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -140,7 +140,7 @@ __device__ __forceinline__ int sab_tet_filter32b(const float *__restrict__ tab, 
     return 2;
 }
 
-// exact float64 test of one (site, atom) in one frame, operands from global memory (rare path)
+// exact float64 test of one (site, atom) in one frame, operands from global memory (deferred pass)
 __device__ __noinline__ bool sab_tet_exact_global(const double *__restrict__ frame, const int32_t *__restrict__ wrow,
                                                   const SabPolyTables &T, int s, int atom)
 {
@@ -157,45 +157,6 @@ __device__ __forceinline__ int sab_cell_of_f(const float *x, int G)
     const float g = (float)G;
     int c0 = min(G - 1, (int)(x[0] * g)), c1 = min(G - 1, (int)(x[1] * g)), c2 = min(G - 1, (int)(x[2] * g));
     return (c0 * G + c1) * G + c2;
-}
-
-// full test of one (site, atom-frame): FP32 first, float64 when undecided
-__device__ __forceinline__ bool sab_tile_test(const float *__restrict__ row, const float *__restrict__ xk, int s,
-                                              const double *__restrict__ frame, const int32_t *__restrict__ wrow, int atom,
-                                              const SabPolyTables &T, const SabTileTables &C)
-{
-    int v = 2;
-    if (C.use_f32) v = sab_tet_filter32b(row, sab_tet_rec(C.rec + (size_t)s * 12), xk);
-    if (v == 2) v = sab_tet_exact_global(frame, wrow, T, s, atom);
-    return v != 0;
-}
-
-// result of one atom-frame whose containing sites were counted (c) and partly kept (h); `last` follows
-// the certainty rules of the file header.  Lists longer than KEEP are rescanned in ascending order.
-__device__ __noinline__ int sab_tile_finish(int c, int *h, int &last, const float *__restrict__ row, const float *xk,
-                                            const double *__restrict__ frame, const int32_t *__restrict__ wrow, int atom,
-                                            const SabPolyTables &T, const SabTileTables &C, int32_t *__restrict__ spill,
-                                            long long spill_capacity, unsigned long long *__restrict__ counters)
-{
-    if (c == 0) return SAB_NONE;
-    if (c == 1) { last = h[0]; return h[0]; }
-    last = -1;                                        // several sites: the resolver decides; history uncertain
-    atomicAdd(&counters[0], 1ULL);
-    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
-    if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; return SAB_NONE; }
-    spill[off] = c;
-    if (c <= SAB_POLY_KEEP) {                         // ascending list positions
-        for (int i = 1; i < c; i++) { int v = h[i], j = i; while (j > 0 && h[j - 1] > v) { h[j] = h[j - 1]; j--; } h[j] = v; }
-        for (int i = 0; i < c; i++) spill[off + 1 + i] = h[i];
-    } else {                                          // atom on a vertex / edge shared by many sites: rescan
-        const int cell = sab_cell_of_f(xk, C.G);
-        int k = 0;
-        for (int i = C.cell_off[cell]; i < C.cell_off[cell + 1] && k < c; i++) {
-            const int s = C.cell_sites[i];
-            if (sab_tile_test(row, xk, s, frame, wrow, atom, T, C)) spill[off + 1 + k++] = s;
-        }
-    }
-    return SAB_AMBIGUOUS_BASE - (int)off;
 }
 
 // ---- mbarrier / bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP) -------------------------------------
@@ -220,6 +181,19 @@ __device__ __forceinline__ void sab_bulk_g2s(void *smem_dst, const void *gmem_sr
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// spill a short list of containing sites (2..KEEP, any order) in ascending list position
+__device__ __noinline__ int sab_tile_spill(int c, int *h, int32_t *__restrict__ spill, long long spill_capacity,
+                                           unsigned long long *__restrict__ counters)
+{
+    atomicAdd(&counters[0], 1ULL);
+    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+    if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; return SAB_NONE; }
+    spill[off] = c;
+    for (int i = 1; i < c; i++) { int v = h[i], j = i; while (j > 0 && h[j - 1] > v) { h[j] = h[j - 1]; j--; } h[j] = v; }
+    for (int i = 0; i < c; i++) spill[off + 1 + i] = h[i];
+    return SAB_AMBIGUOUS_BASE - (int)off;
+}
+
 __global__ void __launch_bounds__(SAB_TILE_THREADS, SAB_TILE_MINBLOCKS)
 k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int chunk, int tile, int n_atoms, int n_mobile,
                          const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabTileTables C,
@@ -232,15 +206,17 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
     double *rawd = reinterpret_cast<double *>(sm_tile);                         // [tile][3 N] raw frames (copy engine)
     int32_t *wbuf = reinterpret_cast<int32_t *>(rawd + (size_t)tile * n3);      // [tile][m3] wrap rows (copy engine)
     float *tab = reinterpret_cast<float *>(wbuf + (((size_t)tile * C.m3 + 3) & ~(size_t)3));   // [tile][stride] rows
-    int *pairs = reinterpret_cast<int *>(tab + (size_t)tile * C.stride);        // [SAB_TILE_PAIRS]
-    int *cnt = pairs + SAB_TILE_PAIRS;                                          // [A] hits of the pending atom-frame
+    int *blocks = reinterpret_cast<int *>(tab + (size_t)tile * C.stride);       // [SAB_TILE_BLOCKS][3] {tag, first entry, count}
+    int *singles = blocks + 3 * SAB_TILE_BLOCKS;                                // [SAB_TILE_SINGLES] (atom, frame, site)
+    int *cnt = singles + SAB_TILE_SINGLES;                                      // [A] hits of the pending search; bit 16 = undecided
     int *hits = cnt + n_mobile;                                                 // [A][KEEP]
-    int *last = hits + (size_t)n_mobile * SAB_POLY_KEEP;                        // [A]
-    int *pos = last + n_mobile;                                                 // [A] next frame of the tile; bit 8 = verdict pending
+    int *okb = hits + (size_t)n_mobile * SAB_POLY_KEEP;                         // [A] frames on which `last` certainly holds
+    int *last = okb + n_mobile;                                                 // [A]
+    int *pos = last + n_mobile;                                                 // [A] next frame | state << 8
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ int n_pairs[2];
+    __shared__ int n_blocks[2], n_singles[2];
     __shared__ int bad_mask;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
     unsigned phase = 0;
     if (tid == 0) { sab_mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -265,15 +241,15 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
         for (int a = tid; a < n_mobile; a += nthr) last[a] = -1;              // owner-private
         {
             const int tn0 = (int)min((int64_t)tile, c1 - c0);
-            if (tid == 0 && tma_ok(c0, tn0)) issue(c0, tn0);                 // buffers are free: see the barrier after conversion
+            if (tid == 0 && tma_ok(c0, tn0)) issue(c0, tn0);                 // buffers are idle here
         }
         for (int64_t f0 = c0; f0 < c1; f0 += tile) {
             const int tn = (int)min((int64_t)tile, c1 - f0);
             const double *gframe = frac + (size_t)f0 * n3;
             const int32_t *gwrow = wrows + (size_t)f0 * C.m3;
             int32_t *res = result + (size_t)f0 * n_mobile;
-            // every thread is past the final barrier A of the previous tile: nobody reads rows, bad_mask or counters
-            if (tid == 0) { bad_mask = 0; n_pairs[0] = 0; n_pairs[1] = 0; }
+            // every thread is past the last barrier of the previous tile: nobody reads rows, bad_mask or the queues
+            if (tid == 0) { bad_mask = 0; n_blocks[0] = n_blocks[1] = 0; n_singles[0] = n_singles[1] = 0; }
             if (tma_ok(f0, tn)) {
                 sab_mbar_wait(&mbar, phase);
                 phase ^= 1;
@@ -285,32 +261,22 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
             // ---- conversion: raw frames -> float rows -------------------------------------------------
             {
                 int bad = 0;
-                for (int i = tid; i < C.m3; i += nthr) {
-                    const int goff = __ldg(C.col_goff + i), vb = __ldg(C.var_off + i), ve = __ldg(C.var_off + i + 1);
-                    const double anc = __ldg(C.anchor + i);
-                    double r[SAB_TILE_MAX]; int w[SAB_TILE_MAX];
+                for (int j = tid; j < C.n_used; j += nthr) {
+                    const int4 e = __ldg(C.vars + j);
+                    const float sh = __int_as_float(e.z), anc = __int_as_float(e.w);
 #pragma unroll
                     for (int k = 0; k < SAB_TILE_MAX; k++)
                         if (k < tn) {
-                            r[k] = rawd[k * n3 + goff]; w[k] = wbuf[k * C.m3 + i];
-                            if (fabs((r[k] - (double)w[k]) - anc) > C.delta) bad |= 1 << k;
+                            const float base = (float)(rawd[k * n3 + e.x] - (double)wbuf[k * C.m3 + e.y]);
+                            if (fabsf(base - anc) > C.delta_f) bad |= 1 << k;
+                            tab[k * C.stride + j] = base + sh;
                         }
-                    for (int v = vb; v < ve; v++) {
-                        const int2 e = __ldg(C.vars + v);
-#pragma unroll
-                        for (int k = 0; k < SAB_TILE_MAX; k++)
-                            if (k < tn) {
-                                const double val = r[k] + (double)(e.x - w[k]);            // pbc_utils.py:220, one rounding
-                                if (!(fabs(val) < 3.5)) bad |= 1 << k;                      // FP32 error budget assumes |coordinate| < 4
-                                tab[k * C.stride + e.y] = (float)val;
-                            }
-                    }
                 }
                 for (int q = tid; q < 3 * n_mobile; q += nthr) {
                     const int a = q / 3, goff = __ldg(mobile + a) * 3 + (q - 3 * a);
 #pragma unroll
                     for (int k = 0; k < SAB_TILE_MAX; k++)
-                        if (k < tn) tab[k * C.stride + C.n_used + q] = (float)sab_pymod1(rawd[k * n3 + goff]);   // atom.py:104
+                        if (k < tn) { const double x = rawd[k * n3 + goff]; tab[k * C.stride + C.n_used + q] = (float)(x - floor(x)); }   // atom.py:104
                 }
                 if (T.legacy_init && legacy_init_frame >= f0 && legacy_init_frame < f0 + tn) bad |= 1 << (int)(legacy_init_frame - f0);
                 if (bad) atomicOr(&bad_mask, bad);
@@ -327,24 +293,46 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
             const int badm = bad_mask;
             // ---- rounds -----------------------------------------------------------------------------
             for (int round = 0;; round++) {
-                int *np = &n_pairs[round & 1];
+                int *nb = &n_blocks[round & 1], *ns = &n_singles[round & 1];
                 int pending = 0;
-                for (int a0 = tid - lane; a0 < n_mobile; a0 += nthr) {       // warp-uniform trip count
-                    const int a = a0 + lane;
-                    int m_len = 0, m_b = 0, m_off = 0, m_tag = 0;            // candidate list to queue (this lane)
-                    if (a < n_mobile) {
-                        int k = pos[a], la = last[a];
-                        const float *xa = tab + C.n_used + 3 * a;
-                        if (k & 256) {                               // R3: verdict of the queued atom-frame
-                            k &= 255;
-                            const int out = sab_tile_finish(cnt[a], hits + a * SAB_POLY_KEEP, la, tab + k * C.stride, xa + k * C.stride,
-                                                            gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, mobile[a], T, C,
-                                                            spill, spill_capacity, counters);
+                for (int a = tid; a < n_mobile; a += nthr) {
+                    // st: 0 idle, 1 search pending, 2 continuation pending, 3 / 4 search / continuation found its queue full
+                    int k = pos[a] & 255, st = pos[a] >> 8, la = last[a];
+                    const float *xa = tab + C.n_used + 3 * a;
+                    bool walk = la >= 0 && st != 3;
+                    if (st == 1) {                                // verdict of the search at frame k
+                        const int cv = cnt[a], c = cv & 0xffff;
+                        int out;
+                        if ((cv >> 16) || c > SAB_POLY_KEEP) {    // float32 could not decide (or a long list): exact pass later
+                            out = SAB_DEFERRED; la = -1;
+                            const unsigned long long di = atomicAdd(&counters[9], 1ULL);
+                            if ((long long)di < C.defer_cap) C.defer[di] = (long long)(f0 + k) * n_mobile + a;
+                        } else if (c == 0) out = SAB_NONE;
+                        else if (c == 1) { out = hits[a * SAB_POLY_KEEP]; la = out; }
+                        else { out = sab_tile_spill(c, hits + a * SAB_POLY_KEEP, spill, spill_capacity, counters); la = -1; }
+                        res[k * n_mobile + a] = out;
+                        k++;
+                        walk = la >= 0;
+                    } else if (st == 2) {                         // verdicts of the queued tests of `last`
+                        const int ok = okb[a];
+                        while (k < tn && ((ok >> k) & 1)) { res[k * n_mobile + a] = la; k++; }
+                        walk = false;
+                    }
+                    st = 0;
+                    while (k < tn) {
+                        if ((badm >> k) & 1) {                    // outside the validity tube: generic path
+                            int c = 0;
+                            const int out = sab_exhaustive_atom(gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, f0 + k,
+                                                                legacy_init_frame, mobile[a], n_sites, T, spill, spill_capacity,
+                                                                counters, &c);
+                            if (c == 1) la = out; else if (c > 1) la = -1;
                             res[k * n_mobile + a] = out;
                             k++;
+                            walk = la >= 0;
+                            continue;
                         }
-                        while (k < tn) {                             // R1
-                            if (la >= 0 && C.use_f32) {
+                        if (walk && C.use_f32) {
+                            if (round == 0) {                     // dense: test in-thread, frames are independent
                                 const SabTetRec R = sab_tet_rec(C.rec + (size_t)la * 12);
                                 int ok = 0;
 #pragma unroll
@@ -352,74 +340,130 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
                                     if (kk >= k && kk < tn && !((badm >> kk) & 1))
                                         ok |= (sab_tet_filter32b(tab + kk * C.stride, R, xa + kk * C.stride) == 1) << kk;
                                 while (k < tn && ((ok >> k) & 1)) { res[k * n_mobile + a] = la; k++; }
-                                if (k == tn) break;
-                            }
-                            if ((badm >> k) & 1) {                   // outside the validity tube: generic path
-                                int c = 0;
-                                const int out = sab_exhaustive_atom(gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, f0 + k,
-                                                                    legacy_init_frame, mobile[a], n_sites, T, spill, spill_capacity,
-                                                                    counters, &c);
-                                if (c == 1) la = out; else if (c > 1) la = -1;
-                                res[k * n_mobile + a] = out;
-                                k++;
+                                walk = false;
                                 continue;
                             }
-                            // full search over the cell list of the atom-frame
-                            const float *xk = xa + k * C.stride;
-                            const int cell = sab_cell_of_f(xk, C.G);
-                            const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
-                            if (len == 0) { res[k * n_mobile + a] = SAB_NONE; k++; continue; }
-                            const int off = atomicAdd(np, len);
-                            if (off + len <= SAB_TILE_PAIRS) {
-                                m_len = len; m_b = b; m_off = off; m_tag = (a << 19) | (k << 16);
-                                cnt[a] = 0;
-                                k |= 256; pending = 1;
-                                break;
-                            }
-                            for (int i = off; i < SAB_TILE_PAIRS; i++) pairs[i] = -1;      // queue full: test the list here
-                            int c = 0, h[SAB_POLY_KEEP];
-                            for (int i = 0; i < len; i++) {
-                                const int s = __ldg(C.cell_sites + b + i);
-                                if (sab_tile_test(tab + k * C.stride, xk, s, gframe + (size_t)k * n3, gwrow + (size_t)k * C.m3, mobile[a], T, C)) {
-                                    if (c < SAB_POLY_KEEP) h[c] = s;
-                                    c++;
-                                }
-                            }
-                            const int out = sab_tile_finish(c, h, la, tab + k * C.stride, xk, gframe + (size_t)k * n3,
-                                                            gwrow + (size_t)k * C.m3, mobile[a], T, C, spill, spill_capacity, counters);
-                            res[k * n_mobile + a] = out;
-                            k++;
+                            int n = 0;                            // sparse: queue the tests of the frames up to the next bad one
+                            while (k + n < tn && !((badm >> (k + n)) & 1)) n++;
+                            const int off = atomicAdd(ns, n);
+                            if (off + n <= SAB_TILE_SINGLES) {
+                                for (int i = 0; i < n; i++) singles[off + i] = (a << 19) | ((k + i) << 16) | la;
+                                okb[a] = 0;
+                                st = 2;
+                            } else st = 4;                        // queue full: retry next round
+                            break;
                         }
-                        pos[a] = k;
-                        last[a] = la;
+                        // search: the cell list of the atom-frame, in blocks of 16 candidates
+                        const int cell = sab_cell_of_f(xa + k * C.stride, C.G);
+                        const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
+                        if (len == 0) { res[k * n_mobile + a] = SAB_NONE; k++; walk = la >= 0; continue; }
+                        const int nbk = (len + 15) >> 4;
+                        const int off = atomicAdd(nb, nbk);
+                        if (off + nbk <= SAB_TILE_BLOCKS) {
+                            for (int i = 0; i < nbk; i++) {
+                                blocks[3 * (off + i)] = (a << 19) | (k << 16);
+                                blocks[3 * (off + i) + 1] = b + 16 * i;
+                                blocks[3 * (off + i) + 2] = min(16, len - 16 * i);
+                            }
+                            cnt[a] = 0;
+                            st = 1;
+                        } else {
+                            for (int i = off; i < SAB_TILE_BLOCKS; i++) blocks[3 * i + 2] = 0;   // unusable tail of the queue
+                            st = 3;                               // retry next round
+                        }
+                        break;
                     }
-                    // warp-cooperative copy of the queued candidate lists
-                    unsigned m = __ballot_sync(0xffffffffu, m_len > 0);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int len = __shfl_sync(0xffffffffu, m_len, src), b = __shfl_sync(0xffffffffu, m_b, src);
-                        const int off = __shfl_sync(0xffffffffu, m_off, src), tag = __shfl_sync(0xffffffffu, m_tag, src);
-                        for (int i = lane; i < len; i += 32) pairs[off + i] = tag | (int)__ldg(C.cell_sites + b + i);
-                    }
+                    if (st) pending = 1;
+                    pos[a] = k | (st << 8);
+                    last[a] = la;
                 }
-                if (__syncthreads_or(pending) == 0) break;       // barrier A: queue complete / tile finished
-                const int total = min(*np, SAB_TILE_PAIRS);
-                if (tid == 0) n_pairs[(round + 1) & 1] = 0;
-                // ---- R2: queued pairs over all threads ---------------------------------------------
-                for (int p = tid; p < total; p += nthr) {
-                    const int e = pairs[p];
-                    if (e < 0) continue;
-                    const int a = e >> 19, k = (e >> 16) & 7, s = e & 0xffff;
-                    if (sab_tile_test(tab + k * C.stride, tab + k * C.stride + C.n_used + 3 * a, s, gframe + (size_t)k * n3,
-                                      gwrow + (size_t)k * C.m3, mobile[a], T, C)) {
-                        const int c = atomicAdd(&cnt[a], 1);
+                if (__syncthreads_or(pending) == 0) break;       // barrier A: queues complete / tile finished
+                const int nblk = min(*nb, SAB_TILE_BLOCKS), nsing = min(*ns, SAB_TILE_SINGLES);
+                if (tid == 0) { n_blocks[(round + 1) & 1] = 0; n_singles[(round + 1) & 1] = 0; }
+                // ---- all threads: queued tests ------------------------------------------------------
+                for (int p = tid; p < nblk * 16; p += nthr) {
+                    const int d = p >> 4, i = p & 15;
+                    if (i >= blocks[3 * d + 2]) continue;
+                    const int tag = blocks[3 * d], a = tag >> 19, k = (tag >> 16) & 7;
+                    const int s = __ldg(C.cell_sites + blocks[3 * d + 1] + i);
+                    const int v = C.use_f32 ? sab_tet_filter32b(tab + k * C.stride, sab_tet_rec(C.rec + (size_t)s * 12),
+                                                                tab + k * C.stride + C.n_used + 3 * a) : 2;
+                    if (v == 1) {
+                        const int c = atomicAdd(&cnt[a], 1) & 0xffff;
                         if (c < SAB_POLY_KEEP) hits[a * SAB_POLY_KEEP + c] = s;
-                    }
+                    } else if (v == 2) atomicOr(&cnt[a], 0x10000);
+                }
+                for (int p = tid; p < nsing; p += nthr) {
+                    const int e = singles[p], a = e >> 19, k = (e >> 16) & 7, s = e & 0xffff;
+                    if (sab_tet_filter32b(tab + k * C.stride, sab_tet_rec(C.rec + (size_t)s * 12),
+                                          tab + k * C.stride + C.n_used + 3 * a) == 1) atomicOr(&okb[a], 1 << k);
                 }
                 __syncthreads();                                 // barrier B: verdicts complete
             }
         }
         __syncthreads();                                         // chunk done: raw buffers idle before the next chunk's copy
+    }
+}
+
+// Settles the DEFERRED atom-frames of k_polyhedral_assign_tile with the exact float64 test over the whole cell
+// list: one warp per entry, one candidate per lane.  `scan` != 0: the list overflowed -- every warp scans a slice
+// of the result array for the marker instead (adversarial inputs only).
+__global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n_frames, int n_atoms, int n_mobile,
+                                      const int32_t *__restrict__ mobile, SabPolyTables T, int G,
+                                      const int32_t *__restrict__ cell_off, const uint16_t *__restrict__ cell_sites,
+                                      const int32_t *__restrict__ wrows, int m3, const long long *__restrict__ defer,
+                                      long long defer_cap, int32_t *__restrict__ result, int32_t *__restrict__ spill,
+                                      long long spill_capacity, unsigned long long *__restrict__ counters)
+{
+    const long long n_def = (long long)counters[9];
+    if (n_def == 0) return;
+    const bool scan = n_def > defer_cap;
+    const long long total = scan ? (long long)n_frames * n_mobile : n_def;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w0 = warp; w0 < total; w0 += n_warps) {
+        const long long idx = scan ? w0 : defer[w0];
+        if (result[idx] != SAB_DEFERRED) continue;               // warp-uniform
+        const int64_t f = idx / n_mobile; const int a = (int)(idx - f * n_mobile);
+        const double *frame = frac + (size_t)f * n_atoms * 3;
+        const int32_t *wrow = wrows + (size_t)f * m3;
+        const int atom = mobile[a];
+        double x[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)atom * 3 + d]);
+        const int cell = sab_cell_of(x, G);
+        const int b = cell_off[cell], len = cell_off[cell + 1] - b;
+        int c = 0, first = -1;
+        for (int i0 = 0; i0 < len; i0 += 32) {                   // pass 1: count
+            const int i = i0 + lane;
+            bool in = false;
+            if (i < len) in = sab_tet_exact_global(frame, wrow, T, cell_sites[b + i], atom);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (m && first < 0) first = cell_sites[b + i0 + __ffs(m) - 1];
+            c += __popc(m);
+        }
+        int out;
+        if (c == 0) out = SAB_NONE;
+        else if (c == 1) out = first;
+        else {
+            unsigned long long off = 0;
+            if (lane == 0) { atomicAdd(&counters[0], 1ULL); off = atomicAdd(&counters[1], (unsigned long long)(c + 1)); }
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { if (lane == 0) counters[2] = 1ULL; out = SAB_NONE; }
+            else {
+                if (lane == 0) spill[off] = c;
+                int k = 0;
+                for (int i0 = 0; i0 < len; i0 += 32) {           // pass 2: ascending list positions
+                    const int i = i0 + lane;
+                    bool in = false;
+                    if (i < len) in = sab_tet_exact_global(frame, wrow, T, cell_sites[b + i], atom);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) spill[off + 1 + k + __popc(m & ((1u << lane) - 1))] = cell_sites[b + i];
+                    k += __popc(m);
+                }
+                out = SAB_AMBIGUOUS_BASE - (int)off;
+            }
+        }
+        if (lane == 0) result[idx] = out;
     }
 }

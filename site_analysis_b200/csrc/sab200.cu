@@ -100,8 +100,8 @@ struct sab_engine {
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
     uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
     // tile kernel: compact staging table and float-table site records (derived in sab_set_cell_lists)
-    bool tile_ok = false; int n_used = 0; int2 *d_tile_vars = nullptr; uint16_t *d_tile_rec = nullptr;
-    int32_t *d_tile_goff = nullptr, *d_tile_voff = nullptr; int tile_frames = 0;   // SAB_OPT_TILE_FRAMES (0 = automatic)
+    bool tile_ok = false; int n_used = 0; int4 *d_tile_vars = nullptr; uint16_t *d_tile_rec = nullptr;
+    int tile_frames = 0;                   // SAB_OPT_TILE_FRAMES (0 = automatic)
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -136,7 +136,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
-                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec, e->d_tile_goff, e->d_tile_voff};
+                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
@@ -295,22 +295,27 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
                 if (idx >= nk * m3) return fail(SAB_EINVAL, "sab_set_cell_lists: record offset out of range (site %d)", s);
                 slot[idx] = 0;
             }
-        std::vector<int2> vars;
-        std::vector<int32_t> goff(m3), voff(m3 + 1, 0);
-        bool ok = e->A <= 4096 && (int64_t)e->N * 3 * SAB_TILE_MAX < INT_MAX;
-        for (int i = 0; i < m3; i++) {
-            goff[i] = e->fw_atoms[i / 3] * 3 + i % 3;
+        std::vector<int4> vars;
+        bool ok = e->A <= 4096 && (int64_t)e->N * 3 * SAB_TILE_MAX < INT_MAX && delta > 1e-6;
+        for (int i = 0; i < m3; i++)
             for (int k = 0; k < nk; k++)
                 if (slot[(size_t)k * m3 + i] == 0) {
                     slot[(size_t)k * m3 + i] = (int)vars.size();
-                    vars.push_back(make_int2(kmin + k, (int)vars.size()));
-                    // FP32 pre-test precondition: unwrapped vertex coordinates stay below 2 inside the validity tube
-                    if (!(anchor[i] + (double)(kmin + k) + delta < 2.0 - 1e-6)) ok = false;
+                    const float sh = (float)(kmin + k), anc = (float)anchor[i];
+                    int4 e4;
+                    e4.x = e->fw_atoms[i / 3] * 3 + i % 3; e4.y = i;
+                    memcpy(&e4.z, &sh, 4); memcpy(&e4.w, &anc, 4);
+                    vars.push_back(e4);
+                    // FP32 pre-test preconditions inside the validity tube: unwrapped vertex coordinates stay
+                    // below 2 (image rule) and below 3.5 in magnitude (error budget)
+                    const double v = anchor[i] + (double)(kmin + k);
+                    if (!(v + delta < 2.0 - 1e-6) || !(fabs(v) + delta < 3.5)) ok = false;
                 }
-            voff[i + 1] = (int32_t)vars.size();
-        }
         const size_t stride = (vars.size() + 3 * (size_t)e->A + 3) & ~(size_t)3;
         if (stride * 4 > 65535 || vars.empty()) ok = false;          // 16-bit byte offsets into a row
+        size_t longest = 0;
+        for (size_t c = 0; c < ncell; c++) longest = std::max(longest, (size_t)(cell_off[c + 1] - cell_off[c]));
+        if (longest > 16 * (size_t)SAB_TILE_BLOCKS) ok = false;
         e->tile_ok = false;
         if (ok) {
             std::vector<uint16_t> rec2((size_t)e->S * 12);
@@ -318,8 +323,6 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
                 for (int v = 0; v < 12; v++) rec2[(size_t)s * 12 + v] = (uint16_t)(4 * slot[records[(size_t)s * SAB_TET_REC + v] / 8]);
             CU(upload(&e->d_tile_vars, vars.data(), vars.size()));
             CU(upload(&e->d_tile_rec, rec2.data(), rec2.size()));
-            CU(upload(&e->d_tile_goff, goff.data(), goff.size()));
-            CU(upload(&e->d_tile_voff, voff.data(), voff.size()));
             e->n_used = (int)vars.size();
             e->tile_ok = true;
         }
@@ -383,6 +386,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
 struct Workspace {
     int n_chunks = 0; int m3 = 0;
     int32_t *totals = nullptr; double *chunk_exc = nullptr; int32_t *rows = nullptr;
+    long long *defer = nullptr; long long defer_cap = 0;      // deferred atom-frames of the tile kernel
     size_t bytes = 0;
 };
 
@@ -399,6 +403,10 @@ static Workspace layout(const sab_engine *e, int64_t F, void *base)
     w.totals = (int32_t *)(b + off); off += align256(sizeof(int32_t) * (size_t)w.n_chunks * w.m3);
     w.chunk_exc = (double *)(b + off); off += align256(sizeof(double) * 2 * (size_t)w.n_chunks * w.m3);
     w.rows = (int32_t *)(b + off); off += align256(sizeof(int32_t) * (size_t)F * w.m3);
+    if (e->kind == SAB_POLYHEDRAL) {
+        w.defer_cap = std::max<long long>(4096, (long long)F * e->A / 16);
+        w.defer = (long long *)(b + off); off += align256(sizeof(long long) * (size_t)w.defer_cap);
+    }
     w.bytes = off + 256;
     return w;
 }
@@ -534,18 +542,19 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         const size_t stride = ((size_t)e->n_used + 3 * (size_t)e->A + 3) & ~(size_t)3;
         auto smem_for = [&](int t) {
             return sizeof(double) * (size_t)t * 3 * e->N + sizeof(int32_t) * (((size_t)t * 3 * e->M + 3) & ~(size_t)3) +
-                   sizeof(float) * (size_t)t * stride + sizeof(int) * ((size_t)SAB_TILE_PAIRS + (size_t)e->A * (3 + SAB_POLY_KEEP)) + 128;
+                   sizeof(float) * (size_t)t * stride +
+                   sizeof(int) * ((size_t)3 * SAB_TILE_BLOCKS + SAB_TILE_SINGLES + (size_t)e->A * (4 + SAB_POLY_KEEP)) + 128;
         };
         int tile = (e->tile_frames >= 1 && e->tile_frames <= SAB_TILE_MAX) ? e->tile_frames : SAB_TILE_MAX;
         if (e->tile_frames <= 0)
             while (tile > 1 && smem_for(tile) > (size_t)(226 * 1024 / SAB_TILE_MINBLOCKS)) tile--;
-        if (smem_for(tile) <= 226 * 1024) {
+        if (smem_for(tile) <= 226 * 1024 && (size_t)e->A * (tile - 1) <= SAB_TILE_SINGLES && w.defer) {
             const size_t smem = smem_for(tile);
             CU(cudaFuncSetAttribute(k_polyhedral_assign_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp,
                             e->d_legacy_init};
-            SabTileTables C{e->n_used, (int)stride, 3 * e->M, e->d_tile_goff, e->d_tile_voff, e->d_tile_vars, e->d_tile_rec, e->G,
-                            e->d_cell_off, e->d_cell_sites, e->d_anchor, e->delta, e->fp32_filter};
+            SabTileTables C{e->n_used, (int)stride, 3 * e->M, e->d_tile_vars, e->d_tile_rec, e->G, e->d_cell_off, e->d_cell_sites,
+                            (float)e->delta - 4e-7f, e->fp32_filter, w.defer, w.defer_cap};
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_tile, block, smem);
             const int64_t resident = (int64_t)std::max(1, per_sm) * e->sm_count;
@@ -556,6 +565,10 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             const int grid2 = (int)std::min<int64_t>(n_chunks, resident);
             k_polyhedral_assign_tile<<<grid2, block, smem, st>>>(d_frac, F, (int)chunk, tile, e->N, e->A, e->d_mobile, e->S, T, C,
                 w.rows, e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+            // exact float64 pass over the atom-frames float32 could not decide (returns at once when there are none)
+            k_polyhedral_deferred<<<e->sm_count * 8, 256, 0, st>>>(d_frac, F, e->N, e->A, e->d_mobile, T, e->G, e->d_cell_off,
+                e->d_cell_sites, w.rows, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters);
+            e->launches++;
             break;
         }
     }
@@ -679,6 +692,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     info[3] = (h[CNT_FIRST_BAD] == ~0ULL) ? -1 : (int64_t)h[CNT_FIRST_BAD];
     info[4] = (int64_t)h[CNT_FULL27];
     info[8] = (int64_t)h[CNT_SPAN];
+    info[9] = (int64_t)h[9];                 // atom-frames settled by the exact float64 pass of the tile kernel
     {
         float ms_wrap = 0.f, ms_main = 0.f;          // CUDA events on the launching stream
         cudaEventElapsedTime(&ms_wrap, e->ev_t[0], e->ev_t[1]);
@@ -817,7 +831,7 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         CU(cudaMemcpyAsync(h_result + (size_t)f0 * e->A, base + o_res, res_b * nf, cudaMemcpyDeviceToHost, s_comp));
         CU(cudaEventRecord(ev_done[b], s_comp));
         tot_info[0] += ci[0]; tot_info[1] += ci[1]; tot_info[4] += ci[4]; tot_info[5] += ci[5];
-        tot_info[6] += ci[6]; tot_info[7] += ci[7];
+        tot_info[6] += ci[6]; tot_info[7] += ci[7]; tot_info[9] += ci[9];
         tot_info[8] = std::max(tot_info[8], ci[8]);
         if (ci[3] >= 0 && tot_info[3] < 0) tot_info[3] = f0 + ci[3];
     }
