@@ -132,8 +132,9 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
  * against the 0.3 step bound (used right after the host re-initialised a group at that frame,
  * dynamic_voronoi_site_collection.py:188-195). */
 #define SAB_OPT_SKIP_STEP_CHECK_ONCE 1
-/* SAB_OPT_POLY_KERNEL (tetrahedral sites with cell lists set): 0 = tile kernel, "previous site first" over tiles of
- * frames with an FP32 pre-test (default); 4 = the per-frame chunk-sequential kernel it replaced; 1 = frame-parallel
+/* SAB_OPT_POLY_KERNEL (tetrahedral sites with cell lists set): 0 = stream kernel (default): warp-specialised frame
+ * pipeline, "previous site first" with an FP32 pre-test and the PBC wrap scan fused in; 5 = tile kernel (same tests over
+ * tiles of frames after the separate wrap-scan kernels); 4 = per-frame chunk-sequential float64 kernel; 1 = frame-parallel
  * cell-list kernel; 3 = experimental prefetch variant.  All give identical results (cross-check twins).
  * SAB_OPT_SEQ_CHUNK: consecutive frames per CTA chunk (default: automatic). */
 #define SAB_OPT_POLY_KERNEL 2
@@ -143,6 +144,7 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
  * point is within the stated error band of a face (results identical either way); 0: float64 only. */
 #define SAB_OPT_FP32_FILTER 5
 #define SAB_OPT_TILE_FRAMES 6 /* frames per tile of the tile kernel, 1..4 (0 = automatic) */
+#define SAB_OPT_STREAM_PRODUCERS 7 /* producer warps per CTA of the stream kernel (0 = automatic) */
 int sab_set_option(sab_engine *e, int key, int64_t value);
 
 /* ---- the hot path -------------------------------------------------------------------- */
@@ -169,7 +171,8 @@ int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_frames, void 
  *   the PBC wrap-scan kernels in ns (both from CUDA events on `stream`), [8] bit pattern of the
  *   largest excursion span max(raw - W) - min(raw - W) over all framework coordinates so far (double;
  *   guard of the scan formulation), [9] atom-frames that the float32 pre-test of the
- *   tetrahedral kernel could not decide and that were settled by its exact float64 pass, [10..11] reserved.
+ *   tetrahedral kernel could not decide and that were settled by its exact float64 pass, [10] 1 when the stream
+ *   kernel's wrap-count chain check failed and the batch was redone with the scan kernels, [11] reserved.
  * When info[3] < 0 the PBC state advances to the end of the batch.  When info[3] = t >= 0 the
  * results of frames < t are valid, the PBC state is left untouched, and the caller commits
  * the valid prefix with sab_commit_pbc(..., n_commit = t) (same workspace, unmodified). */

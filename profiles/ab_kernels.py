@@ -12,9 +12,10 @@ g = syn.argyrodite_geometry(2)
 d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
-VARIANTS = [("tile kernel (default)", {}), ("seq1 (previous default)", {nat.OPT_POLY_KERNEL: 4}),
-            ("tile, 3 frames", {nat.OPT_TILE_FRAMES: 3}), ("tile, 2 frames", {nat.OPT_TILE_FRAMES: 2}),
-            ("tile, chunk 128", {nat.OPT_SEQ_CHUNK: 128}), ("tile, fp64 only", {nat.OPT_FP32_FILTER: 0})]
+VARIANTS = [("tile kernel + wrap scan", {nat.OPT_POLY_KERNEL: 5}), ("stream kernel (default)", {}),
+            ("stream, 2 producer warps", {nat.OPT_STREAM_PRODUCERS: 2}), ("stream, 4 producer warps", {nat.OPT_STREAM_PRODUCERS: 4}),
+            ("stream, chunk 128", {nat.OPT_SEQ_CHUNK: 128}), ("stream, fp64 only", {nat.OPT_FP32_FILTER: 0}),
+            ("seq1 + wrap scan", {nat.OPT_POLY_KERNEL: 4})]
 if len(sys.argv) > 2:
     VARIANTS = VARIANTS[:int(sys.argv[2])]
 for label, opts in VARIANTS:
@@ -25,8 +26,8 @@ for label, opts in VARIANTS:
     for i in range(5):
         r = e.assign_device(d_frac, d_lat)
         e._pending = []
-        ts.append(e.last_info["assign_ns"] * 1e-6)
+        ts.append((e.last_info["assign_ns"] + e.last_info["wrap_ns"]) * 1e-6)
     r = r.cpu().numpy()
     if ref is None:
         ref = r
-    print(f"{label:32s} assign kernel ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}  fallback frames={e.last_info['full27']} deferred={e.last_info.get('deferred')}", flush=True)
+    print(f"{label:32s} wrap scan + assign ms: min {min(ts[1:]):.3f} median {np.median(ts[1:]):.3f}   identical={np.array_equal(r, ref)}  fallback frames={e.last_info['full27']} deferred={e.last_info.get('deferred')} scan_redo={e.last_info.get('scan_redo')}", flush=True)

@@ -35,8 +35,11 @@ struct SabPolyTables {
 // Unwrapped vertices of one polyhedron in one frame + bounding box + centroid.
 __device__ __forceinline__ void sab_poly_vertices(const double *__restrict__ frame, const SabPolyTables &T,
                                                   int s, const int32_t *__restrict__ wrow, bool legacy_now,
-                                                  double (*vc)[3], int &nv, double *lo, double *hi, double *cen)
+                                                  double (*vc)[3], int &nv, double *lo, double *hi, double *cen,
+                                                  const double *__restrict__ anchor = nullptr)
 {
+    // wrow == nullptr: the wrap count comes from the anchor formulation W = rint(raw - anchor) of the stream
+    // kernel (k_polyhedral_stream.cuh), which equals the scanned count while its chain check holds
     nv = T.n_slot[s];
     const int32_t *sa = T.slot_atom + (size_t)s * T.smax;
     const int32_t *sf = T.slot_fw + (size_t)s * T.smax;
@@ -44,7 +47,11 @@ __device__ __forceinline__ void sab_poly_vertices(const double *__restrict__ fra
     for (int v = 0; v < nv; v++)
 #pragma unroll
         for (int d = 0; d < 3; d++)
-            vc[v][d] = frame[(size_t)sa[v] * 3 + d] + (double)(ss[3 * v + d] - wrow[3 * sf[v] + d]);
+        {
+            const double raw = frame[(size_t)sa[v] * 3 + d];
+            const int W = wrow ? wrow[3 * sf[v] + d] : (int)rint(raw - anchor[3 * sf[v] + d]);
+            vc[v][d] = raw + (double)(ss[3 * v + d] - W);
+        }
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         double mn = vc[0][d];

@@ -40,7 +40,7 @@ __device__ __noinline__ int sab_exhaustive_atom(const double *__restrict__ frame
                                                 int64_t f, int64_t legacy_init_frame, int atom, int n_sites,
                                                 const SabPolyTables &T, int32_t *__restrict__ spill,
                                                 long long spill_capacity, unsigned long long *__restrict__ counters,
-                                                int *count)
+                                                int *count, const double *__restrict__ anchor = nullptr)
 {
     double x[3];
     for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)atom * 3 + d]);
@@ -52,7 +52,7 @@ __device__ __noinline__ int sab_exhaustive_atom(const double *__restrict__ frame
             double vc[SAB_MAX_VERT][3], lo[3], hi[3], cen[3];
             int nv;
             bool legacy_now = T.legacy_init && T.legacy_init[s] && f == legacy_init_frame;
-            sab_poly_vertices(frame, T, s, wrow, legacy_now, vc, nv, lo, hi, cen);
+            sab_poly_vertices(frame, T, s, wrow, legacy_now, vc, nv, lo, hi, cen, anchor);
             if (sab_poly_contains_atom(vc, cen, T.simp + (size_t)s * T.fmax * 3, T.n_face[s], lo, hi, x)) {
                 if (pass == 0) { if (c == 0) first = s; c++; }
                 else spill[off + 1 + k++] = s;

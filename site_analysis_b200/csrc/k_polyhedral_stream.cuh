@@ -1,0 +1,306 @@
+// k_polyhedral_stream.cuh -- the production tetrahedral kernel: a warp-specialised frame pipeline.
+//
+// Same contract and bit-identical results as k_polyhedral_assign_tile (k_polyhedral_tile.cuh), but
+//   * ONE pass over the trajectory: the PBC wrap scan (k_wrap.cuh) is fused in, so the only global traffic is
+//     the raw frames in (copy engine) and the int32 site ids out;
+//   * no CTA-wide barrier in the steady state: producer warps turn raw frames into float rows, consumer
+//     warps own 32 mobile atoms each and walk the frames on their own, coupled only through mbarriers
+//     on a ring of row slots.
+//
+// A CTA owns a contiguous chunk of frames.
+//   copy engine  cp.async.bulk of whole raw frames into a ring of SAB_STREAM raw slots (mbarrier complete_tx).
+//   producers    (P warps) per frame:
+//       column pass  for every referenced framework coordinate j: raw, W = rint(raw - anchor[j]),
+//                    u = raw - W (the unwrapped coordinate raw + (shift - W) is formed from it, pbc_utils.py:220),
+//                    excursion min/max of u, validity tube |float(u) - anchor| <= delta of the cell lists, and
+//                    the CHAIN CHECK  W_t - W_{t-1} == rint(raw_t - raw_{t-1})  (the reference's own update,
+//                    pbc_utils.py:210-217) together with its 0.3 step bound (:216).  The chain starts from the
+//                    engine's carried wrap counts (first chunk) or from rint(raw - anchor) of the frame before
+//                    the chunk, which is what the CTA of the previous chunk ends with, so while no check fails
+//                    W is EXACTLY the sequential wrap count of k_wrap_rows.  A failed check raises the
+//                    `invalid` counter and the host redoes the batch with the scan kernels (never observed
+//                    inside guard G1, DESIGN.md section 4: the anchors sit mid-range of an excursion < 0.3).
+//       row pass     float row of the frame: float(u) + shift for every (coordinate, shift) pair in use, then
+//                    the wrapped mobile coordinates (atom.py:104) -- the operands of sab_tet_filter32b.
+//   consumers    (C warps) per frame and group of 32 atoms: lane a tests `last` (the atom's most recent site as
+//                    far as it is certain), the reference's first test (site_collection.py:147-152,
+//                    polyhedral_site_collection.py:104-107); "certainly inside" is the reference's answer.  Every
+//                    other verdict makes the WARP search that atom's cell list, 32 candidates at a time:
+//                    none -> None, one -> that site, 2..4 -> spilled list for the priority resolver, anything
+//                    float32 cannot decide -> deferred to the exact float64 pass (k_polyhedral_deferred).
+// Frames outside the validity tube (and the legacy first-frame rule) take the exhaustive generic path per atom.
+#pragma once
+#include "k_polyhedral_tile.cuh"
+
+#define SAB_STREAM_ROWS 4         // ring of float rows (producers run at most this far ahead of the slowest consumer)
+#define SAB_STREAM_MAXRAW 4       // ring of raw frames (copy engine runs SAB raw - 1 frames ahead)
+#define SAB_STREAM_MAXTHREADS 320
+#ifndef SAB_STREAM_MINBLOCKS
+#define SAB_STREAM_MINBLOCKS 2
+#endif
+#define SAB_CNT_INVALID 10        // counters[]: the anchor formulation of the wrap count failed its chain check
+
+struct SabStreamTables {
+    int n_used;                   // staged (framework coordinate, slot shift) pairs
+    int stride;                   // floats per row: n_used + 3 A, rounded up to a multiple of 4
+    int m3;                       // framework coordinates
+    const int4 *vars;             // [n_used] {3 * atom + d, framework column j, float bits of the shift, -}
+    const uint16_t *rec;          // [S][12] byte offsets into a row, vertices in slot order
+    int G;
+    const int32_t *cell_off;      // [G^3 + 1]
+    const uint16_t *cell_sites;   // CSR entries, ascending per cell
+    float delta_f;
+    int use_f32;
+    long long *defer;
+    long long defer_cap;
+    const double *anchor;         // [m3] anchors of raw - W
+    const int32_t *fw_atoms;      // [M] structure index of framework atom m
+    const double *prev_raw;       // [m3] carry: raw coordinates of the frame before this batch
+    const int32_t *wraps;         // [m3] carry: wrap counts at that frame
+    int skip_check_frame0;
+    int n_raw;                    // raw slots in use (2..SAB_STREAM_MAXRAW)
+    int n_prod;                   // producer warps
+    int use_tma;                  // frames are 16-byte aligned and sized
+    double *chunk_exc;            // out [n_chunks][m3][2]: excursion (min, max) of u per chunk
+};
+
+__device__ __forceinline__ void sab_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void sab_bar_producers(int n_threads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+__global__ void __launch_bounds__(SAB_STREAM_MAXTHREADS, SAB_STREAM_MINBLOCKS)
+k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, int64_t chunk, int n_atoms, int n_mobile,
+                           const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabStreamTables C,
+                           int64_t legacy_init_frame, int32_t *__restrict__ result, int32_t *__restrict__ spill,
+                           long long spill_capacity, unsigned long long *__restrict__ counters,
+                           unsigned long long *__restrict__ n_fallback)
+{
+    extern __shared__ __align__(128) unsigned char sm_stream[];
+    const int n3 = 3 * n_atoms, m3 = C.m3, a3 = 3 * n_mobile;
+    double *rawd = reinterpret_cast<double *>(sm_stream);                        // [n_raw][n3] raw frames (copy engine)
+    double *ancd = rawd + (size_t)C.n_raw * n3;                                   // [m3] anchors
+    double *prevcol = ancd + m3;                                                  // [m3] raw of the previous frame
+    double *exc = prevcol + m3;                                                   // [m3][2] running (min, max) of u
+    float *rows = reinterpret_cast<float *>(exc + 2 * (size_t)m3);               // [ROWS][stride]
+    float *colbase = rows + (size_t)SAB_STREAM_ROWS * C.stride;                  // [2][m3] float(u) of the current frame (double-buffered)
+    int *prevW = reinterpret_cast<int *>(colbase + 2 * (size_t)m3);                           // [m3] W of the previous frame
+    int *fwcol = prevW + m3;                                                      // [m3] 3 * atom + d
+    int *mobcol = fwcol + m3;                                                     // [3 A] 3 * atom + d of the mobile coordinates
+    int2 *svars = reinterpret_cast<int2 *>(mobcol + ((a3 + 1) & ~1));             // [n_used] {column, shift bits}
+    int *last = reinterpret_cast<int *>(svars + C.n_used);                        // [A]
+    __shared__ __align__(8) uint64_t raw_full[SAB_STREAM_MAXRAW], row_full[SAB_STREAM_ROWS], row_empty[SAB_STREAM_ROWS];
+    __shared__ int pbad[4], rowflag[SAB_STREAM_ROWS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_prod_thr = C.n_prod * 32, n_cons = (blockDim.x >> 5) - C.n_prod, n_cons_thr = n_cons * 32;
+    const int RS = C.n_raw;
+    const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
+
+    // ---- one-time setup (all threads) ----------------------------------------------------------------------
+    for (int j = tid; j < m3; j += blockDim.x) {
+        ancd[j] = C.anchor[j];
+        fwcol[j] = C.fw_atoms[j / 3] * 3 + j % 3;
+    }
+    for (int q = tid; q < a3; q += blockDim.x) mobcol[q] = mobile[q / 3] * 3 + q % 3;
+    for (int j = tid; j < C.n_used; j += blockDim.x) { const int4 e = C.vars[j]; svars[j] = make_int2(e.y, e.z); }
+    if (tid == 0) {
+        for (int i = 0; i < SAB_STREAM_MAXRAW; i++) sab_mbar_init(&raw_full[i], 1);
+        for (int i = 0; i < SAB_STREAM_ROWS; i++) { sab_mbar_init(&row_full[i], n_prod_thr); sab_mbar_init(&row_empty[i], n_cons_thr); rowflag[i] = 0; }
+        for (int i = 0; i < 4; i++) pbad[i] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < C.n_prod) {
+        // =========================================== producers ===========================================
+        const int pt = tid;                                     // 0 .. n_prod_thr - 1
+        auto issue = [&](int64_t f, unsigned it) {              // thread 0 only: raw frame f -> slot it % RS
+            const unsigned bytes = (unsigned)((size_t)n3 * 8);
+            const int slot = (int)(it % (unsigned)RS);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            sab_mbar_expect_tx(&raw_full[slot], bytes);
+            sab_bulk_g2s(rawd + (size_t)slot * n3, frac + (size_t)f * n3, bytes, &raw_full[slot]);
+        };
+        unsigned it = 0;                                        // frames processed by this CTA so far
+        for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
+            sab_bar_producers(n_prod_thr);                      // previous chunk fully converted: raw slots idle
+            if (pt == 0 && C.use_tma)
+                for (int i = 0; i < RS - 1 && c0 + i < c1; i++) issue(c0 + i, it + i);
+            for (int j = pt; j < m3; j += n_prod_thr) {         // chain start (owner-private state)
+                double p; int w;
+                if (c0 == 0) { p = C.prev_raw[j]; w = C.wraps[j]; }
+                else { p = frac[(size_t)(c0 - 1) * n3 + fwcol[j]]; w = (int)rint(p - ancd[j]); }
+                prevcol[j] = p; prevW[j] = w;
+                exc[2 * j] = INFINITY; exc[2 * j + 1] = -INFINITY;
+            }
+            for (int64_t f = c0; f < c1; f++, it++) {
+                const int rslot = (int)(it % (unsigned)RS), wslot = (int)(it % SAB_STREAM_ROWS);
+                double *raw = rawd + (size_t)rslot * n3;
+                if (C.use_tma) sab_mbar_wait(&raw_full[rslot], (it / (unsigned)RS) & 1);
+                else {
+                    sab_bar_producers(n_prod_thr);              // everybody is done with the frame before
+                    const double *g = frac + (size_t)f * n3;
+                    for (int q = pt; q < n3; q += n_prod_thr) raw[q] = g[q];
+                    sab_bar_producers(n_prod_thr);
+                }
+                // ---- column pass --------------------------------------------------------------------------
+                int bad = 0;
+                float *cb = colbase + (size_t)(it & 1) * m3;     // a slow producer may still read the other half (row pass of f - 1)
+                for (int j = pt; j < m3; j += n_prod_thr) {
+                    const double r = raw[fwcol[j]], anc = ancd[j], p = prevcol[j];
+                    const int W = (int)rint(r - anc);
+                    const double diff = r - p, w = rint(diff), phys = diff - w;      // pbc_utils.py:210-216
+                    if ((phys >= 0.3 || phys <= -0.3) && !(C.skip_check_frame0 && f == 0))
+                        atomicMin(&counters[3], (unsigned long long)f);
+                    if (W - prevW[j] != (int)w) counters[SAB_CNT_INVALID] = 1ULL;
+                    const double u = r - (double)W;
+                    const float base = (float)u;
+                    if (fabsf(base - (float)anc) > C.delta_f) bad = 1;
+                    if (u < exc[2 * j]) exc[2 * j] = u;
+                    if (u > exc[2 * j + 1]) exc[2 * j + 1] = u;
+                    cb[j] = base; prevcol[j] = r; prevW[j] = W;
+                }
+                if (bad) atomicOr(&pbad[it & 3], 1);
+                sab_bar_producers(n_prod_thr);                  // colbase and pbad complete; frame f - 1 fully converted
+                if (pt == 0) {
+                    if (C.use_tma && f + RS - 1 < c1) issue(f + RS - 1, it + RS - 1);       // into the slot of frame f - 1
+                    pbad[(it + 2) & 3] = 0;
+                }
+                int flag = pbad[it & 3];
+                if (T.legacy_init && legacy_init_frame == f) flag = 1;
+                if (it >= SAB_STREAM_ROWS) sab_mbar_wait(&row_empty[wslot], ((it / SAB_STREAM_ROWS) - 1) & 1);
+                // ---- row pass -----------------------------------------------------------------------------
+                float *row = rows + (size_t)wslot * C.stride;
+                for (int j = pt; j < C.n_used; j += n_prod_thr) {
+                    const int2 e = svars[j];
+                    row[j] = cb[e.x] + __int_as_float(e.y);
+                }
+                for (int q = pt; q < a3; q += n_prod_thr) {
+                    const double x = raw[mobcol[q]];
+                    row[C.n_used + q] = (float)(x - floor(x));                               // atom.py:104
+                }
+                if (pt == 0) {
+                    rowflag[wslot] = flag;
+                    if (flag) atomicAdd(n_fallback, 1ULL);
+                }
+                sab_mbar_arrive(&row_full[wslot]);
+            }
+            for (int j = pt; j < m3; j += n_prod_thr) {
+                C.chunk_exc[((size_t)ch * m3 + j) * 2] = exc[2 * j];
+                C.chunk_exc[((size_t)ch * m3 + j) * 2 + 1] = exc[2 * j + 1];
+            }
+        }
+    } else {
+        // =========================================== consumers ===========================================
+        const int cw = warp - C.n_prod;
+        const unsigned FULL = 0xffffffffu;
+        unsigned it = 0;
+        for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
+            for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = -1;   // owner-private
+            for (int64_t f = c0; f < c1; f++, it++) {
+                const int wslot = (int)(it % SAB_STREAM_ROWS);
+                sab_mbar_wait(&row_full[wslot], (it / SAB_STREAM_ROWS) & 1);
+                const float *row = rows + (size_t)wslot * C.stride;
+                const float *xrow = row + C.n_used;
+                const int flag = rowflag[wslot];
+                int32_t *res = result + (size_t)f * n_mobile;
+                for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {
+                    const int a = g0 + lane;
+                    const bool valid = a < n_mobile;
+                    int la = valid ? last[a] : -1;
+                    int out = SAB_NONE;
+                    if (flag) {                                  // outside the validity tube: generic path
+                        if (valid) {
+                            int c = 0;
+                            out = sab_exhaustive_atom(frac + (size_t)f * n3, nullptr, f, legacy_init_frame, mobile[a], n_sites, T,
+                                                      spill, spill_capacity, counters, &c, C.anchor);
+                            if (c == 1) la = out; else if (c > 1) la = -1;
+                        }
+                    } else {
+                        int v = 0;
+                        if (valid && la >= 0 && C.use_f32)
+                            v = sab_tet_filter32b(row, sab_tet_rec(C.rec + (size_t)la * 12), xrow + 3 * a);
+                        if (v == 1) out = la;
+                        unsigned m = __ballot_sync(FULL, valid && v != 1);
+                        while (m) {                              // warp-uniform: one search per atom that needs it
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float *xs = xrow + 3 * (g0 + src);
+                            const int cell = sab_cell_of_f(xs, C.G);
+                            const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
+                            int c = 0, h0 = -1, h1 = -1, h2 = -1, h3 = -1;
+                            unsigned und = C.use_f32 ? 0u : 1u;
+                            if (C.use_f32)
+                                for (int i0 = 0; i0 < len; i0 += 32) {
+                                    const int i = i0 + lane;
+                                    int s = 0, vv = 0;
+                                    if (i < len) {
+                                        s = __ldg(C.cell_sites + b + i);
+                                        vv = sab_tet_filter32b(row, sab_tet_rec(C.rec + (size_t)s * 12), xs);
+                                    }
+                                    unsigned m1 = __ballot_sync(FULL, vv == 1);
+                                    und |= __ballot_sync(FULL, vv == 2);
+                                    while (m1 && c < SAB_POLY_KEEP) {
+                                        const int l = __ffs(m1) - 1;
+                                        m1 &= m1 - 1;
+                                        const int sv = __shfl_sync(FULL, s, l);
+                                        if (c == 0) h0 = sv; else if (c == 1) h1 = sv; else if (c == 2) h2 = sv; else h3 = sv;
+                                        c++;
+                                    }
+                                    c += __popc(m1);
+                                }
+                            if (lane == src) {
+                                if (und || c > SAB_POLY_KEEP) {  // float32 could not decide (or a long list): exact pass later
+                                    out = SAB_DEFERRED; la = -1;
+                                    const unsigned long long di = atomicAdd(&counters[9], 1ULL);
+                                    if ((long long)di < C.defer_cap) C.defer[di] = (long long)f * n_mobile + a;
+                                } else if (c == 0) out = SAB_NONE;
+                                else if (c == 1) { out = h0; la = h0; }
+                                else {
+                                    int h[SAB_POLY_KEEP] = {h0, h1, h2, h3};
+                                    out = sab_tile_spill(c, h, spill, spill_capacity, counters);
+                                    la = -1;
+                                }
+                            }
+                        }
+                    }
+                    if (valid) { res[a] = out; last[a] = la; }
+                }
+                sab_mbar_arrive(&row_empty[wslot]);
+            }
+        }
+    }
+}
+
+// Fused-path commit (1 thread per framework coordinate): advance the carry to the end of the batch from the
+// per-chunk excursions the stream kernel wrote.  Skipped by the kernel itself when the batch must be redone:
+// spill overflow, an invalidating step, or a failed chain check.
+__global__ void k_wrap_commit_stream(const double *__restrict__ frac, int64_t n_frames, int n_atoms,
+                                     const int32_t *__restrict__ fw_atoms, int m3, int n_chunks,
+                                     const double *__restrict__ chunk_exc, const double *__restrict__ anchor,
+                                     double *__restrict__ prev_raw, int32_t *__restrict__ wraps,
+                                     double *__restrict__ excursion, unsigned long long *__restrict__ counters)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= m3 || n_frames <= 0) return;
+    if (counters[2] != 0ULL || counters[3] != ~0ULL || counters[SAB_CNT_INVALID] != 0ULL) return;
+    double lo = excursion[2 * col], hi = excursion[2 * col + 1];
+#pragma unroll 8
+    for (int c = 0; c < n_chunks; c++) {
+        const double2 e2 = *reinterpret_cast<const double2 *>(chunk_exc + ((size_t)c * m3 + col) * 2);
+        lo = fmin(lo, e2.x);
+        hi = fmax(hi, e2.y);
+    }
+    excursion[2 * col] = lo; excursion[2 * col + 1] = hi;
+    atomicMax(&counters[8], (unsigned long long)__double_as_longlong(fmax(hi - lo, 0.0)));        // guard G1, read by the host
+    const double r = frac[((size_t)(n_frames - 1) * n_atoms + fw_atoms[col / 3]) * 3 + col % 3];
+    wraps[col] = (int)rint(r - anchor[col]);
+    prev_raw[col] = r;
+}

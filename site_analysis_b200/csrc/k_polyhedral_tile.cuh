@@ -142,13 +142,14 @@ __device__ __forceinline__ int sab_tet_filter32b(const float *__restrict__ tab, 
 
 // exact float64 test of one (site, atom) in one frame, operands from global memory (deferred pass)
 __device__ __noinline__ bool sab_tet_exact_global(const double *__restrict__ frame, const int32_t *__restrict__ wrow,
-                                                  const SabPolyTables &T, int s, int atom)
+                                                  const SabPolyTables &T, int s, int atom,
+                                                  const double *__restrict__ anchor = nullptr)
 {
     double x[3], vc[SAB_MAX_VERT][3], lo[3], hi[3], cen[3];
     int nv;
 #pragma unroll
     for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)atom * 3 + d]);
-    sab_poly_vertices(frame, T, s, wrow, false, vc, nv, lo, hi, cen);
+    sab_poly_vertices(frame, T, s, wrow, false, vc, nv, lo, hi, cen, anchor);
     return sab_poly_contains_atom(vc, cen, T.simp + (size_t)s * T.fmax * 3, T.n_face[s], lo, hi, x);
 }
 
@@ -413,7 +414,8 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
                                       const int32_t *__restrict__ cell_off, const uint16_t *__restrict__ cell_sites,
                                       const int32_t *__restrict__ wrows, int m3, const long long *__restrict__ defer,
                                       long long defer_cap, int32_t *__restrict__ result, int32_t *__restrict__ spill,
-                                      long long spill_capacity, unsigned long long *__restrict__ counters)
+                                      long long spill_capacity, unsigned long long *__restrict__ counters,
+                                      const double *__restrict__ anchor = nullptr)   // wrows == nullptr: W = rint(raw - anchor)
 {
     const long long n_def = (long long)counters[9];
     if (n_def == 0) return;
@@ -426,7 +428,7 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
         if (result[idx] != SAB_DEFERRED) continue;               // warp-uniform
         const int64_t f = idx / n_mobile; const int a = (int)(idx - f * n_mobile);
         const double *frame = frac + (size_t)f * n_atoms * 3;
-        const int32_t *wrow = wrows + (size_t)f * m3;
+        const int32_t *wrow = wrows ? wrows + (size_t)f * m3 : nullptr;
         const int atom = mobile[a];
         double x[3];
 #pragma unroll
@@ -437,7 +439,7 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
         for (int i0 = 0; i0 < len; i0 += 32) {                   // pass 1: count
             const int i = i0 + lane;
             bool in = false;
-            if (i < len) in = sab_tet_exact_global(frame, wrow, T, cell_sites[b + i], atom);
+            if (i < len) in = sab_tet_exact_global(frame, wrow, T, cell_sites[b + i], atom, anchor);
             const unsigned m = __ballot_sync(0xffffffffu, in);
             if (m && first < 0) first = cell_sites[b + i0 + __ffs(m) - 1];
             c += __popc(m);
@@ -456,7 +458,7 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
                 for (int i0 = 0; i0 < len; i0 += 32) {           // pass 2: ascending list positions
                     const int i = i0 + lane;
                     bool in = false;
-                    if (i < len) in = sab_tet_exact_global(frame, wrow, T, cell_sites[b + i], atom);
+                    if (i < len) in = sab_tet_exact_global(frame, wrow, T, cell_sites[b + i], atom, anchor);
                     const unsigned m = __ballot_sync(0xffffffffu, in);
                     if (in) spill[off + 1 + k + __popc(m & ((1u << lane) - 1))] = cell_sites[b + i];
                     k += __popc(m);

@@ -20,6 +20,7 @@
 #include "k_polyhedral_seq.cuh"
 #include "k_polyhedral_seq1.cuh"
 #include "k_polyhedral_tile.cuh"
+#include "k_polyhedral_stream.cuh"
 #include "k_resolve.cuh"
 #include "k_resolve_fast.cuh"
 #include "k_spherical.cuh"
@@ -102,6 +103,8 @@ struct sab_engine {
     // tile kernel: compact staging table and float-table site records (derived in sab_set_cell_lists)
     bool tile_ok = false; int n_used = 0; int4 *d_tile_vars = nullptr; uint16_t *d_tile_rec = nullptr;
     int tile_frames = 0;                   // SAB_OPT_TILE_FRAMES (0 = automatic)
+    int stream_prod = 0;                   // SAB_OPT_STREAM_PRODUCERS (0 = automatic)
+    bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -376,6 +379,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
     if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
     if (key == SAB_OPT_TILE_FRAMES) { e->tile_frames = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_STREAM_PRODUCERS) { if (value < 0 || value > 8) return fail(SAB_EINVAL, "producer warps: 0..8"); e->stream_prod = (int)value; return SAB_OK; }
     if (key == SAB_OPT_FP32_FILTER) { e->fp32_filter = value != 0; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
@@ -385,6 +389,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
 // ---------------------------------------------------------------- workspace layout
 struct Workspace {
     int n_chunks = 0; int m3 = 0;
+    int64_t exc_chunks = 0;                                   // capacity of chunk_exc in chunks (>= n_chunks; stream kernel: up to 2048)
     int32_t *totals = nullptr; double *chunk_exc = nullptr; int32_t *rows = nullptr;
     long long *defer = nullptr; long long defer_cap = 0;      // deferred atom-frames of the tile kernel
     size_t bytes = 0;
@@ -401,7 +406,8 @@ static Workspace layout(const sab_engine *e, int64_t F, void *base)
     size_t off = 0;
     char *b = (char *)base;
     w.totals = (int32_t *)(b + off); off += align256(sizeof(int32_t) * (size_t)w.n_chunks * w.m3);
-    w.chunk_exc = (double *)(b + off); off += align256(sizeof(double) * 2 * (size_t)w.n_chunks * w.m3);
+    w.exc_chunks = std::max<int64_t>(w.n_chunks, std::min<int64_t>(F, 2048));
+    w.chunk_exc = (double *)(b + off); off += align256(sizeof(double) * 2 * (size_t)w.exc_chunks * w.m3);
     w.rows = (int32_t *)(b + off); off += align256(sizeof(int32_t) * (size_t)F * w.m3);
     if (e->kind == SAB_POLYHEDRAL) {
         w.defer_cap = std::max<long long>(4096, (long long)F * e->A / 16);
@@ -485,6 +491,62 @@ extern "C" int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n
     return SAB_OK;
 }
 
+// ---------------------------------------------------------------- stream kernel (tetrahedral sites, fused wrap scan)
+struct StreamPlan { bool ok = false; int n_prod = 0, n_cons = 0, n_raw = 0, use_tma = 0; size_t smem = 0, stride = 0; int64_t chunk = 0; int grid = 0; };
+
+static StreamPlan plan_stream(sab_engine *e, const double *d_frac, int64_t F, const Workspace &w)
+{
+    StreamPlan p;
+    if (e->kind != SAB_POLYHEDRAL || !e->cells_set || !e->tile_ok || e->poly_kernel != 0 || e->force_scan || !w.defer) return p;
+    p.n_cons = std::min(6, (e->A + 31) / 32);
+    p.n_prod = e->stream_prod > 0 ? e->stream_prod : std::max(2, (p.n_cons + 1) / 2);
+    if ((p.n_prod + p.n_cons) * 32 > SAB_STREAM_MAXTHREADS) p.n_prod = SAB_STREAM_MAXTHREADS / 32 - p.n_cons;
+    if (p.n_prod < 1) return p;
+    const size_t n3 = 3 * (size_t)e->N, m3 = 3 * (size_t)e->M, a3 = 3 * (size_t)e->A;
+    p.stride = ((size_t)e->n_used + a3 + 3) & ~(size_t)3;
+    p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
+    auto smem_for = [&](int n_raw) {
+        return sizeof(double) * ((size_t)n_raw * n3 + 4 * m3) + sizeof(float) * (SAB_STREAM_ROWS * p.stride + 2 * m3) +
+               sizeof(int) * (2 * m3 + ((a3 + 1) & ~(size_t)1) + 2 * (size_t)e->n_used + (size_t)e->A) + 128;
+    };
+    p.n_raw = SAB_STREAM_MAXRAW;
+    while (p.n_raw > 2 && smem_for(p.n_raw) > (size_t)(226 * 1024 / SAB_STREAM_MINBLOCKS)) p.n_raw--;
+    p.smem = smem_for(p.n_raw);
+    if (p.smem > 226 * 1024) return p;
+    if (cudaFuncSetAttribute(k_polyhedral_assign_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_stream, (p.n_prod + p.n_cons) * 32, p.smem);
+    const int64_t resident = (int64_t)std::max(1, per_sm) * e->sm_count;
+    // one contiguous chunk per resident CTA (the history-free first frame of a chunk costs a full search); the
+    // per-chunk excursion records go to the workspace's chunk_exc area
+    p.chunk = e->seq_chunk > 0 ? e->seq_chunk : std::max<int64_t>(1, (F + resident - 1) / resident);
+    const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
+    if (n_chunks > w.exc_chunks) return p;
+    p.grid = (int)std::min<int64_t>(n_chunks, resident);
+    p.ok = true;
+    return p;
+}
+
+static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_frac, int64_t F, int32_t *d_result,
+                         int32_t *d_spill, int64_t spill_cap, const Workspace &w, cudaStream_t st)
+{
+    SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp, e->d_legacy_init};
+    SabStreamTables C{e->n_used, (int)p.stride, 3 * e->M, e->d_tile_vars, e->d_tile_rec, e->G, e->d_cell_off, e->d_cell_sites,
+                      (float)e->delta - 4e-7f, e->fp32_filter, w.defer, w.defer_cap, e->d_anchor, e->d_fw_atoms, e->d_prev_raw,
+                      e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc};
+    const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
+    k_polyhedral_assign_stream<<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+        e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+    // exact float64 pass over the atom-frames float32 could not decide (returns at once when there are none)
+    k_polyhedral_deferred<<<e->sm_count * 8, 256, 0, st>>>(d_frac, F, e->N, e->A, e->d_mobile, T, e->G, e->d_cell_off,
+        e->d_cell_sites, nullptr, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor);
+    k_wrap_commit_stream<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, (int)n_chunks, w.chunk_exc, e->d_anchor,
+        e->d_prev_raw, e->d_wraps, e->d_excursion, e->d_counters);
+    e->launches += 3;
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
+
 static int launch_assign(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride, int64_t F,
                          int32_t *d_result, int32_t *d_spill, int64_t spill_cap, const Workspace &w, cudaStream_t st,
                          double *d_centres_out)
@@ -536,7 +598,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, e->d_rcut, e->d_rcut_q, d_result, d_spill, (long long)spill_cap, e->d_counters);
         break;
     }
-    case SAB_POLYHEDRAL: if (e->cells_set && e->poly_kernel == 0 && e->tile_ok) {
+    case SAB_POLYHEDRAL: if (e->cells_set && (e->poly_kernel == 0 || e->poly_kernel == 5) && e->tile_ok) {
         // tile kernel: frames per tile chosen so that SAB_TILE_MINBLOCKS CTAs stay resident per SM
         const int block = SAB_TILE_THREADS;
         const size_t stride = ((size_t)e->n_used + 3 * (size_t)e->A + 3) & ~(size_t)3;
@@ -672,12 +734,15 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
     CU(cudaEventRecord(e->ev_t[0], st));
-    if (w.m3) { run_wrap_pass(e, d_frac, n_frames, w, st, true); CU(cudaGetLastError()); }
+    // tetrahedral sites: one fused kernel (wrap scan + assignment + commit); everything else: scan kernels, then assignment
+    const StreamPlan sp = plan_stream(e, d_frac, n_frames, w);
+    if (!sp.ok && w.m3) { run_wrap_pass(e, d_frac, n_frames, w, st, true); CU(cudaGetLastError()); }
     CU(cudaEventRecord(e->ev_t[1], st));
-    rc = launch_assign(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, w, st, nullptr);
+    rc = sp.ok ? launch_stream(e, sp, d_frac, n_frames, d_result, d_spill, spill_capacity, w, st)
+               : launch_assign(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, w, st, nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev_t[2], st));
-    if (w.m3) {      // device-side conditional commit: skipped by the kernel itself on overflow / invalidating step
+    if (w.m3 && !sp.ok) {      // device-side conditional commit: skipped by the kernel itself on overflow / invalidating step
         k_wrap_commit<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, n_frames, n_frames, e->N, e->d_fw_atoms, w.m3, w.n_chunks,
                                                           w.rows, w.chunk_exc, e->d_prev_raw, e->d_wraps, e->d_excursion,
                                                           e->d_counters + CNT_OVERFLOW, e->d_counters + CNT_SPAN);
@@ -687,6 +752,14 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     unsigned long long h[CNT_N];
     CU(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (sp.ok && h[SAB_CNT_INVALID]) {       // anchor formulation of the wrap count failed its chain check: nothing was
+        e->force_scan = true;                // committed; redo this batch with the scan kernels (identical results)
+        rc = sab_assign_device(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, d_workspace,
+                               workspace_bytes, stream, info);
+        e->force_scan = false;
+        info[10] = 1;
+        return rc;
+    }
     e->skip_step_check_once = false;
     info[0] = (int64_t)h[CNT_AMBIGUOUS]; info[1] = (int64_t)h[CNT_SPILL]; info[2] = (int64_t)h[CNT_OVERFLOW];
     info[3] = (h[CNT_FIRST_BAD] == ~0ULL) ? -1 : (int64_t)h[CNT_FIRST_BAD];

@@ -498,7 +498,7 @@ class AssignmentEngine:
             self._build_dynvor_lists(d_frac, (d_lattice[0] if stride else d_lattice).cpu().numpy())
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
-        total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0, deferred=0)
+        total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0, deferred=0, scan_redo=0)
         span_bits = 0
         while f0 < F:
             nf = F - f0
@@ -524,6 +524,7 @@ class AssignmentEngine:
             if self._cells is not None and info[4] > max(1, nf // 50):
                 self._cells_stale = True                 # too many frames left the tube: re-anchor next batch
             total["full27"] += int(info[4]); total["launches"] += int(info[5]); total["deferred"] += int(info[9])
+            total["scan_redo"] += int(info[10])
             span_bits = max(span_bits, int(info[8]))
             total["assign_ns"] += int(info[6]); total["wrap_ns"] += int(info[7])
             if info[3] >= 0:

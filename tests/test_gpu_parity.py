@@ -113,10 +113,14 @@ def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
     outs = []
     for use_cells, opts in ((True, {}), (True, {nat.OPT_SEQ_CHUNK: 7}), (True, {nat.OPT_POLY_KERNEL: 1}),
                             (True, {nat.OPT_POLY_KERNEL: 3}), (True, {nat.OPT_POLY_KERNEL: 4}), (True, {nat.OPT_FP32_FILTER: 0}),
-                            (True, {nat.OPT_POLY_KERNEL: 4, nat.OPT_FP32_FILTER: 0}), (True, {nat.OPT_SEQ_CHUNK: 3}), (False, {})):
+                            (True, {nat.OPT_POLY_KERNEL: 4, nat.OPT_FP32_FILTER: 0}), (True, {nat.OPT_SEQ_CHUNK: 3}),
+                            (True, {nat.OPT_POLY_KERNEL: 5}), (True, {nat.OPT_POLY_KERNEL: 5, nat.OPT_SEQ_CHUNK: 7}),
+                            (True, {nat.OPT_POLY_KERNEL: 5, nat.OPT_FP32_FILTER: 0}),
+                            (True, {nat.OPT_STREAM_PRODUCERS: 1, nat.OPT_SEQ_CHUNK: 5}), (True, {nat.OPT_STREAM_PRODUCERS: 4}),
+                            (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
-        t.site_collection.engine_options = opts          # chunk-sequential (default) / odd chunk / frame-parallel
+        t.site_collection.engine_options = opts          # stream (default) / odd chunk / frame-parallel / tile / ...
         outs.append(t.trajectory_from_arrays(case["frac"], case["lattice"]))
         eng = t.site_collection._engine
         assert (eng._cells is not None) == use_cells, (name, use_cells, eng._cells)
@@ -262,7 +266,7 @@ def test_fp32_pretest_never_changes_a_result():
     kw = lambda: syn.polyhedral_engine_kwargs(g, frac[0], lat[0])                # noqa: E731
     want = bench.oracle_for(g, frac[0], lat[0])().run(frac, lat, positions=True)
     outs = []
-    for kernel, flt in ((0, 1), (0, 0), (4, 1), (4, 0)):          # tile kernel / previous chunk-sequential kernel
+    for kernel, flt in ((0, 1), (0, 0), (5, 1), (5, 0), (4, 1), (4, 0)):   # stream / tile / chunk-sequential kernel
         eng = AssignmentEngine("polyhedral", g.n_atoms, mob, device=0, **kw())
         eng.set_option(nat.OPT_POLY_KERNEL, kernel)
         eng.set_option(nat.OPT_FP32_FILTER, flt)
@@ -270,6 +274,38 @@ def test_fp32_pretest_never_changes_a_result():
         assert eng._cells is not None
     for o in outs:
         assert np.array_equal(o, want)
+
+
+def test_stream_kernel_chain_check_falls_back_to_the_scan_kernels():
+    """The stream kernel takes the wrap count as rint(raw - anchor) and checks it against the reference's
+    sequential update frame by frame.  A framework atom that drifts more than half a cell away from its
+    anchor (outside guard G1, hence strict=False) breaks the chain: the batch must be redone with the scan
+    kernels and agree with them exactly; the PBC carry must continue correctly afterwards."""
+    import warnings
+    from site_analysis_b200 import AssignmentEngine, _native as nat, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    frac, lat = syn.argyrodite_trajectory(g, 700, device="cpu")
+    frac, lat = frac.numpy().copy(), lat.numpy().copy()
+    victim = int(np.asarray(g.tetrahedra)[0][0])
+    drift = np.zeros(700)
+    drift[250:450] = np.linspace(0.0, 0.56, 200)          # slow (0.0028 per frame), then stays displaced
+    drift[450:] = 0.56
+    frac[:, victim, 0] = (frac[:, victim, 0] + drift) % 1.0
+    kw = lambda: syn.polyhedral_engine_kwargs(g, frac[0], lat[0])                # noqa: E731
+    outs, redo = [], []
+    for kernel in (0, 5, 4):
+        eng = AssignmentEngine("polyhedral", g.n_atoms, g.mobile_idx, device=0, strict=False, **kw())
+        eng.set_option(nat.OPT_POLY_KERNEL, kernel)
+        parts = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for a, b in ((0, 200), (200, 500), (500, 700)):
+                parts.append(eng.assign(frac[a:b], lat[a:b]))
+                redo.append((kernel, eng.last_info.get("scan_redo", 0)))
+        outs.append(np.concatenate(parts))
+    assert (0, 1) in redo, redo                              # the stream kernel did hit its fallback
+    assert all(r == 0 for k, r in redo if k != 0), redo
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
 def test_fast_path_is_the_one_that_runs():
@@ -283,3 +319,4 @@ def test_fast_path_is_the_one_that_runs():
     eng.assign_device(frac, lat)
     assert eng._cells is not None
     assert eng.last_info["full27"] == 0, eng.last_info
+    assert eng.last_info["scan_redo"] == 0, eng.last_info
