@@ -3,5 +3,7 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/../libsab200.so"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false \
-    -Xcompiler -fPIC -shared "$@" -o "$HERE/../libsab200.so" "$HERE/sab200.cu" -lcudart
+    -Xcompiler -fPIC -shared "$@" -o "$OUT.tmp.$$" "$HERE/sab200.cu" -lcudart
+mv -f "$OUT.tmp.$$" "$OUT"     # atomic: a snapshot taken meanwhile never sees a half-written library

@@ -105,6 +105,8 @@ struct sab_engine {
     int tile_frames = 0;                   // SAB_OPT_TILE_FRAMES (0 = automatic)
     int stream_prod = 0;                   // SAB_OPT_STREAM_PRODUCERS (0 = automatic)
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
+    size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
+    unsigned long long *h_pinned = nullptr;               // pinned [2][CNT_N]: counter initialiser | read-back
 };
 
 extern "C" int sab_abi_version(void) { return SAB_ABI_VERSION; }
@@ -141,6 +143,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
         if (e->streams[i]) cudaStreamDestroy(e->streams[i]);
@@ -513,9 +516,14 @@ static StreamPlan plan_stream(sab_engine *e, const double *d_frac, int64_t F, co
     while (p.n_raw > 2 && smem_for(p.n_raw) > (size_t)(226 * 1024 / SAB_STREAM_MINBLOCKS)) p.n_raw--;
     p.smem = smem_for(p.n_raw);
     if (p.smem > 226 * 1024) return p;
-    if (cudaFuncSetAttribute(k_polyhedral_assign_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_polyhedral_assign_stream, (p.n_prod + p.n_cons) * 32, p.smem);
+    const size_t key = (p.smem << 12) | (size_t)((p.n_prod + p.n_cons) * 32);
+    if (key != e->stream_occ_key) {
+        if (cudaFuncSetAttribute(k_polyhedral_assign_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
+        int q = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_polyhedral_assign_stream, (p.n_prod + p.n_cons) * 32, p.smem);
+        e->stream_per_sm = q; e->stream_occ_key = key;
+    }
+    const int per_sm = e->stream_per_sm;
     const int64_t resident = (int64_t)std::max(1, per_sm) * e->sm_count;
     // one contiguous chunk per resident CTA (the history-free first frame of a chunk costs a full search); the
     // per-chunk excursion records go to the workspace's chunk_exc area
@@ -730,8 +738,12 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     if (w.m3 && (!d_workspace || (int64_t)w.bytes > workspace_bytes))
         return fail(SAB_EINVAL, "workspace too small: need %zu bytes, got %lld", w.bytes, (long long)workspace_bytes);
     int64_t l0 = e->launches;
-    unsigned long long init[CNT_N] = {0, 0, 0, ~0ULL, 0, 0, 0, 0, 0, 0, 0, 0};
-    CU(cudaMemcpyAsync(e->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    if (!e->h_pinned) {
+        CU(cudaMallocHost((void **)&e->h_pinned, 2 * CNT_N * sizeof(unsigned long long)));
+        for (int i = 0; i < 2 * CNT_N; i++) e->h_pinned[i] = 0ULL;
+        e->h_pinned[CNT_FIRST_BAD] = ~0ULL;
+    }
+    CU(cudaMemcpyAsync(e->d_counters, e->h_pinned, CNT_N * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
     CU(cudaEventRecord(e->ev_t[0], st));
     // tetrahedral sites: one fused kernel (wrap scan + assignment + commit); everything else: scan kernels, then assignment
@@ -749,8 +761,8 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
         e->launches++;
         CU(cudaGetLastError());
     }
-    unsigned long long h[CNT_N];
-    CU(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+    unsigned long long *h = e->h_pinned + CNT_N;
+    CU(cudaMemcpyAsync(h, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (sp.ok && h[SAB_CNT_INVALID]) {       // anchor formulation of the wrap count failed its chain check: nothing was
         e->force_scan = true;                // committed; redo this batch with the scan kernels (identical results)
