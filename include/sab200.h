@@ -91,6 +91,15 @@ int sab_set_pbc_state(sab_engine *e, const int32_t *slot_shift, const double *pr
 int sab_get_pbc_state(sab_engine *e, int32_t *slot_shift, double *prev_raw, int32_t *wraps,
                       double *excursion);
 
+/* Multi-GPU shard carry, all on the device and stream-ordered (no host round trip).  d_halo_raw double[M][3]: raw
+ * framework coordinates of the frame BEFORE this shard (the previous rank's last frame); d_anchor0 double[M][3]: the
+ * unwrapped coordinates raw - W of the trajectory's first frame.  Sets prev_raw = halo, W = rint(halo - anchor0) and
+ * excursion = (u, u).  Exact while the excursion guard holds over the whole trajectory: the sum
+ * of the earlier shards' wrap totals (pbc_utils.py:210-217 applied frame by frame) equals rint(halo - anchor0).
+ * sab_get_excursion_device copies the running excursion double[M][3][2] to a device buffer for the cross-rank guard. */
+int sab_set_carry_device(sab_engine *e, const double *d_halo_raw, const double *d_anchor0, void *stream);
+int sab_get_excursion_device(sab_engine *e, double *d_out, void *stream);
+
 /* Sites whose PBC state was initialised by the legacy spread rule (reference_center is None,
  * pbc_utils.py:16-41 via correct_pbc :140-145) get NO non-negative offset in the frame of
  * initialisation; site_flags uint8[S] marks them and frames_from_now is that frame's index

@@ -142,3 +142,20 @@ __global__ void k_wrap_reduce(const double *__restrict__ frac, int64_t n_frames,
     out_tot[col] = t;
     out_last[col] = sab_fw_raw(frac, n_frames - 1, n_atoms, fw_atoms, col);
 }
+
+// Shard carry without a scan (multi-GPU, polyhedral): 1 thread per framework coordinate.  `halo` is the raw frame
+// before the shard, anchor0 the unwrapped coordinates u = raw - W of the trajectory's FIRST frame.  While guard G1
+// holds over the whole trajectory (every u within 0.3 of every other, checked by the caller from the gathered
+// excursions) |u(halo) - anchor0| < 0.5, hence W(halo) = rint(halo - anchor0) exactly -- the sum of the wrap
+// totals of all earlier shards, without exchanging them.
+__global__ void k_carry_from_halo(const double *__restrict__ halo, const double *__restrict__ anchor0, int m3,
+                                  double *__restrict__ prev_raw, int32_t *__restrict__ wraps, double *__restrict__ excursion)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= m3) return;
+    const double r = halo[col];
+    const int W = (int)rint(r - anchor0[col]);
+    const double u = r - (double)W;
+    prev_raw[col] = r; wraps[col] = W;
+    excursion[2 * col] = u; excursion[2 * col + 1] = u;
+}

@@ -264,6 +264,27 @@ extern "C" int sab_get_pbc_state(sab_engine *e, int32_t *slot_shift, double *pre
     return SAB_OK;
 }
 
+extern "C" int sab_set_carry_device(sab_engine *e, const double *d_halo_raw, const double *d_anchor0, void *stream)
+{
+    if (!e || !d_halo_raw || !d_anchor0) return fail(SAB_EINVAL, "sab_set_carry_device: null argument");
+    if (!e->pbc_set) return fail(SAB_ESTATE, "sab_set_carry_device: PBC state not set");
+    CU(cudaSetDevice(e->device));
+    const int m3 = 3 * e->M;
+    k_carry_from_halo<<<(m3 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_halo_raw, d_anchor0, m3, e->d_prev_raw, e->d_wraps, e->d_excursion);
+    e->launches++;
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
+
+extern "C" int sab_get_excursion_device(sab_engine *e, double *d_out, void *stream)
+{
+    if (!e || !d_out) return fail(SAB_EINVAL, "sab_get_excursion_device: null argument");
+    if (!e->pbc_set) return fail(SAB_ESTATE, "sab_get_excursion_device: PBC state not set");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(d_out, e->d_excursion, sizeof(double) * (size_t)e->M * 6, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SAB_OK;
+}
+
 extern "C" int sab_set_legacy_init(sab_engine *e, const uint8_t *site_flags, int64_t frames_from_now)
 {
     if (!e) return fail(SAB_EINVAL, "sab_set_legacy_init: null engine");

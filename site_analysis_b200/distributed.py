@@ -7,8 +7,11 @@ frame ranges, one per rank.  Two things cross rank boun
   the sum of the wrap totals of all earlier shards (reference state: ``_pbc_image_shifts`` of
   ``polyhedral_site.py:377-416`` / ``_CentreGroup.pbc_shifts`` of
   ``dynamic_voronoi_site_collection.py:38-105``, here a per-atom prefix scan).  Each rank needs the
-  last frame of its predecessor (a halo of ``M x 3`` doubles) and the per-rank totals
-  (``M x 3`` int32): two tiny all-gathers;
+  last frame of its predecessor (a halo of ``M x 3`` doubles).  Polyhedral sites: the carry is
+  ``rint(halo - anchor0)`` with ``anchor0`` the unwrapped first frame of the trajectory, set on the
+  device -- exact under the excursion guard that this path enforces anyway (``carry_from_halo``).
+  Dynamic Voronoi (no such guard): one extra pass for the per-shard totals (``M x 3`` int32) and a
+  second tiny all-gather;
 * the **result**: one all-gather of ``int32[F_local, A]`` reassembles ``atoms_trajectory``
   (``trajectory.py:375-383``) on every rank.
 
@@ -88,6 +91,83 @@ def gather_assignments(local_rows, group, equal_shards: bool = False):
     return torch.cat([out[r * fmax:r * fmax + c] for r, c in enumerate(counts)], dim=0)
 
 
+def carry_from_halo(halo, anchor0):
+    """Wrap counts and unwrapped coordinates at the frame before a shard, WITHOUT the per-shard totals:
+    ``W = rint(halo - anchor0)``, ``u = halo - W`` (the host statement of ``k_carry_from_halo``).
+
+    ``anchor0`` = unwrapped coordinates of the trajectory's first frame.  The reference's caches count
+    ``rint(raw_t - raw_{t-1})`` frame by frame (pbc_utils.py:210-217); as long as every unwrapped coordinate
+    stays within 0.3 of every other over the whole trajectory (guard G1, checked on the gathered
+    excursions), ``|u(halo) - anchor0| < 0.5`` and the two are the same integer."""
+    halo = np.asarray(halo, dtype=np.float64)
+    W = np.rint(halo - np.asarray(anchor0, dtype=np.float64)).astype(np.int32)
+    return W, halo - W
+
+
+def _initial_state(engine, first_frame_global, first_lattice_global):
+    from . import _native as nat
+    if not engine._pbc_ready:
+        engine._init_pbc(np.asarray(first_frame_global, dtype=np.float64), np.asarray(first_lattice_global, dtype=np.float64))
+    if getattr(engine, "_initial_pbc", None) is None:            # state at the start of the (global) trajectory
+        M = len(engine.fw_atoms)
+        sh = np.zeros_like(engine.slot_shift)
+        p0 = np.zeros((M, 3)); w0 = np.zeros((M, 3), dtype=np.int32); e0 = np.zeros((M, 3, 2))
+        nat.check(engine.L.sab_get_pbc_state(engine.h, nat.ptr(sh), nat.ptr(p0), nat.ptr(w0), nat.ptr(e0)))
+        engine._initial_pbc = (sh, p0, w0, e0)
+    return engine._initial_pbc
+
+
+def _carry_by_totals(engine, d_frac_local, group):
+    """Exact for any data: halo exchange, one extra pass over the shard for its wrap totals, exclusive prefix."""
+    import torch
+    import torch.distributed as dist
+    from . import _native as nat
+    rank = dist.get_rank(group)
+    dev = d_frac_local.device
+    sh, p0, w0, e0 = engine._initial_pbc
+    M = len(engine.fw_atoms)
+    fw = torch.as_tensor(engine.fw_atoms.astype(np.int64), device=dev)
+    last_raw = d_frac_local[-1].index_select(0, fw).cpu().numpy()
+    halos = exchange_halo(last_raw, group, device=dev)
+    prev_raw = p0 if rank == 0 else np.ascontiguousarray(halos[rank - 1])
+    nat.check(engine.L.sab_set_pbc_state(engine.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(w0), nat.ptr(e0)))
+    F = int(d_frac_local.shape[0])
+    ws_bytes = int(engine.L.sab_workspace_bytes(engine.h, F))
+    d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    totals = np.zeros((M, 3), dtype=np.int32); lr = np.zeros((M, 3))
+    nat.check(engine.L.sab_wrap_totals(engine.h, d_frac_local.data_ptr(), F, d_ws.data_ptr(), ws_bytes,
+                                       torch.cuda.current_stream(dev).cuda_stream, nat.ptr(totals), nat.ptr(lr)))
+    base, _ = exchange_wrap_totals(totals, group, device=dev)
+    if rank > 0:
+        wraps = np.ascontiguousarray(w0 + base.astype(np.int32))
+        u0 = prev_raw - wraps                                # the halo frame in the global unwrapped frame
+        exc = np.ascontiguousarray(np.stack([u0, u0], axis=-1))
+        nat.check(engine.L.sab_set_pbc_state(engine.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
+
+
+def _carry_by_anchor(engine, d_frac_local, group):
+    """Polyhedral sites (guard G1 makes it exact, see ``carry_from_halo``): one tiny all-gather of the halo frames,
+    then the carry is set ON THE DEVICE (sab_set_carry_device) -- no pass over the data, no host round trip."""
+    import torch
+    import torch.distributed as dist
+    from . import _native as nat
+    rank = dist.get_rank(group)
+    dev = d_frac_local.device
+    st = getattr(engine, "_shard_dev", None)
+    if st is None:
+        sh, p0, w0, e0 = engine._initial_pbc
+        st = engine._shard_dev = dict(
+            fw=torch.as_tensor(engine.fw_atoms.astype(np.int64), device=dev),
+            p0=torch.as_tensor(np.ascontiguousarray(p0), device=dev),
+            anchor0=torch.as_tensor(np.ascontiguousarray(p0 - w0), device=dev))
+    last_raw = d_frac_local[-1].index_select(0, st["fw"])
+    halos = _all_gather(last_raw, group)
+    halo = st["p0"] if rank == 0 else halos[rank - 1]
+    nat.check(engine.L.sab_set_carry_device(engine.h, halo.data_ptr(), st["anchor0"].data_ptr(),
+                                            torch.cuda.current_stream(dev).cuda_stream))
+    st["keep"] = (halos, last_raw)                           # alive until the stream has consumed them
+
+
 def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group,
                    equal_shards: bool = False):
     """Assign this rank's contiguous shard with the correct PBC carry and return the FULL
@@ -97,51 +177,28 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
     lattice (3, 3) as numpy, identical on every rank -- the structure from which unprimed sites take
     their initial image shifts (polyhedral_site.py:410-416)."""
     import torch
-    import torch.distributed as dist
     from . import _native as nat
-    rank = dist.get_rank(group)
     dev = d_frac_local.device
     if engine.slots is not None:
-        if not engine._pbc_ready:
-            engine._init_pbc(np.asarray(first_frame_global, dtype=np.float64), np.asarray(first_lattice_global, dtype=np.float64))
-        M = len(engine.fw_atoms)
-        if getattr(engine, "_initial_pbc", None) is None:        # state at the start of the (global) trajectory
-            sh = np.zeros_like(engine.slot_shift)
-            p0 = np.zeros((M, 3)); w0 = np.zeros((M, 3), dtype=np.int32); e0 = np.zeros((M, 3, 2))
-            nat.check(engine.L.sab_get_pbc_state(engine.h, nat.ptr(sh), nat.ptr(p0), nat.ptr(w0), nat.ptr(e0)))
-            engine._initial_pbc = (sh, p0, w0, e0)
-        sh, p0, w0, e0 = engine._initial_pbc
-        fw = torch.as_tensor(engine.fw_atoms.astype(np.int64), device=dev)
-        last_raw = d_frac_local[-1].index_select(0, fw).cpu().numpy()
-        halos = exchange_halo(last_raw, group, device=dev)
-        prev_raw = p0 if rank == 0 else np.ascontiguousarray(halos[rank - 1])
-        nat.check(engine.L.sab_set_pbc_state(engine.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(w0), nat.ptr(e0)))
-        F = int(d_frac_local.shape[0])
-        ws_bytes = int(engine.L.sab_workspace_bytes(engine.h, F))
-        d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        totals = np.zeros((M, 3), dtype=np.int32); lr = np.zeros((M, 3))
-        nat.check(engine.L.sab_wrap_totals(engine.h, d_frac_local.data_ptr(), F, d_ws.data_ptr(), ws_bytes,
-                                           torch.cuda.current_stream(dev).cuda_stream, nat.ptr(totals), nat.ptr(lr)))
-        base, _ = exchange_wrap_totals(totals, group, device=dev)
-        if rank > 0:
-            wraps = np.ascontiguousarray(w0 + base.astype(np.int32))
-            u0 = prev_raw - wraps                                # the halo frame in the global unwrapped frame
-            exc = np.ascontiguousarray(np.stack([u0, u0], axis=-1))
-            nat.check(engine.L.sab_set_pbc_state(engine.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
+        _initial_state(engine, first_frame_global, first_lattice_global)
+        if engine.k == nat.POLYHEDRAL:
+            _carry_by_anchor(engine, d_frac_local, group)
+        else:
+            _carry_by_totals(engine, d_frac_local, group)
     local = engine.assign_device(d_frac_local, d_lattice_local)
     if engine.last_info.get("ambiguous", 0) > 0:
         raise NotImplementedError("atom-frames contained by several sites in a sharded run need the gathered resolver "
                                   "(run the affected trajectory on one GPU)")
     engine._pending = []
+    full = gather_assignments(local, group, equal_shards)       # enqueued first: the guard below overlaps with it
     if engine.slots is not None and engine.k == nat.POLYHEDRAL:
-        # the scan formulation's guard holds over the WHOLE trajectory: combine the shards' excursions
+        # guard G1 holds over the WHOLE trajectory: combine the shards' excursions (device all-gather, one sync)
         M = len(engine.fw_atoms)
-        exc = np.zeros((M, 3, 2))
-        nat.check(engine.L.sab_get_pbc_state(engine.h, None, None, None, nat.ptr(exc)))
-        parts = _all_gather(torch.as_tensor(exc, device=dev), group)
-        lo = torch.stack([x[..., 0] for x in parts]).amin(dim=0)
-        hi = torch.stack([x[..., 1] for x in parts]).amax(dim=0)
+        exc = torch.empty((M, 3, 2), dtype=torch.float64, device=dev)
+        nat.check(engine.L.sab_get_excursion_device(engine.h, exc.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        parts = torch.stack(_all_gather(exc, group))
+        span = (parts[..., 1].amax(dim=0) - parts[..., 0].amin(dim=0)).max()
         from .engine import EXCURSION_LIMIT, GuardError
-        if float((hi - lo).max().item()) >= EXCURSION_LIMIT and engine.strict:
+        if float(span.item()) >= EXCURSION_LIMIT and engine.strict:
             raise GuardError("a framework atom moved over >= 0.3 fractional units across the sharded trajectory")
-    return gather_assignments(local, group, equal_shards)
+    return full

@@ -48,6 +48,18 @@ def _worker(rank, world, port, F, seed, out_dir):
         # unwrapped coordinates raw - W are continuous across the shard boundary
         W_first = base + np.rint(mine[0] - prev).astype(np.int32)
         assert np.abs((mine[0] - W_first) - (prev - base)).max() < 0.3
+        # polyhedral carry without totals (distributed.carry_from_halo / k_carry_from_halo): bounded vibration
+        # (excursion < 0.3, guard G1) around centres on and off the cell faces, so coordinates flip 0 <-> 1
+        centre = rng.choice([0.0, 0.999, 0.5, 0.27, 1e-4], size=(1, M, 3))
+        t = np.arange(F)[:, None, None]
+        vib = (centre + 0.12 * np.sin(0.31 * t + rng.uniform(0, 6.28, size=(1, M, 3))) + rng.normal(scale=0.008, size=(F, M, 3))) % 1.0
+        full_v = np.rint(np.diff(np.concatenate([vib[:1], vib]), axis=0)).cumsum(axis=0).astype(np.int32)
+        assert np.ptp(vib - full_v, axis=0).max() < 0.3
+        halos_v = sd.exchange_halo(vib[f0:f1][-1], dist.group.WORLD)
+        if rank > 0:
+            W, u = sd.carry_from_halo(halos_v[rank - 1], vib[0])        # anchor0 = unwrapped first frame (W = 0 there)
+            assert np.array_equal(W, full_v[f0 - 1]), (rank, W, full_v[f0 - 1])
+            assert np.array_equal(u, vib[f0 - 1] - full_v[f0 - 1])
         # result all-gather (ragged shards)
         rows = torch.arange(f0, f1, dtype=torch.int32)[:, None].repeat(1, A) * 10 + torch.arange(A, dtype=torch.int32)
         full_rows = sd.gather_assignments(rows, dist.group.WORLD)
