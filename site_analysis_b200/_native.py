@@ -26,6 +26,7 @@ OPT_SEQ_BLOCK = 4
 OPT_FP32_FILTER = 5
 OPT_TILE_FRAMES = 6
 OPT_STREAM_PRODUCERS = 7
+OPT_STREAM_REC_SMEM = 8
 
 # every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = [

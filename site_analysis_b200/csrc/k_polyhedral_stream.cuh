@@ -8,32 +8,35 @@
 //     on a ring of row slots.
 //
 // A CTA owns a contiguous chunk of frames.
-//   copy engine  cp.async.bulk of whole raw frames into a ring of SAB_STREAM raw slots (mbarrier complete_tx).
-//   producers    (P warps) per frame:
-//       column pass  for every referenced framework coordinate j: raw, W = rint(raw - anchor[j]),
-//                    u = raw - W (the unwrapped coordinate raw + (shift - W) is formed from it, pbc_utils.py:220),
-//                    excursion min/max of u, validity tube |float(u) - anchor| <= delta of the cell lists, and
-//                    the CHAIN CHECK  W_t - W_{t-1} == rint(raw_t - raw_{t-1})  (the reference's own update,
-//                    pbc_utils.py:210-217) together with its 0.3 step bound (:216).  The chain starts from the
-//                    engine's carried wrap counts (first chunk) or from rint(raw - anchor) of the frame before
-//                    the chunk, which is what the CTA of the previous chunk ends with, so while no check fails
-//                    W is EXACTLY the sequential wrap count of k_wrap_rows.  A failed check raises the
-//                    `invalid` counter and the host redoes the batch with the scan kernels (never observed
-//                    inside guard G1, DESIGN.md section 4: the anchors sit mid-range of an excursion < 0.3).
-//       row pass     float row of the frame: float(u) + shift for every (coordinate, shift) pair in use, then
-//                    the wrapped mobile coordinates (atom.py:104) -- the operands of sab_tet_filter32b.
-//   consumers    (C warps) per frame and group of 32 atoms: lane a tests `last` (the atom's most recent site as
-//                    far as it is certain), the reference's first test (site_collection.py:147-152,
-//                    polyhedral_site_collection.py:104-107); "certainly inside" is the reference's answer.  Every
-//                    other verdict makes the WARP search that atom's cell list, 32 candidates at a time:
-//                    none -> None, one -> that site, 2..4 -> spilled list for the priority resolver, anything
-//                    float32 cannot decide -> deferred to the exact float64 pass (k_polyhedral_deferred).
+//   copy engine  cp.async.bulk of whole raw frames into a ring of raw slots (mbarrier complete_tx).
+//   producers    (P warps) per frame, for every referenced framework coordinate j: raw, W = rint(raw - anchor[j]),
+//                u = raw - W, excursion min/max of u, validity tube |float(u) - anchor| <= delta of the cell lists,
+//                and the float row entries float(u) + shift for every slot shift in use (the unwrapped vertex
+//                coordinate raw + (shift - W), pbc_utils.py:220, to within 2^-22); then the wrapped mobile
+//                coordinates (atom.py:104).  These are the operands of sab_tet_filter32b.
+//       CHAIN CHECK.  The reference counts wraps sequentially, W_t = W_{t-1} + rint(raw_t - raw_{t-1}), and
+//                invalidates on a step >= 0.3 (pbc_utils.py:210-217).  W = rint(raw - anchor) equals that count as
+//                long as W_t - W_{t-1} == rint(raw_t - raw_{t-1}) for every frame, starting from the engine's
+//                carried count (first chunk) or from rint(raw - anchor) of the frame before the chunk -- which is
+//                what the CTA of the previous chunk ends with.  Two consecutive frames INSIDE the validity tube
+//                (|u - anchor| <= delta <= 0.12 each) satisfy the identity and the step bound automatically:
+//                raw_t - raw_{t-1} = (u_t - u_{t-1}) + (W_t - W_{t-1}) with |u_t - u_{t-1}| <= 0.24.  Every other
+//                pair (first frame of a chunk, a frame outside the tube or right after one) is checked explicitly.
+//                A failed check raises the `invalid` counter and the host redoes the batch with the scan kernels
+//                (only reachable outside guard G1).
+//   consumers    (C warps) per frame and group of 32 atoms: lane a tests the atom's most recent site and, when that
+//                certainly fails, its previous one -- the reference's first two tests (site_collection.py:147-152,
+//                atom.py:181-192), as far as both are certain inside the chunk; a certain hit is the reference's
+//                answer (first hit in priority order, polyhedral_site_collection.py:104-107).  Every other verdict
+//                makes the WARP search that atom's cell list, 32 candidates at a time: none -> None, one -> that
+//                site, 2..4 -> spilled list for the priority resolver, anything float32 cannot decide -> deferred
+//                to the exact float64 pass (k_polyhedral_deferred).
 // Frames outside the validity tube (and the legacy first-frame rule) take the exhaustive generic path per atom.
 #pragma once
 #include "k_polyhedral_tile.cuh"
 
 #define SAB_STREAM_ROWS 4         // ring of float rows (producers run at most this far ahead of the slowest consumer)
-#define SAB_STREAM_MAXRAW 4       // ring of raw frames (copy engine runs SAB raw - 1 frames ahead)
+#define SAB_STREAM_MAXRAW 4       // ring of raw frames (the copy engine runs raw slots - 2 frames ahead)
 #define SAB_STREAM_MAXTHREADS 320
 #ifndef SAB_STREAM_MINBLOCKS
 #define SAB_STREAM_MINBLOCKS 2
@@ -62,17 +65,38 @@ struct SabStreamTables {
     int n_prod;                   // producer warps
     int use_tma;                  // frames are 16-byte aligned and sized
     double *chunk_exc;            // out [n_chunks][m3][2]: excursion (min, max) of u per chunk
+    int always_explicit;          // validity tube wider than 0.12: the in-tube shortcut of the chain check does not apply
 };
 
 __device__ __forceinline__ void sab_mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+__device__ __forceinline__ void sab_mbar_wait_backoff(uint64_t *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(32);
+    }
+}
+template <bool SMEM> __device__ __forceinline__ SabTetRec sab_tet_rec_at(const uint16_t *__restrict__ rec)
+{
+    const uint2 *r2 = reinterpret_cast<const uint2 *>(rec);
+    SabTetRec r;
+    if (SMEM) { r.q0 = r2[0]; r.q1 = r2[1]; r.q2 = r2[2]; }
+    else { r.q0 = __ldg(r2); r.q1 = __ldg(r2 + 1); r.q2 = __ldg(r2 + 2); }
+    return r;
+}
 __device__ __forceinline__ void sab_bar_producers(int n_threads)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
 }
 
+template <bool REC_SMEM>
 __global__ void __launch_bounds__(SAB_STREAM_MAXTHREADS, SAB_STREAM_MINBLOCKS)
 k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, int64_t chunk, int n_atoms, int n_mobile,
                            const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabStreamTables C,
@@ -84,15 +108,14 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
     const int n3 = 3 * n_atoms, m3 = C.m3, a3 = 3 * n_mobile;
     double *rawd = reinterpret_cast<double *>(sm_stream);                        // [n_raw][n3] raw frames (copy engine)
     double *ancd = rawd + (size_t)C.n_raw * n3;                                   // [m3] anchors
-    double *prevcol = ancd + m3;                                                  // [m3] raw of the previous frame
-    double *exc = prevcol + m3;                                                   // [m3][2] running (min, max) of u
+    double *exc = ancd + m3;                                                      // [m3][2] running (min, max) of u
     float *rows = reinterpret_cast<float *>(exc + 2 * (size_t)m3);               // [ROWS][stride]
-    float *colbase = rows + (size_t)SAB_STREAM_ROWS * C.stride;                  // [2][m3] float(u) of the current frame (double-buffered)
-    int *prevW = reinterpret_cast<int *>(colbase + 2 * (size_t)m3);                           // [m3] W of the previous frame
-    int *fwcol = prevW + m3;                                                      // [m3] 3 * atom + d
+    float *shf = rows + (size_t)SAB_STREAM_ROWS * C.stride;                      // [n_used] slot shift of every staged pair
+    int2 *colvar = reinterpret_cast<int2 *>(shf + ((C.n_used + 1) & ~1));         // [m3] {first, end} staged pair of the column
+    int *fwcol = reinterpret_cast<int *>(colvar + m3);                            // [m3] 3 * atom + d
     int *mobcol = fwcol + m3;                                                     // [3 A] 3 * atom + d of the mobile coordinates
-    int2 *svars = reinterpret_cast<int2 *>(mobcol + ((a3 + 1) & ~1));             // [n_used] {column, shift bits}
-    int *last = reinterpret_cast<int *>(svars + C.n_used);                        // [A]
+    int2 *last = reinterpret_cast<int2 *>(fwcol + ((m3 + a3 + 1) & ~1));          // [A] {most recent, previous} site, -1 = unknown
+    uint16_t *srec = reinterpret_cast<uint16_t *>(last + n_mobile);               // [S][12] site records (REC_SMEM)
     __shared__ __align__(8) uint64_t raw_full[SAB_STREAM_MAXRAW], row_full[SAB_STREAM_ROWS], row_empty[SAB_STREAM_ROWS];
     __shared__ int pbad[4], rowflag[SAB_STREAM_ROWS];
 
@@ -105,9 +128,20 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
     for (int j = tid; j < m3; j += blockDim.x) {
         ancd[j] = C.anchor[j];
         fwcol[j] = C.fw_atoms[j / 3] * 3 + j % 3;
+        colvar[j] = make_int2(0, 0);
     }
     for (int q = tid; q < a3; q += blockDim.x) mobcol[q] = mobile[q / 3] * 3 + q % 3;
-    for (int j = tid; j < C.n_used; j += blockDim.x) { const int4 e = C.vars[j]; svars[j] = make_int2(e.y, e.z); }
+    __syncthreads();
+    for (int v = tid; v < C.n_used; v += blockDim.x) {       // staged pairs are sorted by column
+        const int4 e = C.vars[v];
+        shf[v] = __int_as_float(e.z);
+        if (v == 0 || C.vars[v - 1].y != e.y) colvar[e.y].x = v;
+        if (v == C.n_used - 1 || C.vars[v + 1].y != e.y) colvar[e.y].y = v + 1;
+    }
+    if (REC_SMEM)
+        for (int i = tid; i < n_sites * 3; i += blockDim.x)
+            reinterpret_cast<uint2 *>(srec)[i] = reinterpret_cast<const uint2 *>(C.rec)[i];
+    const uint16_t *recs = REC_SMEM ? srec : C.rec;
     if (tid == 0) {
         for (int i = 0; i < SAB_STREAM_MAXRAW; i++) sab_mbar_init(&raw_full[i], 1);
         for (int i = 0; i < SAB_STREAM_ROWS; i++) { sab_mbar_init(&row_full[i], n_prod_thr); sab_mbar_init(&row_empty[i], n_cons_thr); rowflag[i] = 0; }
@@ -132,62 +166,62 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
             sab_bar_producers(n_prod_thr);                      // previous chunk fully converted: raw slots idle
             if (pt == 0 && C.use_tma)
                 for (int i = 0; i < RS - 1 && c0 + i < c1; i++) issue(c0 + i, it + i);
-            for (int j = pt; j < m3; j += n_prod_thr) {         // chain start (owner-private state)
-                double p; int w;
-                if (c0 == 0) { p = C.prev_raw[j]; w = C.wraps[j]; }
-                else { p = frac[(size_t)(c0 - 1) * n3 + fwcol[j]]; w = (int)rint(p - ancd[j]); }
-                prevcol[j] = p; prevW[j] = w;
-                exc[2 * j] = INFINITY; exc[2 * j + 1] = -INFINITY;
-            }
+            for (int j = pt; j < m3; j += n_prod_thr) { exc[2 * j] = INFINITY; exc[2 * j + 1] = -INFINITY; }   // owner-private
             for (int64_t f = c0; f < c1; f++, it++) {
                 const int rslot = (int)(it % (unsigned)RS), wslot = (int)(it % SAB_STREAM_ROWS);
                 double *raw = rawd + (size_t)rslot * n3;
-                if (C.use_tma) sab_mbar_wait(&raw_full[rslot], (it / (unsigned)RS) & 1);
-                else {
-                    sab_bar_producers(n_prod_thr);              // everybody is done with the frame before
+                if (C.use_tma) sab_mbar_wait_backoff(&raw_full[rslot], (it / (unsigned)RS) & 1);
+                else {                                          // frames the copy engine cannot take: plain loads
                     const double *g = frac + (size_t)f * n3;
                     for (int q = pt; q < n3; q += n_prod_thr) raw[q] = g[q];
                     sab_bar_producers(n_prod_thr);
                 }
-                // ---- column pass --------------------------------------------------------------------------
+                if (it >= SAB_STREAM_ROWS) sab_mbar_wait_backoff(&row_empty[wslot], ((it / SAB_STREAM_ROWS) - 1) & 1);
+                float *row = rows + (size_t)wslot * C.stride;
+                // ---- framework columns -> row entries ------------------------------------------------------
                 int bad = 0;
-                float *cb = colbase + (size_t)(it & 1) * m3;     // a slow producer may still read the other half (row pass of f - 1)
                 for (int j = pt; j < m3; j += n_prod_thr) {
-                    const double r = raw[fwcol[j]], anc = ancd[j], p = prevcol[j];
-                    const int W = (int)rint(r - anc);
-                    const double diff = r - p, w = rint(diff), phys = diff - w;      // pbc_utils.py:210-216
-                    if ((phys >= 0.3 || phys <= -0.3) && !(C.skip_check_frame0 && f == 0))
-                        atomicMin(&counters[3], (unsigned long long)f);
-                    if (W - prevW[j] != (int)w) counters[SAB_CNT_INVALID] = 1ULL;
-                    const double u = r - (double)W;
+                    const double r = raw[fwcol[j]], anc = ancd[j];
+                    const double u = r - rint(r - anc);
                     const float base = (float)u;
                     if (fabsf(base - (float)anc) > C.delta_f) bad = 1;
                     if (u < exc[2 * j]) exc[2 * j] = u;
                     if (u > exc[2 * j + 1]) exc[2 * j + 1] = u;
-                    cb[j] = base; prevcol[j] = r; prevW[j] = W;
-                }
-                if (bad) atomicOr(&pbad[it & 3], 1);
-                sab_bar_producers(n_prod_thr);                  // colbase and pbad complete; frame f - 1 fully converted
-                if (pt == 0) {
-                    if (C.use_tma && f + RS - 1 < c1) issue(f + RS - 1, it + RS - 1);       // into the slot of frame f - 1
-                    pbad[(it + 2) & 3] = 0;
-                }
-                int flag = pbad[it & 3];
-                if (T.legacy_init && legacy_init_frame == f) flag = 1;
-                if (it >= SAB_STREAM_ROWS) sab_mbar_wait(&row_empty[wslot], ((it / SAB_STREAM_ROWS) - 1) & 1);
-                // ---- row pass -----------------------------------------------------------------------------
-                float *row = rows + (size_t)wslot * C.stride;
-                for (int j = pt; j < C.n_used; j += n_prod_thr) {
-                    const int2 e = svars[j];
-                    row[j] = cb[e.x] + __int_as_float(e.y);
+                    const int2 cv = colvar[j];
+                    for (int v = cv.x; v < cv.y; v++) row[v] = base + shf[v];
                 }
                 for (int q = pt; q < a3; q += n_prod_thr) {
                     const double x = raw[mobcol[q]];
                     row[C.n_used + q] = (float)(x - floor(x));                               // atom.py:104
                 }
+                if (bad) atomicOr(&pbad[it & 3], 1);
+                sab_bar_producers(n_prod_thr);                  // pbad complete; everybody is done with the frame before
+                const int tube_bad = pbad[it & 3];
+                const bool explicit_check = tube_bad || f == c0 || pbad[(it + 3) & 3] || C.always_explicit;
                 if (pt == 0) {
+                    pbad[(it + 2) & 3] = 0;
+                    const int flag = tube_bad || (T.legacy_init && legacy_init_frame == f);
                     rowflag[wslot] = flag;
                     if (flag) atomicAdd(n_fallback, 1ULL);
+                    if (!explicit_check && C.use_tma && f + RS - 1 < c1) issue(f + RS - 1, it + RS - 1);   // into the slot of frame f - 1
+                }
+                if (explicit_check) {                           // chain check against the reference's sequential update
+                    const double *praw = rawd + (size_t)((it + (unsigned)RS - 1) % (unsigned)RS) * n3;        // frame f - 1 (f > c0)
+                    for (int j = pt; j < m3; j += n_prod_thr) {
+                        const double r = raw[fwcol[j]], anc = ancd[j];
+                        double p; int Wp;
+                        if (f > c0) { p = praw[fwcol[j]]; Wp = (int)rint(p - anc); }
+                        else if (c0 == 0) { p = C.prev_raw[j]; Wp = C.wraps[j]; }
+                        else { p = frac[(size_t)(c0 - 1) * n3 + fwcol[j]]; Wp = (int)rint(p - anc); }
+                        const double diff = r - p, w = rint(diff), phys = diff - w;          // pbc_utils.py:210-216
+                        if ((phys >= 0.3 || phys <= -0.3) && !(C.skip_check_frame0 && f == 0))
+                            atomicMin(&counters[3], (unsigned long long)f);
+                        if ((int)rint(r - anc) - Wp != (int)w) counters[SAB_CNT_INVALID] = 1ULL;
+                    }
+                    if (C.use_tma) {
+                        sab_bar_producers(n_prod_thr);          // frame f - 1 no longer needed
+                        if (pt == 0 && f + RS - 1 < c1) issue(f + RS - 1, it + RS - 1);
+                    }
                 }
                 sab_mbar_arrive(&row_full[wslot]);
             }
@@ -203,10 +237,10 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
         unsigned it = 0;
         for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
             const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
-            for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = -1;   // owner-private
+            for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = make_int2(-1, -1);   // owner-private
             for (int64_t f = c0; f < c1; f++, it++) {
                 const int wslot = (int)(it % SAB_STREAM_ROWS);
-                sab_mbar_wait(&row_full[wslot], (it / SAB_STREAM_ROWS) & 1);
+                sab_mbar_wait_backoff(&row_full[wslot], (it / SAB_STREAM_ROWS) & 1);
                 const float *row = rows + (size_t)wslot * C.stride;
                 const float *xrow = row + C.n_used;
                 const int flag = rowflag[wslot];
@@ -214,20 +248,29 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                 for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {
                     const int a = g0 + lane;
                     const bool valid = a < n_mobile;
-                    int la = valid ? last[a] : -1;
+                    int2 rc = valid ? last[a] : make_int2(-1, -1);            // {most recent, previous} site
                     int out = SAB_NONE;
+                    // a definite site h: Atom.update_recent_site (atom.py:189-192)
+                    #define SAB_RECENT_PUSH(h) do { if ((h) != rc.x) { rc.y = rc.x; rc.x = (h); } } while (0)
                     if (flag) {                                  // outside the validity tube: generic path
                         if (valid) {
                             int c = 0;
                             out = sab_exhaustive_atom(frac + (size_t)f * n3, nullptr, f, legacy_init_frame, mobile[a], n_sites, T,
                                                       spill, spill_capacity, counters, &c, C.anchor);
-                            if (c == 1) la = out; else if (c > 1) la = -1;
+                            if (c == 1) SAB_RECENT_PUSH(out); else if (c > 1) rc = make_int2(-1, -1);
                         }
                     } else {
                         int v = 0;
-                        if (valid && la >= 0 && C.use_f32)
-                            v = sab_tet_filter32b(row, sab_tet_rec(C.rec + (size_t)la * 12), xrow + 3 * a);
-                        if (v == 1) out = la;
+                        if (valid && rc.x >= 0 && C.use_f32)
+                            v = sab_tet_filter32b(row, sab_tet_rec_at<REC_SMEM>(recs + (size_t)rc.x * 12), xrow + 3 * a);
+                        if (v == 1) out = rc.x;
+                        // most recent site certainly failed: the reference tests the previous one next
+                        const bool second = valid && v == 0 && rc.x >= 0 && rc.y >= 0;
+                        if (__any_sync(FULL, second)) {
+                            if (second && sab_tet_filter32b(row, sab_tet_rec_at<REC_SMEM>(recs + (size_t)rc.y * 12), xrow + 3 * a) == 1) {
+                                out = rc.y; rc = make_int2(rc.y, rc.x); v = 1;
+                            }
+                        }
                         unsigned m = __ballot_sync(FULL, valid && v != 1);
                         while (m) {                              // warp-uniform: one search per atom that needs it
                             const int src = __ffs(m) - 1;
@@ -243,7 +286,7 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                                     int s = 0, vv = 0;
                                     if (i < len) {
                                         s = __ldg(C.cell_sites + b + i);
-                                        vv = sab_tet_filter32b(row, sab_tet_rec(C.rec + (size_t)s * 12), xs);
+                                        vv = sab_tet_filter32b(row, sab_tet_rec_at<REC_SMEM>(recs + (size_t)s * 12), xs);
                                     }
                                     unsigned m1 = __ballot_sync(FULL, vv == 1);
                                     und |= __ballot_sync(FULL, vv == 2);
@@ -258,20 +301,21 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                                 }
                             if (lane == src) {
                                 if (und || c > SAB_POLY_KEEP) {  // float32 could not decide (or a long list): exact pass later
-                                    out = SAB_DEFERRED; la = -1;
+                                    out = SAB_DEFERRED; rc = make_int2(-1, -1);
                                     const unsigned long long di = atomicAdd(&counters[9], 1ULL);
                                     if ((long long)di < C.defer_cap) C.defer[di] = (long long)f * n_mobile + a;
                                 } else if (c == 0) out = SAB_NONE;
-                                else if (c == 1) { out = h0; la = h0; }
+                                else if (c == 1) { out = h0; SAB_RECENT_PUSH(h0); }
                                 else {
                                     int h[SAB_POLY_KEEP] = {h0, h1, h2, h3};
                                     out = sab_tile_spill(c, h, spill, spill_capacity, counters);
-                                    la = -1;
+                                    rc = make_int2(-1, -1);
                                 }
                             }
                         }
                     }
-                    if (valid) { res[a] = out; last[a] = la; }
+                    #undef SAB_RECENT_PUSH
+                    if (valid) { res[a] = out; last[a] = rc; }
                 }
                 sab_mbar_arrive(&row_empty[wslot]);
             }

@@ -104,6 +104,7 @@ struct sab_engine {
     bool tile_ok = false; int n_used = 0; int4 *d_tile_vars = nullptr; uint16_t *d_tile_rec = nullptr;
     int tile_frames = 0;                   // SAB_OPT_TILE_FRAMES (0 = automatic)
     int stream_prod = 0;                   // SAB_OPT_STREAM_PRODUCERS (0 = automatic)
+    int stream_rec_smem = 1;               // SAB_OPT_STREAM_REC_SMEM (1 = site records in shared memory when they fit)
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
     size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
     unsigned long long *h_pinned = nullptr;               // pinned [2][CNT_N]: counter initialiser | read-back
@@ -403,6 +404,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (key == SAB_OPT_SKIP_STEP_CHECK_ONCE) { e->skip_step_check_once = value != 0; return SAB_OK; }
     if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
     if (key == SAB_OPT_TILE_FRAMES) { e->tile_frames = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_STREAM_REC_SMEM) { e->stream_rec_smem = value != 0; return SAB_OK; }
     if (key == SAB_OPT_STREAM_PRODUCERS) { if (value < 0 || value > 8) return fail(SAB_EINVAL, "producer warps: 0..8"); e->stream_prod = (int)value; return SAB_OK; }
     if (key == SAB_OPT_FP32_FILTER) { e->fp32_filter = value != 0; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
@@ -516,7 +518,7 @@ extern "C" int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n
 }
 
 // ---------------------------------------------------------------- stream kernel (tetrahedral sites, fused wrap scan)
-struct StreamPlan { bool ok = false; int n_prod = 0, n_cons = 0, n_raw = 0, use_tma = 0; size_t smem = 0, stride = 0; int64_t chunk = 0; int grid = 0; };
+struct StreamPlan { bool ok = false; int n_prod = 0, n_cons = 0, n_raw = 0, use_tma = 0, rec_smem = 0; size_t smem = 0, stride = 0; int64_t chunk = 0; int grid = 0; };
 
 static StreamPlan plan_stream(sab_engine *e, const double *d_frac, int64_t F, const Workspace &w)
 {
@@ -529,19 +531,23 @@ static StreamPlan plan_stream(sab_engine *e, const double *d_frac, int64_t F, co
     const size_t n3 = 3 * (size_t)e->N, m3 = 3 * (size_t)e->M, a3 = 3 * (size_t)e->A;
     p.stride = ((size_t)e->n_used + a3 + 3) & ~(size_t)3;
     p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
-    auto smem_for = [&](int n_raw) {
-        return sizeof(double) * ((size_t)n_raw * n3 + 4 * m3) + sizeof(float) * (SAB_STREAM_ROWS * p.stride + 2 * m3) +
-               sizeof(int) * (2 * m3 + ((a3 + 1) & ~(size_t)1) + 2 * (size_t)e->n_used + (size_t)e->A) + 128;
+    auto smem_for = [&](int n_raw, int rec_smem) {
+        return sizeof(double) * ((size_t)n_raw * n3 + 3 * m3) + sizeof(float) * (SAB_STREAM_ROWS * p.stride + (((size_t)e->n_used + 1) & ~(size_t)1)) +
+               sizeof(int) * (2 * m3 + ((m3 + a3 + 1) & ~(size_t)1) + 2 * (size_t)e->A) + (rec_smem ? (size_t)e->S * 24 : 0) + 128;
     };
+    const size_t budget = (size_t)(226 * 1024 / SAB_STREAM_MINBLOCKS);
     p.n_raw = SAB_STREAM_MAXRAW;
-    while (p.n_raw > 2 && smem_for(p.n_raw) > (size_t)(226 * 1024 / SAB_STREAM_MINBLOCKS)) p.n_raw--;
-    p.smem = smem_for(p.n_raw);
+    p.rec_smem = (e->stream_rec_smem && smem_for(3, 1) <= budget) ? 1 : 0;               // site records next to the rows when they fit
+    while (p.n_raw > 3 && smem_for(p.n_raw, p.rec_smem) > budget) p.n_raw--;
+    p.smem = smem_for(p.n_raw, p.rec_smem);
     if (p.smem > 226 * 1024) return p;
-    const size_t key = (p.smem << 12) | (size_t)((p.n_prod + p.n_cons) * 32);
+    const size_t key = (p.smem << 13) | (size_t)((p.n_prod + p.n_cons) * 32) << 1 | (size_t)p.rec_smem;
     if (key != e->stream_occ_key) {
-        if (cudaFuncSetAttribute(k_polyhedral_assign_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
+        const void *fn = p.rec_smem ? (const void *)k_polyhedral_assign_stream<true> : (const void *)k_polyhedral_assign_stream<false>;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
         int q = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_polyhedral_assign_stream, (p.n_prod + p.n_cons) * 32, p.smem);
+        if (p.rec_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_polyhedral_assign_stream<true>, (p.n_prod + p.n_cons) * 32, p.smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_polyhedral_assign_stream<false>, (p.n_prod + p.n_cons) * 32, p.smem);
         e->stream_per_sm = q; e->stream_occ_key = key;
     }
     const int per_sm = e->stream_per_sm;
@@ -562,10 +568,14 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
     SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp, e->d_legacy_init};
     SabStreamTables C{e->n_used, (int)p.stride, 3 * e->M, e->d_tile_vars, e->d_tile_rec, e->G, e->d_cell_off, e->d_cell_sites,
                       (float)e->delta - 4e-7f, e->fp32_filter, w.defer, w.defer_cap, e->d_anchor, e->d_fw_atoms, e->d_prev_raw,
-                      e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc};
+                      e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc, e->delta > 0.12 ? 1 : 0};
     const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
-    k_polyhedral_assign_stream<<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
-        e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+    if (p.rec_smem)
+        k_polyhedral_assign_stream<true><<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+            e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
+    else
+        k_polyhedral_assign_stream<false><<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
+            e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
     // exact float64 pass over the atom-frames float32 could not decide (returns at once when there are none)
     k_polyhedral_deferred<<<e->sm_count * 8, 256, 0, st>>>(d_frac, F, e->N, e->A, e->d_mobile, T, e->G, e->d_cell_off,
         e->d_cell_sites, nullptr, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor);

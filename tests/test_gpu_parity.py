@@ -116,7 +116,7 @@ def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
                             (True, {nat.OPT_POLY_KERNEL: 4, nat.OPT_FP32_FILTER: 0}), (True, {nat.OPT_SEQ_CHUNK: 3}),
                             (True, {nat.OPT_POLY_KERNEL: 5}), (True, {nat.OPT_POLY_KERNEL: 5, nat.OPT_SEQ_CHUNK: 7}),
                             (True, {nat.OPT_POLY_KERNEL: 5, nat.OPT_FP32_FILTER: 0}),
-                            (True, {nat.OPT_STREAM_PRODUCERS: 1, nat.OPT_SEQ_CHUNK: 5}), (True, {nat.OPT_STREAM_PRODUCERS: 4}),
+                            (True, {nat.OPT_STREAM_PRODUCERS: 1, nat.OPT_SEQ_CHUNK: 5}), (True, {nat.OPT_STREAM_PRODUCERS: 4, nat.OPT_STREAM_REC_SMEM: 0}),
                             (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
