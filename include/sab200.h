@@ -155,6 +155,7 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
 #define SAB_OPT_TILE_FRAMES 6 /* frames per tile of the tile kernel, 1..4 (0 = automatic) */
 #define SAB_OPT_STREAM_PRODUCERS 7 /* producer warps per CTA of the stream kernel (0 = automatic) */
 #define SAB_OPT_STREAM_REC_SMEM 8  /* 1 (default): site records staged in shared memory when they fit; 0: read through L1 */
+#define SAB_OPT_STREAM_REG_COLS 9  /* 1 (default): producer threads keep their columns' metadata and excursions in registers when they fit */
 int sab_set_option(sab_engine *e, int key, int64_t value);
 
 /* ---- the hot path -------------------------------------------------------------------- */

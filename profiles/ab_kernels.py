@@ -13,8 +13,9 @@ d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
 VARIANTS = [("tile kernel + wrap scan", {nat.OPT_POLY_KERNEL: 5}), ("stream kernel (default)", {}),
-            ("stream, 2 producer warps", {nat.OPT_STREAM_PRODUCERS: 2}), ("stream, 4 producer warps", {nat.OPT_STREAM_PRODUCERS: 4}),
-            ("stream, records via L1", {nat.OPT_STREAM_REC_SMEM: 0}), ("stream, 2 producers, records via L1", {nat.OPT_STREAM_PRODUCERS: 2, nat.OPT_STREAM_REC_SMEM: 0}),
+            ("stream, column metadata in shared memory", {nat.OPT_STREAM_REG_COLS: 0}),
+            ("stream, 3 producer warps", {nat.OPT_STREAM_PRODUCERS: 3}), ("stream, 2 producer warps", {nat.OPT_STREAM_PRODUCERS: 2}),
+            ("stream, records via L1", {nat.OPT_STREAM_REC_SMEM: 0}),
             ("stream, chunk 128", {nat.OPT_SEQ_CHUNK: 128}), ("stream, fp64 only", {nat.OPT_FP32_FILTER: 0}),
             ("seq1 + wrap scan", {nat.OPT_POLY_KERNEL: 4})]
 if len(sys.argv) > 2:

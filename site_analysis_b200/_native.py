@@ -7,6 +7,7 @@ or no CUDA device is present, every entry point raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -27,6 +28,7 @@ OPT_FP32_FILTER = 5
 OPT_TILE_FRAMES = 6
 OPT_STREAM_PRODUCERS = 7
 OPT_STREAM_REC_SMEM = 8
+OPT_STREAM_REG_COLS = 9
 
 # every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = [
@@ -62,12 +64,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = Path(os.environ.get("SAB200_LIB", LIB_PATH))       # SAB200_LIB: an alternative BUILD of the same backend (A/B timing)
+    if not path.exists():
         raise NativeError(
-            f"{LIB_PATH} is missing: the CUDA backend has not been built "
+            f"{path} is missing: the CUDA backend has not been built "
             "(run site_analysis_b200/csrc/build.sh or __graft_entry__.build()). "
             "site_analysis_b200 has no CPU fallback.")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     sig = {
         "sab_abi_version": (i32, []),

@@ -13,6 +13,8 @@ the same library calls give the same answers:
 """
 from __future__ import annotations
 
+import itertools
+
 import numpy as np
 
 _SHIFTS27 = np.array([[i, j, k] for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)],
@@ -224,38 +226,43 @@ def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: f
     position; then d(x, s_t) is within +-move of d(x, anchor_s), D gains +move, the keep test -move.
 
     Returns (offsets int32 [G^3 + 1], entries uint16 ascending per cell, excl float64 [G^3])."""
+    from scipy.spatial import cKDTree
     centres = np.asarray(centres, dtype=np.float64) % 1.0
     S = len(centres)
     idx = np.stack(np.meshgrid(*[np.arange(G)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)
     p = (idx + 0.5) / G
     corners = np.array([[a, b, c] for a in (-1, 1) for b in (-1, 1) for c in (-1, 1)], dtype=float) * (0.5 / G)
     R = float(np.linalg.norm(corners @ lattice0, axis=1).max()) * (1.0 + 1e-12)
-    offsets = np.zeros(G ** 3 + 1, dtype=np.int64)
-    entries = []
-    excl = np.empty(G ** 3)
-    # perpendicular heights: |D . L| >= max_i |D_i| h_i for every image, so max_i |d_i| h_i (reduced d)
-    # is a cheap lower bound of the 27-image minimum; the central image is a cheap upper bound
     a0, a1, a2 = lattice0
     vol = abs(np.dot(a0, np.cross(a1, a2)))
     h = vol / np.array([np.linalg.norm(np.cross(a1, a2)), np.linalg.norm(np.cross(a2, a0)), np.linalg.norm(np.cross(a0, a1))])
-    step = max(1, 6_000_000 // max(S, 1))
-    for a in range(0, G ** 3, step):
-        df = centres[None, :, :] - p[a:a + step, None, :]
-        df -= np.round(df)
-        upper = np.linalg.norm(df @ lattice0, axis=-1)                      # central image
-        lower = (np.abs(df) * h).max(axis=-1) * (1.0 - 1e-12)
-        D = (upper + R).min(axis=1) + move
-        for _ in range(2):                                                  # tighten D with exact distances where needed
-            unsure = (lower - R - move <= rho * D[:, None]) & (upper > lower * (1 + 1e-9))
-            ci, si = np.nonzero(unsure)
-            if len(ci):
-                exact = _mic_cartesian(df[ci, si], lattice0)
-                upper[ci, si] = exact
-                lower[ci, si] = exact * (1.0 - 1e-12)
-            D = (upper + R).min(axis=1) + move
-        keep = (lower - R - move) <= rho * D[:, None]
-        excl[a:a + step] = rho * D
-        offsets[a + 1:a + step + 1] = keep.sum(axis=1)
-        entries.append(np.nonzero(keep)[1])
+    p_cart = p @ lattice0
+
+    def image_tree(reach, margin):
+        """k-d tree over the images c + n, n in {-reach..reach}^3, that lie within ``margin`` (Cartesian) of the cell."""
+        n = np.array(list(itertools.product(range(-reach, reach + 1), repeat=3)), dtype=float)
+        pts = (centres[None, :, :] + n[:, None, :]).reshape(-1, 3)
+        site = np.tile(np.arange(S), len(n))
+        m = margin / h                                            # fractional margin per axis
+        ok = np.all((pts >= -m) & (pts <= 1.0 + m), axis=1)
+        return cKDTree(pts[ok] @ lattice0), site[ok]
+
+    # D: upper bound of the nearest-centre distance anywhere in the cell (27 images around the cell centre's own
+    # reduced separations; only the efficiency of the lists depends on it, not their validity)
+    tree27, _ = image_tree(1, float(np.linalg.norm(lattice0, axis=1).sum()))
+    D = (tree27.query(p_cart)[0] + R) * (1.0 + 1e-12) + move
+    excl = rho * D
+    # keep every site with min_n |p - c - n| - R - move <= rho D over n in {-2..2}^3, a superset of the 27 images
+    # the kernels take around the reduced separation of any wrapped point (distances.py:175-189), so a site left
+    # out is farther than excl from every point of the cell for the kernels' own distance as well
+    radius = (excl + R + move) * (1.0 + 1e-9)
+    tree125, site125 = image_tree(2, float(radius.max()) * 1.01 + 1e-9)
+    hits = tree125.query_ball_point(p_cart, radius)
+    offsets = np.zeros(G ** 3 + 1, dtype=np.int64)
+    entries = []
+    for c, hit in enumerate(hits):
+        u = np.unique(site125[hit])
+        offsets[c + 1] = len(u)
+        entries.append(u)
     offsets = np.cumsum(offsets).astype(np.int32)
     return offsets, np.concatenate(entries).astype(np.uint16), excl

@@ -41,6 +41,9 @@
 #ifndef SAB_STREAM_MINBLOCKS
 #define SAB_STREAM_MINBLOCKS 2
 #endif
+#ifndef SAB_STREAM_KMAX
+#define SAB_STREAM_KMAX 5         // register-resident producer form: framework / mobile columns owned by one producer thread
+#endif
 #define SAB_CNT_INVALID 10        // counters[]: the anchor formulation of the wrap count failed its chain check
 
 struct SabStreamTables {
@@ -66,6 +69,7 @@ struct SabStreamTables {
     int use_tma;                  // frames are 16-byte aligned and sized
     double *chunk_exc;            // out [n_chunks][m3][2]: excursion (min, max) of u per chunk
     int always_explicit;          // validity tube wider than 0.12: the in-tube shortcut of the chain check does not apply
+    int reg_cols;                 // every producer thread owns <= SAB_STREAM_KMAX columns: their metadata and excursions live in registers
 };
 
 __device__ __forceinline__ void sab_mbar_arrive(uint64_t *bar)
@@ -161,12 +165,30 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
             sab_bulk_g2s(rawd + (size_t)slot * n3, frac + (size_t)f * n3, bytes, &raw_full[slot]);
         };
         unsigned it = 0;                                        // frames processed by this CTA so far
+        // register-resident form: thread pt owns framework columns pt + k n_prod_thr and the same mobile coordinates
+        int r_fcol[SAB_STREAM_KMAX], r_cv[SAB_STREAM_KMAX], r_mcol[SAB_STREAM_KMAX];
+        double r_anc[SAB_STREAM_KMAX], r_lo[SAB_STREAM_KMAX], r_hi[SAB_STREAM_KMAX];
+        float r_ancf[SAB_STREAM_KMAX];
+#pragma unroll
+        for (int k = 0; k < SAB_STREAM_KMAX; k++) {
+            const int j = pt + k * n_prod_thr;
+            const bool ok = C.reg_cols && j < m3, okm = C.reg_cols && j < a3;
+            const int2 cv = ok ? colvar[j] : make_int2(0, 0);
+            r_fcol[k] = ok ? fwcol[j] : -1;
+            r_cv[k] = cv.x | ((cv.y - cv.x) << 16);
+            r_anc[k] = ok ? ancd[j] : 0.0;
+            r_ancf[k] = (float)r_anc[k];
+            r_mcol[k] = okm ? mobcol[j] : -1;
+            r_lo[k] = INFINITY; r_hi[k] = -INFINITY;
+        }
         for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
             const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
             sab_bar_producers(n_prod_thr);                      // previous chunk fully converted: raw slots idle
             if (pt == 0 && C.use_tma)
                 for (int i = 0; i < RS - 1 && c0 + i < c1; i++) issue(c0 + i, it + i);
             for (int j = pt; j < m3; j += n_prod_thr) { exc[2 * j] = INFINITY; exc[2 * j + 1] = -INFINITY; }   // owner-private
+#pragma unroll
+            for (int k = 0; k < SAB_STREAM_KMAX; k++) { r_lo[k] = INFINITY; r_hi[k] = -INFINITY; }
             for (int64_t f = c0; f < c1; f++, it++) {
                 const int rslot = (int)(it % (unsigned)RS), wslot = (int)(it % SAB_STREAM_ROWS);
                 double *raw = rawd + (size_t)rslot * n3;
@@ -180,6 +202,26 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                 float *row = rows + (size_t)wslot * C.stride;
                 // ---- framework columns -> row entries ------------------------------------------------------
                 int bad = 0;
+                if (C.reg_cols) {
+#pragma unroll
+                    for (int k = 0; k < SAB_STREAM_KMAX; k++)
+                        if (r_fcol[k] >= 0) {
+                            const double r = raw[r_fcol[k]];
+                            const double u = r - rint(r - r_anc[k]);
+                            const float base = (float)u;
+                            if (fabsf(base - r_ancf[k]) > C.delta_f) bad = 1;
+                            r_lo[k] = fmin(r_lo[k], u);
+                            r_hi[k] = fmax(r_hi[k], u);
+                            const int v0 = r_cv[k] & 0xffff, v1 = v0 + (r_cv[k] >> 16);
+                            for (int v = v0; v < v1; v++) row[v] = base + shf[v];
+                        }
+#pragma unroll
+                    for (int k = 0; k < SAB_STREAM_KMAX; k++)
+                        if (r_mcol[k] >= 0) {
+                            const double x = raw[r_mcol[k]];
+                            row[C.n_used + pt + k * n_prod_thr] = (float)(x - floor(x));        // atom.py:104
+                        }
+                } else {
                 for (int j = pt; j < m3; j += n_prod_thr) {
                     const double r = raw[fwcol[j]], anc = ancd[j];
                     const double u = r - rint(r - anc);
@@ -193,6 +235,7 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                 for (int q = pt; q < a3; q += n_prod_thr) {
                     const double x = raw[mobcol[q]];
                     row[C.n_used + q] = (float)(x - floor(x));                               // atom.py:104
+                }
                 }
                 if (bad) atomicOr(&pbad[it & 3], 1);
                 sab_bar_producers(n_prod_thr);                  // pbad complete; everybody is done with the frame before
@@ -225,6 +268,15 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                 }
                 sab_mbar_arrive(&row_full[wslot]);
             }
+            if (C.reg_cols) {
+#pragma unroll
+                for (int k = 0; k < SAB_STREAM_KMAX; k++)
+                    if (r_fcol[k] >= 0) {
+                        const int j = pt + k * n_prod_thr;
+                        C.chunk_exc[((size_t)ch * m3 + j) * 2] = r_lo[k];
+                        C.chunk_exc[((size_t)ch * m3 + j) * 2 + 1] = r_hi[k];
+                    }
+            } else
             for (int j = pt; j < m3; j += n_prod_thr) {
                 C.chunk_exc[((size_t)ch * m3 + j) * 2] = exc[2 * j];
                 C.chunk_exc[((size_t)ch * m3 + j) * 2 + 1] = exc[2 * j + 1];
@@ -234,10 +286,12 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
         // =========================================== consumers ===========================================
         const int cw = warp - C.n_prod;
         const unsigned FULL = 0xffffffffu;
+        const bool one_group = n_mobile <= n_cons_thr;
         unsigned it = 0;
         for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
             const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
             for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = make_int2(-1, -1);   // owner-private
+            int2 rc_reg = make_int2(-1, -1);                    // the same history in a register when a lane owns one atom
             for (int64_t f = c0; f < c1; f++, it++) {
                 const int wslot = (int)(it % SAB_STREAM_ROWS);
                 sab_mbar_wait_backoff(&row_full[wslot], (it / SAB_STREAM_ROWS) & 1);
@@ -248,7 +302,7 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                 for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {
                     const int a = g0 + lane;
                     const bool valid = a < n_mobile;
-                    int2 rc = valid ? last[a] : make_int2(-1, -1);            // {most recent, previous} site
+                    int2 rc = one_group ? rc_reg : (valid ? last[a] : make_int2(-1, -1));   // {most recent, previous} site
                     int out = SAB_NONE;
                     // a definite site h: Atom.update_recent_site (atom.py:189-192)
                     #define SAB_RECENT_PUSH(h) do { if ((h) != rc.x) { rc.y = rc.x; rc.x = (h); } } while (0)
@@ -315,7 +369,8 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                         }
                     }
                     #undef SAB_RECENT_PUSH
-                    if (valid) { res[a] = out; last[a] = rc; }
+                    if (valid) res[a] = out;
+                    if (one_group) rc_reg = rc; else if (valid) last[a] = rc;
                 }
                 sab_mbar_arrive(&row_empty[wslot]);
             }

@@ -105,6 +105,7 @@ struct sab_engine {
     int tile_frames = 0;                   // SAB_OPT_TILE_FRAMES (0 = automatic)
     int stream_prod = 0;                   // SAB_OPT_STREAM_PRODUCERS (0 = automatic)
     int stream_rec_smem = 1;               // SAB_OPT_STREAM_REC_SMEM (1 = site records in shared memory when they fit)
+    int stream_reg_cols = 1;               // SAB_OPT_STREAM_REG_COLS (1 = producer column metadata in registers when they fit)
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
     size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
     unsigned long long *h_pinned = nullptr;               // pinned [2][CNT_N]: counter initialiser | read-back
@@ -405,6 +406,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (key == SAB_OPT_POLY_KERNEL) { e->poly_kernel = (int)value; return SAB_OK; }
     if (key == SAB_OPT_TILE_FRAMES) { e->tile_frames = (int)value; return SAB_OK; }
     if (key == SAB_OPT_STREAM_REC_SMEM) { e->stream_rec_smem = value != 0; return SAB_OK; }
+    if (key == SAB_OPT_STREAM_REG_COLS) { e->stream_reg_cols = value != 0; return SAB_OK; }
     if (key == SAB_OPT_STREAM_PRODUCERS) { if (value < 0 || value > 8) return fail(SAB_EINVAL, "producer warps: 0..8"); e->stream_prod = (int)value; return SAB_OK; }
     if (key == SAB_OPT_FP32_FILTER) { e->fp32_filter = value != 0; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
@@ -525,7 +527,7 @@ static StreamPlan plan_stream(sab_engine *e, const double *d_frac, int64_t F, co
     StreamPlan p;
     if (e->kind != SAB_POLYHEDRAL || !e->cells_set || !e->tile_ok || e->poly_kernel != 0 || e->force_scan || !w.defer) return p;
     p.n_cons = std::min(6, (e->A + 31) / 32);
-    p.n_prod = e->stream_prod > 0 ? e->stream_prod : std::max(2, (p.n_cons + 1) / 2);
+    p.n_prod = e->stream_prod > 0 ? e->stream_prod : std::max(2, (2 * p.n_cons + 2) / 3);   // measured: 4 producers for 6 consumers
     if ((p.n_prod + p.n_cons) * 32 > SAB_STREAM_MAXTHREADS) p.n_prod = SAB_STREAM_MAXTHREADS / 32 - p.n_cons;
     if (p.n_prod < 1) return p;
     const size_t n3 = 3 * (size_t)e->N, m3 = 3 * (size_t)e->M, a3 = 3 * (size_t)e->A;
@@ -568,7 +570,9 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
     SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp, e->d_legacy_init};
     SabStreamTables C{e->n_used, (int)p.stride, 3 * e->M, e->d_tile_vars, e->d_tile_rec, e->G, e->d_cell_off, e->d_cell_sites,
                       (float)e->delta - 4e-7f, e->fp32_filter, w.defer, w.defer_cap, e->d_anchor, e->d_fw_atoms, e->d_prev_raw,
-                      e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc, e->delta > 0.12 ? 1 : 0};
+                      e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc, e->delta > 0.12 ? 1 : 0,
+                      (e->stream_reg_cols && 3 * e->M <= SAB_STREAM_KMAX * 32 * p.n_prod && 3 * e->A <= SAB_STREAM_KMAX * 32 * p.n_prod &&
+                       e->n_used < 65536) ? 1 : 0};
     const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
     if (p.rec_smem)
         k_polyhedral_assign_stream<true><<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
@@ -601,7 +605,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_centres, NL, d_result, e->d_counters + CNT_FULL27);
         break;
     } else {
-        int block = std::min(1024, ((e->A + 31) / 32) * 32);
+        int block = std::min(512, ((e->A + 31) / 32) * 32);
         size_t smem = sizeof(double) * 3 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_nearest_assign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_nearest_assign<false><<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile,
@@ -621,7 +625,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->legacy_init_frame, NL, e->d_nl_anchor, e->d_nl_l0, e->nl_dmax, d_result, e->d_counters + CNT_FULL27);
         break;
     } else {
-        int block = std::min(1024, ((std::max(e->A, 128) + 31) / 32) * 32);
+        int block = std::min(512, ((std::max(e->A, 128) + 31) / 32) * 32);
         size_t smem = sizeof(double) * 3 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_nearest_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_nearest_assign<true><<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile,
@@ -630,7 +634,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
         break;
     }
     case SAB_SPHERICAL: {
-        int block = std::min(1024, ((e->A + 31) / 32) * 32);
+        int block = std::min(512, ((e->A + 31) / 32) * 32);
         size_t smem = sizeof(double) * 5 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_spherical_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_spherical_assign<<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile, e->S,

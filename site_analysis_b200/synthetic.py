@@ -1,4 +1,4 @@
-"""Synthetic argyrodite workloads (BASELINE.json configs 2/3/5).
+"""Synthetic workloads: argyrodite (BASELINE.json configs 2/3/5) and LLZO garnet (config 4); SURVEY.md section 8(d).
 
 Geometry: the F-4 3m Li6PS5Cl reference of the reference's own benchmark scripts
 (tests/benchmark_all_site_types.py:29-46 -- P on 4b, anions on 4a/4c/16e, and the five Li site
@@ -7,6 +7,11 @@ of every Li-site position (cutoff 3.0 A), exactly what the reference workflow de
 structure.  Dynamics: framework atoms vibrate around their ideal positions (Gaussian, sigma in
 Angstrom), mobile ions hop between neighbouring type-5 / type-2 sites and jitter around the
 site centre; coordinates are stored wrapped into [0, 1) so atoms near a cell face flip 0 <-> 1.
+
+Garnet (:func:`garnet_geometry`): cubic Li7La3Zr2O12, Ia-3d, a = 12.97 A, 192 atoms per cell (56 Li, 24 La on 24c,
+16 Zr on 16a, 96 O on 96h); dynamic-Voronoi sites from the oxygen coordination of the Li positions: 24d tetrahedra
+(4 reference atoms) and 48g octahedra (6), i.e. two centre groups
+(reference dynamic_voronoi_site_collection.py:151-164).
 
 Trajectories are generated with torch on the requested device from a seeded generator, so the
 same call gives the same data on every run and a host copy of any frame range is exactly what
@@ -157,3 +162,83 @@ def polyhedral_engine_kwargs(geom: ArgyroditeGeometry, frame0: np.ndarray, latti
         raw = frame0[t]
         primed.append((tab.full_pbc_unwrap(raw, c, lattice0), raw.copy()))
     return dict(slots=slots, reference_centres=list(geom.site_centres), primed=primed)
+
+
+# ------------------------------------------------------------------------------------------------ LLZO garnet
+A_GARNET = 12.97
+_GARNET_FRAMEWORK = [("La", (0.125, 0.0, 0.25)), ("Zr", (0.0, 0.0, 0.0)), ("O", (-0.0318, 0.0546, 0.1498))]
+_GARNET_SITES = [("24d", (0.375, 0.0, 0.25), 4), ("48g", (0.125, 0.6838, 0.5662), 6)]
+
+
+def _ia3d_operations():
+    """The 96 operations (R, t) of Ia-3d, closed from the generators listed in International Tables A, No. 230."""
+    def op(R, t):
+        return np.array(R, dtype=float), np.array(t, dtype=float) % 1.0
+    gens = [op([[-1, 0, 0], [0, -1, 0], [0, 0, 1]], [.5, 0, .5]), op([[-1, 0, 0], [0, 1, 0], [0, 0, -1]], [0, .5, .5]),
+            op([[0, 0, 1], [1, 0, 0], [0, 1, 0]], [0, 0, 0]), op([[0, 1, 0], [1, 0, 0], [0, 0, -1]], [.75, .25, .25]),
+            op(-np.eye(3), [0, 0, 0]), op(np.eye(3), [.5, .5, .5])]
+
+    def key(o):
+        return tuple(o[0].astype(int).ravel()), tuple(np.round(o[1] * 8).astype(int) % 8)
+    group = [op(np.eye(3), [0, 0, 0])]
+    seen = {key(group[0])}
+    frontier = list(group)
+    while frontier:
+        new = []
+        for a in frontier:
+            for g in gens:
+                c = (g[0] @ a[0], (g[0] @ a[1] + g[1]) % 1.0)
+                if key(c) not in seen:
+                    seen.add(key(c)); new.append(c); group.append(c)
+        frontier = new
+    assert len(group) == 96
+    return group
+
+
+def _orbit(ops, xyz, tol=1e-6):
+    pts: list[np.ndarray] = []
+    for R, t in ops:
+        p = (R @ np.asarray(xyz, dtype=float) + t) % 1.0
+        p[np.abs(p - 1.0) < tol] = 0.0
+        if not any(np.all(np.abs((p - q) - np.round(p - q)) < tol) for q in pts):
+            pts.append(p)
+    return np.array(pts)
+
+
+@dataclass
+class GarnetGeometry(ArgyroditeGeometry):
+    reference_slots: list = None   # per site, the structure indices of its 4 (24d) or 6 (48g) oxygen atoms
+
+
+def garnet_geometry(n: int = 2, hop_radius: float = 2.6) -> GarnetGeometry:
+    """LLZO n x n x n: N = 192 n^3 atoms, A = 56 n^3 Li, S = 72 n^3 dynamic-Voronoi sites in two centre groups."""
+    ops = _ia3d_operations()
+    lattice = np.eye(3) * (A_GARNET * n) + 1e-4 * np.array([[0, 1.7, -0.9], [1.7, 0, 0.4], [-0.9, 0.4, 0]])
+    fw_species, fw = [], []
+    for sp, xyz in _GARNET_FRAMEWORK:
+        orb = _supercell(_orbit(ops, xyz), n)
+        fw.append(orb); fw_species += [sp] * len(orb)
+    fw = np.vstack(fw)
+    n_mobile = 56 * n ** 3
+    oxygen = np.array([i for i, s in enumerate(fw_species) if s == "O"])
+    centres, labels, slots = [], [], []
+    for lab, xyz, n_ref in _GARNET_SITES:                    # all tetrahedra first, then all octahedra: two groups
+        for c in _supercell(_orbit(ops, xyz), n):
+            d = _mic_cart(fw[oxygen] - c, lattice)
+            order = np.argsort(d, kind="stable")
+            assert d[order[n_ref - 1]] < 2.6 < d[order[n_ref]], "unexpected oxygen coordination"
+            centres.append(c); labels.append(lab)
+            slots.append([int(n_mobile + oxygen[j]) for j in order[:n_ref]])
+    centres = np.array(centres)
+    k = 8
+    nb = np.tile(np.arange(len(centres))[:, None], (1, k))
+    for i in range(len(centres)):
+        d = _mic_cart(centres - centres[i], lattice)
+        near = [q for q in np.argsort(d, kind="stable")[1:k + 1] if d[q] < hop_radius]
+        nb[i, :len(near)] = near
+    return GarnetGeometry(n=n, lattice=lattice, species=["Li"] * n_mobile + fw_species, ideal_framework=fw,
+                          n_mobile=n_mobile, site_centres=centres, site_labels=labels, tetrahedra=None,
+                          hop_sites=np.arange(len(centres)), hop_neighbours=nb, reference_slots=slots)
+
+
+synthetic_trajectory = argyrodite_trajectory      # the dynamics only need the fields both geometries share

@@ -186,6 +186,62 @@ def test_dynamic_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
     assert np.array_equal(outs[0][:60], want)
 
 
+def test_baseline_config3_voronoi_4x4x4_supercell(oracle_mod):
+    """BASELINE.json config 3: synthetic 4x4x4 argyrodite, N = 3328, A = 1536, S = 8448 Voronoi centres,
+    coordinates wrapped into [0, 1), fluctuating slightly triclinic lattice.  Cell-list kernel == exhaustive kernel on
+    every frame; both == the oracle on the frames the CPU can afford (0.7 s per frame)."""
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.argyrodite_geometry(4)
+    assert (g.n_atoms, g.n_mobile, len(g.site_centres)) == (3328, 1536, 8448)
+    frac, lat = syn.argyrodite_trajectory(g, 96, device="cuda", seed=20260103)
+    outs = []
+    for use_cells in (True, False):
+        eng = AssignmentEngine("voronoi", g.n_atoms, g.mobile_idx, centres=g.site_centres)
+        eng.use_cells = use_cells
+        outs.append(eng.assign_device(frac, lat).cpu().numpy())
+        assert (eng._cells is not None) == use_cells
+    assert np.array_equal(outs[0], outs[1])
+    assert outs[0].min() >= 0                                   # Voronoi never yields None
+    o = oracle_mod.SiteOracle("voronoi", g.mobile_idx, centres=g.site_centres)
+    sel = np.r_[0:3, 93:96]
+    want = o.run(frac.cpu().numpy()[sel], lat.cpu().numpy()[sel], positions=True)
+    assert np.array_equal(outs[0][sel], want)
+
+
+def test_baseline_config4_garnet_dynamic_voronoi_two_centre_groups(oracle_mod):
+    """BASELINE.json config 4: LLZO garnet 2x2x2, N = 1536, A = 448, S = 576 dynamic-Voronoi sites from the oxygen
+    coordination -- 24d tetrahedra (4 reference atoms) and 48g octahedra (6), i.e. two centre groups
+    (dynamic_voronoi_site_collection.py:151-164).  Assignments and centres (bit patterns) against the oracle."""
+    import torch
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.garnet_geometry(2)
+    S = len(g.site_centres)
+    assert (g.n_atoms, g.n_mobile, S) == (1536, 448, 576) and {len(s) for s in g.reference_slots} == {4, 6}
+    frac, lat = syn.synthetic_trajectory(g, 400, device="cuda", seed=20260104)
+    outs = []
+    for use_cells in (True, False):
+        eng = AssignmentEngine("dynamic_voronoi", g.n_atoms, g.mobile_idx, slots=g.reference_slots,
+                               reference_centres=list(g.site_centres))
+        eng.use_cells = use_cells
+        outs.append(eng.assign_device(frac, lat).cpu().numpy())
+        assert (eng._cells is not None) == use_cells
+    assert list(np.unique(eng.group_of_site)) == [0, 1]
+    assert np.array_equal(outs[0], outs[1])
+    ref = np.zeros((S, 6), dtype=np.int32)
+    for i, sl in enumerate(g.reference_slots):
+        ref[i, :len(sl)] = sl
+    o = oracle_mod.SiteOracle("dynamic_voronoi", g.mobile_idx, ref_idx=ref, n_ref=np.array([len(s) for s in g.reference_slots], np.int32),
+                              has_ref_center=np.ones(S, np.uint8), ref_center=g.site_centres)
+    n = 120
+    want = o.run(frac.cpu().numpy()[:n], lat.cpu().numpy()[:n], positions=True)
+    assert np.array_equal(outs[0][:n], want)
+    eng2 = AssignmentEngine("dynamic_voronoi", g.n_atoms, g.mobile_idx, slots=g.reference_slots, reference_centres=list(g.site_centres))
+    eng2.assign_device(frac[:n].contiguous(), lat[:n].contiguous())
+    cen = eng2.dynvor_centres(frac[n - 1:n].contiguous())[0].cpu().numpy()
+    assert np.array_equal(cen.view(np.int64), np.asarray(o.centres(), dtype=np.float64).view(np.int64))
+    assert torch.cuda.is_available()
+
+
 def test_reset_and_replay(oracle_mod):
     """Trajectory.reset(): history and PBC caches cleared, topology kept, same answers again."""
     case = oracle_mod.load_case("fuzz_polyhedral_1")
