@@ -14,6 +14,7 @@ kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().num
 ref = None
 VARIANTS = [("tile kernel + wrap scan", {nat.OPT_POLY_KERNEL: 5}), ("stream kernel (default)", {}),
             ("stream, column metadata in shared memory", {nat.OPT_STREAM_REG_COLS: 0}),
+            ("stream, 6 producer warps (needs a 384-thread build)", {nat.OPT_STREAM_PRODUCERS: 6}),
             ("stream, 3 producer warps", {nat.OPT_STREAM_PRODUCERS: 3}), ("stream, 2 producer warps", {nat.OPT_STREAM_PRODUCERS: 2}),
             ("stream, records via L1", {nat.OPT_STREAM_REC_SMEM: 0}),
             ("stream, chunk 128", {nat.OPT_SEQ_CHUNK: 128}), ("stream, fp64 only", {nat.OPT_FP32_FILTER: 0}),

@@ -37,7 +37,9 @@
 
 #define SAB_STREAM_ROWS 4         // ring of float rows (producers run at most this far ahead of the slowest consumer)
 #define SAB_STREAM_MAXRAW 4       // ring of raw frames (the copy engine runs raw slots - 2 frames ahead)
+#ifndef SAB_STREAM_MAXTHREADS
 #define SAB_STREAM_MAXTHREADS 320
+#endif
 #ifndef SAB_STREAM_MINBLOCKS
 #define SAB_STREAM_MINBLOCKS 2
 #endif
@@ -76,15 +78,17 @@ __device__ __forceinline__ void sab_mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+#ifndef SAB_STREAM_SUSPEND_NS
+#define SAB_STREAM_SUSPEND_NS 4000   // try_wait suspends the warp in hardware for up to this long: a waiting warp issues nothing
+#endif
 __device__ __forceinline__ void sab_mbar_wait_backoff(uint64_t *bar, unsigned parity)
 {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     for (;;) {
         unsigned ok;
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(SAB_STREAM_SUSPEND_NS) : "memory");
         if (ok) break;
-        __nanosleep(32);
     }
 }
 template <bool SMEM> __device__ __forceinline__ SabTetRec sab_tet_rec_at(const uint16_t *__restrict__ rec)
@@ -168,7 +172,7 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
         // register-resident form: thread pt owns framework columns pt + k n_prod_thr and the same mobile coordinates
         int r_fcol[SAB_STREAM_KMAX], r_cv[SAB_STREAM_KMAX], r_mcol[SAB_STREAM_KMAX];
         double r_anc[SAB_STREAM_KMAX], r_lo[SAB_STREAM_KMAX], r_hi[SAB_STREAM_KMAX];
-        float r_ancf[SAB_STREAM_KMAX];
+        float r_ancf[SAB_STREAM_KMAX], r_s0[SAB_STREAM_KMAX], r_s1[SAB_STREAM_KMAX];
 #pragma unroll
         for (int k = 0; k < SAB_STREAM_KMAX; k++) {
             const int j = pt + k * n_prod_thr;
@@ -178,6 +182,8 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
             r_cv[k] = cv.x | ((cv.y - cv.x) << 16);
             r_anc[k] = ok ? ancd[j] : 0.0;
             r_ancf[k] = (float)r_anc[k];
+            r_s0[k] = (ok && cv.y > cv.x) ? shf[cv.x] : 0.f;
+            r_s1[k] = (ok && cv.y > cv.x + 1) ? shf[cv.x + 1] : 0.f;
             r_mcol[k] = okm ? mobcol[j] : -1;
             r_lo[k] = INFINITY; r_hi[k] = -INFINITY;
         }
@@ -210,10 +216,12 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                             const double u = r - rint(r - r_anc[k]);
                             const float base = (float)u;
                             if (fabsf(base - r_ancf[k]) > C.delta_f) bad = 1;
-                            r_lo[k] = fmin(r_lo[k], u);
-                            r_hi[k] = fmax(r_hi[k], u);
-                            const int v0 = r_cv[k] & 0xffff, v1 = v0 + (r_cv[k] >> 16);
-                            for (int v = v0; v < v1; v++) row[v] = base + shf[v];
+                            r_lo[k] = u < r_lo[k] ? u : r_lo[k];
+                            r_hi[k] = u > r_hi[k] ? u : r_hi[k];
+                            const int v0 = r_cv[k] & 0xffff, nv = r_cv[k] >> 16;           // nearly always one or two slot shifts
+                            if (nv > 0) row[v0] = base + r_s0[k];
+                            if (nv > 1) row[v0 + 1] = base + r_s1[k];
+                            for (int v = v0 + 2; v < v0 + nv; v++) row[v] = base + shf[v];
                         }
 #pragma unroll
                     for (int k = 0; k < SAB_STREAM_KMAX; k++)

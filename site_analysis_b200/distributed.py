@@ -168,6 +168,34 @@ def _carry_by_anchor(engine, d_frac_local, group):
     st["keep"] = (halos, last_raw)                           # alive until the stream has consumed them
 
 
+def relay_history(engine, group) -> None:
+    """Sequential hand-over of the history the priority order depends on (``Atom._recent_sites`` atom.py:55, the
+    previous trajectory entry, ``Site.transitions`` site.py:71; read by site_collection.py:113-182).
+
+    Rank after rank: take the history the preceding shard ended with, fold / resolve this shard's batches in frame
+    order (``engine.sync_history``), pass the result on.  Each shard's frames stay on their GPU; only
+    (A x 3 ints + the transition Counters) travel, world_size - 1 times.  After the call every engine holds the
+    history at the end of the WHOLE trajectory and every rank's result tensor is final."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    for r in range(world):
+        if rank == r:
+            engine.sync_history()
+            box = [(engine.recent, engine.prev, engine.transitions)]
+        else:
+            box = [None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, r), group=group)
+        if rank != r:
+            recent, prev, transitions = box[0]
+            if rank > r:                                   # not yet processed: start from the predecessor's state
+                engine.recent, engine.prev = np.array(recent, dtype=np.int32), np.array(prev, dtype=np.int32)
+                engine.transitions = [dict(t) for t in transitions]
+            elif r == world - 1:                           # done earlier: adopt the final state
+                engine._pending = []
+                engine.recent, engine.prev = np.array(recent, dtype=np.int32), np.array(prev, dtype=np.int32)
+                engine.transitions = [dict(t) for t in transitions]
+
+
 def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group,
                    equal_shards: bool = False):
     """Assign this rank's contiguous shard with the correct PBC carry and return the FULL
@@ -185,10 +213,13 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
             _carry_by_anchor(engine, d_frac_local, group)
         else:
             _carry_by_totals(engine, d_frac_local, group)
-    local = engine.assign_device(d_frac_local, d_lattice_local)
-    if engine.last_info.get("ambiguous", 0) > 0:
-        raise NotImplementedError("atom-frames contained by several sites in a sharded run need the gathered resolver "
-                                  "(run the affected trajectory on one GPU)")
+    import torch.distributed as dist
+    local = engine.assign_device(d_frac_local, d_lattice_local, defer_resolve=True)
+    if engine.k in (nat.SPHERICAL, nat.POLYHEDRAL):            # sites may overlap: does ANY shard need the priority order?
+        flag = torch.tensor([1 if engine.last_info.get("ambiguous", 0) > 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()):
+            relay_history(engine, group)                       # resolves `local` in place, shard after shard
     engine._pending = []
     full = gather_assignments(local, group, equal_shards)       # enqueued first: the guard below overlaps with it
     if engine.slots is not None and engine.k == nat.POLYHEDRAL:

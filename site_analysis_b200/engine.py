@@ -212,12 +212,17 @@ class AssignmentEngine:
         self.frames_done = 0
 
     def sync_history(self):
-        """Fold every finished batch into (recent, prev, transitions)."""
-        for rows, append in self._pending:
+        """Fold every finished batch into (recent, prev, transitions), in order; batches whose ambiguous
+        atom-frames were left for later (``assign_device(defer_resolve=True)``) go through the resolver here."""
+        pending, self._pending = self._pending, []
+        for item in pending:
+            if isinstance(item[0], str):
+                self._resolve_now(*item[1:])
+                continue
+            rows, append = item
             if not isinstance(rows, np.ndarray):
                 rows = rows.cpu().numpy()
             fold_history(self.recent, self.prev, self.transitions, rows, append)
-        self._pending = []
 
     # ------------------------------------------------------------------ PBC state initialisation
     def _init_pbc(self, raw0: np.ndarray, lat0: np.ndarray):
@@ -443,6 +448,9 @@ class AssignmentEngine:
 
     def _resolve(self, d_frac, F, d_result, d_spill, stream, append):
         self.sync_history()
+        self._resolve_now(d_frac, F, d_result, d_spill, stream, append)
+
+    def _resolve_now(self, d_frac, F, d_result, d_spill, stream, append):
         self._upload_priority_tables()
         width = max(12, 2 * max((len(t) for t in self.transitions), default=0))
         while True:
@@ -471,9 +479,13 @@ class AssignmentEngine:
                             for s in range(self.S)]
 
     # ------------------------------------------------------------------ the hot path
-    def assign_device(self, d_frac, d_lattice, *, append: bool = True):
+    def assign_device(self, d_frac, d_lattice, *, append: bool = True, defer_resolve: bool = False):
         """Assign a device-resident batch.  ``d_frac`` (F, N, 3) float64 cuda tensor, ``d_lattice`` (3, 3)
-        or (F, 3, 3).  Returns an (F, A) int32 cuda tensor of site list positions (-1 = None)."""
+        or (F, 3, 3).  Returns an (F, A) int32 cuda tensor of site list positions (-1 = None).
+
+        ``defer_resolve``: atom-frames in several sites keep their spill codes (<= -2) in the returned tensor
+        until :meth:`sync_history` runs the priority resolver over them IN PLACE -- the sharded driver sets the
+        history left by the preceding shard first (``distributed.relay_history``)."""
         torch = _torch()
         assert d_frac.is_cuda and d_frac.dtype == torch.float64 and d_frac.is_contiguous()
         F = int(d_frac.shape[0])
@@ -536,7 +548,10 @@ class AssignmentEngine:
                 nat.check(self.L.sab_commit_pbc(self.h, sub.data_ptr(), nf, n_ok, d_ws.data_ptr(), ws_bytes, stream))
             if n_ok:
                 ambiguous = bool(info[0]) and bool((sub_res[:n_ok] <= nat.AMBIGUOUS_BASE).any().item())
-                if ambiguous:
+                if ambiguous and defer_resolve:
+                    self._pending.append(("resolve", sub, n_ok, sub_res, d_spill, stream, append))
+                    total["ambiguous"] += int(info[0])
+                elif ambiguous:
                     self._resolve(sub, n_ok, sub_res, d_spill, stream, append)
                     total["ambiguous"] += int(info[0])
                 else:

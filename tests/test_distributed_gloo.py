@@ -70,6 +70,53 @@ def _worker(rank, world, port, F, seed, out_dir):
         dist.destroy_process_group()
 
 
+class _HistoryOnly:
+    """The part of AssignmentEngine that relay_history touches, with the host fold as the 'resolver'."""
+
+    def __init__(self, A, S):
+        self.recent = -np.ones((A, 2), dtype=np.int32)
+        self.prev = np.full(A, -2, dtype=np.int32)
+        self.transitions = [dict() for _ in range(S)]
+        self._pending = []
+
+    def sync_history(self):
+        from site_analysis_b200.engine import fold_history
+        pending, self._pending = self._pending, []
+        for rows, append in pending:
+            fold_history(self.recent, self.prev, self.transitions, rows, append)
+
+
+def _relay_worker(rank, world, port, F, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        A, S = 9, 6
+        rows = rng.integers(-1, S, size=(F, A)).astype(np.int32)
+        rows[1:][rng.random((F - 1, A)) < 0.6] = -3                 # mostly "stay": copy the frame before
+        for f in range(1, F):
+            rows[f] = np.where(rows[f] == -3, rows[f - 1], rows[f])
+        whole = _HistoryOnly(A, S)
+        whole._pending = [(rows, True)]
+        whole.sync_history()
+        f0, f1 = sd.shard_bounds(F, world, rank)
+        mine = _HistoryOnly(A, S)
+        mine._pending = [(rows[f0:(f0 + f1) // 2], True), (rows[(f0 + f1) // 2:f1], True)]
+        sd.relay_history(mine, dist.group.WORLD)
+        assert np.array_equal(mine.recent, whole.recent) and np.array_equal(mine.prev, whole.prev)
+        assert [list(t.items()) for t in mine.transitions] == [list(t.items()) for t in whole.transitions]   # insertion order too
+        open(os.path.join(out_dir, f"relay{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_history_relay_world2(tmp_path):
+    """Shard-after-shard hand-over of (recent sites, previous entry, transition Counters) == one sequential fold."""
+    port = _free_port()
+    mp.spawn(_relay_worker, args=(2, port, 41, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "relay0").exists() and (tmp_path / "relay1").exists()
+
+
 @pytest.mark.parametrize("F", [64, 37])
 def test_wrap_carry_and_gather_world2(tmp_path, F):
     port = _free_port()
