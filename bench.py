@@ -162,9 +162,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
-    ap.add_argument("--ref-frames-per-thread", type=int, default=4000)
+    ap.add_argument("--ref-frames-per-thread", type=int, default=10000)
     ap.add_argument("--parity-frames", type=int, default=400)
-    ap.add_argument("--cpu-baseline-frames", type=int, default=4000)
+    ap.add_argument("--cpu-baseline-frames", type=int, default=0,
+                    help="frames per host thread of the cpu_baseline sample (0 = the whole shard split over all cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -272,8 +273,8 @@ def main():
         bytes_per_launch = algorithmic_bytes_per_frame(A, n_fw) * F
         assign_s = assign_ns * 1e-9 / args.steps
         achieved = bytes_per_launch / assign_s / 1e9
-        cb_frames = args.cpu_baseline_frames
         cores = os.cpu_count() or 1
+        cb_frames = args.cpu_baseline_frames or max(1, F // cores)
         nb = min(F, cores * cb_frames)
         cpu_v, cpu_n, cpu_dt = time_oracle_all_cores(oracle_for(geom, frame0, lat0), d_frac[:nb].cpu().numpy(),
                                                      d_lat[:nb].cpu().numpy(), cb_frames)
@@ -291,7 +292,7 @@ def main():
                     "equals_device_result": same},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_polyhedral_assign", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_polyhedral_assign_stream", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": int(bytes_per_launch), "kernel_ms": assign_s * 1e3,
                          "wrap_scan_ms": wrap_ns * 1e-6 / args.steps},

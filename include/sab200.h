@@ -125,6 +125,14 @@ int sab_set_cell_lists(sab_engine *e, int G, double delta, const double *anchor,
 int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice0_inverse, const int32_t *cell_off,
                           const uint16_t *cell_sites, const double *excl);
 
+/* Exact-pruning table of the spherical kernel (csrc/k_spherical.cuh, k_spherical_assign_cells): a G^3 cell list of the
+ * sites whose sphere inflated by `rho` (>= 1) can reach each cell in the metric of the lattice whose INVERSE is passed,
+ * over the periodic images {-2..2}^3.  Frames whose lattice is strained by more than the head-room rho allows take the
+ * exhaustive loop, so the table never decides a result on its own (replaces the site loop of
+ * spherical_site_collection.py:86-91 only as a candidate filter).  cell_off == NULL clears the table. */
+int sab_set_sphere_lists(sab_engine *e, int G, const double *lattice0_inverse, double rho, const int32_t *cell_off,
+                         const uint16_t *cell_sites);
+
 /* The same for dynamic-Voronoi sites: lists built around ANCHOR centres double[S][3] with head-room
  * max_move (metric of lattice0) for the centres' motion; frames in which a centre is farther than
  * max_move from its anchor take the exhaustive path. */

@@ -266,3 +266,42 @@ def nearest_cell_lists(centres: np.ndarray, lattice0: np.ndarray, G: int, rho: f
         entries.append(u)
     offsets = np.cumsum(offsets).astype(np.int32)
     return offsets, np.concatenate(entries).astype(np.uint16), excl
+
+
+def sphere_cell_lists(centres: np.ndarray, rcut: np.ndarray, lattice0: np.ndarray, G: int, rho: float = 1.06):
+    """For each of the G^3 cells of the unit cube: the spherical sites that can contain some point of the cell.
+
+    Site s is listed for cell c (centre p, circumradius R in the metric of ``lattice0``) when
+    min over n in {-2..2}^3 of |p - c_s - n| <= rho * rcut_s + R.  Hence for every point x of the cell and every
+    unlisted site, |x - c_s - n| > rho * rcut_s for all those images -- a superset of the 27 images the reference takes
+    around the reduced separation of a wrapped point (distances.py:27-66).  ``rho`` is head-room for lattice strain:
+    the kernel uses the lists only in frames with (1 - ||L0^-1 L_t - I||_F) * rho >= 1.
+
+    Returns (offsets int32 [G^3 + 1], entries uint16 ascending per cell)."""
+    from scipy.spatial import cKDTree
+    centres = np.asarray(centres, dtype=np.float64) % 1.0
+    rcut = np.broadcast_to(np.asarray(rcut, dtype=np.float64), (len(centres),))
+    S = len(centres)
+    idx = np.stack(np.meshgrid(*[np.arange(G)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)
+    p = (idx + 0.5) / G
+    corners = np.array([[a, b, c] for a in (-1, 1) for b in (-1, 1) for c in (-1, 1)], dtype=float) * (0.5 / G)
+    R = float(np.linalg.norm(corners @ lattice0, axis=1).max()) * (1.0 + 1e-12)
+    a0, a1, a2 = lattice0
+    vol = abs(np.dot(a0, np.cross(a1, a2)))
+    h = vol / np.array([np.linalg.norm(np.cross(a1, a2)), np.linalg.norm(np.cross(a2, a0)), np.linalg.norm(np.cross(a0, a1))])
+    reach = (rho * rcut + R) * (1.0 + 1e-9) + 1e-12
+    n = np.array(list(itertools.product(range(-2, 3), repeat=3)), dtype=float)
+    pts = (centres[None, :, :] + n[:, None, :]).reshape(-1, 3)
+    site = np.tile(np.arange(S), len(n))
+    m = float(reach.max()) * 1.01 / h
+    ok = np.all((pts >= -m) & (pts <= 1.0 + m), axis=1)
+    pts, site = pts[ok], site[ok]
+    tree = cKDTree(p @ lattice0)
+    hits = tree.query_ball_point(pts @ lattice0, reach[site])          # per site image: the cells it can reach
+    cell = np.concatenate([np.asarray(hh, dtype=np.int64) for hh in hits]) if len(hits) else np.zeros(0, np.int64)
+    who = np.repeat(site, [len(hh) for hh in hits])
+    key = np.unique(cell * S + who)                                     # ascending cell, then ascending site
+    cell_u, site_u = key // S, key % S
+    offsets = np.zeros(G ** 3 + 1, dtype=np.int64)
+    np.add.at(offsets, cell_u + 1, 1)
+    return np.cumsum(offsets).astype(np.int32), site_u.astype(np.uint16)

@@ -82,3 +82,99 @@ __global__ void k_spherical_assign(const double *__restrict__ frac, const double
         }
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same containment test with exact spatial pruning.  A static G^3 cell list (host: _tables.sphere_cell_lists)
+// gives every cell the sites whose sphere, inflated by the factor rho, can reach the cell in the metric of the
+// lattice L0 the list was built with: a site NOT in the list of the atom's cell is farther than rho * rcut from the
+// atom for every periodic image n in {-2..2}^3 -- a superset of the images the test above looks at.  In the
+// frame's own metric every length is at least (1 - eta) times its L0 value, eta = ||L0^-1 L_t - I||_F, so while
+// (1 - eta) rho >= 1 an unlisted site cannot contain the atom and only the listed ones are tested, with the very
+// same arithmetic (sab_sphere_contains).  A frame whose lattice is strained beyond that takes the exhaustive
+// loop.  Candidates are visited in ascending list position, so spilled sets equal those of k_spherical_assign.
+struct SabSphereLists {
+    int G;
+    const int32_t *cell_off;    // [G^3 + 1]
+    const uint16_t *cell_sites; // ascending site list positions
+    double rho;                 // inflation the lists were built with
+    double l0inv[9];
+};
+
+__global__ void k_spherical_assign_cells(const double *__restrict__ frac, const double *__restrict__ lattice,
+                                         int lattice_stride, int64_t n_frames, int n_atoms, int n_mobile,
+                                         const int32_t *__restrict__ mobile, int n_sites,
+                                         const double *__restrict__ centres, const double *__restrict__ rcut,
+                                         const double *__restrict__ rcut_q, SabSphereLists SL,
+                                         int32_t *__restrict__ result, int32_t *__restrict__ spill, long long spill_capacity,
+                                         unsigned long long *__restrict__ counters, unsigned long long *__restrict__ n_exhaustive)
+{
+    __shared__ SabLattice lat;
+    __shared__ int lists_ok;
+    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const double *frame = frac + (size_t)f * n_atoms * 3;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sab_lattice_load(lattice + (size_t)f * lattice_stride, lat);
+            double eta2 = 0.0;
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    double m = SL.l0inv[3 * i] * lat.m[j] + SL.l0inv[3 * i + 1] * lat.m[3 + j] + SL.l0inv[3 * i + 2] * lat.m[6 + j];
+                    if (i == j) m -= 1.0;
+                    eta2 += m * m;
+                }
+            const double shrink = 1.0 - sqrt(eta2) * (1.0 + 1e-9) - 1e-12;
+            lists_ok = shrink * SL.rho >= 1.0 + 1e-9;
+            if (!lists_ok) atomicAdd(n_exhaustive, 1ULL);
+        }
+        __syncthreads();
+        const bool use_lists = lists_ok != 0;
+        for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
+            double x[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
+            int b = 0, e = n_sites;
+            if (use_lists) {
+                int c0 = min(SL.G - 1, (int)(x[0] * (double)SL.G)), c1 = min(SL.G - 1, (int)(x[1] * (double)SL.G)),
+                    c2 = min(SL.G - 1, (int)(x[2] * (double)SL.G));
+                const int cell = (c0 * SL.G + c1) * SL.G + c2;
+                b = __ldg(SL.cell_off + cell); e = __ldg(SL.cell_off + cell + 1);
+            }
+            int cnt = 0;
+            int keep[SAB_SPH_KEEP];
+            for (int i = b; i < e; i++) {
+                const int s = use_lists ? (int)__ldg(SL.cell_sites + i) : i;
+                const double cs[3] = {__ldg(centres + 3 * s), __ldg(centres + 3 * s + 1), __ldg(centres + 3 * s + 2)};
+                if (sab_sphere_contains(cs, x, __ldg(rcut + s), __ldg(rcut_q + s), lat)) {
+                    if (cnt < SAB_SPH_KEEP) keep[cnt] = s;
+                    cnt++;
+                }
+            }
+            int out;
+            if (cnt == 0) out = SAB_NONE;
+            else if (cnt == 1) out = keep[0];
+            else {
+                atomicAdd(&counters[0], 1ULL);
+                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(cnt + 1));
+                if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
+                    counters[2] = 1ULL;
+                    out = SAB_NONE;
+                } else {
+                    spill[off] = cnt;
+                    if (cnt <= SAB_SPH_KEEP) {
+                        for (int i = 0; i < cnt; i++) spill[off + 1 + i] = keep[i];
+                    } else {
+                        int k = 0;
+                        for (int i = b; i < e; i++) {
+                            const int s = use_lists ? (int)__ldg(SL.cell_sites + i) : i;
+                            const double cs[3] = {__ldg(centres + 3 * s), __ldg(centres + 3 * s + 1), __ldg(centres + 3 * s + 2)};
+                            if (sab_sphere_contains(cs, x, __ldg(rcut + s), __ldg(rcut_q + s), lat)) spill[off + 1 + k++] = s;
+                        }
+                    }
+                    out = SAB_AMBIGUOUS_BASE - (int)off;
+                }
+            }
+            result[(size_t)f * n_mobile + a] = out;
+        }
+    }
+}

@@ -97,6 +97,7 @@ struct sab_engine {
     bool nl_set = false; int nl_G = 0; double nl_l0inv[9] = {0};
     int32_t *d_nl_off = nullptr; uint16_t *d_nl_sites = nullptr; double *d_nl_excl = nullptr;
     double *d_nl_anchor = nullptr, *d_nl_l0 = nullptr; double nl_dmax = 0.0;   // dynamic Voronoi: anchor centres, L0, motion head-room
+    double nl_rho = 1.0;                   // spherical: inflation factor of the sphere lists
     // exact-pruning tables of the tetrahedral kernel
     bool cells_set = false; int G = 0, kmin = 0, nk = 0; double delta = 0.0;
     uint16_t *d_rec = nullptr, *d_cell_sites = nullptr; int32_t *d_cell_off = nullptr; double *d_anchor = nullptr;
@@ -378,6 +379,23 @@ extern "C" int sab_set_nearest_lists(sab_engine *e, int G, const double *lattice
     return SAB_OK;
 }
 
+extern "C" int sab_set_sphere_lists(sab_engine *e, int G, const double *lattice0_inverse, double rho, const int32_t *cell_off,
+                                    const uint16_t *cell_sites)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_sphere_lists: null engine");
+    CU(cudaSetDevice(e->device));
+    if (!cell_off) { e->nl_set = false; return SAB_OK; }
+    if (e->kind != SAB_SPHERICAL || !e->d_centres) return fail(SAB_ESTATE, "sab_set_sphere_lists: spherical sites not set");
+    if (G < 1 || G > 256 || !lattice0_inverse || !cell_sites || e->S > 65535 || !(rho >= 1.0))
+        return fail(SAB_EINVAL, "sab_set_sphere_lists: bad arguments");
+    size_t ncell = (size_t)G * G * G;
+    CU(upload(&e->d_nl_off, cell_off, ncell + 1));
+    CU(upload(&e->d_nl_sites, cell_sites, (size_t)std::max(cell_off[ncell], 1)));
+    for (int i = 0; i < 9; i++) e->nl_l0inv[i] = lattice0_inverse[i];
+    e->nl_G = G; e->nl_rho = rho; e->nl_set = true;
+    return SAB_OK;
+}
+
 extern "C" int sab_set_dynvor_lists(sab_engine *e, int G, const double *lattice0, const double *lattice0_inverse,
                                     const double *anchors, double max_move, const int32_t *cell_off,
                                     const uint16_t *cell_sites, const double *excl)
@@ -633,7 +651,16 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->d_legacy_init, e->legacy_init_frame, d_centres_out, d_result, e->d_counters + CNT_FULL27);
         break;
     }
-    case SAB_SPHERICAL: {
+    case SAB_SPHERICAL: if (e->nl_set) {
+        int block = std::min(256, ((e->A + 31) / 32) * 32);
+        SabSphereLists SL{e->nl_G, e->d_nl_off, e->d_nl_sites, e->nl_rho, {0}};
+        for (int i = 0; i < 9; i++) SL.l0inv[i] = e->nl_l0inv[i];
+        int grid2 = (int)std::min<int64_t>(F, (int64_t)e->sm_count * 16);
+        k_spherical_assign_cells<<<grid2, block, 0, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile, e->S,
+            e->d_centres, e->d_rcut, e->d_rcut_q, SL, d_result, d_spill, (long long)spill_cap, e->d_counters,
+            e->d_counters + CNT_FULL27);
+        break;
+    } else {
         int block = std::min(512, ((e->A + 31) / 32) * 32);
         size_t smem = sizeof(double) * 5 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_spherical_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

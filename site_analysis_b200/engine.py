@@ -353,6 +353,17 @@ class AssignmentEngine:
                                                nat.ptr(np.ascontiguousarray(ent)), nat.ptr(np.ascontiguousarray(excl))))
         self._cells = dict(G=G, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3)
 
+    def _build_sphere_lists(self, lattice0, rho: float = 1.06):
+        """Spherical: cell lists of the sites whose (inflated) sphere reaches a cell (``_tables.sphere_cell_lists``)."""
+        lattice0 = np.asarray(lattice0, dtype=np.float64)
+        length = float(np.mean(np.linalg.norm(lattice0, axis=1)))
+        G = int(min(64, max(2, round(length / max(0.7 * float(self.rcut.max()), 0.5)))))
+        off, ent = tab.sphere_cell_lists(self.centres, self.rcut, lattice0, G, rho)
+        ent = np.ascontiguousarray(ent if len(ent) else np.zeros(1, dtype=np.uint16))
+        inv = np.ascontiguousarray(np.linalg.inv(lattice0))
+        nat.check(self.L.sab_set_sphere_lists(self.h, G, nat.ptr(inv), float(rho), nat.ptr(np.ascontiguousarray(off)), nat.ptr(ent)))
+        self._cells = dict(G=G, entries=int(off[-1]), mean_candidates=float(off[-1]) / G ** 3, rho=rho)
+
     def _build_dynvor_lists(self, d_frac, lattice0):
         """Dynamic Voronoi: anchors = centres of the batch's first frame, head-room from a strided sample."""
         torch = _torch()
@@ -508,6 +519,8 @@ class AssignmentEngine:
             self._build_nearest_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
         if self.k == nat.DYNAMIC_VORONOI and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
             self._build_dynvor_lists(d_frac, (d_lattice[0] if stride else d_lattice).cpu().numpy())
+        if self.k == nat.SPHERICAL and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+            self._build_sphere_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
         total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0, deferred=0, scan_redo=0)
@@ -620,6 +633,8 @@ class AssignmentEngine:
         if self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
             if self.k == nat.VORONOI:
                 self._build_nearest_lists(lat0)
+            elif self.k == nat.SPHERICAL:
+                self._build_sphere_lists(lat0)
             elif self.k == nat.DYNAMIC_VORONOI:
                 torch = _torch()
                 stride = max(1, F // 256)

@@ -186,6 +186,32 @@ def test_dynamic_voronoi_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
     assert np.array_equal(outs[0][:60], want)
 
 
+def test_spherical_cell_lists_equal_exhaustive_and_oracle(oracle_mod):
+    """k_spherical_assign_cells vs k_spherical_assign (all sites) vs the oracle: overlapping spheres (so the spilled
+    candidate sets and the resolver are exercised), per-site radii, a fluctuating lattice, then frames strained beyond
+    the lists' head-room, which must take the exhaustive loop."""
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    frac, lat = syn.argyrodite_trajectory(g, 300, device="cuda", seed=77)
+    lat[200:] *= 1.09
+    rcut = np.where(np.arange(len(g.site_centres)) % 3 == 0, 1.1, 1.6)
+    outs, infos = [], []
+    for use_cells in (True, False):
+        eng = AssignmentEngine("spherical", g.n_atoms, g.mobile_idx, centres=g.site_centres, rcut=rcut)
+        eng.use_cells = use_cells
+        outs.append(eng.assign_device(frac, lat).cpu().numpy())
+        eng.sync_history()
+        infos.append((eng.last_info, eng.transitions))
+        assert (eng._cells is not None) == use_cells
+    assert infos[0][0]["full27"] == 100                  # exactly the strained frames fell back
+    assert infos[0][0]["ambiguous"] == infos[1][0]["ambiguous"] > 0
+    assert np.array_equal(outs[0], outs[1]) and infos[0][1] == infos[1][1]
+    o = oracle_mod.SiteOracle("spherical", g.mobile_idx, centres=g.site_centres, rcut=rcut)
+    want = o.run(frac.cpu().numpy(), lat.cpu().numpy(), positions=True)
+    assert np.array_equal(outs[0], want)
+    assert (want < 0).any() and (want >= 0).any()
+
+
 def test_baseline_config3_voronoi_4x4x4_supercell(oracle_mod):
     """BASELINE.json config 3: synthetic 4x4x4 argyrodite, N = 3328, A = 1536, S = 8448 Voronoi centres,
     coordinates wrapped into [0, 1), fluctuating slightly triclinic lattice.  Cell-list kernel == exhaustive kernel on
