@@ -35,8 +35,12 @@
 #pragma once
 #include "k_polyhedral_tile.cuh"
 
-#define SAB_STREAM_ROWS 4         // ring of float rows (producers run at most this far ahead of the slowest consumer)
+#ifndef SAB_STREAM_ROWS
+#define SAB_STREAM_ROWS 6         // ring of float rows (producers run at most this far ahead of the slowest consumer)
+#endif
+#ifndef SAB_STREAM_MAXRAW
 #define SAB_STREAM_MAXRAW 4       // ring of raw frames (the copy engine runs raw slots - 2 frames ahead)
+#endif
 #ifndef SAB_STREAM_MAXTHREADS
 #define SAB_STREAM_MAXTHREADS 320
 #endif
