@@ -12,6 +12,13 @@
 #pragma once
 #include "k_nearest.cuh"
 
+#ifndef SAB_NEAREST_BATCH
+#define SAB_NEAREST_BATCH 4
+#endif
+#ifndef SAB_NEAREST_MINBLOCKS
+#define SAB_NEAREST_MINBLOCKS 2
+#endif
+
 struct SabNearestLists {
     int G;
     const int32_t *cell_off;    // [G^3 + 1]
@@ -20,7 +27,7 @@ struct SabNearestLists {
     double l0inv[9];            // inverse of the lattice the lists were built with
 };
 
-__global__ void k_nearest_assign_cells(const double *__restrict__ frac, const double *__restrict__ lattice,
+__global__ void __launch_bounds__(256, SAB_NEAREST_MINBLOCKS) k_nearest_assign_cells(const double *__restrict__ frac, const double *__restrict__ lattice,
                                        int lattice_stride, int64_t n_frames, int n_atoms, int n_mobile,
                                        const int32_t *__restrict__ mobile, int n_sites,
                                        const double *__restrict__ centres, SabNearestLists NL,
@@ -44,6 +51,9 @@ __global__ void k_nearest_assign_cells(const double *__restrict__ frac, const do
         }
         __syncthreads();
         const double thr = (0.5 * lat.hmin) * (0.5 * lat.hmin) * (1.0 - SAB_REL_MARGIN);
+        double L[9];                                     // the frame's lattice in registers
+#pragma unroll
+        for (int k = 0; k < 9; k++) L[k] = lat.m[k];
         for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
             double x[3];
 #pragma unroll
@@ -54,12 +64,35 @@ __global__ void k_nearest_assign_cells(const double *__restrict__ frac, const do
             const int b = __ldg(NL.cell_off + cell), e = __ldg(NL.cell_off + cell + 1);
             double best_q = INFINITY, best_s = INFINITY;
             int best_i = -1;
-            for (int i = b; i < e; i++) {
+            int i = b;
+            for (; i + SAB_NEAREST_BATCH <= e; i += SAB_NEAREST_BATCH) {     // loads of a batch issue together, the argmin stays in list order
+                int sb[SAB_NEAREST_BATCH];
+                double cb[SAB_NEAREST_BATCH][3], qb[SAB_NEAREST_BATCH];
+#pragma unroll
+                for (int k = 0; k < SAB_NEAREST_BATCH; k++) sb[k] = __ldg(NL.cell_sites + i + k);
+#pragma unroll
+                for (int k = 0; k < SAB_NEAREST_BATCH; k++) {
+                    cb[k][0] = __ldg(centres + 3 * sb[k]); cb[k][1] = __ldg(centres + 3 * sb[k] + 1); cb[k][2] = __ldg(centres + 3 * sb[k] + 2);
+                }
+#pragma unroll
+                for (int k = 0; k < SAB_NEAREST_BATCH; k++) {
+                    double d0, d1, d2;
+                    sab_dbase(cb[k], x, d0, d1, d2);
+                    qb[k] = sab_image_q(d0, d1, d2, L);
+                }
+#pragma unroll
+                for (int k = 0; k < SAB_NEAREST_BATCH; k++)
+                    if (qb[k] < best_q) {
+                        double r = sqrt(qb[k]);
+                        if (r < best_s) { best_s = r; best_q = qb[k]; best_i = sb[k]; }
+                    }
+            }
+            for (; i < e; i++) {
                 const int s = __ldg(NL.cell_sites + i);
                 double cs[3] = {__ldg(centres + 3 * s), __ldg(centres + 3 * s + 1), __ldg(centres + 3 * s + 2)};
                 double d0, d1, d2;
                 sab_dbase(cs, x, d0, d1, d2);
-                double q = sab_image_q(d0, d1, d2, lat.m);
+                double q = sab_image_q(d0, d1, d2, L);
                 if (q < best_q) {
                     double r = sqrt(q);
                     if (r < best_s) { best_s = r; best_q = q; best_i = s; }
@@ -91,7 +124,7 @@ __global__ void k_nearest_assign_cells(const double *__restrict__ frac, const do
 // (lattice-L0 metric) for the centres' motion.  While every centre of the frame is within dmax of its
 // anchor the exclusion bound holds for the moving centres too (see _tables.nearest_cell_lists:
 // `move`); otherwise the whole frame takes the exhaustive path.
-__global__ void k_dynvor_assign_cells(const double *__restrict__ frac, const double *__restrict__ lattice,
+__global__ void __launch_bounds__(256, SAB_NEAREST_MINBLOCKS) k_dynvor_assign_cells(const double *__restrict__ frac, const double *__restrict__ lattice,
                                       int lattice_stride, int64_t n_frames, int n_atoms, int n_mobile,
                                       const int32_t *__restrict__ mobile, int n_sites,
                                       int smax, const int32_t *__restrict__ n_slot,
@@ -134,6 +167,9 @@ __global__ void k_dynvor_assign_cells(const double *__restrict__ frac, const dou
         moved = __syncthreads_or(moved);
         if (moved && threadIdx.x == 0) atomicAdd(n_exhaustive, (unsigned long long)n_mobile);
         const double thr = (0.5 * lat.hmin) * (0.5 * lat.hmin) * (1.0 - SAB_REL_MARGIN);
+        double L[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) L[k] = lat.m[k];
         for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
             double x[3];
 #pragma unroll
@@ -146,11 +182,30 @@ __global__ void k_dynvor_assign_cells(const double *__restrict__ frac, const dou
                     c2 = min(NL.G - 1, (int)(x[2] * (double)NL.G));
                 const int cell = (c0 * NL.G + c1) * NL.G + c2;
                 const int b = __ldg(NL.cell_off + cell), e = __ldg(NL.cell_off + cell + 1);
-                for (int i = b; i < e; i++) {
+                int i = b;
+                for (; i + SAB_NEAREST_BATCH <= e; i += SAB_NEAREST_BATCH) {
+                    int sb[SAB_NEAREST_BATCH];
+                    double qb[SAB_NEAREST_BATCH];
+#pragma unroll
+                    for (int k = 0; k < SAB_NEAREST_BATCH; k++) sb[k] = __ldg(NL.cell_sites + i + k);
+#pragma unroll
+                    for (int k = 0; k < SAB_NEAREST_BATCH; k++) {
+                        double d0, d1, d2;
+                        sab_dbase(sm_centres + 3 * sb[k], x, d0, d1, d2);
+                        qb[k] = sab_image_q(d0, d1, d2, L);
+                    }
+#pragma unroll
+                    for (int k = 0; k < SAB_NEAREST_BATCH; k++)
+                        if (qb[k] < best_q) {
+                            double r = sqrt(qb[k]);
+                            if (r < best_s) { best_s = r; best_q = qb[k]; best_i = sb[k]; }
+                        }
+                }
+                for (; i < e; i++) {
                     const int s = __ldg(NL.cell_sites + i);
                     double d0, d1, d2;
                     sab_dbase(sm_centres + 3 * s, x, d0, d1, d2);
-                    double q = sab_image_q(d0, d1, d2, lat.m);
+                    double q = sab_image_q(d0, d1, d2, L);
                     if (q < best_q) {
                         double r = sqrt(q);
                         if (r < best_s) { best_s = r; best_q = q; best_i = s; }

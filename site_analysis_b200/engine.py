@@ -15,6 +15,7 @@ PyTorch is used for device memory, pinned staging and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Sequence
 
 import numpy as np
@@ -157,6 +158,7 @@ class AssignmentEngine:
         self.last_info: dict = {}
         # exact-pruning tables of the tetrahedral kernel (built lazily from the first sizeable batch)
         self.use_cells = True
+        self.nearest_cell_factor = float(os.environ.get("SAB_NEAREST_CELL_FACTOR", "0.2"))   # cell edge / mean centre spacing
         self.cells_min_frames = 64
         self._cells = None              # dict(G, delta, n_entries) once uploaded
         self._cells_stale = False
@@ -346,7 +348,7 @@ class AssignmentEngine:
         lattice0 = np.asarray(lattice0, dtype=np.float64)
         length = float(np.mean(np.linalg.norm(lattice0, axis=1)))
         spacing = (abs(np.linalg.det(lattice0)) / self.S) ** (1.0 / 3.0)        # mean centre spacing
-        G = int(min(64, max(2, round(length / max(0.6 * spacing, 0.5)))))
+        G = int(min(64, max(2, round(length / max(self.nearest_cell_factor * spacing, 0.25)))))
         off, ent, excl = tab.nearest_cell_lists(self.centres, lattice0, G)
         inv = np.ascontiguousarray(np.linalg.inv(lattice0))
         nat.check(self.L.sab_set_nearest_lists(self.h, G, nat.ptr(inv), nat.ptr(np.ascontiguousarray(off)),
@@ -372,12 +374,14 @@ class AssignmentEngine:
         stride = max(1, F // 256)
         sample = d_frac[::stride][:256].contiguous()
         cen = self.dynvor_centres(sample).cpu().numpy()                         # (n, S, 3)
-        anchors = np.ascontiguousarray(cen[0])
+        rel = cen - cen[:1]
+        rel -= np.round(rel)                                                     # displacement from the first sample
+        anchors = np.ascontiguousarray(cen[0] + rel.mean(axis=0))                # mean position: half the head-room
         d = tab._mic_cartesian(cen - anchors[None], lattice0)
         move = float(d.max() * 1.5 + 0.05)
         length = float(np.mean(np.linalg.norm(lattice0, axis=1)))
         spacing = (abs(np.linalg.det(lattice0)) / self.S) ** (1.0 / 3.0)
-        G = int(min(64, max(2, round(length / max(0.6 * spacing, 0.5)))))
+        G = int(min(64, max(2, round(length / max(self.nearest_cell_factor * spacing, 0.25)))))
         off, ent, excl = tab.nearest_cell_lists(anchors, lattice0, G, move=move)
         inv = np.ascontiguousarray(np.linalg.inv(lattice0))
         nat.check(self.L.sab_set_dynvor_lists(self.h, G, nat.ptr(np.ascontiguousarray(lattice0)), nat.ptr(inv), nat.ptr(anchors),
