@@ -174,21 +174,30 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
         };
         unsigned it = 0;                                        // frames processed by this CTA so far
         // register-resident form: thread pt owns framework columns pt + k n_prod_thr and the same mobile coordinates
-        int r_fcol[SAB_STREAM_KMAX], r_cv[SAB_STREAM_KMAX], r_mcol[SAB_STREAM_KMAX];
+        // Branch-free: a column that does not exist reads raw[0] and writes the spare float at the end of the row (its
+        // anchor is NaN, so it never raises the tube flag); a column with one slot shift writes its second value there too.
+        int r_fcol[SAB_STREAM_KMAX], r_v0[SAB_STREAM_KMAX], r_v1[SAB_STREAM_KMAX], r_mcol[SAB_STREAM_KMAX], r_mdst[SAB_STREAM_KMAX];
         double r_anc[SAB_STREAM_KMAX], r_lo[SAB_STREAM_KMAX], r_hi[SAB_STREAM_KMAX];
         float r_ancf[SAB_STREAM_KMAX], r_s0[SAB_STREAM_KMAX], r_s1[SAB_STREAM_KMAX];
+        const int spare = C.stride - 1;                         // >= n_used + 3 A by construction (plan_stream)
+        unsigned r_valid = 0, r_extra = 0;                      // bit k: column exists / has more than two slot shifts
 #pragma unroll
         for (int k = 0; k < SAB_STREAM_KMAX; k++) {
             const int j = pt + k * n_prod_thr;
             const bool ok = C.reg_cols && j < m3, okm = C.reg_cols && j < a3;
             const int2 cv = ok ? colvar[j] : make_int2(0, 0);
-            r_fcol[k] = ok ? fwcol[j] : -1;
-            r_cv[k] = cv.x | ((cv.y - cv.x) << 16);
+            const int nv = cv.y - cv.x;
+            r_fcol[k] = ok ? fwcol[j] : 0;
+            r_v0[k] = nv > 0 ? cv.x : spare;
+            r_v1[k] = nv > 1 ? cv.x + 1 : spare;
             r_anc[k] = ok ? ancd[j] : 0.0;
-            r_ancf[k] = (float)r_anc[k];
-            r_s0[k] = (ok && cv.y > cv.x) ? shf[cv.x] : 0.f;
-            r_s1[k] = (ok && cv.y > cv.x + 1) ? shf[cv.x + 1] : 0.f;
-            r_mcol[k] = okm ? mobcol[j] : -1;
+            r_ancf[k] = ok ? (float)r_anc[k] : __int_as_float(0x7fc00000);
+            r_s0[k] = nv > 0 ? shf[cv.x] : 0.f;
+            r_s1[k] = nv > 1 ? shf[cv.x + 1] : 0.f;
+            r_mcol[k] = okm ? mobcol[j] : 0;
+            r_mdst[k] = okm ? C.n_used + j : spare;
+            if (ok) r_valid |= 1u << k;
+            if (nv > 2) r_extra |= 1u << k;
             r_lo[k] = INFINITY; r_hi[k] = -INFINITY;
         }
         for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
@@ -213,26 +222,34 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                 // ---- framework columns -> row entries ------------------------------------------------------
                 int bad = 0;
                 if (C.reg_cols) {
+                    float fbase[SAB_STREAM_KMAX];
 #pragma unroll
-                    for (int k = 0; k < SAB_STREAM_KMAX; k++)
-                        if (r_fcol[k] >= 0) {
-                            const double r = raw[r_fcol[k]];
-                            const double u = r - rint(r - r_anc[k]);
-                            const float base = (float)u;
-                            if (fabsf(base - r_ancf[k]) > C.delta_f) bad = 1;
-                            r_lo[k] = u < r_lo[k] ? u : r_lo[k];
-                            r_hi[k] = u > r_hi[k] ? u : r_hi[k];
-                            const int v0 = r_cv[k] & 0xffff, nv = r_cv[k] >> 16;           // nearly always one or two slot shifts
-                            if (nv > 0) row[v0] = base + r_s0[k];
-                            if (nv > 1) row[v0 + 1] = base + r_s1[k];
-                            for (int v = v0 + 2; v < v0 + nv; v++) row[v] = base + shf[v];
-                        }
+                    for (int k = 0; k < SAB_STREAM_KMAX; k++) {
+                        const double r = raw[r_fcol[k]];
+                        const double u = r - rint(r - r_anc[k]);
+                        fbase[k] = (float)u;
+                        r_lo[k] = u < r_lo[k] ? u : r_lo[k];
+                        r_hi[k] = u > r_hi[k] ? u : r_hi[k];
+                    }
 #pragma unroll
-                    for (int k = 0; k < SAB_STREAM_KMAX; k++)
-                        if (r_mcol[k] >= 0) {
-                            const double x = raw[r_mcol[k]];
-                            row[C.n_used + pt + k * n_prod_thr] = (float)(x - floor(x));        // atom.py:104
-                        }
+                    for (int k = 0; k < SAB_STREAM_KMAX; k++) {
+                        bad |= fabsf(fbase[k] - r_ancf[k]) > C.delta_f;      // false for the NaN anchor of a missing column
+                        row[r_v0[k]] = fbase[k] + r_s0[k];
+                        row[r_v1[k]] = fbase[k] + r_s1[k];
+                    }
+                    if (r_extra) {                                           // rare: a coordinate used with > 2 slot shifts
+#pragma unroll
+                        for (int k = 0; k < SAB_STREAM_KMAX; k++)
+                            if (r_extra >> k & 1u) {
+                                const int2 cv = colvar[pt + k * n_prod_thr];
+                                for (int v = cv.x + 2; v < cv.y; v++) row[v] = fbase[k] + shf[v];
+                            }
+                    }
+#pragma unroll
+                    for (int k = 0; k < SAB_STREAM_KMAX; k++) {
+                        const double x = raw[r_mcol[k]];
+                        row[r_mdst[k]] = (float)(x - floor(x));                  // atom.py:104
+                    }
                 } else {
                 for (int j = pt; j < m3; j += n_prod_thr) {
                     const double r = raw[fwcol[j]], anc = ancd[j];
@@ -283,7 +300,7 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
             if (C.reg_cols) {
 #pragma unroll
                 for (int k = 0; k < SAB_STREAM_KMAX; k++)
-                    if (r_fcol[k] >= 0) {
+                    if (r_valid >> k & 1u) {
                         const int j = pt + k * n_prod_thr;
                         C.chunk_exc[((size_t)ch * m3 + j) * 2] = r_lo[k];
                         C.chunk_exc[((size_t)ch * m3 + j) * 2 + 1] = r_hi[k];

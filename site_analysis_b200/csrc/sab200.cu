@@ -549,7 +549,7 @@ static StreamPlan plan_stream(sab_engine *e, const double *d_frac, int64_t F, co
     if ((p.n_prod + p.n_cons) * 32 > SAB_STREAM_MAXTHREADS) p.n_prod = SAB_STREAM_MAXTHREADS / 32 - p.n_cons;
     if (p.n_prod < 1) return p;
     const size_t n3 = 3 * (size_t)e->N, m3 = 3 * (size_t)e->M, a3 = 3 * (size_t)e->A;
-    p.stride = ((size_t)e->n_used + a3 + 3) & ~(size_t)3;
+    p.stride = ((size_t)e->n_used + a3 + 1 + 3) & ~(size_t)3;         // at least one spare float behind the mobile coordinates
     p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
     auto smem_for = [&](int n_raw, int rec_smem) {
         return sizeof(double) * ((size_t)n_raw * n3 + 3 * m3) + sizeof(float) * (SAB_STREAM_ROWS * p.stride + (((size_t)e->n_used + 1) & ~(size_t)1)) +
