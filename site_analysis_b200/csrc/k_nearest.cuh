@@ -25,13 +25,42 @@
 // == :191-193 with correct_pbc when the site has a reference centre (pbc_utils.py:102-104).
 // `legacy_init` reproduces the first-frame legacy path (no reference centre), which applies
 // no non-negative offset (pbc_utils.py:16-41).
-__device__ __forceinline__ void sab_dyn_centre(const double *__restrict__ frame, int n_ref,
+#define SAB_DYN_RMAX 6     // reference atoms per site handled with every operand loaded once into registers
+
+__device__ __noinline__ void sab_dyn_centre(const double *__restrict__ frame, int n_ref,
                                                const int32_t *__restrict__ slot_atom,
                                                const int32_t *__restrict__ slot_fw,
                                                const int32_t *__restrict__ slot_shift,
                                                const int32_t *__restrict__ wrow, bool legacy_init,
                                                double *out)
 {
+    if (n_ref <= SAB_DYN_RMAX) {
+        // same operations in the same order as the general loop below; each unwrapped coordinate
+        // raw + (shift - W) (pbc_utils.py:220) is formed once and reused by the min and the sum
+        double v[SAB_DYN_RMAX][3];
+#pragma unroll
+        for (int r = 0; r < SAB_DYN_RMAX; r++)
+            if (r < n_ref) {
+                const double *x = frame + (size_t)__ldg(slot_atom + r) * 3;
+                const int32_t *w = wrow + 3 * __ldg(slot_fw + r);
+#pragma unroll
+                for (int d = 0; d < 3; d++) v[r][d] = x[d] + (double)(__ldg(slot_shift + 3 * r + d) - w[d]);
+            }
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            double mn = INFINITY;
+#pragma unroll
+            for (int r = 0; r < SAB_DYN_RMAX; r++) if (r < n_ref) mn = fmin(mn, v[r][d]);
+            double nn = ceil(-mn);
+            if (!(nn > 0.0) || legacy_init) nn = 0.0;
+            double sum = 0.0;
+#pragma unroll
+            for (int r = 0; r < SAB_DYN_RMAX; r++)
+                if (r < n_ref) { const double t = v[r][d] + nn; sum = (r == 0) ? t : sum + t; }
+            out[d] = sab_pymod1(sum / (double)n_ref);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int d = 0; d < 3; d++) {
         double mn = INFINITY;

@@ -407,25 +407,38 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
     }
 }
 
-// Fused-path commit (1 thread per framework coordinate): advance the carry to the end of the batch from the
-// per-chunk excursions the stream kernel wrote.  Skipped by the kernel itself when the batch must be redone:
-// spill overflow, an invalidating step, or a failed chain check.
-__global__ void k_wrap_commit_stream(const double *__restrict__ frac, int64_t n_frames, int n_atoms,
-                                     const int32_t *__restrict__ fw_atoms, int m3, int n_chunks,
-                                     const double *__restrict__ chunk_exc, const double *__restrict__ anchor,
-                                     double *__restrict__ prev_raw, int32_t *__restrict__ wraps,
-                                     double *__restrict__ excursion, unsigned long long *__restrict__ counters)
+// Fused-path commit: advance the carry to the end of the batch from the per-chunk excursions the stream kernel
+// wrote.  A CTA of 32 x SAB_COMMIT_GROUPS threads owns 32 framework coordinates; group g folds chunks g, g + G, ...
+// (coalesced across the 32 coordinates), shared memory combines the groups.  Skipped by the kernel itself when the
+// batch must be redone: spill overflow, an invalidating step, or a failed chain check.
+#define SAB_COMMIT_GROUPS 8
+__global__ void __launch_bounds__(32 * SAB_COMMIT_GROUPS)
+k_wrap_commit_stream(const double *__restrict__ frac, int64_t n_frames, int n_atoms,
+                     const int32_t *__restrict__ fw_atoms, int m3, int n_chunks,
+                     const double *__restrict__ chunk_exc, const double *__restrict__ anchor,
+                     double *__restrict__ prev_raw, int32_t *__restrict__ wraps,
+                     double *__restrict__ excursion, unsigned long long *__restrict__ counters)
 {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= m3 || n_frames <= 0) return;
-    if (counters[2] != 0ULL || counters[3] != ~0ULL || counters[SAB_CNT_INVALID] != 0ULL) return;
-    double lo = excursion[2 * col], hi = excursion[2 * col + 1];
-#pragma unroll 8
-    for (int c = 0; c < n_chunks; c++) {
-        const double2 e2 = *reinterpret_cast<const double2 *>(chunk_exc + ((size_t)c * m3 + col) * 2);
-        lo = fmin(lo, e2.x);
-        hi = fmax(hi, e2.y);
+    __shared__ double s_lo[SAB_COMMIT_GROUPS][32], s_hi[SAB_COMMIT_GROUPS][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    if (n_frames <= 0) return;
+    if (counters[2] != 0ULL || counters[3] != ~0ULL || counters[SAB_CNT_INVALID] != 0ULL) return;   // uniform over the grid
+    double lo = INFINITY, hi = -INFINITY;
+    if (col < m3) {
+#pragma unroll 4
+        for (int c = grp; c < n_chunks; c += SAB_COMMIT_GROUPS) {
+            const double2 e2 = *reinterpret_cast<const double2 *>(chunk_exc + ((size_t)c * m3 + col) * 2);
+            lo = fmin(lo, e2.x);
+            hi = fmax(hi, e2.y);
+        }
     }
+    s_lo[grp][lane] = lo; s_hi[grp][lane] = hi;
+    __syncthreads();
+    if (grp != 0 || col >= m3) return;
+    lo = excursion[2 * col]; hi = excursion[2 * col + 1];
+#pragma unroll
+    for (int g = 0; g < SAB_COMMIT_GROUPS; g++) { lo = fmin(lo, s_lo[g][lane]); hi = fmax(hi, s_hi[g][lane]); }
     excursion[2 * col] = lo; excursion[2 * col + 1] = hi;
     atomicMax(&counters[8], (unsigned long long)__double_as_longlong(fmax(hi - lo, 0.0)));        // guard G1, read by the host
     const double r = frac[((size_t)(n_frames - 1) * n_atoms + fw_atoms[col / 3]) * 3 + col % 3];

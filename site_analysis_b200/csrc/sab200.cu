@@ -601,7 +601,7 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
     // exact float64 pass over the atom-frames float32 could not decide (returns at once when there are none)
     k_polyhedral_deferred<<<e->sm_count * 8, 256, 0, st>>>(d_frac, F, e->N, e->A, e->d_mobile, T, e->G, e->d_cell_off,
         e->d_cell_sites, nullptr, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor);
-    k_wrap_commit_stream<<<(w.m3 + 127) / 128, 128, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, (int)n_chunks, w.chunk_exc, e->d_anchor,
+    k_wrap_commit_stream<<<(w.m3 + 31) / 32, 32 * SAB_COMMIT_GROUPS, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, (int)n_chunks, w.chunk_exc, e->d_anchor,
         e->d_prev_raw, e->d_wraps, e->d_excursion, e->d_counters);
     e->launches += 3;
     CU(cudaGetLastError());
@@ -643,7 +643,7 @@ static int launch_assign(sab_engine *e, const double *d_frac, const double *d_la
             e->legacy_init_frame, NL, e->d_nl_anchor, e->d_nl_l0, e->nl_dmax, d_result, e->d_counters + CNT_FULL27);
         break;
     } else {
-        int block = std::min(512, ((std::max(e->A, 128) + 31) / 32) * 32);
+        int block = std::min(256, ((std::max(e->A, 128) + 31) / 32) * 32);   // 256 x <= 255 registers always fits
         size_t smem = sizeof(double) * 3 * (size_t)e->S;
         CU(cudaFuncSetAttribute(k_nearest_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_nearest_assign<true><<<grid, block, smem, st>>>(d_frac, d_lattice, lattice_stride, F, e->N, e->A, e->d_mobile,
