@@ -235,6 +235,30 @@ int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames, int32_t *
 int sab_dynvor_centres(sab_engine *e, const double *d_frac, int64_t n_frames, double *d_centres,
                        void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- folds over a finished result array -----------------------
+ * One pass over d_result int32[F][A] (site list positions, SAB_NONE = no site; ambiguous entries must have been
+ * resolved) replaces the per-object Python lists the reference walks afterwards:
+ *   runs   maximal stretches of consecutive frames in which one atom stays in one site, sorted by
+ *          (site, atom, start): d_run_site int32[R], d_run_atom int32[R] (column of d_result), d_run_start int64[R],
+ *          d_run_length int64[R].  This is the run-length form of every Site.trajectory (trajectory.py:357-360),
+ *          from which Site.residence_times (site.py:241-325, gap filter :327-352) and Site.average_occupation
+ *          (site.py:225-239) follow without touching the frames again.
+ *   pairs  every (previous site -> site) change between consecutive frames of one atom, i.e. the increments of
+ *          Site.transitions (site_collection.py:300-302): d_pair_src / d_pair_dst int32[P], d_pair_count int64[P],
+ *          d_pair_first int64[P] = smallest frame * A + atom of the pair (Counter insertion order), unordered.
+ *          d_prev int32[A] (device, may be NULL = empty history): the atoms' previous trajectory entries
+ *          (-2 = none, SAB_NONE, or a site position), used for frame 0.  table_slots (power of two, 0 = skip the
+ *          pairs) sizes the open-addressing hash table in the workspace.
+ * info[6] (host): [0] runs R, [1] pairs P, [2] kernels launched, [3] device time in ns, [4] error bits, [5] reserved.
+ * SAB_EOVERFLOW when R > run_capacity or P > pair_capacity (info[0], info[1] are valid: call again with room) or when
+ * the hash table is full; SAB_ESTATE for unresolved entries.  All d_* pointers are caller-owned device memory. */
+int64_t sab_fold_workspace_bytes(int64_t n_frames, int n_mobile, int n_sites, int64_t run_capacity, int64_t table_slots);
+int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n_mobile, int n_sites,
+                    const int32_t *d_prev, int64_t run_capacity, int32_t *d_run_site, int32_t *d_run_atom,
+                    int64_t *d_run_start, int64_t *d_run_length, int64_t table_slots, int64_t pair_capacity,
+                    int32_t *d_pair_src, int32_t *d_pair_dst, int64_t *d_pair_count, int64_t *d_pair_first,
+                    void *d_workspace, int64_t workspace_bytes, void *stream, int64_t *info);
+
 #ifdef __cplusplus
 }
 #endif

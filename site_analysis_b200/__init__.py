@@ -18,6 +18,8 @@ from .site_collection import (DynamicVoronoiSiteCollection, PolyhedralSiteCollec
 from .spherical_site import SphericalSite  # noqa: F401
 from .structure import SimpleStructure  # noqa: F401
 from .trajectory import Trajectory  # noqa: F401
+from .transition_table import TransitionTable  # noqa: F401
 from .voronoi_site import VoronoiSite  # noqa: F401
+from .folds import fold_rows  # noqa: F401
 
 __version__ = "0.1.0"

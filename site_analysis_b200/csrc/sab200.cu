@@ -1085,3 +1085,135 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);
     return SAB_OK;
 }
+
+// ---------------------------------------------------------------- folds over a finished result array
+#include "k_fold.cuh"
+
+struct FoldLayout { size_t keys_a, keys_b, cub_tmp, cub_bytes, t_key, t_cnt, t_first, flags, bytes; };
+
+static int fold_end_bit(int64_t n_frames, int n_mobile, int n_sites)
+{
+    // keys are < n_sites * n_mobile * n_frames * 2
+    long double top = (long double)n_sites * n_mobile * (long double)n_frames * 2.0L;
+    int bits = 1;
+    while (bits < 64 && (long double)(1ULL << bits) < top) bits++;
+    return bits;
+}
+
+static int fold_layout(int64_t n_frames, int n_mobile, int n_sites, int64_t key_capacity, int64_t table_slots, FoldLayout *L)
+{
+    if (n_frames < 0 || n_mobile <= 0 || n_sites <= 0 || key_capacity < 0 || table_slots < 0)
+        return fail(SAB_EINVAL, "sab_fold: negative size");
+    if (table_slots & (table_slots - 1)) return fail(SAB_EINVAL, "sab_fold: table_slots must be a power of two (or 0)");
+    if ((long double)n_sites * n_mobile * (long double)std::max<int64_t>(n_frames, 1) * 2.0L >= 9.0e18L)
+        return fail(SAB_EINVAL, "sab_fold: n_sites * n_mobile * n_frames does not fit the 63-bit run keys");
+    size_t cub_bytes = 0;
+    if (key_capacity > 0) {
+        unsigned long long *nul = nullptr;
+        cudaError_t ce = cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, nul, nul, (long long)key_capacity, 0,
+                                                        fold_end_bit(n_frames, n_mobile, n_sites));
+        if (ce != cudaSuccess) return fail(SAB_ECUDA, "cub::DeviceRadixSort size query failed: %s", cudaGetErrorString(ce));
+    }
+    size_t off = 0;
+    L->keys_a = off; off += align256(sizeof(unsigned long long) * (size_t)key_capacity);
+    L->keys_b = off; off += align256(sizeof(unsigned long long) * (size_t)key_capacity);
+    L->cub_tmp = off; L->cub_bytes = cub_bytes; off += align256(cub_bytes);
+    L->t_key = off; off += align256(sizeof(unsigned long long) * (size_t)table_slots);
+    L->t_cnt = off; off += align256(sizeof(unsigned long long) * (size_t)table_slots);
+    L->t_first = off; off += align256(sizeof(unsigned long long) * (size_t)table_slots);
+    L->flags = off; off += 256;
+    L->bytes = off;
+    return SAB_OK;
+}
+
+extern "C" int64_t sab_fold_workspace_bytes(int64_t n_frames, int n_mobile, int n_sites, int64_t run_capacity, int64_t table_slots)
+{
+    FoldLayout L;
+    if (fold_layout(n_frames, n_mobile, n_sites, 2 * run_capacity, table_slots, &L)) return -1;
+    return (int64_t)L.bytes;
+}
+
+extern "C" int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n_mobile, int n_sites,
+                               const int32_t *d_prev, int64_t run_capacity, int32_t *d_run_site, int32_t *d_run_atom,
+                               int64_t *d_run_start, int64_t *d_run_length, int64_t table_slots, int64_t pair_capacity,
+                               int32_t *d_pair_src, int32_t *d_pair_dst, int64_t *d_pair_count, int64_t *d_pair_first,
+                               void *d_workspace, int64_t workspace_bytes, void *stream, int64_t *info)
+{
+    if (!info) return fail(SAB_EINVAL, "sab_fold_result: info is NULL");
+    for (int i = 0; i < 6; i++) info[i] = 0;
+    if (n_frames == 0) return SAB_OK;
+    if (!d_result || !d_workspace) return fail(SAB_EINVAL, "sab_fold_result: null argument");
+    if (run_capacity > 0 && (!d_run_site || !d_run_atom || !d_run_start || !d_run_length))
+        return fail(SAB_EINVAL, "sab_fold_result: run arrays missing");
+    if (table_slots > 0 && pair_capacity > 0 && (!d_pair_src || !d_pair_dst || !d_pair_count || !d_pair_first))
+        return fail(SAB_EINVAL, "sab_fold_result: pair arrays missing");
+    FoldLayout L;
+    int rc = fold_layout(n_frames, n_mobile, n_sites, 2 * run_capacity, table_slots, &L);
+    if (rc) return rc;
+    if ((int64_t)L.bytes > workspace_bytes) return fail(SAB_EINVAL, "sab_fold_result: workspace too small: need %zu bytes", L.bytes);
+    CU(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    char *b = (char *)d_workspace;
+    unsigned long long *keys_a = (unsigned long long *)(b + L.keys_a), *keys_b = (unsigned long long *)(b + L.keys_b);
+    unsigned long long *t_key = table_slots ? (unsigned long long *)(b + L.t_key) : nullptr;
+    unsigned long long *t_cnt = (unsigned long long *)(b + L.t_cnt), *t_first = (unsigned long long *)(b + L.t_first);
+    unsigned long long *flags = (unsigned long long *)(b + L.flags);
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    CU(cudaMemsetAsync(flags, 0, 256, st));
+    if (table_slots) {
+        CU(cudaMemsetAsync(t_key, 0xff, sizeof(unsigned long long) * (size_t)table_slots, st));
+        CU(cudaMemsetAsync(t_cnt, 0, sizeof(unsigned long long) * (size_t)table_slots, st));
+        CU(cudaMemsetAsync(t_first, 0xff, sizeof(unsigned long long) * (size_t)table_slots, st));
+    }
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    const long long total = (long long)n_frames * n_mobile;
+    const long long groups = (total + 31) / 32;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)sm * 8));   // 8 resident CTAs of 256 per SM
+    CU(cudaEventRecord(ev0, st));
+    k_fold_scan<<<grid, 256, 0, st>>>(d_result, (long long)n_frames, n_mobile, n_sites, d_prev, keys_a, (long long)(2 * run_capacity),
+                                      t_key, t_cnt, t_first, table_slots ? (unsigned long long)table_slots - 1 : 0ULL, flags);
+    CU(cudaGetLastError());
+    int launches = 1;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const long long n_keys = (long long)h[0];
+    info[0] = n_keys / 2; info[1] = (int64_t)h[1]; info[4] = (int64_t)h[2];
+    auto finish = [&](int code, const char *msg) {
+        cudaEventRecord(ev1, st); cudaEventSynchronize(ev1);
+        float ms = 0.f; cudaEventElapsedTime(&ms, ev0, ev1);
+        info[2] = launches; info[3] = (int64_t)(ms * 1e6);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        return code == SAB_OK ? SAB_OK : fail(code, "%s", msg);
+    };
+    if (h[2] & SAB_FOLD_ERR_UNRESOLVED) return finish(SAB_ESTATE, "sab_fold_result: the result array holds unresolved (ambiguous) or out-of-range entries");
+    if (h[2] & SAB_FOLD_ERR_TABLE) return finish(SAB_EOVERFLOW, "sab_fold_result: transition hash table full; pass more table_slots");
+    if (n_keys & 1) return finish(SAB_ESTATE, "sab_fold_result: odd number of run boundaries");
+    if (n_keys / 2 > run_capacity) return finish(SAB_EOVERFLOW, "sab_fold_result: run_capacity too small (info[0] holds the number of runs)");
+    if (table_slots && (int64_t)h[1] > pair_capacity) return finish(SAB_EOVERFLOW, "sab_fold_result: pair_capacity too small (info[1] holds the number of pairs)");
+    if (n_keys > 0) {
+        size_t tmp = L.cub_bytes;
+        cudaError_t ce = cub::DeviceRadixSort::SortKeys((void *)(b + L.cub_tmp), tmp, keys_a, keys_b, n_keys, 0,
+                                                        fold_end_bit(n_frames, n_mobile, n_sites), st);
+        if (ce != cudaSuccess) return finish(SAB_ECUDA, cudaGetErrorString(ce));
+        launches += 4;                          // CUB's histogram + onesweep passes (library code, not counted as ours elsewhere)
+        const long long n_runs = n_keys / 2;
+        const int g2 = (int)std::max<long long>(1, std::min<long long>((n_runs + 255) / 256, (long long)sm * 8));
+        k_fold_decode<<<g2, 256, 0, st>>>(keys_b, n_runs, (long long)n_frames, n_mobile, d_run_site, d_run_atom, d_run_start, d_run_length, flags);
+        CU(cudaGetLastError());
+        launches++;
+    }
+    if (table_slots && h[1] > 0) {
+        const int g3 = (int)std::max<long long>(1, std::min<long long>((table_slots + 255) / 256, (long long)sm * 8));
+        k_fold_compact<<<g3, 256, 0, st>>>(t_key, t_cnt, t_first, (unsigned long long)table_slots, n_sites, (long long)pair_capacity,
+                                           d_pair_src, d_pair_dst, d_pair_count, d_pair_first, flags);
+        CU(cudaGetLastError());
+        launches++;
+    }
+    CU(cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h[2] & SAB_FOLD_ERR_PAIRING) return finish(SAB_ESTATE, "sab_fold_result: run boundaries do not pair up");
+    return finish(SAB_OK, "");
+}

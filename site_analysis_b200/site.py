@@ -11,6 +11,9 @@ from typing import Any
 
 import numpy as np
 
+from .folds import (BlockFolds, occupied_frames_from_runs, residence_times_from_runs,
+                    site_runs_over_blocks)
+
 
 class Site:
     _newid = 0
@@ -29,14 +32,28 @@ class Site:
     def trajectory(self) -> list[list[int]]:
         """Atom indices occupying this site at each appended timestep (atom list order)."""
         if self._lazy_blocks:
-            for block, atom_index in self._lazy_blocks:
-                frames, cols = np.nonzero(block == self.index)
-                per_frame: list[list[int]] = [[] for _ in range(block.shape[0])]
-                for f, a in zip(frames.tolist(), atom_index[cols].tolist()):
-                    per_frame[f].append(a)
+            for block, second in self._lazy_blocks:
+                if isinstance(block, BlockFolds):            # GPU-folded batch: only this site's own runs are touched
+                    per_frame = [[] for _ in range(block.n_frames)]
+                    col, start, length = block.site_runs(second)
+                    for a, f0, n in zip(block.atom_index[col].tolist(), start.tolist(), length.tolist()):
+                        for f in range(f0, f0 + n):          # runs come in atom LIST order, so every frame's list does too
+                            per_frame[f].append(a)
+                else:                                        # hand-made (rows, atom_index) block
+                    frames, cols = np.nonzero(block == self.index)
+                    per_frame = [[] for _ in range(block.shape[0])]
+                    for f, a in zip(frames.tolist(), second[cols].tolist()):
+                        per_frame[f].append(a)
                 self._trajectory.extend(per_frame)
             self._lazy_blocks = []
         return self._trajectory
+
+    def _folded_runs(self):
+        """(atom index, start, end, n_frames) of this site's runs when its whole history sits in GPU-folded batches,
+        else ``None`` (then the list form is authoritative)."""
+        if self._trajectory or not self._lazy_blocks or not all(isinstance(b, BlockFolds) for b, _ in self._lazy_blocks):
+            return None
+        return site_runs_over_blocks([b for b, _ in self._lazy_blocks], [p for _, p in self._lazy_blocks])
 
     @trajectory.setter
     def trajectory(self, value) -> None:
@@ -75,10 +92,47 @@ class Site:
 
     @property
     def average_occupation(self) -> float | None:
+        """site.py:225-239: fraction of appended timesteps with at least one atom in the site."""
+        runs = self._folded_runs()
+        if runs is not None:
+            _, start, end, n_frames = runs
+            return occupied_frames_from_runs(start, end) / n_frames if n_frames else None
         traj = self.trajectory
         if not traj:
             return None
         return sum(1 for ts in traj if ts) / len(traj)
+
+    def residence_times(self, filter_length: int = 0, include_edge_runs: bool = False) -> tuple[int, ...]:
+        """Per-atom run lengths of consecutive occupation (reference site.py:241-325; gap filter :327-352).
+
+        Same arguments, result order (atoms by ascending index, runs in time order) and exceptions as the
+        reference.  Histories appended by ``trajectory_from_arrays`` are answered from their GPU-folded run-length
+        form; anything else from the list form."""
+        if not isinstance(filter_length, int):
+            raise TypeError(f"filter_length must be an integer, got {type(filter_length).__name__}")
+        if filter_length < 0:
+            raise ValueError(f"filter_length must be non-negative, got {filter_length}")
+        runs = self._folded_runs()
+        if runs is None:
+            traj = self.trajectory
+            if not traj:
+                return ()
+            n = len(traj)
+            first: dict[int, list[list[int]]] = {}
+            for f, ts in enumerate(traj):                    # list form -> runs [start, end) per atom
+                for a in ts:
+                    r = first.setdefault(a, [])
+                    if r and r[-1][1] == f:
+                        r[-1][1] = f + 1
+                    elif not r or r[-1][1] < f:
+                        r.append([f, f + 1])
+            atoms = sorted(first)
+            atom = np.array([a for a in atoms for _ in first[a]], dtype=np.int64)
+            start = np.array([r[0] for a in atoms for r in first[a]], dtype=np.int64)
+            end = np.array([r[1] for a in atoms for r in first[a]], dtype=np.int64)
+            runs = (atom, start, end, n)
+        atom, start, end, n_frames = runs
+        return residence_times_from_runs(atom, start, end, n_frames, filter_length, include_edge_runs)
 
     def as_dict(self) -> dict:
         d = {"index": self.index, "contains_atoms": self.contains_atoms, "trajectory": self.trajectory,

@@ -10,13 +10,16 @@ reference's nested lists lazily.
 """
 from __future__ import annotations
 
+import warnings
 from collections import Counter
 from typing import Sequence
 
 import numpy as np
 
 from .atom import Atom
+from .folds import BlockFolds
 from .site import Site
+from .transition_table import TransitionTable
 from .site_collection import (DynamicVoronoiSiteCollection, PolyhedralSiteCollection, SiteCollection,
                               SphericalSiteCollection, VoronoiSiteCollection)
 
@@ -69,6 +72,60 @@ class Trajectory:
     def site_labels(self) -> list[str | None]:
         return [s.label for s in self.sites]
 
+    # -- transition tables (reference trajectory.py:168-321) ---------------------------------------
+    def _transition_entries(self):
+        """(source site, destination index, count) of every Counter entry; unknown destinations raise as the
+        reference does (trajectory.py:179-186)."""
+        known = {s.index for s in self.sites}
+        for site in self.sites:
+            for dest, count in site.transitions.items():
+                if dest not in known:
+                    raise ValueError(f"Site {site.index} has a transition to unknown site index {dest}.")
+                yield site, dest, count
+
+    def transition_counts_by_site(self, *, keys: Sequence[int] | None = None) -> TransitionTable:
+        """Per-site transition counts (trajectory.py:188-219): rows = source site index, sorted unless ``keys``."""
+        order = tuple(sorted(s.index for s in self.sites))
+        where = {k: i for i, k in enumerate(order)}
+        counts = np.zeros((len(order), len(order)), dtype=int)
+        for site, dest, count in self._transition_entries():
+            counts[where[site.index], where[dest]] = count
+        table = TransitionTable(keys=order, matrix=counts)
+        return table if keys is None else table.reorder(keys)
+
+    def transition_counts_by_label(self, *, keys: Sequence[str] | None = None) -> TransitionTable:
+        """Label-aggregated counts (trajectory.py:221-274); transitions touching unlabelled sites are dropped with a
+        warning."""
+        label_of = {s.index: s.label for s in self.sites if s.label is not None}
+        order = tuple(sorted(set(label_of.values())))
+        where = {k: i for i, k in enumerate(order)}
+        counts = np.zeros((len(order), len(order)), dtype=int)
+        dropped = 0
+        for site, dest, count in self._transition_entries():
+            a, b = label_of.get(site.index), label_of.get(dest)
+            if a is None or b is None:
+                dropped += count
+            else:
+                counts[where[a], where[b]] += count
+        if dropped > 0:
+            warnings.warn(f"{dropped} transition(s) involving unlabelled sites were "
+                          f"excluded from the label-aggregated counts.", stacklevel=2)
+        table = TransitionTable(keys=order, matrix=counts)
+        return table if keys is None else table.reorder(keys)
+
+    @staticmethod
+    def _normalise_counts(counts: TransitionTable) -> TransitionTable:
+        """Row-normalise (trajectory.py:168-176); rows without transitions stay zero."""
+        c = counts.matrix.astype(float)
+        total = c.sum(axis=1, keepdims=True)
+        return TransitionTable(keys=counts.keys, matrix=np.divide(c, total, out=np.zeros_like(c), where=total > 0))
+
+    def transition_probabilities_by_site(self, *, keys: Sequence[int] | None = None) -> TransitionTable:
+        return self._normalise_counts(self.transition_counts_by_site(keys=keys))
+
+    def transition_probabilities_by_label(self, *, keys: Sequence[str] | None = None) -> TransitionTable:
+        return self._normalise_counts(self.transition_counts_by_label(keys=keys))
+
     @property
     def atom_sites(self) -> list[int | None]:
         return [atom.in_site for atom in self.atoms]
@@ -116,8 +173,10 @@ class Trajectory:
         atom_index = np.array([a.index for a in self.atoms])
         for a, atom in enumerate(self.atoms):
             atom._lazy_blocks.append(rows[:, a])
-        for site in self.sites:
-            site._lazy_blocks.append((rows, atom_index))
+        # one shared, lazily GPU-folded form of the batch answers every site's trajectory / residence times
+        folds = BlockFolds(rows, atom_index, self.site_collection._index_of_pos)
+        for p, site in enumerate(self.sites):
+            site._lazy_blocks.append((folds, p))
         self.timesteps.extend(range(1, F + 1) if timesteps is None else timesteps)
         return rows
 

@@ -1,0 +1,297 @@
+"""Post-processing folds: residence times, average occupation, per-site trajectories and
+transition counts from a finished int32[F][A] result array.
+
+CPU part: the plain-Python oracle (oracle/folds_oracle.py) against fixtures produced by the UNMODIFIED reference
+(oracle/gen_golden_folds.py), and the host-side run arithmetic of site_analysis_b200.folds against the same fixtures.
+GPU part: sab_fold_result (csrc/k_fold.cuh) through the C ABI against the oracle -- integer work, bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+FOLD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(str(GOLDEN / "folds_*.npz")))
+
+
+def _load(name):
+    return dict(np.load(GOLDEN / f"{name}.npz"))
+
+
+def _golden_rt(case, k, s):
+    off = case[f"rt{k}_off"]
+    return tuple(int(v) for v in case[f"rt{k}_flat"][off[s]:off[s + 1]])
+
+
+def _golden_site_traj(case, s):
+    F = case["rows"].shape[0]
+    off, flat = case["site_traj_off"], case["site_traj_flat"]
+    return [flat[off[s * F + f]:off[s * F + f + 1]].tolist() for f in range(F)]
+
+
+def _golden_transitions(case):
+    out = {}
+    for src, dst, cnt in case["transitions"].tolist():
+        out.setdefault(src, {})[dst] = cnt
+    return out
+
+
+def _pos_rows(case):
+    inv = {int(v): i for i, v in enumerate(case["site_index"])}
+    return np.vectorize(lambda v: inv.get(int(v), -1))(case["rows"]).astype(np.int32)
+
+
+def test_fixture_list_is_complete():
+    assert len(FOLD_CASES) >= 6
+
+
+@pytest.mark.parametrize("name", FOLD_CASES)
+def test_oracle_reproduces_reference_folds(name):
+    import folds_oracle as fo
+    case = _load(name)
+    st = fo.site_trajectories(case["rows"], case["atom_index"], case["site_index"])
+    for s, idx in enumerate(case["site_index"].tolist()):
+        assert st[idx] == _golden_site_traj(case, s)
+        for k, (fl, edge) in enumerate(case["params"].tolist()):
+            assert fo.residence_times(st[idx], fl, bool(edge)) == _golden_rt(case, k, s)
+        want = case["average_occupation"][s]
+        assert fo.average_occupation(st[idx]) == want
+    prev = None if np.all(case["prev"] == -2) else case["prev"]
+    got, want = fo.transitions(case["rows"], prev), _golden_transitions(case)
+    assert got == want and all(list(got[k]) == list(want[k]) for k in got)
+
+
+def test_oracle_docstring_examples():
+    """reference site.py:268-290."""
+    import folds_oracle as fo
+    assert fo.residence_times([[], [1], [1], [1], []]) == (3,)
+    assert fo.residence_times([[1], [1], [1], []]) == ()
+    assert fo.residence_times([[1], [1], [1], []], include_edge_runs=True) == (3,)
+    assert fo.residence_times([[], [1], [], [1], []]) == (1, 1)
+    assert fo.residence_times([[], [1], [], [1], []], filter_length=1) == (3,)
+    with pytest.raises(ValueError):
+        fo.residence_times([[1]], filter_length=-1)
+    with pytest.raises(TypeError):
+        fo.residence_times([[1]], filter_length=1.5)
+
+
+def _blocks_from_oracle_runs(case, cuts):
+    """BlockFolds objects whose device fold is replaced by the oracle's run extraction (host-logic test)."""
+    import folds_oracle as fo
+    from site_analysis_b200.folds import BlockFolds
+    pos = _pos_rows(case)
+    S = len(case["site_index"])
+    blocks = []
+    edges = [0] + list(cuts) + [pos.shape[0]]
+    for a, b in zip(edges[:-1], edges[1:]):
+        blk = BlockFolds(case["rows"][a:b], case["atom_index"], case["site_index"])
+        blk._runs = fo.runs_from_rows(pos[a:b])
+        blk._site_off = np.searchsorted(blk._runs[0], np.arange(S + 1))
+        blocks.append(blk)
+    return blocks
+
+
+@pytest.mark.parametrize("name", FOLD_CASES)
+@pytest.mark.parametrize("n_cuts", [0, 1, 3])
+def test_run_arithmetic_matches_reference(name, n_cuts):
+    """Site.residence_times / average_occupation / trajectory from the run-length form, also when the history arrived
+    in several batches (a stretch continuing across a batch boundary is ONE run)."""
+    import site_analysis_b200 as sab
+    case = _load(name)
+    F = case["rows"].shape[0]
+    rng = np.random.default_rng(5)
+    cuts = sorted(rng.choice(np.arange(1, F), size=min(n_cuts, F - 1), replace=False).tolist())
+    blocks = _blocks_from_oracle_runs(case, cuts)
+    for s, idx in enumerate(case["site_index"].tolist()):
+        site = sab.VoronoiSite(np.zeros(3))
+        site.index = idx
+        site._lazy_blocks = [(b, s) for b in blocks]
+        for k, (fl, edge) in enumerate(case["params"].tolist()):
+            assert site.residence_times(filter_length=fl, include_edge_runs=bool(edge)) == _golden_rt(case, k, s)
+        assert site.average_occupation == case["average_occupation"][s]
+        assert site._lazy_blocks                     # answered without materialising the lists
+        assert site.trajectory == _golden_site_traj(case, s)
+        assert not site._lazy_blocks
+        for k, (fl, edge) in enumerate(case["params"].tolist()):   # and again from the list form
+            assert site.residence_times(filter_length=fl, include_edge_runs=bool(edge)) == _golden_rt(case, k, s)
+        assert site.average_occupation == case["average_occupation"][s]
+
+
+def test_residence_times_argument_checks():
+    import site_analysis_b200 as sab
+    site = sab.VoronoiSite(np.zeros(3))
+    assert site.residence_times() == () and site.average_occupation is None
+    with pytest.raises(ValueError):
+        site.residence_times(filter_length=-1)
+    with pytest.raises(TypeError):
+        site.residence_times(filter_length=2.0)
+    site.trajectory = [[], [4], [4, 9], [9], []]
+    assert site.residence_times() == (2, 2)
+    assert site.residence_times(include_edge_runs=True) == (2, 2)
+    site.trajectory = [[4], [], [4]]
+    assert site.residence_times() == () and site.residence_times(1) == ()
+    assert site.residence_times(1, include_edge_runs=True) == (3,)
+
+
+def test_transition_table_behaves_like_the_reference():
+    """reference transition_table.py:18-234 / tests/test_transition_table.py."""
+    from site_analysis_b200 import TransitionTable
+    t = TransitionTable(keys=(3, 1, 2), matrix=np.array([[0, 5, 1], [2, 0, 0], [0, 7, 0]]))
+    assert t.keys == (3, 1, 2) and t.get(3, 1) == 5 and t.get(2, 1) == 7
+    assert isinstance(t.get(3, 1), int)
+    assert t.to_dict()[1] == {3: 2, 1: 0, 2: 0}
+    r = t.reorder([1, 2, 3])
+    assert r.keys == (1, 2, 3) and r.get(3, 1) == 5 and r.matrix.tolist() == [[0, 0, 2], [7, 0, 0], [5, 1, 0]]
+    f = t.filter([2, 3])
+    assert f.matrix.tolist() == [[0, 0], [1, 0]] and t.filter([]).matrix.shape == (0, 0)
+    assert t == TransitionTable((3, 1, 2), t.matrix) and t != r
+    assert str(TransitionTable((), np.empty((0, 0)))) == ""
+    assert str(TransitionTable(("A", "B"), np.array([[1, 20], [3, 4]]))) == "     A   B\n A   1  20\n B   3   4"
+    assert "<th>a&lt;b</th>" in TransitionTable(("a<b",), np.array([[0.5]]))._repr_html_()
+    assert "0.500" in str(TransitionTable(("x",), np.array([[0.5]])))
+    assert repr(t) == "TransitionTable(keys=(3, 1, 2), shape=3x3)"
+    with pytest.raises(KeyError):
+        t.get(9, 1)
+    with pytest.raises(ValueError, match="permutation"):
+        t.reorder([1, 2])
+    with pytest.raises(ValueError, match="unknown keys"):
+        t.filter([1, 8])
+    with pytest.raises(ValueError, match="duplicates"):
+        t.filter([1, 1])
+    with pytest.raises(ValueError):
+        TransitionTable((1, 2), np.zeros((2, 3)))
+    with pytest.raises(ValueError):
+        TransitionTable((1, 1), np.zeros((2, 2)))
+    with pytest.raises(ValueError):
+        TransitionTable((1,), np.array([["a"]]))
+    with pytest.raises(AttributeError):
+        t.keys = (1,)
+    with pytest.raises(ValueError):
+        t.matrix[0, 0] = 3
+
+
+def test_trajectory_transition_tables():
+    """reference trajectory.py:188-321 (known answers in the style of the reference's tests/test_trajectory.py)."""
+    import site_analysis_b200 as sab
+    sab.Site.reset_index()
+    sites = [sab.VoronoiSite(np.zeros(3), label=l) for l in ("A", "B", "A", None)]
+    t = sab.Trajectory(sites=sites, atoms=[sab.Atom(0)])
+    sites[0].transitions.update({1: 3, 2: 1})
+    sites[1].transitions.update({0: 2})
+    sites[2].transitions.update({3: 4})
+    c = t.transition_counts_by_site()
+    assert c.keys == (0, 1, 2, 3) and c.matrix.tolist() == [[0, 3, 1, 0], [2, 0, 0, 0], [0, 0, 0, 4], [0, 0, 0, 0]]
+    assert t.transition_counts_by_site(keys=[3, 2, 1, 0]).get(0, 1) == 3
+    p = t.transition_probabilities_by_site()
+    assert p.matrix[0].tolist() == [0.0, 0.75, 0.25, 0.0] and p.matrix[3].tolist() == [0.0] * 4
+    with pytest.warns(UserWarning, match="4 transition"):
+        lab = t.transition_counts_by_label()
+    assert lab.keys == ("A", "B") and lab.matrix.tolist() == [[1, 3], [2, 0]]
+    with pytest.warns(UserWarning):
+        assert t.transition_probabilities_by_label().get("A", "B") == 0.75
+    sites[1].transitions[99] = 1
+    with pytest.raises(ValueError, match="unknown site index 99"):
+        t.transition_counts_by_site()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+gpu = [pytest.mark.gpu, pytest.mark.timeout(180)]
+
+
+def _check_fold_against_oracle(pos, S, prev=None):
+    import folds_oracle as fo
+    import site_analysis_b200 as sab
+    out = sab.fold_rows(pos, S, prev=prev)
+    want = fo.runs_from_rows(pos)
+    for g, w in zip(out["runs"], want):
+        assert g.dtype == w.dtype and np.array_equal(g, w)
+    wt = fo.transitions(pos, prev)
+    src, dst, cnt, first = out["pairs"]
+    got = {}
+    for a, b, c in zip(src.tolist(), dst.tolist(), cnt.tolist()):
+        got.setdefault(a, {})[b] = c
+    assert got == wt
+    # pairs arrive sorted by first occurrence == Counter insertion order (site.py:223 ties)
+    assert all(list(got[k]) == list(wt[k]) for k in wt)
+    assert np.all(np.diff(first) > 0)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("name", FOLD_CASES)
+def test_gpu_fold_matches_reference_fixture(name):
+    case = _load(name)
+    prev = None
+    if not np.all(case["prev"] == -2):
+        inv = {int(v): i for i, v in enumerate(case["site_index"])}
+        prev = np.array([inv.get(int(p), int(p)) for p in case["prev"]], dtype=np.int32)
+    _check_fold_against_oracle(_pos_rows(case), len(case["site_index"]), prev)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("F,A,S,stay,none", [(4000, 64, 40, 0.95, 0.02), (3000, 33, 700, 0.5, 0.2), (1, 5, 3, 0.9, 0.1),
+                                             (2500, 1, 2, 0.8, 0.1), (700, 192, 1056, 0.98, 0.0)])
+def test_gpu_fold_random_histories(F, A, S, stay, none):
+    """Includes a history with more runs than the first capacity guess (the EOVERFLOW retry), one frame, one atom."""
+    import folds_oracle as fo
+    rng = np.random.default_rng(F + A)
+    pos = fo.random_rows(rng, F, A, S, stay, none)
+    prev = rng.integers(-2, S, size=A).astype(np.int32)
+    _check_fold_against_oracle(pos, S, prev)
+    _check_fold_against_oracle(pos, S, None)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(180)
+def test_gpu_fold_rejects_unresolved_entries_and_handles_empty():
+    import site_analysis_b200 as sab
+    from site_analysis_b200 import _native as nat
+    rows = np.array([[0, 1], [-5, 1]], dtype=np.int32)
+    with pytest.raises(nat.NativeError, match="unresolved"):
+        sab.fold_rows(rows, 3)
+    with pytest.raises(nat.NativeError, match="unresolved"):
+        sab.fold_rows(np.array([[3]], dtype=np.int32), 3)
+    out = sab.fold_rows(np.empty((0, 4), dtype=np.int32), 3)
+    assert all(len(a) == 0 for a in out["runs"])
+    out = sab.fold_rows(np.full((50, 4), -1, dtype=np.int32), 3)
+    assert all(len(a) == 0 for a in out["runs"]) and all(len(a) == 0 for a in out["pairs"])
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name", ["argyrodite_0p_polyhedral", "simple_cubic_spherical", "fuzz_voronoi_1"])
+def test_trajectory_post_processing_end_to_end(oracle_mod, name):
+    """trajectory_from_arrays (two batches) -> Site.residence_times / average_occupation / trajectory, against the
+    plain-Python restatement applied to the reference's own atoms_trajectory of the fixture."""
+    import folds_oracle as fo
+    from helpers import trajectory_from_case
+    case = oracle_mod.load_case(name)
+    t = trajectory_from_case(case)
+    F = case["frac"].shape[0]
+    cut = F // 3
+    lat = case["lattice"]
+    t.trajectory_from_arrays(case["frac"][:cut], lat if lat.ndim == 2 else lat[:cut])
+    t.trajectory_from_arrays(case["frac"][cut:], lat if lat.ndim == 2 else lat[cut:])
+    want_rows = case["atoms_traj"]
+    st = fo.site_trajectories(want_rows, [a.index for a in t.atoms], [s.index for s in t.sites])
+    checked = 0
+    for site in t.sites:
+        traj = st[site.index]
+        if not any(traj) and checked > 40:
+            continue
+        for fl, edge in [(0, False), (2, True), (7, False)]:
+            assert site.residence_times(fl, edge) == fo.residence_times(traj, fl, edge)
+        assert site.average_occupation == fo.average_occupation(traj)
+        checked += 1
+    some = [s for s in t.sites if any(st[s.index])][:5] + list(t.sites[:2])
+    for site in some:
+        assert site.trajectory == st[site.index]
+    counts = t.transition_counts_by_site()
+    want = fo.transitions(want_rows)
+    for src, d in want.items():
+        for dst, c in d.items():
+            assert counts.get(src, dst) == c
+    assert int(counts.matrix.sum()) == sum(sum(d.values()) for d in want.values())
