@@ -249,6 +249,9 @@ int sab_dynvor_centres(sab_engine *e, const double *d_frac, int64_t n_frames, do
  *          d_prev int32[A] (device, may be NULL = empty history): the atoms' previous trajectory entries
  *          (-2 = none, SAB_NONE, or a site position), used for frame 0.  table_slots (power of two, 0 = skip the
  *          pairs) sizes the open-addressing hash table in the workspace.
+ *   recent d_recent_last / d_recent_other int64[A] (device, both or neither; need run_capacity >= R): per atom
+ *          ((end frame of the run) << 24) | site of its last run and of its last run in a different site, 0 = none --
+ *          what the batch contributes to Atom._recent_sites (atom.py:181-192).
  * info[6] (host): [0] runs R, [1] pairs P, [2] kernels launched, [3] device time in ns, [4] error bits, [5] reserved.
  * SAB_EOVERFLOW when R > run_capacity or P > pair_capacity (info[0], info[1] are valid: call again with room) or when
  * the hash table is full; SAB_ESTATE for unresolved entries.  All d_* pointers are caller-owned device memory. */
@@ -257,6 +260,7 @@ int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n
                     const int32_t *d_prev, int64_t run_capacity, int32_t *d_run_site, int32_t *d_run_atom,
                     int64_t *d_run_start, int64_t *d_run_length, int64_t table_slots, int64_t pair_capacity,
                     int32_t *d_pair_src, int32_t *d_pair_dst, int64_t *d_pair_count, int64_t *d_pair_first,
+                    int64_t *d_recent_last, int64_t *d_recent_other,
                     void *d_workspace, int64_t workspace_bytes, void *stream, int64_t *info);
 
 #ifdef __cplusplus

@@ -102,7 +102,7 @@ def lib():
         "sab_set_carry_device": (i32, [vp, vp, vp, vp]),
         "sab_get_excursion_device": (i32, [vp, vp, vp]),
         "sab_fold_workspace_bytes": (i64, [i64, i32, i32, i64, i64]),
-        "sab_fold_result": (i32, [i32, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i64, vp, vp]),
+        "sab_fold_result": (i32, [i32, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -11,7 +11,7 @@
 // Integer work only, bit-exact by construction.
 //
 //   k_fold_scan     one thread per (frame, atom): emits one 64-bit key per run start and one per run end,
-//                   key = (((site * A + atom) * F + frame) << 1) | is_end   (warp-aggregated append),
+//                   key = (((site * A + atom) * F + frame) << 1) | is_end   (one reservation per 2048-entry tile),
 //                   and inserts (previous site -> site) changes into an open-addressing hash table.
 //   cub::DeviceRadixSort::SortKeys over the significant bits: starts and ends of one (site, atom) alternate in time,
 //                   so after the sort key 2r is the start and key 2r + 1 the end of run r.
@@ -33,6 +33,12 @@ __device__ __forceinline__ unsigned long long sab_fold_hash(unsigned long long k
     return k;
 }
 
+#define SAB_FOLD_PER_THREAD 8
+#define SAB_FOLD_TILE (256 * SAB_FOLD_PER_THREAD)
+
+// One CTA per tile of 2048 consecutive entries (grid-stride).  Thread t owns entries t, t + 256, ... of the tile
+// (coalesced); the CTA reserves room for all of the tile's keys with ONE atomic (block-wide exclusive scan of the
+// per-thread key counts), so the global counter sees F A / 2048 updates instead of one per warp.
 __global__ void __launch_bounds__(256)
 k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile, int n_sites,
             const int32_t *__restrict__ prev, unsigned long long *__restrict__ keys, long long key_capacity,
@@ -40,62 +46,80 @@ k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile
             unsigned long long *__restrict__ t_first, unsigned long long slot_mask,
             unsigned long long *__restrict__ flags)
 {
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
     const long long total = n_frames * (long long)n_mobile;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // every warp walks whole 32-entry groups so that the ballots below are warp-uniform
-    const long long n_groups = (total + 31) / 32;
-    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_groups;
-         g += (long long)gridDim.x * (blockDim.x >> 5)) {
-        const long long i = g * 32 + lane;
-        const bool in = i < total;
-        int cur = -1, before = -2, after = -3;
-        long long f = 0; int a = 0;
-        if (in) {
-            f = i / n_mobile; a = (int)(i - f * n_mobile);
-            cur = result[i];
-            before = f > 0 ? result[i - n_mobile] : (prev ? prev[a] : -2);
-            after = f + 1 < n_frames ? result[i + n_mobile] : -3;
-            if (cur < -1 || cur >= n_sites) { atomicOr(&flags[2], SAB_FOLD_ERR_UNRESOLVED); cur = -1; }
-        }
-        const bool occupied = in && cur >= 0;
-        const bool is_start = occupied && (f == 0 || before != cur);
-        const bool is_end = occupied && after != cur;
-        const unsigned ms = __ballot_sync(FULL, is_start), me = __ballot_sync(FULL, is_end);
-        const int n_s = __popc(ms), n_e = __popc(me);
-        if (n_s + n_e) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&flags[0], (unsigned long long)(n_s + n_e));
-            base = __shfl_sync(FULL, base, 0);
-            const unsigned long long body = (((unsigned long long)cur * n_mobile + a) * (unsigned long long)n_frames + f) << 1;
-            const unsigned below = (1u << lane) - 1u;
-            if (is_start) {
-                const unsigned long long o = base + __popc(ms & below);
-                if ((long long)o < key_capacity) keys[o] = body;
-            }
-            if (is_end) {
-                const unsigned long long o = base + n_s + __popc(me & below);
-                if ((long long)o < key_capacity) keys[o] = body | 1ULL;
-            }
-        }
-        // site_collection.py:300-302: previous trajectory entry is a site and differs from the new one
-        if (occupied && before >= 0 && before != cur && t_key) {
-            const unsigned long long k = (unsigned long long)before * (unsigned long long)n_sites + cur;
-            unsigned long long slot = sab_fold_hash(k) & slot_mask;
-            bool done = false;
-            for (unsigned long long probe = 0; probe <= slot_mask; probe++) {
-                const unsigned long long old = atomicCAS(&t_key[slot], SAB_FOLD_EMPTY, k);
-                if (old == SAB_FOLD_EMPTY) atomicAdd(&flags[1], 1ULL);
-                if (old == SAB_FOLD_EMPTY || old == k) {
-                    atomicAdd(&t_cnt[slot], 1ULL);
-                    atomicMin(&t_first[slot], (unsigned long long)i);
-                    done = true;
-                    break;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n_tiles = (total + SAB_FOLD_TILE - 1) / SAB_FOLD_TILE;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long t0 = tile * SAB_FOLD_TILE;
+        const long long f0 = t0 / n_mobile;                       // uniform: one 64-bit division per tile
+        const unsigned a0 = (unsigned)(t0 - f0 * n_mobile);
+        unsigned long long body[SAB_FOLD_PER_THREAD];
+        unsigned sbits = 0, ebits = 0;
+#pragma unroll
+        for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
+            const long long i = t0 + k * 256 + tid;
+            body[k] = 0;
+            if (i < total) {
+                const unsigned off = a0 + (unsigned)(k * 256 + tid);
+                const unsigned df = off / (unsigned)n_mobile;
+                const int a = (int)(off - df * (unsigned)n_mobile);
+                const long long f = f0 + df;
+                int cur = result[i];
+                const int before = f > 0 ? result[i - n_mobile] : (prev ? prev[a] : -2);
+                const int after = f + 1 < n_frames ? result[i + n_mobile] : -3;
+                if (cur < -1 || cur >= n_sites) { atomicOr(&flags[2], SAB_FOLD_ERR_UNRESOLVED); cur = -1; }
+                if (cur >= 0) {
+                    body[k] = (((unsigned long long)cur * n_mobile + a) * (unsigned long long)n_frames + f) << 1;
+                    if (f == 0 || before != cur) sbits |= 1u << k;
+                    if (after != cur) ebits |= 1u << k;
+                    // site_collection.py:300-302: previous trajectory entry is a site and differs from the new one
+                    if (before >= 0 && before != cur && t_key) {
+                        const unsigned long long key = (unsigned long long)before * (unsigned long long)n_sites + cur;
+                        unsigned long long slot = sab_fold_hash(key) & slot_mask;
+                        bool done = false;
+                        for (unsigned long long probe = 0; probe <= slot_mask; probe++) {
+                            const unsigned long long old = atomicCAS(&t_key[slot], SAB_FOLD_EMPTY, key);
+                            if (old == SAB_FOLD_EMPTY) atomicAdd(&flags[1], 1ULL);
+                            if (old == SAB_FOLD_EMPTY || old == key) {
+                                atomicAdd(&t_cnt[slot], 1ULL);
+                                atomicMin(&t_first[slot], (unsigned long long)i);
+                                done = true;
+                                break;
+                            }
+                            slot = (slot + 1) & slot_mask;
+                        }
+                        if (!done) atomicOr(&flags[2], SAB_FOLD_ERR_TABLE);
+                    }
                 }
-                slot = (slot + 1) & slot_mask;
             }
-            if (!done) atomicOr(&flags[2], SAB_FOLD_ERR_TABLE);
         }
+        // block-wide exclusive scan of the key counts
+        const unsigned n = __popc(sbits) + __popc(ebits);
+        unsigned incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const unsigned v = s_warp[w]; s_warp[w] = run; run += v; }
+            s_base = run ? atomicAdd(&flags[0], (unsigned long long)run) : 0ULL;
+        }
+        __syncthreads();
+        unsigned long long o = s_base + s_warp[warp] + (incl - n);
+#pragma unroll
+        for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
+            if (sbits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body[k]; o++; }
+            if (ebits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body[k] | 1ULL; o++; }
+        }
+        __syncthreads();                                          // s_warp / s_base are reused by the next tile
     }
 }
 
@@ -133,5 +157,21 @@ k_fold_compact(const unsigned long long *__restrict__ t_key, const unsigned long
         p_dst[o] = (int32_t)(k % (unsigned long long)n_sites);
         p_count[o] = (int64_t)t_cnt[s];
         p_first[o] = (int64_t)t_first[s];
+    }
+}
+
+// Per atom, the site of its last run (key = (end frame << 24) | site, largest wins) and, in a second pass, of its last
+// run in a DIFFERENT site: the two entries of Atom._recent_sites after the batch (atom.py:181-192), as far as the
+// batch alone determines them.  0 = the atom was never assigned.
+__global__ void __launch_bounds__(256)
+k_fold_recent(const int32_t *__restrict__ run_site, const int32_t *__restrict__ run_atom,
+              const int64_t *__restrict__ run_start, const int64_t *__restrict__ run_length, long long n_runs,
+              unsigned long long *__restrict__ last, unsigned long long *__restrict__ other, int pass)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += (long long)gridDim.x * blockDim.x) {
+        const int site = run_site[r], atom = run_atom[r];
+        const unsigned long long key = ((unsigned long long)(run_start[r] + run_length[r]) << 24) | (unsigned long long)site;
+        if (pass == 0) atomicMax(&last[atom], key);
+        else if (site != (int)(last[atom] & 0xffffffULL)) atomicMax(&other[atom], key);
     }
 }

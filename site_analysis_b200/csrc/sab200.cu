@@ -1137,6 +1137,7 @@ extern "C" int sab_fold_result(int device, const int32_t *d_result, int64_t n_fr
                                const int32_t *d_prev, int64_t run_capacity, int32_t *d_run_site, int32_t *d_run_atom,
                                int64_t *d_run_start, int64_t *d_run_length, int64_t table_slots, int64_t pair_capacity,
                                int32_t *d_pair_src, int32_t *d_pair_dst, int64_t *d_pair_count, int64_t *d_pair_first,
+                               int64_t *d_recent_last, int64_t *d_recent_other,
                                void *d_workspace, int64_t workspace_bytes, void *stream, int64_t *info)
 {
     if (!info) return fail(SAB_EINVAL, "sab_fold_result: info is NULL");
@@ -1151,6 +1152,8 @@ extern "C" int sab_fold_result(int device, const int32_t *d_result, int64_t n_fr
     int rc = fold_layout(n_frames, n_mobile, n_sites, 2 * run_capacity, table_slots, &L);
     if (rc) return rc;
     if ((int64_t)L.bytes > workspace_bytes) return fail(SAB_EINVAL, "sab_fold_result: workspace too small: need %zu bytes", L.bytes);
+    if ((d_recent_last == nullptr) != (d_recent_other == nullptr)) return fail(SAB_EINVAL, "sab_fold_result: pass both recent arrays or neither");
+    if (d_recent_last && n_sites > (1 << 24)) return fail(SAB_EINVAL, "sab_fold_result: recent-site keys hold 24-bit site numbers");
     CU(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     char *b = (char *)d_workspace;
@@ -1169,8 +1172,8 @@ extern "C" int sab_fold_result(int device, const int32_t *d_result, int64_t n_fr
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
     const long long total = (long long)n_frames * n_mobile;
-    const long long groups = (total + 31) / 32;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)sm * 8));   // 8 resident CTAs of 256 per SM
+    const long long tiles = (total + SAB_FOLD_TILE - 1) / SAB_FOLD_TILE;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm * 8));   // 8 resident CTAs of 256 per SM
     CU(cudaEventRecord(ev0, st));
     k_fold_scan<<<grid, 256, 0, st>>>(d_result, (long long)n_frames, n_mobile, n_sites, d_prev, keys_a, (long long)(2 * run_capacity),
                                       t_key, t_cnt, t_first, table_slots ? (unsigned long long)table_slots - 1 : 0ULL, flags);
@@ -1204,6 +1207,18 @@ extern "C" int sab_fold_result(int device, const int32_t *d_result, int64_t n_fr
         k_fold_decode<<<g2, 256, 0, st>>>(keys_b, n_runs, (long long)n_frames, n_mobile, d_run_site, d_run_atom, d_run_start, d_run_length, flags);
         CU(cudaGetLastError());
         launches++;
+        if (d_recent_last) {
+            CU(cudaMemsetAsync(d_recent_last, 0, sizeof(int64_t) * (size_t)n_mobile, st));
+            CU(cudaMemsetAsync(d_recent_other, 0, sizeof(int64_t) * (size_t)n_mobile, st));
+            for (int pass = 0; pass < 2; pass++)
+                k_fold_recent<<<g2, 256, 0, st>>>(d_run_site, d_run_atom, d_run_start, d_run_length, n_runs,
+                                                  (unsigned long long *)d_recent_last, (unsigned long long *)d_recent_other, pass);
+            CU(cudaGetLastError());
+            launches += 2;
+        }
+    } else if (d_recent_last) {
+        CU(cudaMemsetAsync(d_recent_last, 0, sizeof(int64_t) * (size_t)n_mobile, st));
+        CU(cudaMemsetAsync(d_recent_other, 0, sizeof(int64_t) * (size_t)n_mobile, st));
     }
     if (table_slots && h[1] > 0) {
         const int g3 = (int)std::max<long long>(1, std::min<long long>((table_slots + 255) / 256, (long long)sm * 8));

@@ -83,6 +83,29 @@ def fold_history(recent: np.ndarray, prev: np.ndarray, transitions: list, rows: 
         prev[:] = rows[-1]
 
 
+DEVICE_FOLD_MIN = 1 << 15     # atom-frames per batch from which the history is folded on the GPU
+
+
+def fold_history_device(recent: np.ndarray, prev: np.ndarray, transitions: list, rows, n_sites: int) -> None:
+    """:func:`fold_history` (``append=True``) with the O(F A) part on the GPU: ``sab_fold_result`` (csrc/k_fold.cuh)
+    returns the transition pairs in first-occurrence order and each atom's last / last-different site; only O(A + pairs)
+    work is left for the host.  ``rows`` (F, A) int32 positions, CUDA tensor or numpy array."""
+    from .folds import fold_rows
+    out = fold_rows(rows, n_sites, prev=prev, want_pairs=True, want_recent=True)
+    src, dst, cnt, _ = out["pairs"]
+    for a, b, c in zip(src.tolist(), dst.tolist(), cnt.tolist()):      # sorted by first occurrence: Counter insertion order
+        d = transitions[a]
+        d[b] = d.get(b, 0) + c
+    last_v, other_v = out["recent"]
+    any_assigned, has_other = last_v >= 0, other_v >= 0
+    old0, old1 = recent[:, 0].copy(), recent[:, 1].copy()
+    new1 = np.where(has_other, other_v, np.where(old0 == last_v, old1, old0))
+    recent[:, 0] = np.where(any_assigned, last_v, old0)
+    recent[:, 1] = np.where(any_assigned, new1, old1)
+    last_row = rows[-1]
+    prev[:] = last_row if isinstance(last_row, np.ndarray) else last_row.cpu().numpy()
+
+
 class AssignmentEngine:
     """GPU assignment of every mobile atom in every frame to a site (list positions).
 
@@ -222,6 +245,9 @@ class AssignmentEngine:
                 self._resolve_now(*item[1:])
                 continue
             rows, append = item
+            if append and rows.shape[0] * rows.shape[1] >= DEVICE_FOLD_MIN:
+                fold_history_device(self.recent, self.prev, self.transitions, rows, self.S)
+                continue
             if not isinstance(rows, np.ndarray):
                 rows = rows.cpu().numpy()
             fold_history(self.recent, self.prev, self.transitions, rows, append)

@@ -25,7 +25,8 @@ def _next_pow2(n: int) -> int:
     return 1 << max(int(n) - 1, 1).bit_length()
 
 
-def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: int | None = None):
+def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: int | None = None,
+              want_recent: bool = False):
     """Fold a result array on the GPU.
 
     Args:
@@ -33,6 +34,8 @@ def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: in
         n_sites: number of sites S (positions are ``0 .. S-1``).
         prev: optional (A,) int32, the atoms' trajectory entries before the first row (-2 none, -1 None, position).
         want_pairs: also return the transition pairs.
+        want_recent: also return ``recent`` = (last, other), two (A,) int32 arrays: the site of each atom's last run in
+            the batch and of its last run in a different site (-1 = none), cf. ``Atom._recent_sites`` (atom.py:181-192).
 
     Returns:
         dict with ``runs`` = (site, atom, start, length) numpy arrays sorted by (site, atom, start),
@@ -52,7 +55,9 @@ def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: in
     F, A = int(d_rows.shape[0]), int(d_rows.shape[1])
     empty = (np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.int64), np.empty(0, np.int64))
     if F == 0 or A == 0:
-        return dict(runs=empty, pairs=empty if want_pairs else None, info=dict(kernel_ns=0, launches=0))
+        none = np.full(A, -1, dtype=np.int32)
+        return dict(runs=empty, pairs=empty if want_pairs else None, recent=(none, none.copy()) if want_recent else None,
+                    info=dict(kernel_ns=0, launches=0))
     d_prev = None
     if prev is not None:
         d_prev = torch.from_numpy(np.ascontiguousarray(prev, dtype=np.int32)).to(dev)
@@ -76,10 +81,12 @@ def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: in
             p_dst = torch.empty(max(slots, 1), dtype=torch.int32, device=dev)
             p_cnt = torch.empty(max(slots, 1), dtype=torch.int64, device=dev)
             p_first = torch.empty(max(slots, 1), dtype=torch.int64, device=dev)
+            rec = torch.empty((2, A), dtype=torch.int64, device=dev) if want_recent else None
             rc = L.sab_fold_result(dev.index, d_rows.data_ptr(), F, A, int(n_sites),
                                    None if d_prev is None else d_prev.data_ptr(), run_cap, r_site.data_ptr(),
                                    r_atom.data_ptr(), r_start.data_ptr(), r_len.data_ptr(), slots, slots,
                                    p_src.data_ptr(), p_dst.data_ptr(), p_cnt.data_ptr(), p_first.data_ptr(),
+                                   None if rec is None else rec[0].data_ptr(), None if rec is None else rec[1].data_ptr(),
                                    ws.data_ptr(), ws_bytes, C.c_void_p(stream), nat.ptr(info))
             if rc == 0:
                 break
@@ -100,7 +107,11 @@ def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: in
             src, dst, cnt, first = (t[:P].cpu().numpy() for t in (p_src, p_dst, p_cnt, p_first))
             o = np.argsort(first, kind="stable")
             pairs = (src[o], dst[o], cnt[o], first[o])
-    return dict(runs=runs, pairs=pairs, info=dict(kernel_ns=int(info[3]), launches=int(info[2])))
+        recent = None
+        if want_recent:
+            k = rec.cpu().numpy()
+            recent = tuple(np.where(k[i] > 0, k[i] & 0xffffff, -1).astype(np.int32) for i in range(2))
+    return dict(runs=runs, pairs=pairs, recent=recent, info=dict(kernel_ns=int(info[3]), launches=int(info[2])))
 
 
 class BlockFolds:

@@ -295,3 +295,42 @@ def test_trajectory_post_processing_end_to_end(oracle_mod, name):
         for dst, c in d.items():
             assert counts.get(src, dst) == c
     assert int(counts.matrix.sum()) == sum(sum(d.values()) for d in want.values())
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("F,A,S,stay,none", [(3000, 40, 25, 0.9, 0.05), (800, 192, 1056, 0.97, 0.0), (500, 7, 3, 0.6, 0.5)])
+def test_device_history_fold_equals_host_fold(F, A, S, stay, none):
+    """engine.fold_history_device (GPU) == engine.fold_history (numpy restatement of site_collection.py:300-310 and
+    atom.py:190-192): recent-site pairs, previous entries and transition Counters incl. insertion order, over two
+    consecutive batches starting from a non-trivial history."""
+    import folds_oracle as fo
+    from site_analysis_b200.engine import fold_history, fold_history_device
+    rng = np.random.default_rng(F * 7 + A)
+    pos = fo.random_rows(rng, F, A, S, stay, none)
+    pos[:, 0] = -1                                                   # an atom that is never assigned
+    if A > 2:
+        pos[:, 1] = 2 % S                                            # an atom that never moves
+    state = []
+    for fold in (fold_history, fold_history_device):
+        recent = np.stack([np.arange(A) % S, (np.arange(A) + 1) % S], axis=1).astype(np.int32)
+        recent[::5] = -1
+        prev = (np.arange(A) % (S + 2) - 2).astype(np.int32)
+        tr = [dict() for _ in range(S)]
+        tr[1 % S][0] = 4                                             # existing Counter entries keep their place
+        for a, b in ((0, F // 3), (F // 3, F)):
+            if fold is fold_history:
+                fold(recent, prev, tr, pos[a:b], True)
+            else:
+                fold(recent, prev, tr, pos[a:b], S)
+        state.append((recent, prev, tr))
+    (r0, p0, t0), (r1, p1, t1) = state
+    assert np.array_equal(r0, r1) and np.array_equal(p0, p1)
+    assert t0 == t1 and all(list(x) == list(y) for x, y in zip(t0, t1))
+    want = fo.transitions(pos, (np.arange(A) % (S + 2) - 2))
+    want.setdefault(1 % S, {})
+    got = {s: dict(d) for s, d in enumerate(t1) if d}
+    got[1 % S][0] -= 4
+    if got[1 % S][0] == 0:
+        del got[1 % S][0]
+    assert {k: v for k, v in got.items() if v} == {k: v for k, v in want.items() if v}
