@@ -263,6 +263,16 @@ int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n
                     int64_t *d_recent_last, int64_t *d_recent_other,
                     void *d_workspace, int64_t workspace_bytes, void *stream, int64_t *info);
 
+/* ---- minimum-image distance matrix (stand-alone operator) -----------------------------------
+ * d_out double[n][m] = all_mic_distances(c1, c2, lattice) of the reference (distances.py:147-189, numba kernel
+ * :68-110; one pair = mic_distance :113-144): 27 periodic images, float64, the reference's operation order, no FMA
+ * -- bit-identical.  d_c1 double[n][3], d_c2 double[m][3], d_lattice double[3][3] (rows = lattice vectors), all device
+ * memory; stream-ordered, no synchronisation.  The assignment kernels fuse this with their argmin / cut-off test and
+ * never build the matrix; this entry serves callers that need the matrix (coordination search, index mapping,
+ * alignment objective: tools.py:32-111, reference_workflow/structure_aligner.py:105-147). */
+int sab_mic_distances(int device, const double *d_c1, int n, const double *d_c2, int m,
+                      const double *d_lattice, double *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

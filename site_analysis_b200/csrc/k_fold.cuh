@@ -37,8 +37,28 @@ __device__ __forceinline__ unsigned long long sab_fold_hash(unsigned long long k
 #define SAB_FOLD_TILE (256 * SAB_FOLD_PER_THREAD)
 
 // One CTA per tile of 2048 consecutive entries (grid-stride).  Thread t owns entries t, t + 256, ... of the tile
-// (coalesced); the CTA reserves room for all of the tile's keys with ONE atomic (block-wide exclusive scan of the
-// per-thread key counts), so the global counter sees F A / 2048 updates instead of one per warp.
+// (coalesced); all 24 loads of a thread (entry, row before, row after) are issued before the first use; (frame, atom)
+// advance incrementally (no division per entry); the CTA reserves room for all of the tile's keys with ONE atomic
+// (block-wide exclusive scan of the per-thread key counts); the rare transition inserts run after the loop, all
+// threads that have one at the same time.
+__device__ __forceinline__ void sab_fold_insert(unsigned long long key, unsigned long long i, unsigned long long *t_key,
+                                                unsigned long long *t_cnt, unsigned long long *t_first,
+                                                unsigned long long slot_mask, unsigned long long *flags)
+{
+    unsigned long long slot = sab_fold_hash(key) & slot_mask;
+    for (unsigned long long probe = 0; probe <= slot_mask; probe++) {
+        const unsigned long long old = atomicCAS(&t_key[slot], SAB_FOLD_EMPTY, key);
+        if (old == SAB_FOLD_EMPTY) atomicAdd(&flags[1], 1ULL);
+        if (old == SAB_FOLD_EMPTY || old == key) {
+            atomicAdd(&t_cnt[slot], 1ULL);
+            atomicMin(&t_first[slot], i);
+            return;
+        }
+        slot = (slot + 1) & slot_mask;
+    }
+    atomicOr(&flags[2], SAB_FOLD_ERR_TABLE);
+}
+
 __global__ void __launch_bounds__(256)
 k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile, int n_sites,
             const int32_t *__restrict__ prev, unsigned long long *__restrict__ keys, long long key_capacity,
@@ -52,49 +72,50 @@ k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n_tiles = (total + SAB_FOLD_TILE - 1) / SAB_FOLD_TILE;
+    const unsigned A = (unsigned)n_mobile, step_q = 256u / A, step_r = 256u % A;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long t0 = tile * SAB_FOLD_TILE;
         const long long f0 = t0 / n_mobile;                       // uniform: one 64-bit division per tile
-        const unsigned a0 = (unsigned)(t0 - f0 * n_mobile);
-        unsigned long long body[SAB_FOLD_PER_THREAD];
-        unsigned sbits = 0, ebits = 0;
+        const unsigned off0 = (unsigned)(t0 - f0 * n_mobile) + (unsigned)tid;
+        int cur[SAB_FOLD_PER_THREAD], before[SAB_FOLD_PER_THREAD], after[SAB_FOLD_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {           // loads first: out-of-range entries read entry 0
+            const long long i = t0 + k * 256 + tid;
+            const bool in = i < total;
+            cur[k] = result[in ? i : 0];
+            before[k] = result[in && i >= n_mobile ? i - n_mobile : 0];
+            after[k] = result[in && i + n_mobile < total ? i + n_mobile : 0];
+        }
+        unsigned q = off0 / A, r = off0 - q * A;                  // frame f0 + q, atom r of entry k = 0
+        unsigned sbits = 0, ebits = 0, tbits = 0, bad = 0;
+        unsigned aa[SAB_FOLD_PER_THREAD], qq[SAB_FOLD_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
             const long long i = t0 + k * 256 + tid;
-            body[k] = 0;
+            const long long f = f0 + q;
+            aa[k] = r; qq[k] = q;
             if (i < total) {
-                const unsigned off = a0 + (unsigned)(k * 256 + tid);
-                const unsigned df = off / (unsigned)n_mobile;
-                const int a = (int)(off - df * (unsigned)n_mobile);
-                const long long f = f0 + df;
-                int cur = result[i];
-                const int before = f > 0 ? result[i - n_mobile] : (prev ? prev[a] : -2);
-                const int after = f + 1 < n_frames ? result[i + n_mobile] : -3;
-                if (cur < -1 || cur >= n_sites) { atomicOr(&flags[2], SAB_FOLD_ERR_UNRESOLVED); cur = -1; }
-                if (cur >= 0) {
-                    body[k] = (((unsigned long long)cur * n_mobile + a) * (unsigned long long)n_frames + f) << 1;
-                    if (f == 0 || before != cur) sbits |= 1u << k;
-                    if (after != cur) ebits |= 1u << k;
-                    // site_collection.py:300-302: previous trajectory entry is a site and differs from the new one
-                    if (before >= 0 && before != cur && t_key) {
-                        const unsigned long long key = (unsigned long long)before * (unsigned long long)n_sites + cur;
-                        unsigned long long slot = sab_fold_hash(key) & slot_mask;
-                        bool done = false;
-                        for (unsigned long long probe = 0; probe <= slot_mask; probe++) {
-                            const unsigned long long old = atomicCAS(&t_key[slot], SAB_FOLD_EMPTY, key);
-                            if (old == SAB_FOLD_EMPTY) atomicAdd(&flags[1], 1ULL);
-                            if (old == SAB_FOLD_EMPTY || old == key) {
-                                atomicAdd(&t_cnt[slot], 1ULL);
-                                atomicMin(&t_first[slot], (unsigned long long)i);
-                                done = true;
-                                break;
-                            }
-                            slot = (slot + 1) & slot_mask;
-                        }
-                        if (!done) atomicOr(&flags[2], SAB_FOLD_ERR_TABLE);
-                    }
+                int c = cur[k];
+                const int b = f > 0 ? before[k] : (prev ? prev[r] : -2);
+                const bool last = f + 1 >= n_frames;
+                if (c < -1 || c >= n_sites) { bad = 1; c = -1; cur[k] = -1; }
+                if (c >= 0) {
+                    if (f == 0 || b != c) sbits |= 1u << k;
+                    if (last || after[k] != c) ebits |= 1u << k;
+                    if (b >= 0 && b != c) { tbits |= 1u << k; before[k] = b; }
                 }
             }
+            r += step_r; q += step_q;
+            if (r >= A) { r -= A; q++; }
+        }
+        if (bad) atomicOr(&flags[2], SAB_FOLD_ERR_UNRESOLVED);
+        // site_collection.py:300-302: previous trajectory entry is a site and differs from the new one
+        if (tbits && t_key) {
+#pragma unroll
+            for (int k = 0; k < SAB_FOLD_PER_THREAD; k++)
+                if (tbits >> k & 1u)
+                    sab_fold_insert((unsigned long long)before[k] * (unsigned long long)n_sites + cur[k],
+                                    (unsigned long long)(t0 + k * 256 + tid), t_key, t_cnt, t_first, slot_mask, flags);
         }
         // block-wide exclusive scan of the key counts
         const unsigned n = __popc(sbits) + __popc(ebits);
@@ -114,10 +135,16 @@ k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile
         }
         __syncthreads();
         unsigned long long o = s_base + s_warp[warp] + (incl - n);
+        if (sbits | ebits) {
 #pragma unroll
-        for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
-            if (sbits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body[k]; o++; }
-            if (ebits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body[k] | 1ULL; o++; }
+            for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
+                if ((sbits | ebits) >> k & 1u) {
+                    const unsigned long long body =
+                        (((unsigned long long)cur[k] * A + aa[k]) * (unsigned long long)n_frames + (unsigned long long)(f0 + qq[k])) << 1;
+                    if (sbits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body; o++; }
+                    if (ebits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body | 1ULL; o++; }
+                }
+            }
         }
         __syncthreads();                                          // s_warp / s_base are reused by the next tile
     }

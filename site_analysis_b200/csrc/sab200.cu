@@ -1232,3 +1232,22 @@ extern "C" int sab_fold_result(int device, const int32_t *d_result, int64_t n_fr
     if (h[2] & SAB_FOLD_ERR_PAIRING) return finish(SAB_ESTATE, "sab_fold_result: run boundaries do not pair up");
     return finish(SAB_OK, "");
 }
+
+// ---------------------------------------------------------------- minimum-image distance matrix (stand-alone operator)
+#include "k_distances.cuh"
+
+extern "C" int sab_mic_distances(int device, const double *d_c1, int n, const double *d_c2, int m,
+                                 const double *d_lattice, double *d_out, void *stream)
+{
+    if (n < 0 || m < 0) return fail(SAB_EINVAL, "sab_mic_distances: negative size");
+    if (n == 0 || m == 0) return SAB_OK;
+    if (!d_c1 || !d_c2 || !d_lattice || !d_out) return fail(SAB_EINVAL, "sab_mic_distances: null argument");
+    CU(cudaSetDevice(device));
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    const long long total = (long long)n * m;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm * 8));
+    k_mic_distances<<<grid, 256, 0, (cudaStream_t)stream>>>(d_c1, n, d_c2, m, d_lattice, d_out);
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
