@@ -66,17 +66,22 @@ def exchange_wrap_totals(totals, group, device=None):
     return base, parts
 
 
-def gather_assignments(local_rows, group, equal_shards: bool = False):
+def gather_assignments(local_rows, group, equal_shards: bool = False, async_op: bool = False):
     """All-gather the per-rank (F_local, A) int32 results into (sum F_local, A) on every rank.
     Shards may differ in length by one frame; they are padded for the collective and trimmed
-    (``equal_shards=True`` skips the length exchange when the caller knows all shards are equal)."""
+    (``equal_shards=True`` skips the length exchange when the caller knows all shards are equal).
+
+    ``async_op`` (equal shards only): returns ``(out, work)`` without making the current stream wait for the
+    collective, so the next batch's kernels overlap with it; ``work.wait()`` orders the current stream after it."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     if equal_shards:
         out = torch.empty((world * local_rows.shape[0], local_rows.shape[1]), dtype=local_rows.dtype, device=local_rows.device)
-        dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
-        return out
+        work = dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
+    if async_op:
+        raise ValueError("async_op needs equal_shards=True")
     n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
     counts = [int(x.item()) for x in _all_gather(n_local, group)]
     fmax = max(counts)
@@ -197,15 +202,23 @@ def relay_history(engine, group) -> None:
 
 
 def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group,
-                   equal_shards: bool = False):
+                   equal_shards: bool = False, async_gather: bool = False):
     """Assign this rank's contiguous shard with the correct PBC carry and return the FULL
     (F_total, A) int32 result (device tensor) on every rank.
 
     ``first_frame_global`` / ``first_lattice_global``: the trajectory's very first frame (N, 3) and
     lattice (3, 3) as numpy, identical on every rank -- the structure from which unprimed sites take
-    their initial image shifts (polyhedral_site.py:410-416)."""
+    their initial image shifts (polyhedral_site.py:410-416).
+
+    Cross-rank traffic per call: the halo all-gather (before the kernels), ONE small all-gather after them that
+    carries the excursion record of guard G1 together with the "some atom-frame sits in several sites" flag (one
+    host synchronisation), and the result all-gather.  ``async_gather=True`` (equal shards) returns
+    ``(full, work)`` with the result all-gather still in flight: a caller that streams a long trajectory through
+    in batches calls ``work.wait()`` when it reads ``full``, and the next batch's kernels overlap with the gather."""
     import torch
+    import torch.distributed as dist
     from . import _native as nat
+    from .engine import EXCURSION_LIMIT, GuardError
     dev = d_frac_local.device
     if engine.slots is not None:
         _initial_state(engine, first_frame_global, first_lattice_global)
@@ -213,23 +226,26 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
             _carry_by_anchor(engine, d_frac_local, group)
         else:
             _carry_by_totals(engine, d_frac_local, group)
-    import torch.distributed as dist
     local = engine.assign_device(d_frac_local, d_lattice_local, defer_resolve=True)
-    if engine.k in (nat.SPHERICAL, nat.POLYHEDRAL):            # sites may overlap: does ANY shard need the priority order?
-        flag = torch.tensor([1 if engine.last_info.get("ambiguous", 0) > 0 else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-        if int(flag.item()):
-            relay_history(engine, group)                       # resolves `local` in place, shard after shard
-    engine._pending = []
-    full = gather_assignments(local, group, equal_shards)       # enqueued first: the guard below overlaps with it
-    if engine.slots is not None and engine.k == nat.POLYHEDRAL:
-        # guard G1 holds over the WHOLE trajectory: combine the shards' excursions (device all-gather, one sync)
-        M = len(engine.fw_atoms)
-        exc = torch.empty((M, 3, 2), dtype=torch.float64, device=dev)
-        nat.check(engine.L.sab_get_excursion_device(engine.h, exc.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
-        parts = torch.stack(_all_gather(exc, group))
-        span = (parts[..., 1].amax(dim=0) - parts[..., 0].amin(dim=0)).max()
-        from .engine import EXCURSION_LIMIT, GuardError
-        if float(span.item()) >= EXCURSION_LIMIT and engine.strict:
+    guarded = engine.slots is not None and engine.k == nat.POLYHEDRAL
+    overlapping = engine.k in (nat.SPHERICAL, nat.POLYHEDRAL)      # sites may overlap: does ANY shard need the priority order?
+    if guarded or overlapping:
+        M = len(engine.fw_atoms) if guarded else 0
+        note = torch.zeros(6 * M + 1, dtype=torch.float64, device=dev)
+        if guarded:         # guard G1 holds over the WHOLE trajectory: the shards' excursions travel with the flag
+            nat.check(engine.L.sab_get_excursion_device(engine.h, note.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        if engine.last_info.get("ambiguous", 0) > 0:
+            note[-1] = 1.0
+        parts = torch.stack(_all_gather(note, group))
+        summary = torch.zeros(2, dtype=torch.float64, device=parts.device)
+        summary[0] = parts[:, -1].max()
+        if guarded:
+            exc = parts[:, :-1].reshape(parts.shape[0], M, 3, 2)
+            summary[1] = (exc[..., 1].amax(dim=0) - exc[..., 0].amin(dim=0)).max()
+        any_ambiguous, span = summary.cpu().tolist()                # the one host synchronisation after the kernels
+        if any_ambiguous:
+            relay_history(engine, group)                           # resolves `local` in place, shard after shard
+        if guarded and span >= EXCURSION_LIMIT and engine.strict:
             raise GuardError("a framework atom moved over >= 0.3 fractional units across the sharded trajectory")
-    return full
+    engine._pending = []
+    return gather_assignments(local, group, equal_shards, async_op=async_gather)
