@@ -173,6 +173,7 @@ def main():
     import torch
     import torch.distributed as dist
     from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not precede the JSON line on stdout
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,6 +203,13 @@ def main():
         from site_analysis_b200 import distributed as sd
 
     in_flight = []                                         # (full result, NCCL work) of the previous step
+    peer_bufs, exchange = None, "single GPU"
+    if world > 1:
+        try:     # result rows stored by the kernel itself into every rank's full array (NVLink peer memory)
+            peer_bufs = sd.PeerResultBuffers(F, A, dist.group.WORLD, dev)
+            exchange = "fused: the stream kernel stores its result rows into every rank's full array over NVLink peer memory"
+        except Exception as exc:
+            exchange = f"NCCL all-gather overlapping the next step's kernels (symmetric memory unavailable: {type(exc).__name__})"
 
     def drain():
         while in_flight:
@@ -215,9 +223,10 @@ def main():
             # trajectory streams through in batches: the result all-gather of batch k runs while batch k + 1 computes
             # (it is waited for one step later, and all of them before the timed region closes).
             full, work = sd.assign_sharded(eng, d_frac, d_lat, frame0, lat0, dist.group.WORLD, equal_shards=True,
-                                           async_gather=True)
+                                           async_gather=True, peer_buffers=peer_bufs)
             drain()
-            in_flight.append((full, work))
+            if work is not None:
+                in_flight.append((full, work))
             return full[rank * F:(rank + 1) * F]
         res = eng.assign_device(d_frac, d_lat)
         eng._pending = []                                  # array path: no Python-object history to maintain
@@ -300,9 +309,8 @@ def main():
                             "sample": f"{cpu_n} threads x {cb_frames} frames of this workload ({cpu_dt:.2f} s)"}
         cfg = workload_config(geom, F)
         if world > 1:
-            cfg["multi_gpu"] = ("contiguous frame shards, one per rank; per step: halo all-gather, kernels, guard/flag all-gather, "
-                                "result all-gather of int32[F_local, A] -- the result all-gather of step k overlaps the kernels of "
-                                "step k+1 and all of them complete inside the timed region")
+            cfg["multi_gpu"] = ("contiguous frame shards, one per rank; per step: halo all-gather, kernels, guard/flag all-gather "
+                                "(completion barrier), full int32[F_total, A] result on every rank; result exchange = " + exchange)
         traffic = None
         tp = ROOT / "profiles" / "r1_traffic.json"
         if tp.exists():                                   # one `ncu --set full` capture of this kernel, scaled per frame

@@ -191,7 +191,8 @@ int sab_wrap_totals(sab_engine *e, const double *d_frac, int64_t n_frames, void 
  *   largest excursion span max(raw - W) - min(raw - W) over all framework coordinates so far (double;
  *   guard of the scan formulation), [9] atom-frames that the float32 pre-test of the
  *   tetrahedral kernel could not decide and that were settled by its exact float64 pass, [10] 1 when the stream
- *   kernel's wrap-count chain check failed and the batch was redone with the scan kernels, [11] reserved.
+ *   kernel's wrap-count chain check failed and the batch was redone with the scan kernels, [11] 1 when every result
+ *   row was also stored into the peers registered with sab_set_result_peers.
  * When info[3] < 0 the PBC state advances to the end of the batch.  When info[3] = t >= 0 the
  * results of frames < t are valid, the PBC state is left untouched, and the caller commits
  * the valid prefix with sab_commit_pbc(..., n_commit = t) (same workspace, unmodified). */
@@ -272,6 +273,16 @@ int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n
  * alignment objective: tools.py:32-111, reference_workflow/structure_aligner.py:105-147). */
 int sab_mic_distances(int device, const double *d_c1, int n, const double *d_c2, int m,
                       const double *d_lattice, double *d_out, void *stream);
+
+/* Multi-GPU, frames sharded over ranks: the reference's atoms_trajectory (trajectory.py:375-383) is the concatenation
+ * of the shards' rows.  Instead of an all-gather AFTER the kernels, the stream kernel stores every result row it
+ * produces into the other ranks' copies of the full array as well -- plain stores to NVLink peer memory, overlapped
+ * with the computation frame by frame.  d_peer_slots[q] (host array of n_peers <= 7 DEVICE pointers): where this
+ * rank's rows start inside peer q's int32[F_total][A] array (peer-mapped address, e.g. from CUDA IPC / torch
+ * symmetric memory).  Applies to the following sab_assign_device calls (info[11] tells whether the rows were stored;
+ * kernels other than the tetrahedral stream kernel ignore the peers); n_peers = 0 clears.  The caller orders the
+ * peers' reads after this rank's kernels (any collective issued after them on the same stream does). */
+int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *d_peer_slots);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,8 @@ struct SabStreamTables {
     double *chunk_exc;            // out [n_chunks][m3][2]: excursion (min, max) of u per chunk
     int always_explicit;          // validity tube wider than 0.12: the in-tube shortcut of the chain check does not apply
     int reg_cols;                 // every producer thread owns <= SAB_STREAM_KMAX columns: their metadata and excursions live in registers
+    int n_peer;                   // multi-GPU: copies of every result row stored straight into the other ranks' buffers
+    int32_t *peer[SAB_MAX_PEERS]; // (NVLink peer memory; slot of THIS rank's frames inside the peer's full result array)
 };
 
 __device__ __forceinline__ void sab_mbar_arrive(uint64_t *bar)
@@ -398,7 +400,15 @@ k_polyhedral_assign_stream(const double *__restrict__ frac, int64_t n_frames, in
                         }
                     }
                     #undef SAB_RECENT_PUSH
-                    if (valid) res[a] = out;
+                    if (valid) {
+                        res[a] = out;
+                        // fused result all-gather: the same row goes to every peer's copy of the full array (posted NVLink stores)
+                        if (C.n_peer) {
+                            const size_t o = (size_t)f * n_mobile + a;
+#pragma unroll
+                            for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][o] = out;   // static indices: the parameter stays in constant memory
+                        }
+                    }
                     if (one_group) rc_reg = rc; else if (valid) last[a] = rc;
                 }
                 sab_mbar_arrive(&row_empty[wslot]);

@@ -409,13 +409,19 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
 // Settles the DEFERRED atom-frames of k_polyhedral_assign_tile with the exact float64 test over the whole cell
 // list: one warp per entry, one candidate per lane.  `scan` != 0: the list overflowed -- every warp scans a slice
 // of the result array for the marker instead (adversarial inputs only).
+#ifndef SAB_MAX_PEERS
+#define SAB_MAX_PEERS 7
+#endif
+struct SabPeers { int n; int32_t *p[SAB_MAX_PEERS]; };   // other ranks' slots for this rank's result rows (multi-GPU)
+
 __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n_frames, int n_atoms, int n_mobile,
                                       const int32_t *__restrict__ mobile, SabPolyTables T, int G,
                                       const int32_t *__restrict__ cell_off, const uint16_t *__restrict__ cell_sites,
                                       const int32_t *__restrict__ wrows, int m3, const long long *__restrict__ defer,
                                       long long defer_cap, int32_t *__restrict__ result, int32_t *__restrict__ spill,
                                       long long spill_capacity, unsigned long long *__restrict__ counters,
-                                      const double *__restrict__ anchor = nullptr)   // wrows == nullptr: W = rint(raw - anchor)
+                                      const double *__restrict__ anchor = nullptr,   // wrows == nullptr: W = rint(raw - anchor)
+                                      SabPeers peers = SabPeers{0, {nullptr}})
 {
     const long long n_def = (long long)counters[9];
     if (n_def == 0) return;
@@ -466,6 +472,10 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
                 out = SAB_AMBIGUOUS_BASE - (int)off;
             }
         }
-        if (lane == 0) result[idx] = out;
+        if (lane == 0) {
+            result[idx] = out;
+#pragma unroll
+            for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < peers.n) peers.p[q][idx] = out;
+        }
     }
 }

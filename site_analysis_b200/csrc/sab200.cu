@@ -108,6 +108,8 @@ struct sab_engine {
     int stream_rec_smem = 1;               // SAB_OPT_STREAM_REC_SMEM (1 = site records in shared memory when they fit)
     int stream_reg_cols = 1;               // SAB_OPT_STREAM_REG_COLS (1 = producer column metadata in registers when they fit)
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
+    int n_peer = 0; int32_t *peer[SAB_MAX_PEERS] = {nullptr};   // sab_set_result_peers
+    bool peers_written = false;            // the last sab_assign_device stored its rows into the peers as well
     size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
     unsigned long long *h_pinned = nullptr;               // pinned [2][CNT_N]: counter initialiser | read-back
 };
@@ -590,7 +592,10 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
                       (float)e->delta - 4e-7f, e->fp32_filter, w.defer, w.defer_cap, e->d_anchor, e->d_fw_atoms, e->d_prev_raw,
                       e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc, e->delta > 0.12 ? 1 : 0,
                       (e->stream_reg_cols && 3 * e->M <= SAB_STREAM_KMAX * 32 * p.n_prod && 3 * e->A <= SAB_STREAM_KMAX * 32 * p.n_prod &&
-                       e->n_used < 65536) ? 1 : 0};
+                       e->n_used < 65536) ? 1 : 0, e->n_peer, {nullptr}};
+    SabPeers peers{e->n_peer, {nullptr}};
+    for (int q = 0; q < e->n_peer; q++) { C.peer[q] = e->peer[q]; peers.p[q] = e->peer[q]; }
+    e->peers_written = e->n_peer > 0;
     const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
     if (p.rec_smem)
         k_polyhedral_assign_stream<true><<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
@@ -600,7 +605,7 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
             e->legacy_init_frame, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_counters + CNT_FULL27);
     // exact float64 pass over the atom-frames float32 could not decide (returns at once when there are none)
     k_polyhedral_deferred<<<e->sm_count * 8, 256, 0, st>>>(d_frac, F, e->N, e->A, e->d_mobile, T, e->G, e->d_cell_off,
-        e->d_cell_sites, nullptr, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor);
+        e->d_cell_sites, nullptr, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor, peers);
     k_wrap_commit_stream<<<(w.m3 + 31) / 32, 32 * SAB_COMMIT_GROUPS, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, (int)n_chunks, w.chunk_exc, e->d_anchor,
         e->d_prev_raw, e->d_wraps, e->d_excursion, e->d_counters);
     e->launches += 3;
@@ -800,6 +805,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     if (w.m3 && (!d_workspace || (int64_t)w.bytes > workspace_bytes))
         return fail(SAB_EINVAL, "workspace too small: need %zu bytes, got %lld", w.bytes, (long long)workspace_bytes);
     int64_t l0 = e->launches;
+    e->peers_written = false;
     if (!e->h_pinned) {
         CU(cudaMallocHost((void **)&e->h_pinned, 2 * CNT_N * sizeof(unsigned long long)));
         for (int i = 0; i < 2 * CNT_N; i++) e->h_pinned[i] = 0ULL;
@@ -832,6 +838,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
                                workspace_bytes, stream, info);
         e->force_scan = false;
         info[10] = 1;
+        info[11] = 0;                        // the scan kernels do not store into peers: the caller gathers this batch itself
         return rc;
     }
     e->skip_step_check_once = false;
@@ -840,6 +847,7 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     info[4] = (int64_t)h[CNT_FULL27];
     info[8] = (int64_t)h[CNT_SPAN];
     info[9] = (int64_t)h[9];                 // atom-frames settled by the exact float64 pass of the tile kernel
+    info[11] = e->peers_written ? 1 : 0;
     {
         float ms_wrap = 0.f, ms_main = 0.f;          // CUDA events on the launching stream
         cudaEventElapsedTime(&ms_wrap, e->ev_t[0], e->ev_t[1]);
@@ -1249,5 +1257,15 @@ extern "C" int sab_mic_distances(int device, const double *d_c1, int n, const do
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm * 8));
     k_mic_distances<<<grid, 256, 0, (cudaStream_t)stream>>>(d_c1, n, d_c2, m, d_lattice, d_out);
     CU(cudaGetLastError());
+    return SAB_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU: result rows stored straight into peer memory
+extern "C" int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *d_peer_slots)
+{
+    if (!e || n_peers < 0 || n_peers > SAB_MAX_PEERS || (n_peers > 0 && !d_peer_slots))
+        return fail(SAB_EINVAL, "sab_set_result_peers: between 0 and %d peers", SAB_MAX_PEERS);
+    e->n_peer = n_peers;
+    for (int q = 0; q < SAB_MAX_PEERS; q++) e->peer[q] = q < n_peers ? d_peer_slots[q] : nullptr;
     return SAB_OK;
 }

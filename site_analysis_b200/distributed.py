@@ -32,12 +32,34 @@ def shard_bounds(n_frames: int, world_size: int, rank: int) -> tuple[int, int]:
 
 
 def _all_gather(t, group):
+    """List over ranks of every rank's ``t`` (views of ONE gathered tensor: a single collective, no per-rank copies)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t.contiguous(), group=group)
-    return out
+    t = t.contiguous()
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    try:
+        dist.all_gather_into_tensor(out, t, group=group)
+    except (RuntimeError, NotImplementedError):            # backends without the flat form (old gloo)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        return parts
+    return list(out.unbind(0))
+
+
+_RESULT_GROUPS: dict = {}
+
+
+def _result_group(group):
+    """A second communicator over the same ranks for the big result all-gather: NCCL runs the collectives of one
+    communicator in order, so on the data-path group the next batch's halo exchange (which its kernels wait for) would
+    queue behind the previous batch's result all-gather and nothing would overlap.  Collective call."""
+    import torch.distributed as dist
+    key = id(group)
+    if key not in _RESULT_GROUPS:
+        ranks = dist.get_process_group_ranks(group)
+        _RESULT_GROUPS[key] = dist.new_group(ranks=ranks, backend=dist.get_backend(group))
+    return _RESULT_GROUPS[key]
 
 
 def exchange_halo(last_raw, group, device=None):
@@ -94,6 +116,41 @@ def gather_assignments(local_rows, group, equal_shards: bool = False, async_op: 
     if all(c == fmax for c in counts):
         return out
     return torch.cat([out[r * fmax:r * fmax + c] for r, c in enumerate(counts)], dim=0)
+
+
+class PeerResultBuffers:
+    """Two full result arrays int32[world * F_local, A] per rank in symmetric (peer-mapped) memory.
+
+    With these the result all-gather is FUSED into the assignment kernel: the tetrahedral stream kernel stores every row
+    it produces into its own slot of its own array and, through NVLink peer addresses, into the same slot of every other
+    rank's array (``sab_set_result_peers``), frame by frame while it computes.  The small guard/flag all-gather that
+    follows the kernels anyway is the completion barrier.  Two arrays alternate, so that a rank still reading batch k is
+    not overwritten by a neighbour that has already started batch k + 1 (nobody starts batch k + 2 before everybody has
+    finished the kernels of batch k + 1).  Collective constructor (rendezvous over ``group``)."""
+
+    def __init__(self, n_frames_local: int, n_mobile: int, group, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.F, self.A = int(n_frames_local), int(n_mobile)
+        self.buffers, self.ptrs = [], []
+        for _ in range(2):
+            t = symm_mem.empty((self.world * self.F, self.A), dtype=torch.int32, device=device)
+            h = symm_mem.rendezvous(t, group)
+            self.buffers.append(t)
+            self.ptrs.append([int(p) for p in h.buffer_ptrs])
+        self._handles = None
+        self.turn = 0
+
+    def next(self):
+        """(full array of this turn, its local slot, peer slot addresses for ``engine.set_result_peers``)."""
+        k = self.turn
+        self.turn ^= 1
+        full = self.buffers[k]
+        slot_bytes = self.rank * self.F * self.A * 4
+        peers = [self.ptrs[k][q] + slot_bytes for q in range(self.world) if q != self.rank]
+        return full, full[self.rank * self.F:(self.rank + 1) * self.F], peers
 
 
 def carry_from_halo(halo, anchor0):
@@ -202,7 +259,7 @@ def relay_history(engine, group) -> None:
 
 
 def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group,
-                   equal_shards: bool = False, async_gather: bool = False):
+                   equal_shards: bool = False, async_gather: bool = False, peer_buffers: PeerResultBuffers | None = None):
     """Assign this rank's contiguous shard with the correct PBC carry and return the FULL
     (F_total, A) int32 result (device tensor) on every rank.
 
@@ -212,9 +269,14 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
 
     Cross-rank traffic per call: the halo all-gather (before the kernels), ONE small all-gather after them that
     carries the excursion record of guard G1 together with the "some atom-frame sits in several sites" flag (one
-    host synchronisation), and the result all-gather.  ``async_gather=True`` (equal shards) returns
-    ``(full, work)`` with the result all-gather still in flight: a caller that streams a long trajectory through
-    in batches calls ``work.wait()`` when it reads ``full``, and the next batch's kernels overlap with the gather."""
+    host synchronisation), and the result rows.  The rows travel either
+
+    * fused into the kernel (``peer_buffers``, equal shards, tetrahedral sites): stored straight into every rank's
+      full array over NVLink peer memory while the kernel runs; the small all-gather is the completion barrier and no
+      result collective is issued at all (unless some rank reports overlapping sites or a redone batch -- then this call
+      falls back to the all-gather below), or
+    * by one NCCL all-gather of ``int32[F_local, A]``; ``async_gather=True`` (equal shards) returns ``(full, work)``
+      with it still in flight on its own communicator."""
     import torch
     import torch.distributed as dist
     from . import _native as nat
@@ -226,26 +288,48 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
             _carry_by_anchor(engine, d_frac_local, group)
         else:
             _carry_by_totals(engine, d_frac_local, group)
-    local = engine.assign_device(d_frac_local, d_lattice_local, defer_resolve=True)
+    full = out = None
+    if peer_buffers is not None:
+        if not equal_shards or int(d_frac_local.shape[0]) != peer_buffers.F:
+            raise ValueError("peer_buffers need equal shards of the size they were made for")
+        full, out, peers = peer_buffers.next()
+        engine.set_result_peers(peers)
+    try:
+        local = engine.assign_device(d_frac_local, d_lattice_local, defer_resolve=True, out=out)
+    finally:
+        if peer_buffers is not None:
+            engine.set_result_peers([])
+    fused = peer_buffers is not None and bool(engine.last_info.get("peers_written"))
     guarded = engine.slots is not None and engine.k == nat.POLYHEDRAL
     overlapping = engine.k in (nat.SPHERICAL, nat.POLYHEDRAL)      # sites may overlap: does ANY shard need the priority order?
-    if guarded or overlapping:
+    any_ambiguous = 0.0
+    all_fused = fused
+    if guarded or overlapping or peer_buffers is not None:
         M = len(engine.fw_atoms) if guarded else 0
-        note = torch.zeros(6 * M + 1, dtype=torch.float64, device=dev)
-        if guarded:         # guard G1 holds over the WHOLE trajectory: the shards' excursions travel with the flag
+        note = torch.zeros(6 * M + 2, dtype=torch.float64, device=dev)
+        if guarded:         # guard G1 holds over the WHOLE trajectory: the shards' excursions travel with the flags
             nat.check(engine.L.sab_get_excursion_device(engine.h, note.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         if engine.last_info.get("ambiguous", 0) > 0:
             note[-1] = 1.0
-        parts = torch.stack(_all_gather(note, group))
-        summary = torch.zeros(2, dtype=torch.float64, device=parts.device)
+        if not fused:
+            note[-2] = 1.0
+        parts = torch.stack(_all_gather(note, group))              # also orders every peer's row stores before our reads
+        summary = torch.zeros(3, dtype=torch.float64, device=parts.device)
         summary[0] = parts[:, -1].max()
+        summary[2] = parts[:, -2].max()
         if guarded:
-            exc = parts[:, :-1].reshape(parts.shape[0], M, 3, 2)
+            exc = parts[:, :-2].reshape(parts.shape[0], M, 3, 2)
             summary[1] = (exc[..., 1].amax(dim=0) - exc[..., 0].amin(dim=0)).max()
-        any_ambiguous, span = summary.cpu().tolist()                # the one host synchronisation after the kernels
+        any_ambiguous, span, any_unfused = summary.cpu().tolist()   # the one host synchronisation after the kernels
+        all_fused = fused and not any_unfused and not any_ambiguous
         if any_ambiguous:
             relay_history(engine, group)                           # resolves `local` in place, shard after shard
         if guarded and span >= EXCURSION_LIMIT and engine.strict:
             raise GuardError("a framework atom moved over >= 0.3 fractional units across the sharded trajectory")
     engine._pending = []
-    return gather_assignments(local, group, equal_shards, async_op=async_gather)
+    if peer_buffers is not None:
+        if all_fused:
+            return (full, None) if async_gather else full
+        dist.all_gather_into_tensor(full, local.clone(), group=group)            # some rank could not fuse: plain all-gather
+        return (full, None) if async_gather else full
+    return gather_assignments(local, _result_group(group) if async_gather else group, equal_shards, async_op=async_gather)

@@ -520,13 +520,21 @@ class AssignmentEngine:
                             for s in range(self.S)]
 
     # ------------------------------------------------------------------ the hot path
-    def assign_device(self, d_frac, d_lattice, *, append: bool = True, defer_resolve: bool = False):
+    def set_result_peers(self, peer_slot_ptrs) -> None:
+        """Multi-GPU: device addresses (ints) where THIS rank's result rows start inside every other rank's full result
+        array (``sab_set_result_peers``); the tetrahedral stream kernel then stores each row there as well.  ``[]`` clears."""
+        ptrs = (C.c_void_p * max(len(peer_slot_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_slot_ptrs])
+        nat.check(self.L.sab_set_result_peers(self.h, len(peer_slot_ptrs), ptrs))
+
+    def assign_device(self, d_frac, d_lattice, *, append: bool = True, defer_resolve: bool = False, out=None):
         """Assign a device-resident batch.  ``d_frac`` (F, N, 3) float64 cuda tensor, ``d_lattice`` (3, 3)
         or (F, 3, 3).  Returns an (F, A) int32 cuda tensor of site list positions (-1 = None).
 
         ``defer_resolve``: atom-frames in several sites keep their spill codes (<= -2) in the returned tensor
         until :meth:`sync_history` runs the priority resolver over them IN PLACE -- the sharded driver sets the
-        history left by the preceding shard first (``distributed.relay_history``)."""
+        history left by the preceding shard first (``distributed.relay_history``).  ``out``: (F, A) int32 cuda tensor
+        to write into (default: a new one).  ``last_info["peers_written"]`` tells whether every row also went to the
+        peers set by :meth:`set_result_peers`."""
         torch = _torch()
         assert d_frac.is_cuda and d_frac.dtype == torch.float64 and d_frac.is_contiguous()
         F = int(d_frac.shape[0])
@@ -538,7 +546,11 @@ class AssignmentEngine:
         if stride:
             assert d_lattice.shape[0] == F
         dev = d_frac.device
-        d_result = torch.empty((F, self.A), dtype=torch.int32, device=dev)
+        if out is None:
+            d_result = torch.empty((F, self.A), dtype=torch.int32, device=dev)
+        else:
+            assert out.is_cuda and out.dtype == torch.int32 and out.is_contiguous() and tuple(out.shape) == (F, self.A)
+            d_result = out
         self._last_pending = []
         if F == 0:
             return d_result
@@ -553,7 +565,8 @@ class AssignmentEngine:
             self._build_sphere_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
-        total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0, deferred=0, scan_redo=0)
+        total = dict(ambiguous=0, full27=0, launches=0, reinits=0, assign_ns=0, wrap_ns=0, deferred=0, scan_redo=0,
+                     peers_written=1)
         span_bits = 0
         while f0 < F:
             nf = F - f0
@@ -580,6 +593,7 @@ class AssignmentEngine:
                 self._cells_stale = True                 # too many frames left the tube: re-anchor next batch
             total["full27"] += int(info[4]); total["launches"] += int(info[5]); total["deferred"] += int(info[9])
             total["scan_redo"] += int(info[10])
+            total["peers_written"] &= int(info[11]) if (info[3] < 0 and f0 == 0) else 0   # one clean pass over the whole batch
             span_bits = max(span_bits, int(info[8]))
             total["assign_ns"] += int(info[6]); total["wrap_ns"] += int(info[7])
             if info[3] >= 0:
