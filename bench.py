@@ -173,7 +173,11 @@ def main():
     import torch
     import torch.distributed as dist
     from site_analysis_b200 import AssignmentEngine, synthetic as syn
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not precede the JSON line on stdout
+    # ONE JSON line on stdout: native libraries (NCCL's version banner ...) write to file descriptor 1 directly, so it is
+    # pointed at stderr for the run and the line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -332,7 +336,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "parity": parity,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

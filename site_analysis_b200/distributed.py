@@ -314,13 +314,11 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
         if not fused:
             note[-2] = 1.0
         parts = torch.stack(_all_gather(note, group))              # also orders every peer's row stores before our reads
-        summary = torch.zeros(3, dtype=torch.float64, device=parts.device)
-        summary[0] = parts[:, -1].max()
-        summary[2] = parts[:, -2].max()
+        parts = parts.cpu().numpy()                                # the one host synchronisation after the kernels (a few KB)
+        any_ambiguous, any_unfused, span = float(parts[:, -1].max()), float(parts[:, -2].max()), 0.0
         if guarded:
             exc = parts[:, :-2].reshape(parts.shape[0], M, 3, 2)
-            summary[1] = (exc[..., 1].amax(dim=0) - exc[..., 0].amin(dim=0)).max()
-        any_ambiguous, span, any_unfused = summary.cpu().tolist()   # the one host synchronisation after the kernels
+            span = float((exc[..., 1].max(axis=0) - exc[..., 0].min(axis=0)).max())
         all_fused = fused and not any_unfused and not any_ambiguous
         if any_ambiguous:
             relay_history(engine, group)                           # resolves `local` in place, shard after shard
