@@ -88,35 +88,38 @@ k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile
         }
         unsigned q = off0 / A, r = off0 - q * A;                  // frame f0 + q, atom r of entry k = 0
         unsigned sbits = 0, ebits = 0, tbits = 0, bad = 0;
-        unsigned aa[SAB_FOLD_PER_THREAD], qq[SAB_FOLD_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
             const long long i = t0 + k * 256 + tid;
             const long long f = f0 + q;
-            aa[k] = r; qq[k] = q;
             if (i < total) {
-                int c = cur[k];
+                const int c = cur[k];
                 const int b = f > 0 ? before[k] : (prev ? prev[r] : -2);
-                const bool last = f + 1 >= n_frames;
-                if (c < -1 || c >= n_sites) { bad = 1; c = -1; cur[k] = -1; }
-                if (c >= 0) {
+                if (c < -1 || c >= n_sites) bad = 1;
+                else if (c >= 0) {
                     if (f == 0 || b != c) sbits |= 1u << k;
-                    if (last || after[k] != c) ebits |= 1u << k;
-                    if (b >= 0 && b != c) { tbits |= 1u << k; before[k] = b; }
+                    if (f + 1 >= n_frames || after[k] != c) ebits |= 1u << k;
+                    if (b >= 0 && b != c) tbits |= 1u << k;
                 }
             }
             r += step_r; q += step_q;
             if (r >= A) { r -= A; q++; }
         }
         if (bad) atomicOr(&flags[2], SAB_FOLD_ERR_UNRESOLVED);
+        // Events are rare (a few per cent of the entries): each thread walks only ITS set bits, so a warp spends
+        // max-over-lanes(events per thread) rounds on them instead of one round per entry slot.  The entry is re-read
+        // (L1 hit) and its (frame, atom) recomputed, which keeps the per-entry state out of dynamically indexed arrays.
         // site_collection.py:300-302: previous trajectory entry is a site and differs from the new one
-        if (tbits && t_key) {
-#pragma unroll
-            for (int k = 0; k < SAB_FOLD_PER_THREAD; k++)
-                if (tbits >> k & 1u)
-                    sab_fold_insert((unsigned long long)before[k] * (unsigned long long)n_sites + cur[k],
-                                    (unsigned long long)(t0 + k * 256 + tid), t_key, t_cnt, t_first, slot_mask, flags);
-        }
+        if (t_key)
+            for (unsigned bits = tbits; bits; bits &= bits - 1) {
+                const int k = __ffs(bits) - 1;
+                const long long i = t0 + k * 256 + tid;
+                const unsigned off = off0 + 256u * k;
+                const int c = result[i];
+                const int b = i >= n_mobile ? result[i - n_mobile] : prev[off % A];
+                sab_fold_insert((unsigned long long)b * (unsigned long long)n_sites + c, (unsigned long long)i, t_key, t_cnt,
+                                t_first, slot_mask, flags);
+            }
         // block-wide exclusive scan of the key counts
         const unsigned n = __popc(sbits) + __popc(ebits);
         unsigned incl = n;
@@ -135,16 +138,15 @@ k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile
         }
         __syncthreads();
         unsigned long long o = s_base + s_warp[warp] + (incl - n);
-        if (sbits | ebits) {
-#pragma unroll
-            for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
-                if ((sbits | ebits) >> k & 1u) {
-                    const unsigned long long body =
-                        (((unsigned long long)cur[k] * A + aa[k]) * (unsigned long long)n_frames + (unsigned long long)(f0 + qq[k])) << 1;
-                    if (sbits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body; o++; }
-                    if (ebits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body | 1ULL; o++; }
-                }
-            }
+        for (unsigned bits = sbits | ebits; bits; bits &= bits - 1) {
+            const int k = __ffs(bits) - 1;
+            const long long i = t0 + k * 256 + tid;
+            const unsigned off = off0 + 256u * k;
+            const unsigned dq = off / A;
+            const unsigned long long body =
+                (((unsigned long long)result[i] * A + (off - dq * A)) * (unsigned long long)n_frames + (unsigned long long)(f0 + dq)) << 1;
+            if (sbits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body; o++; }
+            if (ebits >> k & 1u) { if ((long long)o < key_capacity) keys[o] = body | 1ULL; o++; }
         }
         __syncthreads();                                          // s_warp / s_base are reused by the next tile
     }
