@@ -284,6 +284,22 @@ int sab_mic_distances(int device, const double *d_c1, int n, const double *d_c2,
  * peers' reads after this rank's kernels (any collective issued after them on the same stream does). */
 int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *d_peer_slots);
 
+/* ---- XDATCAR text -> arrays (host code) -----------------------------
+ * The reference takes Sequence[Structure] (trajectory.py:413-432), which users build with pymatgen's Xdatcar parser;
+ * these two calls turn the text (already in memory, e.g. an mmap or a decompressed .gz) into the frac / lattice arrays
+ * of sab_assign_host directly.  Numbers are converted exactly as Python float() would (correctly rounded).
+ * sab_xdatcar_index: one pass from body_offset (the byte after the first 7-line header); frame_off[k] = offset of
+ *   frame k's first coordinate line, header_off[k] = offset of the header repeated in front of it (variable-cell
+ *   files) or -1; *n_frames = frames found; SAB_EOVERFLOW when that exceeds capacity (call again with room).
+ * sab_xdatcar_parse: frames split over n_threads host threads; frac double[F][N][3]; lattice (may be NULL)
+ *   double[F][3][3], written only for frames with header_off >= 0 (scale applied; negative scale = volume).
+ * sab_parse_double: one number (testing aid for the conversion). */
+int sab_xdatcar_index(const char *text, int64_t len, int64_t body_offset, int n_atoms, int64_t *frame_off,
+                      int64_t *header_off, int64_t capacity, int64_t *n_frames);
+int sab_xdatcar_parse(const char *text, int64_t len, int n_atoms, int64_t n_frames, const int64_t *frame_off,
+                      const int64_t *header_off, double *frac, double *lattice, int n_threads);
+int sab_parse_double(const char *text, int64_t len, double *out, int64_t *consumed);
+
 #ifdef __cplusplus
 }
 #endif

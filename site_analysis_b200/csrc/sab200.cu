@@ -1269,3 +1269,40 @@ extern "C" int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *
     for (int q = 0; q < SAB_MAX_PEERS; q++) e->peer[q] = q < n_peers ? d_peer_slots[q] : nullptr;
     return SAB_OK;
 }
+
+// ---------------------------------------------------------------- XDATCAR text -> arrays (host code)
+#include "xdatcar_host.h"
+
+extern "C" int sab_xdatcar_index(const char *text, int64_t len, int64_t body_offset, int n_atoms, int64_t *frame_off,
+                                 int64_t *header_off, int64_t capacity, int64_t *n_frames)
+{
+    if (!text || len < 0 || body_offset < 0 || body_offset > len || n_atoms <= 0 || !n_frames || capacity < 0 ||
+        (capacity > 0 && (!frame_off || !header_off)))
+        return fail(SAB_EINVAL, "sab_xdatcar_index: bad arguments");
+    const int64_t n = sabx_index(text, len, body_offset, n_atoms, frame_off, header_off, capacity);
+    if (n < 0) return fail(SAB_EINVAL, "XDATCAR: truncated coordinate block or malformed repeated header");
+    *n_frames = n;
+    return n > capacity ? SAB_EOVERFLOW : SAB_OK;
+}
+
+extern "C" int sab_xdatcar_parse(const char *text, int64_t len, int n_atoms, int64_t n_frames, const int64_t *frame_off,
+                                 const int64_t *header_off, double *frac, double *lattice, int n_threads)
+{
+    if (!text || len < 0 || n_atoms <= 0 || n_frames < 0 || (n_frames > 0 && (!frame_off || !frac)) || (lattice && !header_off))
+        return fail(SAB_EINVAL, "sab_xdatcar_parse: bad arguments");
+    for (int64_t k = 0; k < n_frames; k++)
+        if (frame_off[k] < 0 || frame_off[k] > len || (lattice && header_off[k] > len))
+            return fail(SAB_EINVAL, "sab_xdatcar_parse: frame offset outside the text");
+    const int64_t bad = sabx_parse(text, len, n_atoms, n_frames, frame_off, header_off, frac, lattice, n_threads);
+    if (bad >= 0) return fail(SAB_EINVAL, "XDATCAR: frame %lld holds a line that is not three numbers", (long long)bad);
+    return SAB_OK;
+}
+
+extern "C" int sab_parse_double(const char *text, int64_t len, double *out, int64_t *consumed)
+{
+    if (!text || !out || len < 0) return fail(SAB_EINVAL, "sab_parse_double: bad arguments");
+    const char *p = text;
+    if (!sabx_parse_double(p, text + len, *out)) return fail(SAB_EINVAL, "not a number");
+    if (consumed) *consumed = (int64_t)(p - text);
+    return SAB_OK;
+}

@@ -190,6 +190,13 @@ class Trajectory:
         lattice = lats[0] if np.all(lats == lats[0]) else lats
         self.trajectory_from_arrays(frac, lattice)
 
+    def trajectory_from_xdatcar(self, path, n_threads: int | None = None) -> np.ndarray:
+        """Read an XDATCAR (``.gz`` accepted) with the native parser (:mod:`site_analysis_b200.io`) and append its frames;
+        equivalent to ``trajectory_from_structures(Xdatcar(path).structures)`` without building ``Structure`` objects."""
+        from .io import read_xdatcar
+        species, lattice, frac = read_xdatcar(path, n_threads=n_threads, pinned=True)
+        return self.trajectory_from_arrays(frac, lattice)
+
     @property
     def atoms_trajectory(self):
         return list(map(list, zip(*[atom.trajectory for atom in self.atoms])))
