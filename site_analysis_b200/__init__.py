@@ -7,7 +7,8 @@ The CUDA backend (``libsab200.so``, C ABI in ``include/sab200.h``) is required; 
 fallback.
 """
 from .atom import Atom, atoms_from_indices, atoms_from_species_string, atoms_from_structure  # noqa: F401
-from .builders import (TrajectoryBuilder, create_trajectory_with_spherical_sites,  # noqa: F401
+from .builders import (TrajectoryBuilder, create_trajectory_with_dynamic_voronoi_sites,  # noqa: F401
+                       create_trajectory_with_polyhedral_sites, create_trajectory_with_spherical_sites,
                        create_trajectory_with_voronoi_sites)
 from .dynamic_voronoi_site import DynamicVoronoiSite  # noqa: F401
 from .engine import AssignmentEngine, GuardError  # noqa: F401
