@@ -159,3 +159,20 @@ def test_lazy_trajectories_materialise_like_lists():
     site._lazy_blocks.append((rows, np.array([10, 11])))
     assert site.trajectory == [[10], [11], [10, 11]]
     assert site.average_occupation == 1.0
+
+
+def test_peer_result_buffers_slot_arithmetic():
+    """distributed.PeerResultBuffers.next(): this rank's rows start at rank * F_local * A int32 elements inside every
+    peer's full array; buffers alternate (host logic only; the symmetric-memory allocation itself needs GPUs)."""
+    import torch
+    from site_analysis_b200.distributed import PeerResultBuffers
+    b = PeerResultBuffers.__new__(PeerResultBuffers)
+    b.world, b.rank, b.F, b.A, b.turn = 4, 2, 10, 3, 0
+    b.buffers = [torch.zeros((40, 3), dtype=torch.int32), torch.ones((40, 3), dtype=torch.int32)]
+    b.ptrs = [[1000, 2000, 3000, 4000], [5000, 6000, 7000, 8000]]
+    full, slot, peers = b.next()
+    assert full is b.buffers[0] and slot.shape == (10, 3) and slot.data_ptr() == full[20:].data_ptr()
+    assert peers == [1000 + 240, 2000 + 240, 4000 + 240]          # 2 * 10 * 3 * 4 bytes into ranks 0, 1 and 3
+    full, slot, peers = b.next()
+    assert full is b.buffers[1] and peers == [5240, 6240, 8240]
+    assert b.next()[0] is b.buffers[0]
