@@ -77,28 +77,33 @@ k_fold_scan(const int32_t *__restrict__ result, long long n_frames, int n_mobile
         const long long t0 = tile * SAB_FOLD_TILE;
         const long long f0 = t0 / n_mobile;                       // uniform: one 64-bit division per tile
         const unsigned off0 = (unsigned)(t0 - f0 * n_mobile) + (unsigned)tid;
+        // 32-bit offsets from the tile's base pointer; the neighbour rows are predicated loads (no clamped 64-bit indices)
+        const int32_t *__restrict__ tp = result + t0;
+        const long long rem = total - t0;                         // entries from the tile start to the end of the array
+        const int n_in = rem < SAB_FOLD_TILE ? (int)rem : SAB_FOLD_TILE;
+        const int n_after = rem - n_mobile < SAB_FOLD_TILE ? (int)(rem - n_mobile) : SAB_FOLD_TILE;   // offsets with a row below (may be <= 0)
+        const int first_with_before = t0 >= n_mobile ? 0 : (int)(n_mobile - t0);                        // offsets with a row above
         int cur[SAB_FOLD_PER_THREAD], before[SAB_FOLD_PER_THREAD], after[SAB_FOLD_PER_THREAD];
 #pragma unroll
-        for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {           // loads first: out-of-range entries read entry 0
-            const long long i = t0 + k * 256 + tid;
-            const bool in = i < total;
-            cur[k] = result[in ? i : 0];
-            before[k] = result[in && i >= n_mobile ? i - n_mobile : 0];
-            after[k] = result[in && i + n_mobile < total ? i + n_mobile : 0];
+        for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {           // all loads first
+            const int o = k * 256 + tid;
+            cur[k] = o < n_in ? tp[o] : -1;
+            before[k] = (o < n_in && o >= first_with_before) ? tp[o - n_mobile] : -2;
+            after[k] = o < n_after ? tp[o + n_mobile] : -3;
         }
         unsigned q = off0 / A, r = off0 - q * A;                  // frame f0 + q, atom r of entry k = 0
         unsigned sbits = 0, ebits = 0, tbits = 0, bad = 0;
 #pragma unroll
         for (int k = 0; k < SAB_FOLD_PER_THREAD; k++) {
-            const long long i = t0 + k * 256 + tid;
-            const long long f = f0 + q;
-            if (i < total) {
+            const int o = k * 256 + tid;
+            if (o < n_in) {
                 const int c = cur[k];
-                const int b = f > 0 ? before[k] : (prev ? prev[r] : -2);
+                int b = before[k];
+                if (o < first_with_before && prev) b = prev[r];  // frame 0: the atoms' previous trajectory entries
                 if (c < -1 || c >= n_sites) bad = 1;
                 else if (c >= 0) {
-                    if (f == 0 || b != c) sbits |= 1u << k;
-                    if (f + 1 >= n_frames || after[k] != c) ebits |= 1u << k;
+                    if (o < first_with_before || b != c) sbits |= 1u << k;
+                    if (after[k] != c) ebits |= 1u << k;           // -3 on the last frame: always an end
                     if (b >= 0 && b != c) tbits |= 1u << k;
                 }
             }
