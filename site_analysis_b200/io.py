@@ -35,10 +35,13 @@ def parse_xdatcar_text(text: bytes, n_threads: int | None = None, pinned: bool =
     ``Direct configuration=`` line followed by N coordinate lines; variable-cell runs repeat the 7-line header in
     front of every frame.  A negative scale is the cell volume.  Raises ``ValueError`` on anything else."""
     L = nat.lib()
-    head = text.split(b"\n", 7)
-    if len(head) < 8:
-        raise ValueError("XDATCAR: fewer than 7 header lines")
-    body_off = sum(len(h) + 1 for h in head[:7])
+    body_off = 0
+    for _ in range(7):                                          # end of the 7-line header, without copying the body
+        nl = text.find(b"\n", body_off)
+        if nl < 0:
+            raise ValueError("XDATCAR: fewer than 7 header lines")
+        body_off = nl + 1
+    head = bytes(text[:body_off]).split(b"\n")
     try:
         scale = float(head[1].split()[0])
         vectors = np.array([[float(x) for x in head[i].split()[:3]] for i in (2, 3, 4)], dtype=np.float64)
