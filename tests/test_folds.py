@@ -334,3 +334,129 @@ def test_device_history_fold_equals_host_fold(F, A, S, stay, none):
     if got[1 % S][0] == 0:
         del got[1 % S][0]
     assert {k: v for k, v in got.items() if v} == {k: v for k, v in want.items() if v}
+
+
+# Known answers of the reference's own unit tests (reference tests/test_site.py:157-184, 280-470), re-expressed against the
+# public API: (site trajectory, residence_times keyword arguments, expected tuple).
+_REFERENCE_RESIDENCE_CASES = [
+    ([[], [], []], {}, ()),
+    ([[1], [1], [1]], dict(include_edge_runs=True), (3,)),
+    ([[1], [], [1]], dict(include_edge_runs=True), (1, 1)),
+    ([[], [1], [1]], dict(include_edge_runs=True), (2,)),
+    ([[1], [1], []], dict(include_edge_runs=True), (2,)),
+    ([[1], [1], [2], [2], [2]], dict(include_edge_runs=True), (2, 3)),
+    ([[1, 2], [1, 2], [1]], dict(include_edge_runs=True), (3, 2)),
+    ([[1]], dict(include_edge_runs=True), (1,)),
+    ([[1], [1], [], [1], [1], [1], []], {}, (3,)),
+    ([[], [1], [1], [1], [], [1], [1]], {}, (3,)),
+    ([[1], [], [1], [1], [1], [], [1]], {}, (3,)),
+    ([[1], [1], [1]], {}, ()),
+    ([[1], [1], [], [1], [], [1], [1]], {}, (1,)),
+    ([[], [1], [], [1], []], dict(filter_length=1, include_edge_runs=True), (3,)),
+    ([[], [1], [], [], [1], []], dict(filter_length=1, include_edge_runs=True), (1, 1)),
+    ([[], [1], [], [], [1], []], dict(filter_length=2, include_edge_runs=True), (4,)),
+    ([[], [1], [1]], dict(filter_length=1, include_edge_runs=True), (2,)),
+    ([[1], [1], []], dict(filter_length=1, include_edge_runs=True), (2,)),
+    ([[], [1], [], [2], []], dict(filter_length=1, include_edge_runs=True), (1, 1)),
+    ([[], [1], [], [1], []], dict(filter_length=0), (1, 1)),
+    ([[1], [], [1], [1], [], [], [1]], dict(filter_length=1), ()),
+    ([[], [1], [], [1], []], {}, (1, 1)),
+    ([[], [1], [], [1], []], dict(filter_length=1), (3,)),
+]
+_REFERENCE_OCCUPATION_CASES = [([], None), ([[], [], []], 0.0), ([[1], [2], [1, 2]], 1.0), ([[1], [], [2], [], [3]], 0.6),
+                               ([[1, 2, 3], [], [4, 5], []], 0.5)]
+
+
+def _site_from_history(traj, folded):
+    """A site whose history is ``traj``, either as the plain list or as one GPU-style folded batch (runs from the oracle)."""
+    import folds_oracle as fo
+    import site_analysis_b200 as sab
+    from site_analysis_b200.folds import BlockFolds
+    site = sab.VoronoiSite(np.zeros(3))
+    site.index = 7
+    if not folded or not traj:
+        site.trajectory = [list(ts) for ts in traj]
+        return site
+    atoms = sorted({a for ts in traj for a in ts}) or [1]
+    rows = np.full((len(traj), len(atoms)), -1, dtype=np.int32)
+    for f, ts in enumerate(traj):
+        for a in ts:
+            rows[f, atoms.index(a)] = 0
+    blk = BlockFolds(np.where(rows >= 0, 7, -1), np.array(atoms), np.array([7]))
+    blk._runs = fo.runs_from_rows(rows)
+    blk._site_off = np.searchsorted(blk._runs[0], np.arange(2))
+    site._lazy_blocks = [(blk, 0)]
+    return site
+
+
+@pytest.mark.parametrize("folded", [False, True])
+def test_reference_unit_test_known_answers(folded):
+    for traj, kwargs, want in _REFERENCE_RESIDENCE_CASES:
+        assert _site_from_history(traj, folded).residence_times(**kwargs) == want, (traj, kwargs)
+    for traj, want in _REFERENCE_OCCUPATION_CASES:
+        got = _site_from_history(traj, folded).average_occupation
+        assert got == want or (want is not None and abs(got - want) < 1e-12), traj
+    site = _site_from_history([[1], [], [1]], folded)
+    with pytest.raises(ValueError):
+        site.residence_times(filter_length=-1)
+    with pytest.raises(TypeError):
+        site.residence_times(filter_length=1.5)
+    summary = _site_from_history([[1], []], folded).summary()
+    assert set(summary) == {"index", "site_type", "average_occupation", "transitions"} and summary["average_occupation"] == 0.5
+    empty = _site_from_history([], folded)
+    assert "average_occupation" not in empty.summary()
+    assert empty.summary(metrics=["index", "average_occupation"])["average_occupation"] is None
+
+
+def test_device_history_fold_host_logic(monkeypatch):
+    """engine.fold_history_device with the device fold answered by the oracle == engine.fold_history, over many random
+    histories (the GPU test runs the same comparison through the real kernel on a few)."""
+    import folds_oracle as fo
+    from site_analysis_b200 import engine, folds
+
+    def fake_fold_rows(rows, n_sites, prev=None, want_pairs=True, device=None, want_recent=False):
+        rows = np.asarray(rows)
+        tr = fo.transitions(rows, prev)
+        first = {}
+        last = np.full(rows.shape[1], -2, dtype=np.int64) if prev is None else np.asarray(prev, dtype=np.int64).copy()
+        for f in range(rows.shape[0]):
+            for a in range(rows.shape[1]):
+                v = int(rows[f, a])
+                if v >= 0 and last[a] >= 0 and last[a] != v:
+                    first.setdefault((int(last[a]), v), f * rows.shape[1] + a)
+            last = rows[f].astype(np.int64)
+        items = sorted(first.items(), key=lambda kv: kv[1])
+        src = np.array([k[0] for k, _ in items], dtype=np.int32); dst = np.array([k[1] for k, _ in items], dtype=np.int32)
+        cnt = np.array([tr[k[0]][k[1]] for k, _ in items], dtype=np.int64)
+        lastv, other = np.full(rows.shape[1], -1, dtype=np.int32), np.full(rows.shape[1], -1, dtype=np.int32)
+        for a in range(rows.shape[1]):
+            col = rows[:, a]
+            hit = np.flatnonzero(col >= 0)
+            if len(hit):
+                lastv[a] = col[hit[-1]]
+                diff = np.flatnonzero((col >= 0) & (col != lastv[a]))
+                if len(diff):
+                    other[a] = col[diff[-1]]
+        return dict(runs=fo.runs_from_rows(rows), pairs=(src, dst, cnt, np.array([v for _, v in items], dtype=np.int64)),
+                    recent=(lastv, other), info=dict(kernel_ns=0, launches=0))
+    monkeypatch.setattr(folds, "fold_rows", fake_fold_rows)
+    rng = np.random.default_rng(77)
+    for trial in range(25):
+        F, A, S = int(rng.integers(1, 60)), int(rng.integers(1, 9)), int(rng.integers(1, 6))
+        rows = fo.random_rows(rng, F, A, S, float(rng.uniform(0.3, 0.99)), float(rng.uniform(0, 0.4)))
+        state = []
+        for device in (False, True):
+            recent = rng.integers(-1, S, size=(A, 2)).astype(np.int32) if trial % 2 else np.full((A, 2), -1, dtype=np.int32)
+            prev = rng.integers(-2, S, size=A).astype(np.int32)
+            tr = [dict() for _ in range(S)]
+            if trial % 3 == 0 and S > 1:
+                tr[0][S - 1] = 2
+            state.append((recent, prev, tr))
+        state[1][0][:], state[1][1][:] = state[0][0], state[0][1]
+        cut = int(rng.integers(0, F + 1))
+        for a, b in ((0, cut), (cut, F)):
+            if b > a:
+                engine.fold_history(state[0][0], state[0][1], state[0][2], rows[a:b], True)
+                engine.fold_history_device(state[1][0], state[1][1], state[1][2], rows[a:b], S)
+        assert np.array_equal(state[0][0], state[1][0]) and np.array_equal(state[0][1], state[1][1]), trial
+        assert state[0][2] == state[1][2] and all(list(x) == list(y) for x, y in zip(state[0][2], state[1][2])), trial
