@@ -127,6 +127,7 @@ class BlockFolds:
         self._runs = None
         self._site_off = None
         self.kernel_ns = 0
+        self.frac = None                             # (F, N, 3) coordinates of the batch, kept only for lazy Site.points
 
     def _fold(self):
         if self._runs is None:

@@ -25,7 +25,8 @@ class Site:
         self.contains_atoms: list[int] = []
         self._trajectory: list[list[int]] = []
         self._lazy_blocks: list = []                 # pending (results (F, A), atom_index (A,)) pairs
-        self.points: list[np.ndarray] = []
+        self._points: list[np.ndarray] = []
+        self._lazy_points: list = []                 # pending (BlockFolds with .frac, site position) pairs of long batches
         self.transitions: Counter = Counter()
 
     @property
@@ -47,6 +48,30 @@ class Site:
                 self._trajectory.extend(per_frame)
             self._lazy_blocks = []
         return self._trajectory
+
+    @property
+    def points(self) -> list[np.ndarray]:
+        """Wrapped fractional coordinates of every atom-frame assigned to this site (reference site.py:70,
+        site_collection.py:308: one ``atom.frac_coords`` per ``update_occupation``, frames in order, atoms in list order).
+        Long batches (``Trajectory.trajectory_from_arrays`` above ``POINTS_LIMIT`` atom-frames) are kept as a reference to
+        the caller's coordinate array plus the GPU-folded runs and expanded here, on first access."""
+        if self._lazy_points:
+            pending, self._lazy_points = self._lazy_points, []
+            for block, pos in pending:
+                col, start, length = block.site_runs(pos)
+                if len(col) == 0:
+                    continue
+                frames = np.concatenate([np.arange(f0, f0 + n) for f0, n in zip(start.tolist(), length.tolist())])
+                cols = np.repeat(col, length)
+                order = np.lexsort((cols, frames))                   # frame by frame, atoms in list order
+                xyz = block.frac[frames[order], block.atom_index[cols[order]]] % 1.0      # atom.py:104
+                self._points.extend(xyz)
+        return self._points
+
+    @points.setter
+    def points(self, value) -> None:
+        self._lazy_points = []
+        self._points = value
 
     def _folded_runs(self):
         """(atom index, start, end, n_frames) of this site's runs when its whole history sits in GPU-folded batches,

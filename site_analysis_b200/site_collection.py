@@ -29,7 +29,7 @@ from .site import Site
 from .spherical_site import SphericalSite
 from .voronoi_site import VoronoiSite
 
-POINTS_LIMIT = 2_000_000     # atom-frames per batch above which Site.points is not populated
+POINTS_LIMIT = 2_000_000     # atom-frames per batch above which Site.points is filled lazily (Trajectory) instead of eagerly
 
 
 class SiteCollection:

@@ -20,6 +20,7 @@ from .atom import Atom
 from .folds import BlockFolds
 from .site import Site
 from .transition_table import TransitionTable
+from .site_collection import POINTS_LIMIT  # noqa: E402
 from .site_collection import (DynamicVoronoiSiteCollection, PolyhedralSiteCollection, SiteCollection,
                               SphericalSiteCollection, VoronoiSiteCollection)
 
@@ -175,8 +176,13 @@ class Trajectory:
             atom._lazy_blocks.append(rows[:, a])
         # one shared, lazily GPU-folded form of the batch answers every site's trajectory / residence times
         folds = BlockFolds(rows, atom_index, self.site_collection._index_of_pos)
+        keep_points = rows.size > POINTS_LIMIT          # short batches got their Site.points eagerly (site_collection._run)
+        if keep_points:
+            folds.frac = frac_coords
         for p, site in enumerate(self.sites):
             site._lazy_blocks.append((folds, p))
+            if keep_points and hasattr(site, "_lazy_points"):
+                site._lazy_points.append((folds, p))
         self.timesteps.extend(range(1, F + 1) if timesteps is None else timesteps)
         return rows
 

@@ -460,3 +460,36 @@ def test_device_history_fold_host_logic(monkeypatch):
                 engine.fold_history_device(state[1][0], state[1][1], state[1][2], rows[a:b], S)
         assert np.array_equal(state[0][0], state[1][0]) and np.array_equal(state[0][1], state[1][1]), trial
         assert state[0][2] == state[1][2] and all(list(x) == list(y) for x, y in zip(state[0][2], state[1][2])), trial
+
+
+def test_lazy_site_points_equal_eager_points():
+    """Site.points of a long batch (kept as runs + a reference to the coordinates) == the reference's eager appends
+    (site_collection.py:308: frames in order, atoms in list order, atom.frac_coords = frac[index] % 1.0)."""
+    import folds_oracle as fo
+    import site_analysis_b200 as sab
+    from site_analysis_b200.folds import BlockFolds
+    rng = np.random.default_rng(4)
+    F, A, S, N = 40, 5, 3, 9
+    pos = fo.random_rows(rng, F, A, S, 0.8, 0.1)
+    atom_index = np.array([7, 2, 8, 0, 4])
+    frac = rng.random((F, N, 3)) * 3 - 1
+    site_index = np.array([11, 12, 13])
+    blk = BlockFolds(np.where(pos >= 0, site_index[np.clip(pos, 0, None)], -1), atom_index, site_index)
+    blk._runs = fo.runs_from_rows(pos)
+    blk._site_off = np.searchsorted(blk._runs[0], np.arange(S + 1))
+    blk.frac = frac
+    for s in range(S):
+        site = sab.VoronoiSite(np.zeros(3)); site.index = int(site_index[s])
+        site.points.append(np.array([9.0, 9.0, 9.0]))            # something recorded before the batch stays in front
+        site._lazy_points.append((blk, s))
+        want = [np.array([9.0, 9.0, 9.0])]
+        for f in range(F):
+            for a in range(A):
+                if pos[f, a] == s:
+                    want.append(frac[f, atom_index[a]] % 1.0)
+        got = site.points
+        assert len(got) == len(want) and all(np.array_equal(g, w) for g, w in zip(got, want))
+        site.reset()
+        assert len(site.points) == len(want)                      # reset() leaves points alone (reference site.py:86-88)
+        site.points = []
+        assert site.points == []
