@@ -210,6 +210,8 @@ def main():
     peer_bufs, exchange = None, "single GPU"
     if world > 1:
         try:     # result rows stored by the kernel itself into every rank's full array (NVLink peer memory)
+            if os.environ.get("SAB_NO_PEER_STORE") == "1":      # A/B switch: NCCL all-gather instead
+                raise RuntimeError("disabled by SAB_NO_PEER_STORE=1")
             peer_bufs = sd.PeerResultBuffers(F, A, dist.group.WORLD, dev)
             exchange = "fused: the stream kernel stores its result rows into every rank's full array over NVLink peer memory"
         except Exception as exc:
