@@ -35,12 +35,14 @@ class SphericalSite(Site):
         return site
 
     def contains_point(self, x, *, lattice_matrix=None) -> bool:
-        """Single-point queries are answered by the collection on the GPU
-        (``SphericalSiteCollection.sites_containing``); the per-site Python test of the
-        reference (spherical_site.py:126-146) is not part of the accelerated path."""
+        """``mic_distance(centre, x) <= rcut`` (reference spherical_site.py:126-146), the distance computed by the GPU
+        operator :func:`site_analysis_b200.distances.mic_distance` (bit-identical to the reference's numba kernel).
+        Whole trajectories go through ``SphericalSiteCollection`` instead -- this is the single-point query."""
         if lattice_matrix is None:
             raise ValueError("lattice_matrix is required for SphericalSite.contains_point()")
-        raise NotImplementedError("use SphericalSiteCollection.assign_site_occupations (GPU path)")
+        from .distances import mic_distance
+        return bool(mic_distance(np.asarray(self.frac_coords, dtype=np.float64), np.asarray(x, dtype=np.float64),
+                                 lattice_matrix) <= self.rcut)
 
     def contains_atom(self, atom, *, lattice_matrix=None) -> bool:
         if lattice_matrix is None:
