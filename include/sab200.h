@@ -164,6 +164,10 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
 #define SAB_OPT_STREAM_PRODUCERS 7 /* producer warps per CTA of the stream kernel (0 = automatic) */
 #define SAB_OPT_STREAM_REC_SMEM 8  /* 1 (default): site records staged in shared memory when they fit; 0: read through L1 */
 #define SAB_OPT_STREAM_REG_COLS 9  /* 1 (default): producer threads keep their columns' metadata and excursions in registers when they fit */
+#define SAB_OPT_STREAM_GEN 10      /* 0 (default): generation-5 stream kernel (vertex-image rows) when its tables exist; 4: the previous one */
+#define SAB_OPT_STREAM5_ROWS 11    /* generation 5: row slots of the ring, 2..8 (0 = automatic) */
+#define SAB_OPT_STREAM5_RAW 12     /* generation 5: raw-frame slots of the ring, 2..4 (0 = automatic) */
+#define SAB_OPT_STREAM5_BLOCKS 13  /* generation 5: resident CTAs per SM the shared-memory plan aims for, 1..8 (0 = automatic) */
 int sab_set_option(sab_engine *e, int key, int64_t value);
 
 /* ---- the hot path -------------------------------------------------------------------- */

@@ -29,8 +29,12 @@ OPT_TILE_FRAMES = 6
 OPT_STREAM_PRODUCERS = 7
 OPT_STREAM_REC_SMEM = 8
 OPT_STREAM_REG_COLS = 9
+OPT_STREAM_GEN = 10
+OPT_STREAM5_ROWS = 11
+OPT_STREAM5_RAW = 12
+OPT_STREAM5_BLOCKS = 13
 
-# every symbol include/sab200.h declares (tests/test_abi.py checks the header against this)
+# every symbol include/sab200.h declares (tests/test_host_logic.py checks the header against this)
 SYMBOLS = [
     "sab_abi_version", "sab_last_error", "sab_engine_create", "sab_engine_destroy", "sab_set_centres",
     "sab_set_polyhedra", "sab_set_reference_atoms", "sab_framework_count", "sab_framework_atoms",

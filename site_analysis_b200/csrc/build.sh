@@ -3,7 +3,7 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-OUT="$HERE/../libsab200.so"
+OUT="${SAB200_OUT:-$HERE/../libsab200.so}"     # SAB200_OUT: an alternative build for A/B timing (load it with SAB200_LIB)
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false \
     -Xcompiler -fPIC -shared "$@" -o "$OUT.tmp.$$" "$HERE/sab200.cu" -lcudart
 mv -f "$OUT.tmp.$$" "$OUT"     # atomic: a snapshot taken meanwhile never sees a half-written library

@@ -1,0 +1,420 @@
+// k_polyhedral_stream5.cuh -- the production tetrahedral kernel, generation 5: the warp-specialised frame
+// pipeline of k_polyhedral_stream.cuh with a third of its instructions.
+//
+// Same contract and bit-identical results as k_polyhedral_assign_stream (polyhedral_site_collection.py:86-107 with
+// the "most recent site first" order of site_collection.py:147-152, vertices from pbc_utils.py:193-230, containment
+// polyhedral_site.py:83-123).  What changed, and why (profiles/r1_ncu_full_stream_v4_125kframes.csv: 4,530 warp
+// instructions per frame, issue bound):
+//
+//   * STAGED ROWS ARE VERTEX IMAGES.  A row holds one float4 per (framework atom, integer image shift) pair some
+//     site uses, then one float4 per mobile atom.  A site record is four 16-bit byte offsets; a containment test
+//     loads four vertices and the atom with five 128-bit shared loads (was 15 scalar loads + 12 unpack operations).
+//   * THE RECORD OF THE MOST RECENT SITE LIVES IN REGISTERS and is reloaded only when the atom changes site.
+//   * CONSTANT ERROR THRESHOLDS.  The error budget of the FP32 pre-test (below) is evaluated once on the host for
+//     the largest site of the table; only a test that lands inside that (wider) band recomputes the per-site
+//     budget.  Site records are stored positively oriented (host), so the sign flip of the verdict is gone too.
+//   * IMAGE CHOICE BY THE FIRST VERTEX.  P = (x - a) - rint(x - a) instead of rint(centroid - x): see sab_tet5.
+//   * PRODUCERS WORK PER FRAMEWORK ATOM (three coordinates per task, tasks sorted by their number of images) and
+//     no longer track the float64 excursion of every coordinate: a frame inside the validity tube
+//     |u - anchor| <= delta <= 0.12 cannot widen the excursion beyond [anchor - delta, anchor + delta], which is what
+//     a chunk reports (guard G1 needs < 0.3); frames outside the tube update it explicitly.
+//   * One mbarrier arrival per WARP (after __syncwarp), ring positions advanced without integer division.
+//
+//   * NO COLD CODE IN THE FRAME LOOP.  Frames outside the validity tube (and the legacy first-frame rule) are only
+//     listed; k_polyhedral_flagged settles them with the generic all-sites test after the kernel.  Atom-frames that
+//     several sites contain join the ones float32 cannot decide in the exact float64 pass (k_polyhedral_deferred),
+//     which writes the candidate list for the priority resolver.  Either way the atom's history restarts as
+//     "unknown", which only ever selects the slower path to the same answer.
+//
+// Pipeline (unchanged): copy engine (cp.async.bulk of whole raw frames, mbarrier complete_tx) -> producer warps
+// (raw frame -> float row) -> consumer warps (one mobile atom per lane, frames in order), coupled by full/empty
+// mbarriers on a ring of rows; no CTA-wide barrier in the steady state.  The chain check of the anchor form of the
+// wrap count W = rint(raw - anchor) against the reference's sequential update (pbc_utils.py:210-217) is the one of
+// k_polyhedral_stream.cuh.
+#pragma once
+#include "k_polyhedral_stream.cuh"
+
+#define SAB_S5_MAXTHREADS 256
+#ifndef SAB_S5_MINBLOCKS
+#define SAB_S5_MINBLOCKS 3
+#endif
+#define SAB_S5_MAXRAW 4
+#define SAB_S5_MAXROWS 8
+#define SAB_CNT_FLAGGED 11        // counters[]: frames handed to k_polyhedral_flagged
+#define SAB_S5_DELTA22 2.384185791015625e-7f      // 2^-22: every staged coordinate is within this of its float64 value
+
+struct SabStream5Tables {
+    int n_img;                    // staged vertex images (float4 each)
+    int n_task;                   // framework atoms (one producer task each), sorted by descending image count
+    int stride4;                  // float4 per row: n_img + A
+    int m3;                       // framework coordinates
+    const int4 *task;             // [n_task] {3 * structure index, first image, images, 3 * framework column}
+    const float4 *task_anchor;    // [n_task] anchors of the three coordinates (exactly representable in float)
+    const float4 *img_shift;      // [n_img] integer image shift of the staged vertex
+    const uint2 *rec;             // [S] four uint16 BYTE offsets of the site's vertex images, positively oriented
+    int G;
+    const int32_t *cell_off;      // [G^3 + 1]
+    const uint16_t *cell_sites;   // CSR entries, ascending per cell
+    float delta_f;                // validity tube, shrunk by the float error of the check
+    float T1, T0, TD;             // constant thresholds of the pre-test (largest site of the table, |P| <= 1/2)
+    int use_f32;
+    long long *defer;
+    long long defer_cap;
+    long long *flagged;           // frames outside the validity tube (settled by k_polyhedral_flagged after this kernel)
+    const double *anchor;         // [m3]
+    const int32_t *fw_atoms;      // [M]
+    const double *prev_raw;       // [m3] carry: raw coordinates of the frame before this batch
+    const int32_t *wraps;         // [m3] carry: wrap counts at that frame
+    int skip_check_frame0;
+    int n_raw, n_rows, n_prod, use_tma;
+    double *chunk_exc;            // out [n_chunks][m3][2]
+    double delta_d;               // the validity tube in float64 (>= what delta_f admits)
+    int n_peer;
+    int32_t *peer[SAB_MAX_PEERS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// FP32 pre-test, generation 5.  With a = vertex 0, B = b - a, C = c - a, D = d - a and P = p - a:
+//   det = D . (B x C),  l_b = C . (D x P),  l_c = -B . (D x P),  l_d = P . (B x C),  l_a = det - l_b - l_c - l_d
+// are det times the barycentric coordinates of p; p is inside the closed tetrahedron iff all of them have the
+// sign of det.  These are the reference's four face-plane values (polyhedral_site.py:107-121) up to a positive
+// factor and float64 rounding.  Records are stored with det > 0 at the anchor positions (host).
+//
+// Image choice.  The reference tests the images x + {0,1}^3 against the vertices shifted by u = ceil(-min)^+
+// (tools.py:246-253, pbc_utils.py:221-229).  Sites are smaller than 0.45 per axis (host check), so a point inside
+// the hull is within 0.45 of vertex a on every axis: the only image in reach is p = x + k with k = -rint(x - a),
+// i.e. P = t - rint(t), t = x - a (exact in float: |t - rint(t)| <= 1/2 needs no more bits than t).  If p is
+// strictly inside, x + o = p + u lies in [min + u, max + u], inside [0, 2) by the host check "anchor vertex +
+// delta < 2", so o is 0 or 1 and the reference tests exactly this image.  If p is outside, every other image
+// differs from it by >= 1 on some axis, i.e. lies >= 1/2 - 2^-20 > 0.45 from a on that axis: outside too.
+//
+// Error budget (delta = 2^-22).  Staged vertex coordinates are within delta of their float64 values (|value| < 4,
+// host check), the wrapped atom coordinate within delta / 8; hence every component of B, C, D carries an input
+// error <= 2.03 delta and every component of P <= 1.63 delta.  With Ee >= |components of B, C, D| and
+// Ep >= |components of P|, first-order propagation through the six products of a 3 x 3 determinant plus the
+// roundings of the FMA evaluation (<= 4.5 Ee^2 Ep delta) give
+//   |err(l_b, l_c, l_d)| <= (28 Ee Ep + 16 Ee^2) delta,   |err(det)| <= 44 Ee^2 delta,
+//   |err(l_a)| <= 3 (28 Ee Ep + 16 Ee^2) delta + 44 Ee^2 delta.
+// Thresholds are TWICE these bounds.  A verdict is returned only when every quantity that enters it is beyond its
+// threshold; then the exact plane values -- and the float64 reference arithmetic, whose own error is ~1e-9 of the
+// threshold -- have the same signs.  The fast path uses the bounds for Ee = Ee_max (largest anchor site + tube),
+// Ep = 1/2 (P is a reduced separation); a value inside that wider band is re-judged with the site's own Ee, Ep.
+// Return: 0 = certainly not contained, 1 = certainly contained, 2 = undecided (exact float64 pass decides).
+// ---------------------------------------------------------------------------------------------
+struct SabTet5Off { unsigned o0, o1, o2, o3; };
+__device__ __forceinline__ SabTet5Off sab_tet5_unpack(const uint2 r)
+{
+    SabTet5Off o; o.o0 = r.x & 0xffffu; o.o1 = r.x >> 16; o.o2 = r.y & 0xffffu; o.o3 = r.y >> 16;
+    return o;
+}
+
+__device__ __forceinline__ int sab_tet5_slow(float Bx, float By, float Bz, float Cx, float Cy, float Cz, float Dx, float Dy,
+                                          float Dz, float Px, float Py, float Pz, float det, float lb, float lc, float ld, float la)
+{
+    const float Ee = fmaxf(fmaxf(fmaxf(fabsf(Bx), fabsf(By)), fmaxf(fabsf(Bz), fabsf(Cx))),
+                           fmaxf(fmaxf(fabsf(Cy), fabsf(Cz)), fmaxf(fmaxf(fabsf(Dx), fabsf(Dy)), fabsf(Dz))));
+    const float Ep = fmaxf(fabsf(Px), fmaxf(fabsf(Py), fabsf(Pz)));
+    if (!(Ee < 0.5f) || !(Ep < 0.75f)) return 2;                       // not a small site (or NaN): budget void
+    const float T1 = Ee * (56.f * Ep + 32.f * Ee) * SAB_S5_DELTA22;    // 2 x bound
+    const float TD = Ee * Ee * (88.f * SAB_S5_DELTA22);
+    const float T0 = 3.f * T1 + TD;
+    if (!(fabsf(det) > TD)) return 2;                                  // flat tetrahedron: float64 decides
+    if (det < 0.f) { la = -la; lb = -lb; lc = -lc; ld = -ld; }
+    if (lb < -T1 || lc < -T1 || ld < -T1 || la < -T0) return 0;
+    if (lb > T1 && lc > T1 && ld > T1 && la > T0) return 1;
+    return 2;
+}
+
+__device__ __forceinline__ int sab_tet5(const char *__restrict__ rowb, const SabTet5Off &o, const float4 x,
+                                        const float T1, const float T0, const float TD)
+{
+    const float4 a = *reinterpret_cast<const float4 *>(rowb + o.o0), b = *reinterpret_cast<const float4 *>(rowb + o.o1);
+    const float4 c = *reinterpret_cast<const float4 *>(rowb + o.o2), d = *reinterpret_cast<const float4 *>(rowb + o.o3);
+    const float tx = x.x - a.x, ty = x.y - a.y, tz = x.z - a.z;
+    const float Px = tx - rintf(tx), Py = ty - rintf(ty), Pz = tz - rintf(tz);
+    const float Bx = b.x - a.x, By = b.y - a.y, Bz = b.z - a.z;
+    const float Cx = c.x - a.x, Cy = c.y - a.y, Cz = c.z - a.z;
+    const float Dx = d.x - a.x, Dy = d.y - a.y, Dz = d.z - a.z;
+    // explicit FMAs: the library is compiled with -fmad=false for the float64 reference arithmetic
+    const float Qx = __fmaf_rn(Dy, Pz, -(Dz * Py)), Qy = __fmaf_rn(Dz, Px, -(Dx * Pz)), Qz = __fmaf_rn(Dx, Py, -(Dy * Px));   // D x P
+    const float Nx = __fmaf_rn(By, Cz, -(Bz * Cy)), Ny = __fmaf_rn(Bz, Cx, -(Bx * Cz)), Nz = __fmaf_rn(Bx, Cy, -(By * Cx));   // B x C
+    const float lb = __fmaf_rn(Cz, Qz, __fmaf_rn(Cy, Qy, Cx * Qx));
+    const float lc = -__fmaf_rn(Bz, Qz, __fmaf_rn(By, Qy, Bx * Qx));
+    const float ld = __fmaf_rn(Pz, Nz, __fmaf_rn(Py, Ny, Px * Nx));
+    const float det = __fmaf_rn(Dz, Nz, __fmaf_rn(Dy, Ny, Dx * Nx));
+    const float la = (det - lb) - (lc + ld);
+    const float m = fminf(fminf(lb, lc), ld);
+    if (det > TD) {
+        if (m > T1 && la > T0) return 1;
+        if (m < -T1 || la < -T0) return 0;
+    }
+    return sab_tet5_slow(Bx, By, Bz, Cx, Cy, Cz, Dx, Dy, Dz, Px, Py, Pz, det, lb, lc, ld, la);
+}
+
+__device__ __forceinline__ int sab_cell_of_f4(const float4 x, int G)
+{
+    const float g = (float)G;
+    int c0 = min(G - 1, (int)(x.x * g)), c1 = min(G - 1, (int)(x.y * g)), c2 = min(G - 1, (int)(x.z * g));
+    return (c0 * G + c1) * G + c2;
+}
+
+template <bool ONE_GROUP, bool REC_SMEM>
+__global__ void __launch_bounds__(SAB_S5_MAXTHREADS, SAB_S5_MINBLOCKS)
+k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, int64_t chunk, int n_atoms, int n_mobile,
+                            const int32_t *__restrict__ mobile, int n_sites, SabPolyTables T, SabStream5Tables C,
+                            int64_t legacy_init_frame, int32_t *__restrict__ result,
+                            unsigned long long *__restrict__ counters, unsigned long long *__restrict__ n_fallback)
+{
+    extern __shared__ __align__(128) unsigned char sm_s5[];
+    const int n3 = 3 * n_atoms, m3 = C.m3;
+    double *rawd = reinterpret_cast<double *>(sm_s5);                                        // [n_raw][n3] raw frames (copy engine)
+    float4 *rows = reinterpret_cast<float4 *>(rawd + (((size_t)C.n_raw * n3 + 1) & ~(size_t)1)); // [n_rows][stride4]
+    int4 *s_task = reinterpret_cast<int4 *>(rows + (size_t)C.n_rows * C.stride4);           // [n_task]
+    float4 *s_tanc = reinterpret_cast<float4 *>(s_task + C.n_task);                          // [n_task]
+    float4 *s_shift = s_tanc + C.n_task;                                                     // [n_img]
+    uint2 *s_rec = reinterpret_cast<uint2 *>(s_shift + C.n_img);                             // [S] (REC_SMEM)
+    int2 *last = reinterpret_cast<int2 *>(s_rec + (REC_SMEM ? n_sites : 0));                 // [A] (!ONE_GROUP)
+    int *s_mobcol = reinterpret_cast<int *>(last + (ONE_GROUP ? 0 : n_mobile));              // [A] 3 * structure index
+    __shared__ __align__(8) uint64_t raw_full[SAB_S5_MAXRAW], row_full[SAB_S5_MAXROWS], row_empty[SAB_S5_MAXROWS];
+    __shared__ int pbad[4], rowflag[SAB_S5_MAXROWS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_prod_thr = C.n_prod * 32, n_cons = (blockDim.x >> 5) - C.n_prod, n_cons_thr = n_cons * 32;
+    const int RS = C.n_raw, ROWS = C.n_rows;
+    const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
+
+    // ---- one-time setup (all threads) ----------------------------------------------------------------------
+    for (int t = tid; t < C.n_task; t += blockDim.x) { s_task[t] = C.task[t]; s_tanc[t] = C.task_anchor[t]; }
+    for (int i = tid; i < C.n_img; i += blockDim.x) s_shift[i] = C.img_shift[i];
+    for (int q = tid; q < n_mobile; q += blockDim.x) s_mobcol[q] = mobile[q] * 3;
+    if (REC_SMEM) for (int i = tid; i < n_sites; i += blockDim.x) s_rec[i] = C.rec[i];
+    const uint2 *recs = REC_SMEM ? s_rec : C.rec;
+    if (tid == 0) {
+        for (int i = 0; i < SAB_S5_MAXRAW; i++) sab_mbar_init(&raw_full[i], 1);
+        for (int i = 0; i < SAB_S5_MAXROWS; i++) { sab_mbar_init(&row_full[i], C.n_prod); sab_mbar_init(&row_empty[i], n_cons); rowflag[i] = 0; }
+        for (int i = 0; i < 4; i++) pbad[i] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < C.n_prod) {
+        // =========================================== producers ===========================================
+        const int pt = tid;
+        const unsigned frame_bytes = (unsigned)((size_t)n3 * 8);
+        auto issue = [&](int64_t f, int slot) {                 // thread 0 only: raw frame f -> raw slot
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            sab_mbar_expect_tx(&raw_full[slot], frame_bytes);
+            sab_bulk_g2s(rawd + (size_t)slot * n3, frac + (size_t)f * n3, frame_bytes, &raw_full[slot]);
+        };
+        unsigned it = 0;                                        // frames processed by this CTA so far
+        int rslot = 0, wslot = 0;                               // ring positions of frame `it`
+        unsigned rpar = 0, wpar = 0;                            // phase parities: (it / RS) & 1, (it / ROWS) & 1
+        for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
+            sab_bar_producers(n_prod_thr);                      // previous chunk fully converted: raw slots idle
+            if (pt == 0 && C.use_tma)
+                for (int i = 0; i < RS - 1 && c0 + i < c1; i++) issue(c0 + i, (rslot + i) % RS);
+            // excursion of a chunk whose frames stay inside the validity tube (frames outside widen it below)
+            for (int j = pt; j < m3; j += n_prod_thr) {
+                const double anc = C.anchor[j];
+                C.chunk_exc[((size_t)ch * m3 + j) * 2] = anc - C.delta_d;
+                C.chunk_exc[((size_t)ch * m3 + j) * 2 + 1] = anc + C.delta_d;
+            }
+            for (int64_t f = c0; f < c1; f++, it++) {
+                double *raw = rawd + (size_t)rslot * n3;
+                if (C.use_tma) sab_mbar_wait_backoff(&raw_full[rslot], rpar);
+                else {                                          // frames the copy engine cannot take: plain loads
+                    const double *g = frac + (size_t)f * n3;
+                    for (int q = pt; q < n3; q += n_prod_thr) raw[q] = g[q];
+                    sab_bar_producers(n_prod_thr);
+                }
+                if (it >= (unsigned)ROWS) sab_mbar_wait_backoff(&row_empty[wslot], wpar ^ 1u);
+                float4 *row = rows + (size_t)wslot * C.stride4;
+                // ---- framework atoms -> vertex images ------------------------------------------------------
+                int bad = 0;
+                for (int t = pt; t < C.n_task; t += n_prod_thr) {
+                    const int4 tk = s_task[t];
+                    const float4 an = s_tanc[t];
+                    const double r0 = raw[tk.x], r1 = raw[tk.x + 1], r2 = raw[tk.x + 2];
+                    const float f0 = (float)(r0 - rint(r0 - (double)an.x));       // u = raw - W, W = rint(raw - anchor)
+                    const float f1 = (float)(r1 - rint(r1 - (double)an.y));
+                    const float f2 = (float)(r2 - rint(r2 - (double)an.z));
+                    bad |= (fabsf(f0 - an.x) > C.delta_f) | (fabsf(f1 - an.y) > C.delta_f) | (fabsf(f2 - an.z) > C.delta_f);
+                    for (int i = 0; i < tk.z; i++) {
+                        const float4 sh = s_shift[tk.y + i];
+                        row[tk.y + i] = make_float4(f0 + sh.x, f1 + sh.y, f2 + sh.z, 0.f);   // raw + (shift - W), pbc_utils.py:220
+                    }
+                }
+                for (int q = pt; q < n_mobile; q += n_prod_thr) {
+                    const int col = s_mobcol[q];
+                    const double x0 = raw[col], x1 = raw[col + 1], x2 = raw[col + 2];
+                    row[C.n_img + q] = make_float4((float)(x0 - floor(x0)), (float)(x1 - floor(x1)), (float)(x2 - floor(x2)), 0.f);   // atom.py:104
+                }
+                if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&pbad[it & 3], 1);
+                sab_bar_producers(n_prod_thr);                  // pbad complete; everybody is done with the frame before
+                const int tube_bad = pbad[it & 3];
+                const bool explicit_check = tube_bad || f == c0 || pbad[(it + 3) & 3];
+                const int pslot = rslot == 0 ? RS - 1 : rslot - 1;           // raw slot of frame f - 1 = slot of frame f + RS - 1
+                if (pt == 0) {
+                    pbad[(it + 2) & 3] = 0;
+                    const int flag = tube_bad || (T.legacy_init && legacy_init_frame == f);
+                    rowflag[wslot] = flag;
+                    if (flag) {                                 // outside the validity tube (or the legacy first-frame rule):
+                        atomicAdd(n_fallback, 1ULL);            // the whole frame goes to the generic pass after this kernel
+                        C.flagged[atomicAdd(&counters[SAB_CNT_FLAGGED], 1ULL)] = (long long)f;
+                    }
+                    if (!explicit_check && C.use_tma && f + RS - 1 < c1) issue(f + RS - 1, pslot);
+                }
+                if (explicit_check) {                           // chain check against the reference's sequential update
+                    const double *praw = rawd + (size_t)pslot * n3;                                   // frame f - 1 (f > c0)
+                    for (int j = pt; j < m3; j += n_prod_thr) {
+                        const int col = C.fw_atoms[j / 3] * 3 + j % 3;
+                        const double r = raw[col], anc = C.anchor[j];
+                        double p; int Wp;
+                        if (f > c0) { p = praw[col]; Wp = (int)rint(p - anc); }
+                        else if (c0 == 0) { p = C.prev_raw[j]; Wp = C.wraps[j]; }
+                        else { p = frac[(size_t)(c0 - 1) * n3 + col]; Wp = (int)rint(p - anc); }
+                        const double diff = r - p, w = rint(diff), phys = diff - w;          // pbc_utils.py:210-216
+                        if ((phys >= 0.3 || phys <= -0.3) && !(C.skip_check_frame0 && f == 0))
+                            atomicMin(&counters[3], (unsigned long long)f);
+                        if ((int)rint(r - anc) - Wp != (int)w) counters[SAB_CNT_INVALID] = 1ULL;
+                        if (tube_bad) {                         // outside the tube: the excursion record is explicit
+                            const double u = r - rint(r - anc);
+                            double *e2 = C.chunk_exc + ((size_t)ch * m3 + j) * 2;      // column j is owned by this thread
+                            if (u < e2[0]) e2[0] = u;
+                            if (u > e2[1]) e2[1] = u;
+                        }
+                    }
+                    if (C.use_tma) {
+                        sab_bar_producers(n_prod_thr);          // frame f - 1 no longer needed
+                        if (pt == 0 && f + RS - 1 < c1) issue(f + RS - 1, pslot);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) sab_mbar_arrive(&row_full[wslot]);
+                if (++rslot == RS) { rslot = 0; rpar ^= 1u; }
+                if (++wslot == ROWS) { wslot = 0; wpar ^= 1u; }
+            }
+        }
+    } else {
+        // =========================================== consumers ===========================================
+        const int cw = warp - C.n_prod;
+        const unsigned FULL = 0xffffffffu;
+        const float T1 = C.T1, T0 = C.T0, TD = C.TD;
+        int wslot = 0; unsigned wpar = 0;
+        for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
+            if (!ONE_GROUP)
+                for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = make_int2(-1, -1);   // owner-private
+            int rcx = -1, rcy = -1;                             // {most recent, previous} site as far as certain, -1 = unknown
+            SabTet5Off ofs = {0u, 0u, 0u, 0u};                  // record of rcx (ONE_GROUP: carried from frame to frame)
+            for (int64_t f = c0; f < c1; f++) {
+                sab_mbar_wait_backoff(&row_full[wslot], wpar);
+                const char *rowb = reinterpret_cast<const char *>(rows + (size_t)wslot * C.stride4);
+                const float4 *xrow = reinterpret_cast<const float4 *>(rowb) + C.n_img;
+                const int flag = rowflag[wslot];
+                int32_t *res = result + (size_t)f * n_mobile;
+                for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {
+                    const int a = g0 + lane;
+                    const bool valid = a < n_mobile;
+                    if (!ONE_GROUP) {
+                        const int2 rc = valid ? last[a] : make_int2(-1, -1);
+                        rcx = rc.x; rcy = rc.y;
+                        if (rcx >= 0) ofs = sab_tet5_unpack(recs[rcx]);
+                    }
+                    const float4 x = xrow[valid ? a : 0];
+                    int out = SAB_NONE;
+                    bool dirty = false;                          // rcx changed: its record must be reloaded
+                    // a definite site h: Atom.update_recent_site (atom.py:189-192)
+                    #define SAB_RECENT_PUSH(h) do { if ((h) != rcx) { rcy = rcx; rcx = (h); dirty = true; } } while (0)
+                    if (flag) {                                  // outside the validity tube: k_polyhedral_flagged writes the row;
+                        if (rcx >= 0) dirty = true;              // the history restarts (any shortcut below needs a certain one)
+                        rcx = -1; rcy = -1;
+                    } else {
+                        int v = 0;
+                        if (valid && rcx >= 0 && C.use_f32) v = sab_tet5(rowb, ofs, x, T1, T0, TD);
+                        if (v == 1) out = rcx;
+                        // most recent site certainly failed: the reference tests the previous one next
+                        const bool second = valid && v == 0 && rcx >= 0 && rcy >= 0;
+                        if (__any_sync(FULL, second)) {
+                            if (second) {
+                                const SabTet5Off o2 = sab_tet5_unpack(recs[rcy]);
+                                if (sab_tet5(rowb, o2, x, T1, T0, TD) == 1) {
+                                    out = rcy; const int t = rcx; rcx = rcy; rcy = t; ofs = o2; v = 1;
+                                }
+                            }
+                        }
+                        unsigned m = __ballot_sync(FULL, valid && v != 1);
+                        while (m) {                              // warp-uniform: one search per atom that needs it
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float4 xs = xrow[g0 + src];
+                            const int cell = sab_cell_of_f4(xs, C.G);
+                            const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
+                            int c = 0, h0 = -1;
+                            unsigned und = C.use_f32 ? 0u : 1u;
+                            if (C.use_f32)
+                                for (int i0 = 0; i0 < len; i0 += 32) {
+                                    const int i = i0 + lane;
+                                    int s = 0, vv = 0;
+                                    if (i < len) {
+                                        s = __ldg(C.cell_sites + b + i);
+                                        vv = sab_tet5(rowb, sab_tet5_unpack(recs[s]), xs, T1, T0, TD);
+                                    }
+                                    unsigned m1 = __ballot_sync(FULL, vv == 1);
+                                    und |= __ballot_sync(FULL, vv == 2);
+                                    if (m1 && c == 0) h0 = __shfl_sync(FULL, s, __ffs(m1) - 1);
+                                    c += __popc(m1);
+                                }
+                            if (lane == src) {
+                                if (und || c > 1) {              // float32 could not decide, or several sites: exact pass later
+                                    out = SAB_DEFERRED; rcx = -1; rcy = -1;
+                                    const unsigned long long di = atomicAdd(&counters[9], 1ULL);
+                                    if ((long long)di < C.defer_cap) C.defer[di] = (long long)f * n_mobile + a;
+                                } else if (c == 0) out = SAB_NONE;
+                                else { out = h0; SAB_RECENT_PUSH(h0); }
+                            }
+                        }
+                    }
+                    #undef SAB_RECENT_PUSH
+                    if (valid && !flag) {
+                        res[a] = out;
+                        // fused result all-gather: the same row goes to every peer's copy of the full array (posted NVLink stores)
+                        if (C.n_peer) {
+                            const size_t o = (size_t)f * n_mobile + a;
+#pragma unroll
+                            for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][o] = out;   // static indices: the parameter stays in constant memory
+                        }
+                    }
+                    if (ONE_GROUP) { if (dirty && rcx >= 0) ofs = sab_tet5_unpack(recs[rcx]); }
+                    else if (valid) last[a] = make_int2(rcx, rcy);
+                }
+                __syncwarp();
+                if (lane == 0) sab_mbar_arrive(&row_empty[wslot]);
+                if (++wslot == ROWS) { wslot = 0; wpar ^= 1u; }
+            }
+        }
+    }
+}
+
+// Frames the stream kernel listed as outside the validity tube of its cell lists: every mobile atom against every site
+// with the fully general float64 test (any polyhedron, all 8 images, legacy first-frame rule), one thread per atom-frame.
+__global__ void k_polyhedral_flagged(const double *__restrict__ frac, int n_atoms, int n_mobile, const int32_t *__restrict__ mobile,
+                                     int n_sites, SabPolyTables T, int64_t legacy_init_frame, const long long *__restrict__ flagged,
+                                     int32_t *__restrict__ result, int32_t *__restrict__ spill, long long spill_capacity,
+                                     unsigned long long *__restrict__ counters, const double *__restrict__ anchor, SabPeers peers)
+{
+    const long long n_flag = (long long)counters[SAB_CNT_FLAGGED];
+    const long long total = n_flag * n_mobile;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long f = flagged[i / n_mobile];
+        const int a = (int)(i % n_mobile);
+        int c = 0;
+        const int out = sab_exhaustive_atom(frac + (size_t)f * n_atoms * 3, nullptr, f, legacy_init_frame, mobile[a], n_sites, T,
+                                            spill, spill_capacity, counters, &c, anchor);
+        const size_t o = (size_t)f * n_mobile + a;
+        result[o] = out;
+#pragma unroll
+        for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < peers.n) peers.p[q][o] = out;
+    }
+}

@@ -5,6 +5,7 @@
 #include "../../include/sab200.h"
 
 #include <algorithm>
+#include <array>
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
@@ -21,6 +22,7 @@
 #include "k_polyhedral_seq1.cuh"
 #include "k_polyhedral_tile.cuh"
 #include "k_polyhedral_stream.cuh"
+#include "k_polyhedral_stream5.cuh"
 #include "k_resolve.cuh"
 #include "k_resolve_fast.cuh"
 #include "k_spherical.cuh"
@@ -108,6 +110,12 @@ struct sab_engine {
     int stream_rec_smem = 1;               // SAB_OPT_STREAM_REC_SMEM (1 = site records in shared memory when they fit)
     int stream_reg_cols = 1;               // SAB_OPT_STREAM_REG_COLS (1 = producer column metadata in registers when they fit)
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
+    // generation-5 stream kernel (k_polyhedral_stream5.cuh): vertex-image rows, derived in sab_set_cell_lists
+    bool s5_ok = false; int s5_n_img = 0; int4 *d_s5_task = nullptr; float4 *d_s5_tanc = nullptr, *d_s5_shift = nullptr;
+    uint2 *d_s5_rec = nullptr; float s5_T1 = 0.f, s5_T0 = 0.f, s5_TD = 0.f;
+    int stream_gen = 0;                    // SAB_OPT_STREAM_GEN: 0 automatic (5 when its tables exist), 4 = previous generation
+    int s5_rows = 0, s5_raw = 0, s5_blocks = 0;   // SAB_OPT_STREAM5_ROWS / _RAW / _BLOCKS (0 = automatic)
+    size_t s5_occ_key = 0; int s5_per_sm = 0;
     int n_peer = 0; int32_t *peer[SAB_MAX_PEERS] = {nullptr};   // sab_set_result_peers
     bool peers_written = false;            // the last sab_assign_device stored its rows into the peers as well
     size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
@@ -146,7 +154,8 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_slot_fw, e->d_nface, e->d_simp, e->d_slot_shift, e->d_wraps, e->d_prev_raw, e->d_excursion,
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
-                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec};
+                    e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec,
+                    e->d_s5_task, e->d_s5_tanc, e->d_s5_shift, e->d_s5_rec};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
@@ -359,6 +368,82 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
             e->tile_ok = true;
         }
     }
+    // ---- tables of the generation-5 stream kernel (k_polyhedral_stream5.cuh): one float4 per (framework atom, image shift)
+    e->s5_ok = false;
+    if (e->tile_ok && delta <= 0.12) {
+        const int m3 = 3 * e->M;
+        bool ok = true;
+        for (int i = 0; i < m3; i++) if ((double)(float)anchor[i] != anchor[i]) ok = false;     // anchors travel as float
+        std::vector<std::array<int, 4>> vert((size_t)e->S * 4);                                  // {fw atom, kx, ky, kz}
+        for (int s = 0; s < e->S && ok; s++)
+            for (int v = 0; v < 4; v++) {
+                std::array<int, 4> im{-1, 0, 0, 0};
+                for (int d = 0; d < 3; d++) {
+                    const int idx = records[(size_t)s * SAB_TET_REC + 3 * v + d] / 8, k = idx / m3, i = idx % m3;
+                    if (i % 3 != d || (d > 0 && i / 3 != im[0])) ok = false;
+                    im[0] = i / 3; im[1 + d] = kmin + k;
+                }
+                vert[(size_t)s * 4 + v] = im;
+            }
+        if (ok) {
+            std::vector<std::array<int, 4>> imgs(vert);
+            std::sort(imgs.begin(), imgs.end());
+            imgs.erase(std::unique(imgs.begin(), imgs.end()), imgs.end());
+            std::vector<int> count(e->M, 0), first(e->M, 0);
+            for (auto &im : imgs) count[im[0]]++;
+            std::vector<int> order(e->M);
+            for (int m = 0; m < e->M; m++) order[m] = m;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return count[a] > count[b]; });   // uniform trip counts per warp
+            std::vector<int4> task(e->M); std::vector<float4> tanc(e->M), shift(imgs.size());
+            std::vector<int> img_pos(imgs.size());
+            int next = 0;
+            for (int t = 0; t < e->M; t++) {
+                const int m = order[t];
+                first[m] = next;
+                task[t] = make_int4(e->fw_atoms[m] * 3, next, count[m], 3 * m);
+                tanc[t] = make_float4((float)anchor[3 * m], (float)anchor[3 * m + 1], (float)anchor[3 * m + 2], 0.f);
+                next += count[m];
+            }
+            std::vector<int> seen(e->M, 0);
+            for (size_t i = 0; i < imgs.size(); i++) {                 // imgs sorted by atom: consecutive images of one atom
+                const int m = imgs[i][0];
+                img_pos[i] = first[m] + seen[m]++;
+                shift[img_pos[i]] = make_float4((float)imgs[i][1], (float)imgs[i][2], (float)imgs[i][3], 0.f);
+            }
+            if (imgs.size() * 16 > 65535) ok = false;                  // 16-bit byte offsets into a row
+            std::vector<uint2> rec5(e->S);
+            double ee_max = 0.0;
+            for (int s = 0; s < e->S && ok; s++) {
+                int pos[4]; double P[4][3];
+                for (int v = 0; v < 4; v++) {
+                    const auto &im = vert[(size_t)s * 4 + v];
+                    pos[v] = img_pos[std::lower_bound(imgs.begin(), imgs.end(), im) - imgs.begin()];
+                    for (int d = 0; d < 3; d++) P[v][d] = anchor[3 * im[0] + d] + (double)im[1 + d];
+                }
+                for (int v = 0; v < 4; v++) for (int u = 0; u < v; u++) for (int d = 0; d < 3; d++)
+                    ee_max = std::max(ee_max, fabs(P[v][d] - P[u][d]));
+                double B[3], Cv[3], D[3];
+                for (int d = 0; d < 3; d++) { B[d] = P[1][d] - P[0][d]; Cv[d] = P[2][d] - P[0][d]; D[d] = P[3][d] - P[0][d]; }
+                const double det = D[0] * (B[1] * Cv[2] - B[2] * Cv[1]) + D[1] * (B[2] * Cv[0] - B[0] * Cv[2]) + D[2] * (B[0] * Cv[1] - B[1] * Cv[0]);
+                if (det < 0.0) std::swap(pos[2], pos[3]);              // positively oriented records: no sign flip in the kernel
+                rec5[s].x = (unsigned)(16 * pos[0]) | ((unsigned)(16 * pos[1]) << 16);
+                rec5[s].y = (unsigned)(16 * pos[2]) | ((unsigned)(16 * pos[3]) << 16);
+            }
+            const double ee = ee_max + 2.0 * delta + 1e-5, ep = 0.5 + 1e-6, d22 = 2.384185791015625e-7;
+            if (!(ee < 0.45)) ok = false;
+            if (ok) {
+                const double t1 = 2.0 * (28.0 * ee * ep + 16.0 * ee * ee) * d22 * (1.0 + 1e-5), td = 2.0 * 44.0 * ee * ee * d22 * (1.0 + 1e-5);
+                e->s5_T1 = nextafterf((float)t1, INFINITY); e->s5_TD = nextafterf((float)td, INFINITY);
+                e->s5_T0 = nextafterf((float)(3.0 * (double)e->s5_T1 + (double)e->s5_TD), INFINITY);
+                CU(upload(&e->d_s5_task, task.data(), task.size()));
+                CU(upload(&e->d_s5_tanc, tanc.data(), tanc.size()));
+                CU(upload(&e->d_s5_shift, shift.data(), shift.size()));
+                CU(upload(&e->d_s5_rec, rec5.data(), rec5.size()));
+                e->s5_n_img = (int)imgs.size();
+                e->s5_ok = true;
+            }
+        }
+    }
     return SAB_OK;
 }
 
@@ -429,6 +514,10 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (key == SAB_OPT_STREAM_REG_COLS) { e->stream_reg_cols = value != 0; return SAB_OK; }
     if (key == SAB_OPT_STREAM_PRODUCERS) { if (value < 0 || value > 8) return fail(SAB_EINVAL, "producer warps: 0..8"); e->stream_prod = (int)value; return SAB_OK; }
     if (key == SAB_OPT_FP32_FILTER) { e->fp32_filter = value != 0; return SAB_OK; }
+    if (key == SAB_OPT_STREAM_GEN) { e->stream_gen = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_STREAM5_ROWS) { if (value < 0 || value > SAB_S5_MAXROWS) return fail(SAB_EINVAL, "row slots: 0..%d", SAB_S5_MAXROWS); e->s5_rows = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_STREAM5_RAW) { if (value < 0 || value > SAB_S5_MAXRAW || value == 1) return fail(SAB_EINVAL, "raw slots: 0 or 2..%d", SAB_S5_MAXRAW); e->s5_raw = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_STREAM5_BLOCKS) { if (value < 0 || value > 8) return fail(SAB_EINVAL, "CTAs per SM: 0..8"); e->s5_blocks = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
     return fail(SAB_EINVAL, "unknown option %d", key);
@@ -440,6 +529,7 @@ struct Workspace {
     int64_t exc_chunks = 0;                                   // capacity of chunk_exc in chunks (>= n_chunks; stream kernel: up to 2048)
     int32_t *totals = nullptr; double *chunk_exc = nullptr; int32_t *rows = nullptr;
     long long *defer = nullptr; long long defer_cap = 0;      // deferred atom-frames of the tile kernel
+    long long *flagged = nullptr;                             // [F] frames the generation-5 stream kernel hands to the generic pass
     size_t bytes = 0;
 };
 
@@ -460,6 +550,7 @@ static Workspace layout(const sab_engine *e, int64_t F, void *base)
     if (e->kind == SAB_POLYHEDRAL) {
         w.defer_cap = std::max<long long>(4096, (long long)F * e->A / 16);
         w.defer = (long long *)(b + off); off += align256(sizeof(long long) * (size_t)w.defer_cap);
+        w.flagged = (long long *)(b + off); off += align256(sizeof(long long) * (size_t)F);
     }
     w.bytes = off + 256;
     return w;
@@ -609,6 +700,104 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
     k_wrap_commit_stream<<<(w.m3 + 31) / 32, 32 * SAB_COMMIT_GROUPS, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, (int)n_chunks, w.chunk_exc, e->d_anchor,
         e->d_prev_raw, e->d_wraps, e->d_excursion, e->d_counters);
     e->launches += 3;
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
+
+// ---------------------------------------------------------------- generation-5 stream kernel (vertex-image rows)
+struct StreamPlan5 { bool ok = false; int n_prod = 0, n_cons = 0, n_raw = 0, n_rows = 0, use_tma = 0, rec_smem = 0, one_group = 0;
+                     size_t smem = 0; int stride4 = 0; int64_t chunk = 0; int grid = 0; };
+
+template <bool OG, bool RS> static const void *stream5_fn() { return (const void *)k_polyhedral_assign_stream5<OG, RS>; }
+static const void *stream5_kernel(int one_group, int rec_smem)
+{
+    return one_group ? (rec_smem ? stream5_fn<true, true>() : stream5_fn<true, false>())
+                     : (rec_smem ? stream5_fn<false, true>() : stream5_fn<false, false>());
+}
+
+static StreamPlan5 plan_stream5(sab_engine *e, const double *d_frac, int64_t F, const Workspace &w)
+{
+    StreamPlan5 p;
+    if (e->kind != SAB_POLYHEDRAL || !e->cells_set || !e->s5_ok || e->poly_kernel != 0 || e->stream_gen == 4 || e->force_scan || !w.defer) return p;
+    p.n_cons = std::min(6, (e->A + 31) / 32);
+    p.n_prod = e->stream_prod > 0 ? e->stream_prod : std::max(1, (p.n_cons + 2) / 3);      // measured: 2 producers for 6 consumers
+    if ((p.n_prod + p.n_cons) * 32 > SAB_S5_MAXTHREADS) p.n_prod = SAB_S5_MAXTHREADS / 32 - p.n_cons;
+    if (p.n_prod < 1) return p;
+    p.one_group = e->A <= p.n_cons * 32 ? 1 : 0;
+    const size_t n3 = 3 * (size_t)e->N;
+    p.stride4 = e->s5_n_img + e->A;
+    p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
+    auto smem_for = [&](int n_raw, int n_rows, int rec_smem) {
+        return sizeof(double) * (((size_t)n_raw * n3 + 1) & ~(size_t)1) + 16 * (size_t)n_rows * p.stride4 + 32 * (size_t)e->M +
+               16 * (size_t)e->s5_n_img + (rec_smem ? 8 * (size_t)e->S : 0) + (p.one_group ? 0 : 8 * (size_t)e->A) + 4 * (size_t)e->A + 128;
+    };
+    // shared-memory plan: as many resident CTAs per SM as SAB_S5_MINBLOCKS allows, rings as deep as then fit
+    static const int shapes[][2] = {{3, 4}, {3, 3}, {2, 3}, {2, 2}};        // {raw slots, row slots}, preference order
+    static const int shapes_big[][2] = {{4, 6}, {3, 6}, {3, 4}, {3, 3}, {2, 3}, {2, 2}};
+    bool found = false;
+    for (int blocks = e->s5_blocks > 0 ? e->s5_blocks : SAB_S5_MINBLOCKS; blocks >= 1 && !found; blocks--) {
+        const size_t budget = (size_t)(228 * 1024) / blocks - 1024 - 512;   // 1 KB per CTA is reserved by the system; static barriers
+        const int (*sh)[2] = blocks >= 3 ? shapes : shapes_big;
+        const int n_sh = blocks >= 3 ? 4 : 6;
+        for (int rec = e->stream_rec_smem ? 1 : 0; rec >= 0 && !found; rec--)
+            for (int i = 0; i < n_sh && !found; i++) {
+                const int raw = e->s5_raw > 0 ? e->s5_raw : sh[i][0], rows = e->s5_rows > 0 ? e->s5_rows : sh[i][1];
+                if (smem_for(raw, rows, rec) <= std::min(budget, (size_t)(227 * 1024))) { p.n_raw = raw; p.n_rows = rows; p.rec_smem = rec; found = true; }
+            }
+    }
+    if (!found) return p;
+    p.smem = smem_for(p.n_raw, p.n_rows, p.rec_smem);
+    const int threads = (p.n_prod + p.n_cons) * 32;
+    const size_t key = (p.smem << 14) | (size_t)threads << 2 | (size_t)p.rec_smem << 1 | (size_t)p.one_group;
+    if (key != e->s5_occ_key) {
+        const void *fn = stream5_kernel(p.one_group, p.rec_smem);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
+        int q = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, threads, p.smem) != cudaSuccess) { cudaGetLastError(); return p; }
+        e->s5_per_sm = q; e->s5_occ_key = key;
+    }
+    const int64_t resident = (int64_t)std::max(1, e->s5_per_sm) * e->sm_count;
+    p.chunk = e->seq_chunk > 0 ? e->seq_chunk : std::max<int64_t>(1, (F + resident - 1) / resident);
+    const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
+    if (n_chunks > w.exc_chunks) return p;
+    p.grid = (int)std::min<int64_t>(n_chunks, resident);
+    p.ok = true;
+    return p;
+}
+
+static int launch_stream5(sab_engine *e, const StreamPlan5 &p, const double *d_frac, int64_t F, int32_t *d_result,
+                          int32_t *d_spill, int64_t spill_cap, const Workspace &w, cudaStream_t st)
+{
+    SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp, e->d_legacy_init};
+    SabStream5Tables C{};
+    C.n_img = e->s5_n_img; C.n_task = e->M; C.stride4 = p.stride4; C.m3 = 3 * e->M;
+    C.task = e->d_s5_task; C.task_anchor = e->d_s5_tanc; C.img_shift = e->d_s5_shift; C.rec = e->d_s5_rec;
+    C.G = e->G; C.cell_off = e->d_cell_off; C.cell_sites = e->d_cell_sites;
+    C.delta_f = (float)e->delta - 4e-7f; C.T1 = e->s5_T1; C.T0 = e->s5_T0; C.TD = e->s5_TD;
+    C.use_f32 = e->fp32_filter; C.defer = w.defer; C.defer_cap = w.defer_cap; C.flagged = w.flagged;
+    C.anchor = e->d_anchor; C.fw_atoms = e->d_fw_atoms; C.prev_raw = e->d_prev_raw; C.wraps = e->d_wraps;
+    C.skip_check_frame0 = e->skip_step_check_once ? 1 : 0;
+    C.n_raw = p.n_raw; C.n_rows = p.n_rows; C.n_prod = p.n_prod; C.use_tma = p.use_tma;
+    C.chunk_exc = w.chunk_exc; C.delta_d = e->delta; C.n_peer = e->n_peer;
+    SabPeers peers{e->n_peer, {nullptr}};
+    for (int q = 0; q < e->n_peer; q++) { C.peer[q] = e->peer[q]; peers.p[q] = e->peer[q]; }
+    e->peers_written = e->n_peer > 0;
+    const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
+    const int threads = (p.n_prod + p.n_cons) * 32;
+#define SAB_LAUNCH5(OG, RS) k_polyhedral_assign_stream5<OG, RS><<<p.grid, threads, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, \
+        e->S, T, C, e->legacy_init_frame, d_result, e->d_counters, e->d_counters + CNT_FULL27)
+    if (p.one_group) { if (p.rec_smem) SAB_LAUNCH5(true, true); else SAB_LAUNCH5(true, false); }
+    else { if (p.rec_smem) SAB_LAUNCH5(false, true); else SAB_LAUNCH5(false, false); }
+#undef SAB_LAUNCH5
+    // frames outside the validity tube: generic all-sites pass (returns at once when there are none)
+    k_polyhedral_flagged<<<e->sm_count * 4, 128, 0, st>>>(d_frac, e->N, e->A, e->d_mobile, e->S, T, e->legacy_init_frame, w.flagged,
+        d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor, peers);
+    // exact float64 pass over the atom-frames float32 could not decide (returns at once when there are none)
+    k_polyhedral_deferred<<<e->sm_count * 8, 256, 0, st>>>(d_frac, F, e->N, e->A, e->d_mobile, T, e->G, e->d_cell_off,
+        e->d_cell_sites, nullptr, 3 * e->M, w.defer, w.defer_cap, d_result, d_spill, (long long)spill_cap, e->d_counters, e->d_anchor, peers);
+    k_wrap_commit_stream<<<(w.m3 + 31) / 32, 32 * SAB_COMMIT_GROUPS, 0, st>>>(d_frac, F, e->N, e->d_fw_atoms, w.m3, (int)n_chunks, w.chunk_exc, e->d_anchor,
+        e->d_prev_raw, e->d_wraps, e->d_excursion, e->d_counters);
+    e->launches += 4;
     CU(cudaGetLastError());
     return SAB_OK;
 }
@@ -815,10 +1004,13 @@ extern "C" int sab_assign_device(sab_engine *e, const double *d_frac, const doub
     for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
     CU(cudaEventRecord(e->ev_t[0], st));
     // tetrahedral sites: one fused kernel (wrap scan + assignment + commit); everything else: scan kernels, then assignment
-    const StreamPlan sp = plan_stream(e, d_frac, n_frames, w);
+    const StreamPlan5 sp5 = plan_stream5(e, d_frac, n_frames, w);
+    StreamPlan sp;
+    if (sp5.ok) sp.ok = true; else sp = plan_stream(e, d_frac, n_frames, w);
     if (!sp.ok && w.m3) { run_wrap_pass(e, d_frac, n_frames, w, st, true); CU(cudaGetLastError()); }
     CU(cudaEventRecord(e->ev_t[1], st));
-    rc = sp.ok ? launch_stream(e, sp, d_frac, n_frames, d_result, d_spill, spill_capacity, w, st)
+    rc = sp5.ok ? launch_stream5(e, sp5, d_frac, n_frames, d_result, d_spill, spill_capacity, w, st)
+       : sp.ok ? launch_stream(e, sp, d_frac, n_frames, d_result, d_spill, spill_capacity, w, st)
                : launch_assign(e, d_frac, d_lattice, lattice_stride, n_frames, d_result, d_spill, spill_capacity, w, st, nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev_t[2], st));

@@ -343,7 +343,9 @@ class AssignmentEngine:
             exc[..., 0] = np.minimum(exc[..., 0], self._seen_exc[..., 0])
             exc[..., 1] = np.maximum(exc[..., 1], self._seen_exc[..., 1])
         self._seen_exc = exc
-        anchor = np.ascontiguousarray(0.5 * (exc[..., 0] + exc[..., 1]))
+        # anchors travel to the stream kernel's producers as float: keep them exactly representable (the tube's
+        # margin dwarfs the 6e-8 relative rounding; every kernel uses the same rounded value)
+        anchor = np.ascontiguousarray((0.5 * (exc[..., 0] + exc[..., 1])).astype(np.float32).astype(np.float64))
         delta = float(max(margin * (exc[..., 1] - exc[..., 0]).max() + 1e-6, 5e-3))
         ss = self.slot_shift[:, :4, :].astype(np.int64)
         kmin, kmax = int(ss.min()), int(ss.max())

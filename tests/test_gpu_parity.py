@@ -117,6 +117,11 @@ def test_pruned_kernel_equals_exhaustive_kernel(oracle_mod, name):
                             (True, {nat.OPT_POLY_KERNEL: 5}), (True, {nat.OPT_POLY_KERNEL: 5, nat.OPT_SEQ_CHUNK: 7}),
                             (True, {nat.OPT_POLY_KERNEL: 5, nat.OPT_FP32_FILTER: 0}),
                             (True, {nat.OPT_STREAM_PRODUCERS: 1, nat.OPT_SEQ_CHUNK: 5}), (True, {nat.OPT_STREAM_PRODUCERS: 4, nat.OPT_STREAM_REC_SMEM: 0}),
+                            # generation 4 of the stream kernel (the default is generation 5) and other ring shapes of generation 5
+                            (True, {nat.OPT_STREAM_GEN: 4}), (True, {nat.OPT_STREAM_GEN: 4, nat.OPT_SEQ_CHUNK: 7}),
+                            (True, {nat.OPT_STREAM_GEN: 4, nat.OPT_FP32_FILTER: 0}),
+                            (True, {nat.OPT_STREAM5_RAW: 2, nat.OPT_STREAM5_ROWS: 2, nat.OPT_SEQ_CHUNK: 5}),
+                            (True, {nat.OPT_STREAM5_BLOCKS: 1, nat.OPT_STREAM5_RAW: 4, nat.OPT_STREAM5_ROWS: 8, nat.OPT_STREAM_REC_SMEM: 0}),
                             (False, {})):
         t = trajectory_from_case(case)
         t.site_collection.use_cells = use_cells
@@ -348,8 +353,11 @@ def test_fp32_pretest_never_changes_a_result():
     kw = lambda: syn.polyhedral_engine_kwargs(g, frac[0], lat[0])                # noqa: E731
     want = bench.oracle_for(g, frac[0], lat[0])().run(frac, lat, positions=True)
     outs = []
-    for kernel, flt in ((0, 1), (0, 0), (5, 1), (5, 0), (4, 1), (4, 0)):   # stream / tile / chunk-sequential kernel
+    for kernel, flt in ((0, 1), (0, 0), (5, 1), (5, 0), (4, 1), (4, 0), (-4, 1), (-4, 0)):   # stream gen 5 / tile / chunk-sequential / stream gen 4
         eng = AssignmentEngine("polyhedral", g.n_atoms, mob, device=0, **kw())
+        if kernel < 0:
+            eng.set_option(nat.OPT_STREAM_GEN, -kernel)
+            kernel = 0
         eng.set_option(nat.OPT_POLY_KERNEL, kernel)
         eng.set_option(nat.OPT_FP32_FILTER, flt)
         outs.append(eng.assign(frac, lat))
@@ -375,9 +383,11 @@ def test_stream_kernel_chain_check_falls_back_to_the_scan_kernels():
     frac[:, victim, 0] = (frac[:, victim, 0] + drift) % 1.0
     kw = lambda: syn.polyhedral_engine_kwargs(g, frac[0], lat[0])                # noqa: E731
     outs, redo = [], []
-    for kernel in (0, 5, 4):
+    for kernel in (0, 5, 4, -4):
         eng = AssignmentEngine("polyhedral", g.n_atoms, g.mobile_idx, device=0, strict=False, **kw())
-        eng.set_option(nat.OPT_POLY_KERNEL, kernel)
+        if kernel < 0:
+            eng.set_option(nat.OPT_STREAM_GEN, -kernel)
+        eng.set_option(nat.OPT_POLY_KERNEL, max(kernel, 0))
         parts = []
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -385,9 +395,9 @@ def test_stream_kernel_chain_check_falls_back_to_the_scan_kernels():
                 parts.append(eng.assign(frac[a:b], lat[a:b]))
                 redo.append((kernel, eng.last_info.get("scan_redo", 0)))
         outs.append(np.concatenate(parts))
-    assert (0, 1) in redo, redo                              # the stream kernel did hit its fallback
-    assert all(r == 0 for k, r in redo if k != 0), redo
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert (0, 1) in redo and (-4, 1) in redo, redo          # both stream kernels did hit their fallback
+    assert all(r == 0 for k, r in redo if k > 0), redo
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
 
 
 def test_fast_path_is_the_one_that_runs():
