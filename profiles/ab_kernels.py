@@ -13,20 +13,15 @@ d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
 VARIANTS = [("stream gen 4 (round 1)", {nat.OPT_STREAM_GEN: 4}), ("stream gen 5 (default)", {}),
-            ("gen 5, 1 producer warp", {nat.OPT_STREAM_PRODUCERS: 1}), ("gen 5, 3 producer warps (needs 288 threads)", {nat.OPT_STREAM_PRODUCERS: 3}),
-            ("gen 5, records via L1", {nat.OPT_STREAM_REC_SMEM: 0}),
+            ("gen 5, 1 producer warp", {nat.OPT_STREAM_PRODUCERS: 1}),
+            ("gen 5, records in smem, 2 raw 3 rows", {nat.OPT_STREAM5_RAW: 2, nat.OPT_STREAM5_ROWS: 3}),
             ("gen 5, 2 CTAs/SM, 4 raw, 6 rows", {nat.OPT_STREAM5_BLOCKS: 2}),
             ("gen 5, 2 CTAs/SM, 3 raw, 4 rows", {nat.OPT_STREAM5_BLOCKS: 2, nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 4}),
-            ("gen 5, 3 CTAs/SM, 3 raw, 3 rows", {nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 3}),
-            ("gen 5, 3 CTAs/SM, 2 raw, 4 rows", {nat.OPT_STREAM5_RAW: 2, nat.OPT_STREAM5_ROWS: 4}),
-            ("gen 5, 4 CTAs/SM, 2 raw, 3 rows, L1 records", {nat.OPT_STREAM5_BLOCKS: 4, nat.OPT_STREAM5_RAW: 2, nat.OPT_STREAM5_ROWS: 3, nat.OPT_STREAM_REC_SMEM: 0}),
-            ("gen 5, fp64 only", {nat.OPT_FP32_FILTER: 0}),
+            ("gen 5, 3 raw, 2 rows", {nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 2}),
+            ("gen 5, chunk 128", {nat.OPT_SEQ_CHUNK: 128}),
+            ("gen 5, 4 CTAs/SM (64-register build only)", {nat.OPT_STREAM5_BLOCKS: 4}),
             ("tile kernel + wrap scan", {nat.OPT_POLY_KERNEL: 5}), ("stream kernel gen 4 again", {nat.OPT_STREAM_GEN: 4}),
-            ("stream, column metadata in shared memory", {nat.OPT_STREAM_REG_COLS: 0}),
-            ("stream, 6 producer warps (needs a 384-thread build)", {nat.OPT_STREAM_PRODUCERS: 6}),
-            ("stream, 3 producer warps", {nat.OPT_STREAM_PRODUCERS: 3}), ("stream, 2 producer warps", {nat.OPT_STREAM_PRODUCERS: 2}),
-            ("stream, records via L1", {nat.OPT_STREAM_REC_SMEM: 0}),
-            ("stream, chunk 128", {nat.OPT_SEQ_CHUNK: 128}), ("stream, fp64 only", {nat.OPT_FP32_FILTER: 0}),
+            ("gen 5, fp64 only", {nat.OPT_FP32_FILTER: 0}),
             ("seq1 + wrap scan", {nat.OPT_POLY_KERNEL: 4})]
 if len(sys.argv) > 2:
     VARIANTS = VARIANTS[:int(sys.argv[2])]

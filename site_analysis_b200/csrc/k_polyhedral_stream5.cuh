@@ -18,6 +18,9 @@
 //     no longer track the float64 excursion of every coordinate: a frame inside the validity tube
 //     |u - anchor| <= delta <= 0.12 cannot widen the excursion beyond [anchor - delta, anchor + delta], which is what
 //     a chunk reports (guard G1 needs < 0.3); frames outside the tube update it explicitly.
+//     Their metadata sits in registers, every load of a frame is issued before its first use, and rint / floor are two
+//     additions of 1.5 * 2^52 on the FP64 pipe instead of conversion-pipe instructions (one float64 -> float32
+//     conversion per coordinate is all that is left there).
 //   * One mbarrier arrival per WARP (after __syncwarp), ring positions advanced without integer division.
 //
 //   * NO COLD CODE IN THE FRAME LOOP.  Frames outside the validity tube (and the legacy first-frame rule) are only
@@ -41,6 +44,7 @@
 #define SAB_S5_MAXRAW 4
 #define SAB_S5_MAXROWS 8
 #define SAB_CNT_FLAGGED 11        // counters[]: frames handed to k_polyhedral_flagged
+#define SAB_S5_KT 3               // register-resident producer tasks per thread
 #define SAB_S5_DELTA22 2.384185791015625e-7f      // 2^-22: every staged coordinate is within this of its float64 value
 
 struct SabStream5Tables {
@@ -55,7 +59,9 @@ struct SabStream5Tables {
     int G;
     const int32_t *cell_off;      // [G^3 + 1]
     const uint16_t *cell_sites;   // CSR entries, ascending per cell
-    float delta_f;                // validity tube, shrunk by the float error of the check
+    const uint16_t *cell_rec;     // [G^3][32] fixed-size form of the same lists: {length or 0xffff, entries...} (or null)
+    double delta_t;               // validity tube of the producers' check, shrunk by 5e-7 (float rounding of the staged values)
+    int reg_tasks;                // every producer thread owns <= SAB_S5_KT framework atoms and mobile atoms: metadata in registers
     float T1, T0, TD;             // constant thresholds of the pre-test (largest site of the table, |P| <= 1/2)
     int use_f32;
     long long *defer;
@@ -101,6 +107,10 @@ struct SabStream5Tables {
 // Ep = 1/2 (P is a reduced separation); a value inside that wider band is re-judged with the site's own Ee, Ep.
 // Return: 0 = certainly not contained, 1 = certainly contained, 2 = undecided (exact float64 pass decides).
 // ---------------------------------------------------------------------------------------------
+// round-half-even to an integer without the conversion pipe: exact for |x| < 2^51 (double), |x| < 2^22 (float)
+__device__ __forceinline__ double sab_rint_magic(double x) { return (x + 6755399441055744.0) - 6755399441055744.0; }
+__device__ __forceinline__ float sab_rintf_magic(float x) { return (x + 12582912.f) - 12582912.f; }
+
 struct SabTet5Off { unsigned o0, o1, o2, o3; };
 __device__ __forceinline__ SabTet5Off sab_tet5_unpack(const uint2 r)
 {
@@ -131,7 +141,7 @@ __device__ __forceinline__ int sab_tet5(const char *__restrict__ rowb, const Sab
     const float4 a = *reinterpret_cast<const float4 *>(rowb + o.o0), b = *reinterpret_cast<const float4 *>(rowb + o.o1);
     const float4 c = *reinterpret_cast<const float4 *>(rowb + o.o2), d = *reinterpret_cast<const float4 *>(rowb + o.o3);
     const float tx = x.x - a.x, ty = x.y - a.y, tz = x.z - a.z;
-    const float Px = tx - rintf(tx), Py = ty - rintf(ty), Pz = tz - rintf(tz);
+    const float Px = tx - sab_rintf_magic(tx), Py = ty - sab_rintf_magic(ty), Pz = tz - sab_rintf_magic(tz);
     const float Bx = b.x - a.x, By = b.y - a.y, Bz = b.z - a.z;
     const float Cx = c.x - a.x, Cy = c.y - a.y, Cz = c.z - a.z;
     const float Dx = d.x - a.x, Dy = d.y - a.y, Dz = d.z - a.z;
@@ -170,8 +180,8 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
     double *rawd = reinterpret_cast<double *>(sm_s5);                                        // [n_raw][n3] raw frames (copy engine)
     float4 *rows = reinterpret_cast<float4 *>(rawd + (((size_t)C.n_raw * n3 + 1) & ~(size_t)1)); // [n_rows][stride4]
     int4 *s_task = reinterpret_cast<int4 *>(rows + (size_t)C.n_rows * C.stride4);           // [n_task]
-    float4 *s_tanc = reinterpret_cast<float4 *>(s_task + C.n_task);                          // [n_task]
-    float4 *s_shift = s_tanc + C.n_task;                                                     // [n_img]
+    double *s_tanc = reinterpret_cast<double *>(s_task + C.n_task);                          // [n_task][4] anchors (x, y, z, -)
+    float4 *s_shift = reinterpret_cast<float4 *>(s_tanc + 4 * (size_t)C.n_task);             // [n_img]
     uint2 *s_rec = reinterpret_cast<uint2 *>(s_shift + C.n_img);                             // [S] (REC_SMEM)
     int2 *last = reinterpret_cast<int2 *>(s_rec + (REC_SMEM ? n_sites : 0));                 // [A] (!ONE_GROUP)
     int *s_mobcol = reinterpret_cast<int *>(last + (ONE_GROUP ? 0 : n_mobile));              // [A] 3 * structure index
@@ -184,7 +194,11 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
 
     // ---- one-time setup (all threads) ----------------------------------------------------------------------
-    for (int t = tid; t < C.n_task; t += blockDim.x) { s_task[t] = C.task[t]; s_tanc[t] = C.task_anchor[t]; }
+    for (int t = tid; t < C.n_task; t += blockDim.x) {
+        s_task[t] = C.task[t];
+        const float4 an = C.task_anchor[t];
+        s_tanc[4 * t] = (double)an.x; s_tanc[4 * t + 1] = (double)an.y; s_tanc[4 * t + 2] = (double)an.z; s_tanc[4 * t + 3] = 0.0;
+    }
     for (int i = tid; i < C.n_img; i += blockDim.x) s_shift[i] = C.img_shift[i];
     for (int q = tid; q < n_mobile; q += blockDim.x) s_mobcol[q] = mobile[q] * 3;
     if (REC_SMEM) for (int i = tid; i < n_sites; i += blockDim.x) s_rec[i] = C.rec[i];
@@ -206,6 +220,18 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
             sab_mbar_expect_tx(&raw_full[slot], frame_bytes);
             sab_bulk_g2s(rawd + (size_t)slot * n3, frac + (size_t)f * n3, frame_bytes, &raw_full[slot]);
         };
+        // register-resident tasks: thread pt owns framework atoms pt + k n_prod_thr and the same mobile atoms.  A task that
+        // does not exist reads atom 0 against task 0's anchors (any tube violation it reports is a real one), has no images,
+        // and writes the spare float4 at the end of the row.
+        int r_col[SAB_S5_KT], r_img[SAB_S5_KT], r_mcol[SAB_S5_KT];      // r_img: first image | images << 16
+#pragma unroll
+        for (int k = 0; k < SAB_S5_KT; k++) {
+            const int t = pt + k * n_prod_thr;
+            const bool ok = C.reg_tasks && t < C.n_task, okm = C.reg_tasks && t < n_mobile;
+            const int4 tk = ok ? s_task[t] : make_int4(0, 0, 0, 0);
+            r_col[k] = ok ? tk.x : -1; r_img[k] = tk.y | (tk.z << 16);
+            r_mcol[k] = okm ? s_mobcol[t] : -1;
+        }
         unsigned it = 0;                                        // frames processed by this CTA so far
         int rslot = 0, wslot = 0;                               // ring positions of frame `it`
         unsigned rpar = 0, wpar = 0;                            // phase parities: (it / RS) & 1, (it / ROWS) & 1
@@ -230,25 +256,76 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                 }
                 if (it >= (unsigned)ROWS) sab_mbar_wait_backoff(&row_empty[wslot], wpar ^ 1u);
                 float4 *row = rows + (size_t)wslot * C.stride4;
-                // ---- framework atoms -> vertex images ------------------------------------------------------
+                // ---- framework atoms -> vertex images, mobile atoms -> wrapped coordinates -------------------
                 int bad = 0;
-                for (int t = pt; t < C.n_task; t += n_prod_thr) {
-                    const int4 tk = s_task[t];
-                    const float4 an = s_tanc[t];
-                    const double r0 = raw[tk.x], r1 = raw[tk.x + 1], r2 = raw[tk.x + 2];
-                    const float f0 = (float)(r0 - rint(r0 - (double)an.x));       // u = raw - W, W = rint(raw - anchor)
-                    const float f1 = (float)(r1 - rint(r1 - (double)an.y));
-                    const float f2 = (float)(r2 - rint(r2 - (double)an.z));
-                    bad |= (fabsf(f0 - an.x) > C.delta_f) | (fabsf(f1 - an.y) > C.delta_f) | (fabsf(f2 - an.z) > C.delta_f);
-                    for (int i = 0; i < tk.z; i++) {
-                        const float4 sh = s_shift[tk.y + i];
-                        row[tk.y + i] = make_float4(f0 + sh.x, f1 + sh.y, f2 + sh.z, 0.f);   // raw + (shift - W), pbc_utils.py:220
+                if (C.reg_tasks) {                              // every load of the frame is issued before the first use
+                    double rr[SAB_S5_KT][3], aa[SAB_S5_KT][3];
+#pragma unroll
+                    for (int k = 0; k < SAB_S5_KT; k++) {
+                        const int t = r_col[k] >= 0 ? pt + k * n_prod_thr : 0, col = r_col[k] >= 0 ? r_col[k] : s_task[0].x;
+                        const double2 a01 = *reinterpret_cast<const double2 *>(s_tanc + 4 * t);
+                        aa[k][0] = a01.x; aa[k][1] = a01.y; aa[k][2] = s_tanc[4 * t + 2];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) rr[k][d] = raw[col + d];
                     }
-                }
-                for (int q = pt; q < n_mobile; q += n_prod_thr) {
-                    const int col = s_mobcol[q];
-                    const double x0 = raw[col], x1 = raw[col + 1], x2 = raw[col + 2];
-                    row[C.n_img + q] = make_float4((float)(x0 - floor(x0)), (float)(x1 - floor(x1)), (float)(x2 - floor(x2)), 0.f);   // atom.py:104
+#pragma unroll
+                    for (int k = 0; k < SAB_S5_KT; k++) {
+                        float fv[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const double dd = rr[k][d] - aa[k][d], w = sab_rint_magic(dd);       // W = rint(raw - anchor)
+                            bad |= fabs(dd - w) > C.delta_t;
+                            fv[d] = (float)(rr[k][d] - w);                                       // u = raw - W
+                        }
+                        const int i0 = r_img[k] & 0xffff, i1 = i0 + (r_img[k] >> 16);
+                        for (int i = i0; i < i1; i++) {
+                            const float4 sh = s_shift[i];
+                            row[i] = make_float4(fv[0] + sh.x, fv[1] + sh.y, fv[2] + sh.z, 0.f);   // raw + (shift - W), pbc_utils.py:220
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < SAB_S5_KT; k++)
+#pragma unroll
+                        for (int d = 0; d < 3; d++) rr[k][d] = raw[max(r_mcol[k], 0) + d];
+#pragma unroll
+                    for (int k = 0; k < SAB_S5_KT; k++) {
+                        float fv[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {                                            // x - floor(x), atom.py:104
+                            double e = rr[k][d] - sab_rint_magic(rr[k][d]);
+                            if (e < 0.0) e += 1.0;
+                            fv[d] = (float)e;
+                        }
+                        row[r_mcol[k] >= 0 ? C.n_img + pt + k * n_prod_thr : C.stride4 - 1] = make_float4(fv[0], fv[1], fv[2], 0.f);
+                    }
+                } else {
+                    for (int t = pt; t < C.n_task; t += n_prod_thr) {
+                        const int4 tk = s_task[t];
+                        const double a3[3] = {s_tanc[4 * t], s_tanc[4 * t + 1], s_tanc[4 * t + 2]};
+                        float fv[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const double r = raw[tk.x + d], dd = r - a3[d], w = sab_rint_magic(dd);
+                            bad |= fabs(dd - w) > C.delta_t;
+                            fv[d] = (float)(r - w);
+                        }
+                        for (int i = 0; i < tk.z; i++) {
+                            const float4 sh = s_shift[tk.y + i];
+                            row[tk.y + i] = make_float4(fv[0] + sh.x, fv[1] + sh.y, fv[2] + sh.z, 0.f);
+                        }
+                    }
+                    for (int q = pt; q < n_mobile; q += n_prod_thr) {
+                        const int col = s_mobcol[q];
+                        float fv[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const double x = raw[col + d];
+                            double e = x - sab_rint_magic(x);
+                            if (e < 0.0) e += 1.0;
+                            fv[d] = (float)e;
+                        }
+                        row[C.n_img + q] = make_float4(fv[0], fv[1], fv[2], 0.f);
+                    }
                 }
                 if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&pbad[it & 3], 1);
                 sab_bar_producers(n_prod_thr);                  // pbad complete; everybody is done with the frame before
@@ -307,7 +384,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
             if (!ONE_GROUP)
                 for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = make_int2(-1, -1);   // owner-private
             int rcx = -1, rcy = -1;                             // {most recent, previous} site as far as certain, -1 = unknown
-            SabTet5Off ofs = {0u, 0u, 0u, 0u};                  // record of rcx (ONE_GROUP: carried from frame to frame)
+            SabTet5Off ofs = {0u, 0u, 0u, 0u}, ofs2 = {0u, 0u, 0u, 0u};   // records of rcx, rcy (ONE_GROUP: carried from frame to frame)
             for (int64_t f = c0; f < c1; f++) {
                 sab_mbar_wait_backoff(&row_full[wslot], wpar);
                 const char *rowb = reinterpret_cast<const char *>(rows + (size_t)wslot * C.stride4);
@@ -326,7 +403,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                     int out = SAB_NONE;
                     bool dirty = false;                          // rcx changed: its record must be reloaded
                     // a definite site h: Atom.update_recent_site (atom.py:189-192)
-                    #define SAB_RECENT_PUSH(h) do { if ((h) != rcx) { rcy = rcx; rcx = (h); dirty = true; } } while (0)
+                    #define SAB_RECENT_PUSH(h) do { if ((h) != rcx) { rcy = rcx; ofs2 = ofs; rcx = (h); dirty = true; } } while (0)
                     if (flag) {                                  // outside the validity tube: k_polyhedral_flagged writes the row;
                         if (rcx >= 0) dirty = true;              // the history restarts (any shortcut below needs a certain one)
                         rcx = -1; rcy = -1;
@@ -334,25 +411,42 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                         int v = 0;
                         if (valid && rcx >= 0 && C.use_f32) v = sab_tet5(rowb, ofs, x, T1, T0, TD);
                         if (v == 1) out = rcx;
+                        unsigned m = __ballot_sync(FULL, valid && v != 1);
+                        if (m == 0u) goto row_done;              // warp-uniform
+                        const int mycell = sab_cell_of_f4(x, C.G);
+                        if (valid && v != 1 && C.cell_rec)       // the search's list arrives while the previous site is tested
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.cell_rec + (size_t)mycell * 32));
                         // most recent site certainly failed: the reference tests the previous one next
-                        const bool second = valid && v == 0 && rcx >= 0 && rcy >= 0;
-                        if (__any_sync(FULL, second)) {
-                            if (second) {
-                                const SabTet5Off o2 = sab_tet5_unpack(recs[rcy]);
-                                if (sab_tet5(rowb, o2, x, T1, T0, TD) == 1) {
-                                    out = rcy; const int t = rcx; rcx = rcy; rcy = t; ofs = o2; v = 1;
-                                }
+                        if (valid && v == 0 && rcx >= 0 && rcy >= 0) {
+                            if (!ONE_GROUP) ofs2 = sab_tet5_unpack(recs[rcy]);
+                            if (sab_tet5(rowb, ofs2, x, T1, T0, TD) == 1) {
+                                out = rcy; const int t = rcx; rcx = rcy; rcy = t; v = 1;
+                                const SabTet5Off to = ofs; ofs = ofs2; ofs2 = to;
                             }
                         }
-                        unsigned m = __ballot_sync(FULL, valid && v != 1);
+                        m = __ballot_sync(FULL, valid && v != 1);
                         while (m) {                              // warp-uniform: one search per atom that needs it
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
                             const float4 xs = xrow[g0 + src];
-                            const int cell = sab_cell_of_f4(xs, C.G);
-                            const int b = __ldg(C.cell_off + cell), len = __ldg(C.cell_off + cell + 1) - b;
+                            const int cell = __shfl_sync(FULL, mycell, src);
                             int c = 0, h0 = -1;
                             unsigned und = C.use_f32 ? 0u : 1u;
+                            int b = 0, len = -1;
+                            if (C.cell_rec && C.use_f32) {       // fixed-size cell record: one load for length and entries
+                                const int e = __ldg(C.cell_rec + (size_t)cell * 32 + lane);
+                                const int n = __shfl_sync(FULL, e, 0);
+                                if (n <= 31) {
+                                    len = 0;
+                                    int vv = 0;
+                                    if (lane >= 1 && lane <= n) vv = sab_tet5(rowb, sab_tet5_unpack(recs[e]), xs, T1, T0, TD);
+                                    const unsigned m1 = __ballot_sync(FULL, vv == 1);
+                                    und |= __ballot_sync(FULL, vv == 2);
+                                    if (m1) h0 = __shfl_sync(FULL, e, __ffs(m1) - 1);
+                                    c = __popc(m1);
+                                }
+                            }
+                            if (len < 0) { b = __ldg(C.cell_off + cell); len = __ldg(C.cell_off + cell + 1) - b; }   // long list: CSR form
                             if (C.use_f32)
                                 for (int i0 = 0; i0 < len; i0 += 32) {
                                     const int i = i0 + lane;
@@ -376,6 +470,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                             }
                         }
                     }
+                    row_done:
                     #undef SAB_RECENT_PUSH
                     if (valid && !flag) {
                         res[a] = out;

@@ -112,7 +112,7 @@ struct sab_engine {
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
     // generation-5 stream kernel (k_polyhedral_stream5.cuh): vertex-image rows, derived in sab_set_cell_lists
     bool s5_ok = false; int s5_n_img = 0; int4 *d_s5_task = nullptr; float4 *d_s5_tanc = nullptr, *d_s5_shift = nullptr;
-    uint2 *d_s5_rec = nullptr; float s5_T1 = 0.f, s5_T0 = 0.f, s5_TD = 0.f;
+    uint2 *d_s5_rec = nullptr; uint16_t *d_s5_cellrec = nullptr; float s5_T1 = 0.f, s5_T0 = 0.f, s5_TD = 0.f;
     int stream_gen = 0;                    // SAB_OPT_STREAM_GEN: 0 automatic (5 when its tables exist), 4 = previous generation
     int s5_rows = 0, s5_raw = 0, s5_blocks = 0;   // SAB_OPT_STREAM5_ROWS / _RAW / _BLOCKS (0 = automatic)
     size_t s5_occ_key = 0; int s5_per_sm = 0;
@@ -155,7 +155,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec,
-                    e->d_s5_task, e->d_s5_tanc, e->d_s5_shift, e->d_s5_rec};
+                    e->d_s5_task, e->d_s5_tanc, e->d_s5_shift, e->d_s5_rec, e->d_s5_cellrec};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
@@ -439,6 +439,14 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
                 CU(upload(&e->d_s5_tanc, tanc.data(), tanc.size()));
                 CU(upload(&e->d_s5_shift, shift.data(), shift.size()));
                 CU(upload(&e->d_s5_rec, rec5.data(), rec5.size()));
+                // fixed-size cell records: {length, entries...} in 32 uint16 (one 64-byte load per search); 0xffff = use the CSR form
+                std::vector<uint16_t> crec(ncell * 32, 0);
+                for (size_t c = 0; c < ncell; c++) {
+                    const int n = cell_off[c + 1] - cell_off[c];
+                    crec[c * 32] = n <= 31 ? (uint16_t)n : (uint16_t)0xffff;
+                    for (int i = 0; i < std::min(n, 31); i++) crec[c * 32 + 1 + i] = cell_sites[cell_off[c] + i];
+                }
+                CU(upload(&e->d_s5_cellrec, crec.data(), crec.size()));
                 e->s5_n_img = (int)imgs.size();
                 e->s5_ok = true;
             }
@@ -725,10 +733,10 @@ static StreamPlan5 plan_stream5(sab_engine *e, const double *d_frac, int64_t F, 
     if (p.n_prod < 1) return p;
     p.one_group = e->A <= p.n_cons * 32 ? 1 : 0;
     const size_t n3 = 3 * (size_t)e->N;
-    p.stride4 = e->s5_n_img + e->A;
+    p.stride4 = e->s5_n_img + e->A + 1;                                   // one spare float4 behind the mobile atoms
     p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
     auto smem_for = [&](int n_raw, int n_rows, int rec_smem) {
-        return sizeof(double) * (((size_t)n_raw * n3 + 1) & ~(size_t)1) + 16 * (size_t)n_rows * p.stride4 + 32 * (size_t)e->M +
+        return sizeof(double) * (((size_t)n_raw * n3 + 1) & ~(size_t)1) + 16 * (size_t)n_rows * p.stride4 + 48 * (size_t)e->M +
                16 * (size_t)e->s5_n_img + (rec_smem ? 8 * (size_t)e->S : 0) + (p.one_group ? 0 : 8 * (size_t)e->A) + 4 * (size_t)e->A + 128;
     };
     // shared-memory plan: as many resident CTAs per SM as SAB_S5_MINBLOCKS allows, rings as deep as then fit
@@ -736,11 +744,11 @@ static StreamPlan5 plan_stream5(sab_engine *e, const double *d_frac, int64_t F, 
     static const int shapes_big[][2] = {{4, 6}, {3, 6}, {3, 4}, {3, 3}, {2, 3}, {2, 2}};
     bool found = false;
     for (int blocks = e->s5_blocks > 0 ? e->s5_blocks : SAB_S5_MINBLOCKS; blocks >= 1 && !found; blocks--) {
-        const size_t budget = (size_t)(228 * 1024) / blocks - 1024 - 512;   // 1 KB per CTA is reserved by the system; static barriers
+        const size_t budget = (size_t)(228 * 1024) / blocks - 1024 - 320;   // 1 KB per CTA is reserved by the system; static barriers
         const int (*sh)[2] = blocks >= 3 ? shapes : shapes_big;
         const int n_sh = blocks >= 3 ? 4 : 6;
-        for (int rec = e->stream_rec_smem ? 1 : 0; rec >= 0 && !found; rec--)
-            for (int i = 0; i < n_sh && !found; i++) {
+        for (int i = 0; i < n_sh && !found; i++)
+            for (int rec = e->stream_rec_smem ? 1 : 0; rec >= 0 && !found; rec--) {      // deeper rings before records in shared memory
                 const int raw = e->s5_raw > 0 ? e->s5_raw : sh[i][0], rows = e->s5_rows > 0 ? e->s5_rows : sh[i][1];
                 if (smem_for(raw, rows, rec) <= std::min(budget, (size_t)(227 * 1024))) { p.n_raw = raw; p.n_rows = rows; p.rec_smem = rec; found = true; }
             }
@@ -772,8 +780,10 @@ static int launch_stream5(sab_engine *e, const StreamPlan5 &p, const double *d_f
     SabStream5Tables C{};
     C.n_img = e->s5_n_img; C.n_task = e->M; C.stride4 = p.stride4; C.m3 = 3 * e->M;
     C.task = e->d_s5_task; C.task_anchor = e->d_s5_tanc; C.img_shift = e->d_s5_shift; C.rec = e->d_s5_rec;
-    C.G = e->G; C.cell_off = e->d_cell_off; C.cell_sites = e->d_cell_sites;
-    C.delta_f = (float)e->delta - 4e-7f; C.T1 = e->s5_T1; C.T0 = e->s5_T0; C.TD = e->s5_TD;
+    C.G = e->G; C.cell_off = e->d_cell_off; C.cell_sites = e->d_cell_sites; C.cell_rec = e->d_s5_cellrec;
+    C.delta_t = e->delta - 5e-7;
+    C.reg_tasks = (e->M <= SAB_S5_KT * 32 * p.n_prod && e->A <= SAB_S5_KT * 32 * p.n_prod) ? 1 : 0;
+    C.T1 = e->s5_T1; C.T0 = e->s5_T0; C.TD = e->s5_TD;
     C.use_f32 = e->fp32_filter; C.defer = w.defer; C.defer_cap = w.defer_cap; C.flagged = w.flagged;
     C.anchor = e->d_anchor; C.fw_atoms = e->d_fw_atoms; C.prev_raw = e->d_prev_raw; C.wraps = e->d_wraps;
     C.skip_check_frame0 = e->skip_step_check_once ? 1 : 0;
