@@ -13,6 +13,8 @@ d_frac, d_lat = syn.argyrodite_trajectory(g, F, device="cuda")
 kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().numpy())
 ref = None
 VARIANTS = [("stream gen 4 (round 1)", {nat.OPT_STREAM_GEN: 4}), ("stream gen 5 (default)", {}),
+            ("gen 5, 3 producer warps (288-thread build)", {nat.OPT_STREAM_PRODUCERS: 3}),
+            ("gen 5, 4 producer warps (320-thread build)", {nat.OPT_STREAM_PRODUCERS: 4}),
             ("gen 5, 1 producer warp", {nat.OPT_STREAM_PRODUCERS: 1}),
             ("gen 5, records in smem, 2 raw 3 rows", {nat.OPT_STREAM5_RAW: 2, nat.OPT_STREAM5_ROWS: 3}),
             ("gen 5, 2 CTAs/SM, 4 raw, 6 rows", {nat.OPT_STREAM5_BLOCKS: 2}),

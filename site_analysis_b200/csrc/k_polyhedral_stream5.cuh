@@ -1,43 +1,49 @@
 // k_polyhedral_stream5.cuh -- the production tetrahedral kernel, generation 5: the warp-specialised frame
-// pipeline of k_polyhedral_stream.cuh with a third of its instructions.
+// pipeline of k_polyhedral_stream.cuh with less than half of its instructions and shared-memory traffic.
 //
 // Same contract and bit-identical results as k_polyhedral_assign_stream (polyhedral_site_collection.py:86-107 with
 // the "most recent site first" order of site_collection.py:147-152, vertices from pbc_utils.py:193-230, containment
 // polyhedral_site.py:83-123).  What changed, and why (profiles/r1_ncu_full_stream_v4_125kframes.csv: 4,530 warp
-// instructions per frame, issue bound):
+// instructions per frame, issue bound; profiles/r2_ncu_stream5_*.csv for the steps in between):
 //
-//   * STAGED ROWS ARE VERTEX IMAGES.  A row holds one float4 per (framework atom, integer image shift) pair some
-//     site uses, then one float4 per mobile atom.  A site record is four 16-bit byte offsets; a containment test
-//     loads four vertices and the atom with five 128-bit shared loads (was 15 scalar loads + 12 unpack operations).
-//   * THE RECORD OF THE MOST RECENT SITE LIVES IN REGISTERS and is reloaded only when the atom changes site.
-//   * CONSTANT ERROR THRESHOLDS.  The error budget of the FP32 pre-test (below) is evaluated once on the host for
-//     the largest site of the table; only a test that lands inside that (wider) band recomputes the per-site
-//     budget.  Site records are stored positively oriented (host), so the sign flip of the verdict is gone too.
-//   * IMAGE CHOICE BY THE FIRST VERTEX.  P = (x - a) - rint(x - a) instead of rint(centroid - x): see sab_tet5.
-//   * PRODUCERS WORK PER FRAMEWORK ATOM (three coordinates per task, tasks sorted by their number of images) and
-//     no longer track the float64 excursion of every coordinate: a frame inside the validity tube
-//     |u - anchor| <= delta <= 0.12 cannot widen the excursion beyond [anchor - delta, anchor + delta], which is what
-//     a chunk reports (guard G1 needs < 0.3); frames outside the tube update it explicitly.
-//     Their metadata sits in registers, every load of a frame is issued before its first use, and rint / floor are two
-//     additions of 1.5 * 2^52 on the FP64 pipe instead of conversion-pipe instructions (one float64 -> float32
-//     conversion per coordinate is all that is left there).
+//   * A STAGED ROW IS ONE float4 PER ATOM: the wrapped float32 position of every framework atom some site uses, then
+//     of every mobile atom.  No per-site image shifts are staged: every vertex difference the pre-test needs is a
+//     reduced separation d - rint(d), which equals the reference's unwrapped difference because sites are smaller
+//     than 0.45 per axis (see sab_tet5).  A site record is four 16-bit byte offsets; a containment test loads four
+//     vertices and the atom with five 128-bit shared loads (was 15 scalar loads + 12 unpack operations).
+//   * THE RECORDS OF THE TWO MOST RECENT SITES LIVE IN REGISTERS and are reloaded only when the atom changes site.
+//   * CONSTANT ERROR THRESHOLDS.  The error budget of the FP32 pre-test is evaluated once on the host for the largest
+//     site of the table; only a test that lands inside that (wider) band recomputes the per-site budget.  Site
+//     records are stored positively oriented (host), so the sign flip of the verdict is gone too.
+//   * PRODUCERS WORK IN float32: one float64 -> float32 conversion per coordinate, then W = rint(x - anchor) as two
+//     additions of 1.5 * 2^23, the validity-tube test and the wrapped value.  Metadata (column, three float anchors)
+//     sits in registers, every load of a frame is issued before its first use.  They no longer track the float64
+//     excursion of every coordinate: a frame inside the validity tube |u - anchor| <= delta <= 0.12 cannot widen the
+//     excursion beyond [anchor - delta, anchor + delta], which is what a chunk reports (guard G1 needs < 0.3;
+//     DESIGN.md section 4); frames outside the tube update it explicitly.
 //   * One mbarrier arrival per WARP (after __syncwarp), ring positions advanced without integer division.
-//
 //   * NO COLD CODE IN THE FRAME LOOP.  Frames outside the validity tube (and the legacy first-frame rule) are only
 //     listed; k_polyhedral_flagged settles them with the generic all-sites test after the kernel.  Atom-frames that
 //     several sites contain join the ones float32 cannot decide in the exact float64 pass (k_polyhedral_deferred),
 //     which writes the candidate list for the priority resolver.  Either way the atom's history restarts as
 //     "unknown", which only ever selects the slower path to the same answer.
+//   * THE SEARCH READS ONE 64-BYTE CELL RECORD (length + entries), prefetched while the previous site is tested.
 //
 // Pipeline (unchanged): copy engine (cp.async.bulk of whole raw frames, mbarrier complete_tx) -> producer warps
 // (raw frame -> float row) -> consumer warps (one mobile atom per lane, frames in order), coupled by full/empty
 // mbarriers on a ring of rows; no CTA-wide barrier in the steady state.  The chain check of the anchor form of the
 // wrap count W = rint(raw - anchor) against the reference's sequential update (pbc_utils.py:210-217) is the one of
-// k_polyhedral_stream.cuh.
+// k_polyhedral_stream.cuh; in-tube frames never need W itself any more, only the certainty that the reference's
+// shift caches are the ones the host tables were built from.
 #pragma once
 #include "k_polyhedral_stream.cuh"
 
+#ifndef SAB_S5_MAXTHREADS
 #define SAB_S5_MAXTHREADS 256
+#endif
+#ifndef SAB_S5_SLEEP_NS
+#define SAB_S5_SLEEP_NS 0         // > 0: nanosleep back-off of a waiting warp between two looks at its mbarrier
+#endif
 #ifndef SAB_S5_MINBLOCKS
 #define SAB_S5_MINBLOCKS 3
 #endif
@@ -48,19 +54,16 @@
 #define SAB_S5_DELTA22 2.384185791015625e-7f      // 2^-22: every staged coordinate is within this of its float64 value
 
 struct SabStream5Tables {
-    int n_img;                    // staged vertex images (float4 each)
-    int n_task;                   // framework atoms (one producer task each), sorted by descending image count
-    int stride4;                  // float4 per row: n_img + A
+    int n_task;                   // framework atoms some site uses (M): one producer task and one row entry each
+    int stride4;                  // float4 per row: M + A + 1
     int m3;                       // framework coordinates
-    const int4 *task;             // [n_task] {3 * structure index, first image, images, 3 * framework column}
-    const float4 *task_anchor;    // [n_task] anchors of the three coordinates (exactly representable in float)
-    const float4 *img_shift;      // [n_img] integer image shift of the staged vertex
-    const uint2 *rec;             // [S] four uint16 BYTE offsets of the site's vertex images, positively oriented
+    const float4 *task;           // [M] {3 * structure index (int bits), anchor x, y, z (exactly the float64 anchors)}
+    const uint2 *rec;             // [S] four uint16 BYTE offsets of the site's vertex atoms in a row, positively oriented
     int G;
     const int32_t *cell_off;      // [G^3 + 1]
     const uint16_t *cell_sites;   // CSR entries, ascending per cell
     const uint16_t *cell_rec;     // [G^3][32] fixed-size form of the same lists: {length or 0xffff, entries...} (or null)
-    double delta_t;               // validity tube of the producers' check, shrunk by 5e-7 (float rounding of the staged values)
+    float delta_t;                // validity tube of the producers' check, shrunk by 1e-6 (float rounding)
     int reg_tasks;                // every producer thread owns <= SAB_S5_KT framework atoms and mobile atoms: metadata in registers
     float T1, T0, TD;             // constant thresholds of the pre-test (largest site of the table, |P| <= 1/2)
     int use_f32;
@@ -74,7 +77,7 @@ struct SabStream5Tables {
     int skip_check_frame0;
     int n_raw, n_rows, n_prod, use_tma;
     double *chunk_exc;            // out [n_chunks][m3][2]
-    double delta_d;               // the validity tube in float64 (>= what delta_f admits)
+    double delta_d;               // the validity tube in float64 (>= what delta_t admits)
     int n_peer;
     int32_t *peer[SAB_MAX_PEERS];
 };
@@ -86,30 +89,55 @@ struct SabStream5Tables {
 // sign of det.  These are the reference's four face-plane values (polyhedral_site.py:107-121) up to a positive
 // factor and float64 rounding.  Records are stored with det > 0 at the anchor positions (host).
 //
-// Image choice.  The reference tests the images x + {0,1}^3 against the vertices shifted by u = ceil(-min)^+
-// (tools.py:246-253, pbc_utils.py:221-229).  Sites are smaller than 0.45 per axis (host check), so a point inside
-// the hull is within 0.45 of vertex a on every axis: the only image in reach is p = x + k with k = -rint(x - a),
-// i.e. P = t - rint(t), t = x - a (exact in float: |t - rint(t)| <= 1/2 needs no more bits than t).  If p is
-// strictly inside, x + o = p + u lies in [min + u, max + u], inside [0, 2) by the host check "anchor vertex +
-// delta < 2", so o is 0 or 1 and the reference tests exactly this image.  If p is outside, every other image
-// differs from it by >= 1 on some axis, i.e. lies >= 1/2 - 2^-20 > 0.45 from a on that axis: outside too.
+// Reduced separations.  A row holds WRAPPED positions u = x - rint(x - anchor) of the vertex atoms (any integer
+// image) and x - floor(x) of the mobile atom.  The reference's vertices are raw + (shift - W) (pbc_utils.py:220): the
+// same positions up to integers, and inside the validity tube (|u - anchor| <= delta for every vertex; the producers
+// flag every other frame) they span less than 0.45 per axis (host check on the anchor geometry + 2 delta).  Hence each
+// true difference B, C, D is the separation of the wrapped positions reduced by its nearest integer, d - rint(d),
+// exact in float (|d - rint(d)| <= 1/2 needs no more bits than d).
+// Image choice of the atom.  The reference tests the images x + {0,1}^3 against the vertices shifted by
+// u = ceil(-min)^+ (tools.py:246-253, pbc_utils.py:221-229).  A point inside the hull is within 0.45 of vertex a on
+// every axis, so the only image in reach is the one with P = t - rint(t), t = x - a.  If it is strictly inside,
+// x + o = p + u lies in [min + u, max + u], inside [0, 2) by the host check "anchor vertex + delta < 2", so o is 0
+// or 1 and the reference tests exactly this image.  If it is outside, every other image differs from it by >= 1 on
+// some axis, i.e. lies >= 1/2 - 2^-20 > 0.45 from a on that axis: outside too.
 //
-// Error budget (delta = 2^-22).  Staged vertex coordinates are within delta of their float64 values (|value| < 4,
-// host check), the wrapped atom coordinate within delta / 8; hence every component of B, C, D carries an input
-// error <= 2.03 delta and every component of P <= 1.63 delta.  With Ee >= |components of B, C, D| and
-// Ep >= |components of P|, first-order propagation through the six products of a 3 x 3 determinant plus the
-// roundings of the FMA evaluation (<= 4.5 Ee^2 Ep delta) give
-//   |err(l_b, l_c, l_d)| <= (28 Ee Ep + 16 Ee^2) delta,   |err(det)| <= 44 Ee^2 delta,
-//   |err(l_a)| <= 3 (28 Ee Ep + 16 Ee^2) delta + 44 Ee^2 delta.
-// Thresholds are TWICE these bounds.  A verdict is returned only when every quantity that enters it is beyond its
-// threshold; then the exact plane values -- and the float64 reference arithmetic, whose own error is ~1e-9 of the
-// threshold -- have the same signs.  The fast path uses the bounds for Ee = Ee_max (largest anchor site + tube),
-// Ep = 1/2 (P is a reduced separation); a value inside that wider band is re-judged with the site's own Ee, Ep.
+// Error budget (delta = 2^-22).  Staged values are float(x) - W or float(x) - floor with |x| < 4 (the producers flag
+// every other frame): within delta / 2 of their float64 values.  A difference of two staged values adds one rounding
+// (<= delta / 4, |d| < 4); the reduction is exact.  Every component of B, C, D, P therefore carries an input error
+// <= 1.25 delta.  With Ee >= |components of B, C, D| and Ep >= |components of P|, first-order propagation through
+// the six products of a 3 x 3 determinant plus the roundings of the FMA evaluation (<= 4.5 Ee^2 Ep delta) give
+//   |err(l_b, l_c, l_d)| <= (17.25 Ee Ep + 7.5 Ee^2) delta,   |err(det)| <= 24.75 Ee^2 delta,
+// and l_a = det - l_b - l_c - l_d adds them up.  The thresholds below use the LARGER constants 28 / 16 / 44 of the
+// earlier generations, twice:  T1 = 2 (28 Ee Ep + 16 Ee^2) delta,  TD = 2 * 44 Ee^2 delta,  T0 = 3 T1 + TD.
+// A verdict is returned only when every quantity that enters it is beyond its threshold; then the exact plane
+// values -- and the float64 reference arithmetic, whose own error is ~1e-9 of the threshold -- have the same signs.
+// The fast path uses the bounds for Ee = Ee_max (largest anchor site + tube), Ep = 1/2 (P is a reduced separation);
+// a value inside that wider band is re-judged with the site's own Ee, Ep.
 // Return: 0 = certainly not contained, 1 = certainly contained, 2 = undecided (exact float64 pass decides).
 // ---------------------------------------------------------------------------------------------
 // round-half-even to an integer without the conversion pipe: exact for |x| < 2^51 (double), |x| < 2^22 (float)
 __device__ __forceinline__ double sab_rint_magic(double x) { return (x + 6755399441055744.0) - 6755399441055744.0; }
 __device__ __forceinline__ float sab_rintf_magic(float x) { return (x + 12582912.f) - 12582912.f; }
+__device__ __forceinline__ float sab_mic1(float d) { return d - sab_rintf_magic(d); }
+
+// Wait for an mbarrier phase.  SAB_S5_SLEEP_NS > 0 polls with a nanosleep in between instead of the hardware-suspended
+// try_wait (whose suspension ends at every mbarrier update of the CTA); measured equal within 2 % (profiles/README.md).
+__device__ __forceinline__ void sab_mbar_wait_sleep(uint64_t *bar, unsigned parity)
+{
+#if SAB_S5_SLEEP_NS > 0
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(SAB_S5_SLEEP_NS);
+    }
+#else
+    sab_mbar_wait_backoff(bar, parity);
+#endif
+}
 
 struct SabTet5Off { unsigned o0, o1, o2, o3; };
 __device__ __forceinline__ SabTet5Off sab_tet5_unpack(const uint2 r)
@@ -119,12 +147,12 @@ __device__ __forceinline__ SabTet5Off sab_tet5_unpack(const uint2 r)
 }
 
 __device__ __forceinline__ int sab_tet5_slow(float Bx, float By, float Bz, float Cx, float Cy, float Cz, float Dx, float Dy,
-                                          float Dz, float Px, float Py, float Pz, float det, float lb, float lc, float ld, float la)
+                                             float Dz, float Px, float Py, float Pz, float det, float lb, float lc, float ld, float la)
 {
     const float Ee = fmaxf(fmaxf(fmaxf(fabsf(Bx), fabsf(By)), fmaxf(fabsf(Bz), fabsf(Cx))),
                            fmaxf(fmaxf(fabsf(Cy), fabsf(Cz)), fmaxf(fmaxf(fabsf(Dx), fabsf(Dy)), fabsf(Dz))));
     const float Ep = fmaxf(fabsf(Px), fmaxf(fabsf(Py), fabsf(Pz)));
-    if (!(Ee < 0.5f) || !(Ep < 0.75f)) return 2;                       // not a small site (or NaN): budget void
+    if (!(Ee < 0.45f) || !(Ep < 0.75f)) return 2;                      // not a small site (or NaN): budget void
     const float T1 = Ee * (56.f * Ep + 32.f * Ee) * SAB_S5_DELTA22;    // 2 x bound
     const float TD = Ee * Ee * (88.f * SAB_S5_DELTA22);
     const float T0 = 3.f * T1 + TD;
@@ -140,11 +168,10 @@ __device__ __forceinline__ int sab_tet5(const char *__restrict__ rowb, const Sab
 {
     const float4 a = *reinterpret_cast<const float4 *>(rowb + o.o0), b = *reinterpret_cast<const float4 *>(rowb + o.o1);
     const float4 c = *reinterpret_cast<const float4 *>(rowb + o.o2), d = *reinterpret_cast<const float4 *>(rowb + o.o3);
-    const float tx = x.x - a.x, ty = x.y - a.y, tz = x.z - a.z;
-    const float Px = tx - sab_rintf_magic(tx), Py = ty - sab_rintf_magic(ty), Pz = tz - sab_rintf_magic(tz);
-    const float Bx = b.x - a.x, By = b.y - a.y, Bz = b.z - a.z;
-    const float Cx = c.x - a.x, Cy = c.y - a.y, Cz = c.z - a.z;
-    const float Dx = d.x - a.x, Dy = d.y - a.y, Dz = d.z - a.z;
+    const float Px = sab_mic1(x.x - a.x), Py = sab_mic1(x.y - a.y), Pz = sab_mic1(x.z - a.z);
+    const float Bx = sab_mic1(b.x - a.x), By = sab_mic1(b.y - a.y), Bz = sab_mic1(b.z - a.z);
+    const float Cx = sab_mic1(c.x - a.x), Cy = sab_mic1(c.y - a.y), Cz = sab_mic1(c.z - a.z);
+    const float Dx = sab_mic1(d.x - a.x), Dy = sab_mic1(d.y - a.y), Dz = sab_mic1(d.z - a.z);
     // explicit FMAs: the library is compiled with -fmad=false for the float64 reference arithmetic
     const float Qx = __fmaf_rn(Dy, Pz, -(Dz * Py)), Qy = __fmaf_rn(Dz, Px, -(Dx * Pz)), Qz = __fmaf_rn(Dx, Py, -(Dy * Px));   // D x P
     const float Nx = __fmaf_rn(By, Cz, -(Bz * Cy)), Ny = __fmaf_rn(Bz, Cx, -(Bx * Cz)), Nz = __fmaf_rn(Bx, Cy, -(By * Cx));   // B x C
@@ -168,6 +195,22 @@ __device__ __forceinline__ int sab_cell_of_f4(const float4 x, int G)
     return (c0 * G + c1) * G + c2;
 }
 
+// one coordinate of a framework atom: wrapped float value, tube flag
+__device__ __forceinline__ float sab_s5_wrap_fw(double r, float anc, float delta_t, int &bad)
+{
+    const float rf = (float)r, t = rf - anc, w = sab_rintf_magic(t);   // W = rint(raw - anchor) wherever the frame is inside the tube
+    bad |= !(fabsf(t - w) <= delta_t) | !(fabsf(rf) < 4.f);            // NaN-safe; |x| >= 4 voids the error budget
+    return rf - w;
+}
+// one coordinate of a mobile atom: x - floor(x) (atom.py:104) to within 2^-23
+__device__ __forceinline__ float sab_s5_wrap_mobile(double x)
+{
+    const float xf = (float)x;
+    if (fabsf(xf) < 4.f) { const float e = xf - sab_rintf_magic(xf); return e < 0.f ? e + 1.f : e; }
+    double e = x - floor(x);                                           // far from the cell: reduce in float64 first
+    return (float)e;
+}
+
 template <bool ONE_GROUP, bool REC_SMEM>
 __global__ void __launch_bounds__(SAB_S5_MAXTHREADS, SAB_S5_MINBLOCKS)
 k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, int64_t chunk, int n_atoms, int n_mobile,
@@ -179,10 +222,8 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
     const int n3 = 3 * n_atoms, m3 = C.m3;
     double *rawd = reinterpret_cast<double *>(sm_s5);                                        // [n_raw][n3] raw frames (copy engine)
     float4 *rows = reinterpret_cast<float4 *>(rawd + (((size_t)C.n_raw * n3 + 1) & ~(size_t)1)); // [n_rows][stride4]
-    int4 *s_task = reinterpret_cast<int4 *>(rows + (size_t)C.n_rows * C.stride4);           // [n_task]
-    double *s_tanc = reinterpret_cast<double *>(s_task + C.n_task);                          // [n_task][4] anchors (x, y, z, -)
-    float4 *s_shift = reinterpret_cast<float4 *>(s_tanc + 4 * (size_t)C.n_task);             // [n_img]
-    uint2 *s_rec = reinterpret_cast<uint2 *>(s_shift + C.n_img);                             // [S] (REC_SMEM)
+    float4 *s_task = rows + (size_t)C.n_rows * C.stride4;                                    // [n_task]
+    uint2 *s_rec = reinterpret_cast<uint2 *>(s_task + C.n_task);                             // [S] (REC_SMEM)
     int2 *last = reinterpret_cast<int2 *>(s_rec + (REC_SMEM ? n_sites : 0));                 // [A] (!ONE_GROUP)
     int *s_mobcol = reinterpret_cast<int *>(last + (ONE_GROUP ? 0 : n_mobile));              // [A] 3 * structure index
     __shared__ __align__(8) uint64_t raw_full[SAB_S5_MAXRAW], row_full[SAB_S5_MAXROWS], row_empty[SAB_S5_MAXROWS];
@@ -194,12 +235,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
 
     // ---- one-time setup (all threads) ----------------------------------------------------------------------
-    for (int t = tid; t < C.n_task; t += blockDim.x) {
-        s_task[t] = C.task[t];
-        const float4 an = C.task_anchor[t];
-        s_tanc[4 * t] = (double)an.x; s_tanc[4 * t + 1] = (double)an.y; s_tanc[4 * t + 2] = (double)an.z; s_tanc[4 * t + 3] = 0.0;
-    }
-    for (int i = tid; i < C.n_img; i += blockDim.x) s_shift[i] = C.img_shift[i];
+    for (int t = tid; t < C.n_task; t += blockDim.x) s_task[t] = C.task[t];
     for (int q = tid; q < n_mobile; q += blockDim.x) s_mobcol[q] = mobile[q] * 3;
     if (REC_SMEM) for (int i = tid; i < n_sites; i += blockDim.x) s_rec[i] = C.rec[i];
     const uint2 *recs = REC_SMEM ? s_rec : C.rec;
@@ -221,16 +257,18 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
             sab_bulk_g2s(rawd + (size_t)slot * n3, frac + (size_t)f * n3, frame_bytes, &raw_full[slot]);
         };
         // register-resident tasks: thread pt owns framework atoms pt + k n_prod_thr and the same mobile atoms.  A task that
-        // does not exist reads atom 0 against task 0's anchors (any tube violation it reports is a real one), has no images,
-        // and writes the spare float4 at the end of the row.
-        int r_col[SAB_S5_KT], r_img[SAB_S5_KT], r_mcol[SAB_S5_KT];      // r_img: first image | images << 16
+        // does not exist repeats task 0 / atom 0 (any tube violation it reports is a real one) and writes the spare float4
+        // at the end of the row.
+        int r_col[SAB_S5_KT], r_mcol[SAB_S5_KT];
+        float r_anc[SAB_S5_KT][3];
 #pragma unroll
         for (int k = 0; k < SAB_S5_KT; k++) {
             const int t = pt + k * n_prod_thr;
             const bool ok = C.reg_tasks && t < C.n_task, okm = C.reg_tasks && t < n_mobile;
-            const int4 tk = ok ? s_task[t] : make_int4(0, 0, 0, 0);
-            r_col[k] = ok ? tk.x : -1; r_img[k] = tk.y | (tk.z << 16);
-            r_mcol[k] = okm ? s_mobcol[t] : -1;
+            const float4 tk = s_task[ok ? t : 0];
+            r_col[k] = ok ? __float_as_int(tk.x) : ~__float_as_int(tk.x);     // < 0: no row entry of its own
+            r_anc[k][0] = tk.y; r_anc[k][1] = tk.z; r_anc[k][2] = tk.w;
+            r_mcol[k] = okm ? s_mobcol[t] : ~s_mobcol[0];
         }
         unsigned it = 0;                                        // frames processed by this CTA so far
         int rslot = 0, wslot = 0;                               // ring positions of frame `it`
@@ -248,83 +286,48 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
             }
             for (int64_t f = c0; f < c1; f++, it++) {
                 double *raw = rawd + (size_t)rslot * n3;
-                if (C.use_tma) sab_mbar_wait_backoff(&raw_full[rslot], rpar);
+                if (C.use_tma) sab_mbar_wait_sleep(&raw_full[rslot], rpar);
                 else {                                          // frames the copy engine cannot take: plain loads
                     const double *g = frac + (size_t)f * n3;
                     for (int q = pt; q < n3; q += n_prod_thr) raw[q] = g[q];
                     sab_bar_producers(n_prod_thr);
                 }
-                if (it >= (unsigned)ROWS) sab_mbar_wait_backoff(&row_empty[wslot], wpar ^ 1u);
+                if (it >= (unsigned)ROWS) sab_mbar_wait_sleep(&row_empty[wslot], wpar ^ 1u);
                 float4 *row = rows + (size_t)wslot * C.stride4;
-                // ---- framework atoms -> vertex images, mobile atoms -> wrapped coordinates -------------------
+                // ---- framework atoms and mobile atoms -> wrapped float32 positions ---------------------------
                 int bad = 0;
                 if (C.reg_tasks) {                              // every load of the frame is issued before the first use
-                    double rr[SAB_S5_KT][3], aa[SAB_S5_KT][3];
+                    double rr[SAB_S5_KT][3], xx[SAB_S5_KT][3];
 #pragma unroll
                     for (int k = 0; k < SAB_S5_KT; k++) {
-                        const int t = r_col[k] >= 0 ? pt + k * n_prod_thr : 0, col = r_col[k] >= 0 ? r_col[k] : s_task[0].x;
-                        const double2 a01 = *reinterpret_cast<const double2 *>(s_tanc + 4 * t);
-                        aa[k][0] = a01.x; aa[k][1] = a01.y; aa[k][2] = s_tanc[4 * t + 2];
+                        const int col = r_col[k] ^ (r_col[k] >> 31), mcol = r_mcol[k] ^ (r_mcol[k] >> 31);   // ~v for the stand-ins
 #pragma unroll
-                        for (int d = 0; d < 3; d++) rr[k][d] = raw[col + d];
+                        for (int d = 0; d < 3; d++) { rr[k][d] = raw[col + d]; xx[k][d] = raw[mcol + d]; }
                     }
 #pragma unroll
                     for (int k = 0; k < SAB_S5_KT; k++) {
-                        float fv[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            const double dd = rr[k][d] - aa[k][d], w = sab_rint_magic(dd);       // W = rint(raw - anchor)
-                            bad |= fabs(dd - w) > C.delta_t;
-                            fv[d] = (float)(rr[k][d] - w);                                       // u = raw - W
-                        }
-                        const int i0 = r_img[k] & 0xffff, i1 = i0 + (r_img[k] >> 16);
-                        for (int i = i0; i < i1; i++) {
-                            const float4 sh = s_shift[i];
-                            row[i] = make_float4(fv[0] + sh.x, fv[1] + sh.y, fv[2] + sh.z, 0.f);   // raw + (shift - W), pbc_utils.py:220
-                        }
+                        const float f0 = sab_s5_wrap_fw(rr[k][0], r_anc[k][0], C.delta_t, bad);
+                        const float f1 = sab_s5_wrap_fw(rr[k][1], r_anc[k][1], C.delta_t, bad);
+                        const float f2 = sab_s5_wrap_fw(rr[k][2], r_anc[k][2], C.delta_t, bad);
+                        row[r_col[k] >= 0 ? pt + k * n_prod_thr : C.stride4 - 1] = make_float4(f0, f1, f2, 0.f);
                     }
 #pragma unroll
                     for (int k = 0; k < SAB_S5_KT; k++)
-#pragma unroll
-                        for (int d = 0; d < 3; d++) rr[k][d] = raw[max(r_mcol[k], 0) + d];
-#pragma unroll
-                    for (int k = 0; k < SAB_S5_KT; k++) {
-                        float fv[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {                                            // x - floor(x), atom.py:104
-                            double e = rr[k][d] - sab_rint_magic(rr[k][d]);
-                            if (e < 0.0) e += 1.0;
-                            fv[d] = (float)e;
-                        }
-                        row[r_mcol[k] >= 0 ? C.n_img + pt + k * n_prod_thr : C.stride4 - 1] = make_float4(fv[0], fv[1], fv[2], 0.f);
-                    }
+                        row[r_mcol[k] >= 0 ? C.n_task + pt + k * n_prod_thr : C.stride4 - 1] =
+                            make_float4(sab_s5_wrap_mobile(xx[k][0]), sab_s5_wrap_mobile(xx[k][1]), sab_s5_wrap_mobile(xx[k][2]), 0.f);
                 } else {
                     for (int t = pt; t < C.n_task; t += n_prod_thr) {
-                        const int4 tk = s_task[t];
-                        const double a3[3] = {s_tanc[4 * t], s_tanc[4 * t + 1], s_tanc[4 * t + 2]};
-                        float fv[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            const double r = raw[tk.x + d], dd = r - a3[d], w = sab_rint_magic(dd);
-                            bad |= fabs(dd - w) > C.delta_t;
-                            fv[d] = (float)(r - w);
-                        }
-                        for (int i = 0; i < tk.z; i++) {
-                            const float4 sh = s_shift[tk.y + i];
-                            row[tk.y + i] = make_float4(fv[0] + sh.x, fv[1] + sh.y, fv[2] + sh.z, 0.f);
-                        }
+                        const float4 tk = s_task[t];
+                        const int col = __float_as_int(tk.x);
+                        const float f0 = sab_s5_wrap_fw(raw[col], tk.y, C.delta_t, bad);
+                        const float f1 = sab_s5_wrap_fw(raw[col + 1], tk.z, C.delta_t, bad);
+                        const float f2 = sab_s5_wrap_fw(raw[col + 2], tk.w, C.delta_t, bad);
+                        row[t] = make_float4(f0, f1, f2, 0.f);
                     }
                     for (int q = pt; q < n_mobile; q += n_prod_thr) {
                         const int col = s_mobcol[q];
-                        float fv[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            const double x = raw[col + d];
-                            double e = x - sab_rint_magic(x);
-                            if (e < 0.0) e += 1.0;
-                            fv[d] = (float)e;
-                        }
-                        row[C.n_img + q] = make_float4(fv[0], fv[1], fv[2], 0.f);
+                        row[C.n_task + q] = make_float4(sab_s5_wrap_mobile(raw[col]), sab_s5_wrap_mobile(raw[col + 1]),
+                                                        sab_s5_wrap_mobile(raw[col + 2]), 0.f);
                     }
                 }
                 if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&pbad[it & 3], 1);
@@ -386,9 +389,9 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
             int rcx = -1, rcy = -1;                             // {most recent, previous} site as far as certain, -1 = unknown
             SabTet5Off ofs = {0u, 0u, 0u, 0u}, ofs2 = {0u, 0u, 0u, 0u};   // records of rcx, rcy (ONE_GROUP: carried from frame to frame)
             for (int64_t f = c0; f < c1; f++) {
-                sab_mbar_wait_backoff(&row_full[wslot], wpar);
+                sab_mbar_wait_sleep(&row_full[wslot], wpar);
                 const char *rowb = reinterpret_cast<const char *>(rows + (size_t)wslot * C.stride4);
-                const float4 *xrow = reinterpret_cast<const float4 *>(rowb) + C.n_img;
+                const float4 *xrow = reinterpret_cast<const float4 *>(rowb) + C.n_task;
                 const int flag = rowflag[wslot];
                 int32_t *res = result + (size_t)f * n_mobile;
                 for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {

@@ -111,7 +111,7 @@ struct sab_engine {
     int stream_reg_cols = 1;               // SAB_OPT_STREAM_REG_COLS (1 = producer column metadata in registers when they fit)
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
     // generation-5 stream kernel (k_polyhedral_stream5.cuh): vertex-image rows, derived in sab_set_cell_lists
-    bool s5_ok = false; int s5_n_img = 0; int4 *d_s5_task = nullptr; float4 *d_s5_tanc = nullptr, *d_s5_shift = nullptr;
+    bool s5_ok = false; float4 *d_s5_task = nullptr;
     uint2 *d_s5_rec = nullptr; uint16_t *d_s5_cellrec = nullptr; float s5_T1 = 0.f, s5_T0 = 0.f, s5_TD = 0.f;
     int stream_gen = 0;                    // SAB_OPT_STREAM_GEN: 0 automatic (5 when its tables exist), 4 = previous generation
     int s5_rows = 0, s5_raw = 0, s5_blocks = 0;   // SAB_OPT_STREAM5_ROWS / _RAW / _BLOCKS (0 = automatic)
@@ -155,7 +155,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec,
-                    e->d_s5_task, e->d_s5_tanc, e->d_s5_shift, e->d_s5_rec, e->d_s5_cellrec};
+                    e->d_s5_task, e->d_s5_rec, e->d_s5_cellrec};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
@@ -368,88 +368,56 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
             e->tile_ok = true;
         }
     }
-    // ---- tables of the generation-5 stream kernel (k_polyhedral_stream5.cuh): one float4 per (framework atom, image shift)
+    // ---- tables of the generation-5 stream kernel (k_polyhedral_stream5.cuh): rows of wrapped float positions per atom
     e->s5_ok = false;
     if (e->tile_ok && delta <= 0.12) {
         const int m3 = 3 * e->M;
-        bool ok = true;
+        bool ok = e->M * 16 <= 65535;                                                            // 16-bit byte offsets into a row
         for (int i = 0; i < m3; i++) if ((double)(float)anchor[i] != anchor[i]) ok = false;     // anchors travel as float
-        std::vector<std::array<int, 4>> vert((size_t)e->S * 4);                                  // {fw atom, kx, ky, kz}
-        for (int s = 0; s < e->S && ok; s++)
-            for (int v = 0; v < 4; v++) {
-                std::array<int, 4> im{-1, 0, 0, 0};
+        std::vector<float4> task(e->M);
+        for (int m = 0; m < e->M && ok; m++) {
+            const int col = e->fw_atoms[m] * 3;
+            float cf; memcpy(&cf, &col, 4);
+            task[m] = make_float4(cf, (float)anchor[3 * m], (float)anchor[3 * m + 1], (float)anchor[3 * m + 2]);
+        }
+        std::vector<uint2> rec5(e->S);
+        double ee_max = 0.0;
+        for (int s = 0; s < e->S && ok; s++) {
+            int pos[4]; double P[4][3];
+            for (int v = 0; v < 4; v++)
                 for (int d = 0; d < 3; d++) {
                     const int idx = records[(size_t)s * SAB_TET_REC + 3 * v + d] / 8, k = idx / m3, i = idx % m3;
-                    if (i % 3 != d || (d > 0 && i / 3 != im[0])) ok = false;
-                    im[0] = i / 3; im[1 + d] = kmin + k;
+                    if (i % 3 != d || (d > 0 && i / 3 != pos[v])) ok = false;
+                    pos[v] = i / 3;
+                    P[v][d] = anchor[i] + (double)(kmin + k);                  // anchor vertex, unwrapped
                 }
-                vert[(size_t)s * 4 + v] = im;
-            }
+            for (int v = 0; v < 4; v++) for (int u = 0; u < v; u++) for (int d = 0; d < 3; d++)
+                ee_max = std::max(ee_max, fabs(P[v][d] - P[u][d]));
+            double B[3], Cv[3], D[3];
+            for (int d = 0; d < 3; d++) { B[d] = P[1][d] - P[0][d]; Cv[d] = P[2][d] - P[0][d]; D[d] = P[3][d] - P[0][d]; }
+            const double det = D[0] * (B[1] * Cv[2] - B[2] * Cv[1]) + D[1] * (B[2] * Cv[0] - B[0] * Cv[2]) + D[2] * (B[0] * Cv[1] - B[1] * Cv[0]);
+            if (det < 0.0) std::swap(pos[2], pos[3]);                      // positively oriented records: no sign flip in the kernel
+            rec5[s].x = (unsigned)(16 * pos[0]) | ((unsigned)(16 * pos[1]) << 16);
+            rec5[s].y = (unsigned)(16 * pos[2]) | ((unsigned)(16 * pos[3]) << 16);
+        }
+        // reduced separations equal the reference's unwrapped differences only for sites smaller than half a cell
+        const double ee = ee_max + 2.0 * delta + 1e-5, ep = 0.5 + 1e-6, d22 = 2.384185791015625e-7;
+        if (!(ee < 0.45)) ok = false;
         if (ok) {
-            std::vector<std::array<int, 4>> imgs(vert);
-            std::sort(imgs.begin(), imgs.end());
-            imgs.erase(std::unique(imgs.begin(), imgs.end()), imgs.end());
-            std::vector<int> count(e->M, 0), first(e->M, 0);
-            for (auto &im : imgs) count[im[0]]++;
-            std::vector<int> order(e->M);
-            for (int m = 0; m < e->M; m++) order[m] = m;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return count[a] > count[b]; });   // uniform trip counts per warp
-            std::vector<int4> task(e->M); std::vector<float4> tanc(e->M), shift(imgs.size());
-            std::vector<int> img_pos(imgs.size());
-            int next = 0;
-            for (int t = 0; t < e->M; t++) {
-                const int m = order[t];
-                first[m] = next;
-                task[t] = make_int4(e->fw_atoms[m] * 3, next, count[m], 3 * m);
-                tanc[t] = make_float4((float)anchor[3 * m], (float)anchor[3 * m + 1], (float)anchor[3 * m + 2], 0.f);
-                next += count[m];
+            const double t1 = 2.0 * (28.0 * ee * ep + 16.0 * ee * ee) * d22 * (1.0 + 1e-5), td = 2.0 * 44.0 * ee * ee * d22 * (1.0 + 1e-5);
+            e->s5_T1 = nextafterf((float)t1, INFINITY); e->s5_TD = nextafterf((float)td, INFINITY);
+            e->s5_T0 = nextafterf((float)(3.0 * (double)e->s5_T1 + (double)e->s5_TD), INFINITY);
+            CU(upload(&e->d_s5_task, task.data(), task.size()));
+            CU(upload(&e->d_s5_rec, rec5.data(), rec5.size()));
+            // fixed-size cell records: {length, entries...} in 32 uint16 (one 64-byte load per search); 0xffff = use the CSR form
+            std::vector<uint16_t> crec(ncell * 32, 0);
+            for (size_t c = 0; c < ncell; c++) {
+                const int n = cell_off[c + 1] - cell_off[c];
+                crec[c * 32] = n <= 31 ? (uint16_t)n : (uint16_t)0xffff;
+                for (int i = 0; i < std::min(n, 31); i++) crec[c * 32 + 1 + i] = cell_sites[cell_off[c] + i];
             }
-            std::vector<int> seen(e->M, 0);
-            for (size_t i = 0; i < imgs.size(); i++) {                 // imgs sorted by atom: consecutive images of one atom
-                const int m = imgs[i][0];
-                img_pos[i] = first[m] + seen[m]++;
-                shift[img_pos[i]] = make_float4((float)imgs[i][1], (float)imgs[i][2], (float)imgs[i][3], 0.f);
-            }
-            if (imgs.size() * 16 > 65535) ok = false;                  // 16-bit byte offsets into a row
-            std::vector<uint2> rec5(e->S);
-            double ee_max = 0.0;
-            for (int s = 0; s < e->S && ok; s++) {
-                int pos[4]; double P[4][3];
-                for (int v = 0; v < 4; v++) {
-                    const auto &im = vert[(size_t)s * 4 + v];
-                    pos[v] = img_pos[std::lower_bound(imgs.begin(), imgs.end(), im) - imgs.begin()];
-                    for (int d = 0; d < 3; d++) P[v][d] = anchor[3 * im[0] + d] + (double)im[1 + d];
-                }
-                for (int v = 0; v < 4; v++) for (int u = 0; u < v; u++) for (int d = 0; d < 3; d++)
-                    ee_max = std::max(ee_max, fabs(P[v][d] - P[u][d]));
-                double B[3], Cv[3], D[3];
-                for (int d = 0; d < 3; d++) { B[d] = P[1][d] - P[0][d]; Cv[d] = P[2][d] - P[0][d]; D[d] = P[3][d] - P[0][d]; }
-                const double det = D[0] * (B[1] * Cv[2] - B[2] * Cv[1]) + D[1] * (B[2] * Cv[0] - B[0] * Cv[2]) + D[2] * (B[0] * Cv[1] - B[1] * Cv[0]);
-                if (det < 0.0) std::swap(pos[2], pos[3]);              // positively oriented records: no sign flip in the kernel
-                rec5[s].x = (unsigned)(16 * pos[0]) | ((unsigned)(16 * pos[1]) << 16);
-                rec5[s].y = (unsigned)(16 * pos[2]) | ((unsigned)(16 * pos[3]) << 16);
-            }
-            const double ee = ee_max + 2.0 * delta + 1e-5, ep = 0.5 + 1e-6, d22 = 2.384185791015625e-7;
-            if (!(ee < 0.45)) ok = false;
-            if (ok) {
-                const double t1 = 2.0 * (28.0 * ee * ep + 16.0 * ee * ee) * d22 * (1.0 + 1e-5), td = 2.0 * 44.0 * ee * ee * d22 * (1.0 + 1e-5);
-                e->s5_T1 = nextafterf((float)t1, INFINITY); e->s5_TD = nextafterf((float)td, INFINITY);
-                e->s5_T0 = nextafterf((float)(3.0 * (double)e->s5_T1 + (double)e->s5_TD), INFINITY);
-                CU(upload(&e->d_s5_task, task.data(), task.size()));
-                CU(upload(&e->d_s5_tanc, tanc.data(), tanc.size()));
-                CU(upload(&e->d_s5_shift, shift.data(), shift.size()));
-                CU(upload(&e->d_s5_rec, rec5.data(), rec5.size()));
-                // fixed-size cell records: {length, entries...} in 32 uint16 (one 64-byte load per search); 0xffff = use the CSR form
-                std::vector<uint16_t> crec(ncell * 32, 0);
-                for (size_t c = 0; c < ncell; c++) {
-                    const int n = cell_off[c + 1] - cell_off[c];
-                    crec[c * 32] = n <= 31 ? (uint16_t)n : (uint16_t)0xffff;
-                    for (int i = 0; i < std::min(n, 31); i++) crec[c * 32 + 1 + i] = cell_sites[cell_off[c] + i];
-                }
-                CU(upload(&e->d_s5_cellrec, crec.data(), crec.size()));
-                e->s5_n_img = (int)imgs.size();
-                e->s5_ok = true;
-            }
+            CU(upload(&e->d_s5_cellrec, crec.data(), crec.size()));
+            e->s5_ok = true;
         }
     }
     return SAB_OK;
@@ -733,11 +701,11 @@ static StreamPlan5 plan_stream5(sab_engine *e, const double *d_frac, int64_t F, 
     if (p.n_prod < 1) return p;
     p.one_group = e->A <= p.n_cons * 32 ? 1 : 0;
     const size_t n3 = 3 * (size_t)e->N;
-    p.stride4 = e->s5_n_img + e->A + 1;                                   // one spare float4 behind the mobile atoms
+    p.stride4 = e->M + e->A + 1;                                          // one spare float4 behind the mobile atoms
     p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
     auto smem_for = [&](int n_raw, int n_rows, int rec_smem) {
-        return sizeof(double) * (((size_t)n_raw * n3 + 1) & ~(size_t)1) + 16 * (size_t)n_rows * p.stride4 + 48 * (size_t)e->M +
-               16 * (size_t)e->s5_n_img + (rec_smem ? 8 * (size_t)e->S : 0) + (p.one_group ? 0 : 8 * (size_t)e->A) + 4 * (size_t)e->A + 128;
+        return sizeof(double) * (((size_t)n_raw * n3 + 1) & ~(size_t)1) + 16 * (size_t)n_rows * p.stride4 + 16 * (size_t)e->M +
+               (rec_smem ? 8 * (size_t)e->S : 0) + (p.one_group ? 0 : 8 * (size_t)e->A) + 4 * (size_t)e->A + 128;
     };
     // shared-memory plan: as many resident CTAs per SM as SAB_S5_MINBLOCKS allows, rings as deep as then fit
     static const int shapes[][2] = {{3, 4}, {3, 3}, {2, 3}, {2, 2}};        // {raw slots, row slots}, preference order
@@ -778,10 +746,10 @@ static int launch_stream5(sab_engine *e, const StreamPlan5 &p, const double *d_f
 {
     SabPolyTables T{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_slot_fw, e->d_slot_shift, e->d_nface, e->d_simp, e->d_legacy_init};
     SabStream5Tables C{};
-    C.n_img = e->s5_n_img; C.n_task = e->M; C.stride4 = p.stride4; C.m3 = 3 * e->M;
-    C.task = e->d_s5_task; C.task_anchor = e->d_s5_tanc; C.img_shift = e->d_s5_shift; C.rec = e->d_s5_rec;
+    C.n_task = e->M; C.stride4 = p.stride4; C.m3 = 3 * e->M;
+    C.task = e->d_s5_task; C.rec = e->d_s5_rec;
     C.G = e->G; C.cell_off = e->d_cell_off; C.cell_sites = e->d_cell_sites; C.cell_rec = e->d_s5_cellrec;
-    C.delta_t = e->delta - 5e-7;
+    C.delta_t = (float)(e->delta - 1e-6);
     C.reg_tasks = (e->M <= SAB_S5_KT * 32 * p.n_prod && e->A <= SAB_S5_KT * 32 * p.n_prod) ? 1 : 0;
     C.T1 = e->s5_T1; C.T0 = e->s5_T0; C.TD = e->s5_TD;
     C.use_f32 = e->fp32_filter; C.defer = w.defer; C.defer_cap = w.defer_cap; C.flagged = w.flagged;
