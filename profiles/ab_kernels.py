@@ -14,14 +14,14 @@ kw = syn.polyhedral_engine_kwargs(g, d_frac[0].cpu().numpy(), d_lat[0].cpu().num
 ref = None
 VARIANTS = [("stream gen 4 (round 1)", {nat.OPT_STREAM_GEN: 4}), ("stream gen 5 (default)", {}),
             ("gen 5, 3 producer warps (288-thread build)", {nat.OPT_STREAM_PRODUCERS: 3}),
-            ("gen 5, 4 producer warps (320-thread build)", {nat.OPT_STREAM_PRODUCERS: 4}),
+            ("gen 5, 4 raw, 3 rows", {nat.OPT_STREAM5_RAW: 4, nat.OPT_STREAM5_ROWS: 3}),
+            ("gen 5, 4 raw, 4 rows, records via L1", {nat.OPT_STREAM5_RAW: 4, nat.OPT_STREAM5_ROWS: 4, nat.OPT_STREAM_REC_SMEM: 0}),
+            ("gen 5, 3 raw, 5 rows", {nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 5}),
+            ("gen 5, 3 raw, 3 rows", {nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 3}),
+            ("gen 5, records via L1", {nat.OPT_STREAM_REC_SMEM: 0}),
             ("gen 5, 1 producer warp", {nat.OPT_STREAM_PRODUCERS: 1}),
-            ("gen 5, records in smem, 2 raw 3 rows", {nat.OPT_STREAM5_RAW: 2, nat.OPT_STREAM5_ROWS: 3}),
             ("gen 5, 2 CTAs/SM, 4 raw, 6 rows", {nat.OPT_STREAM5_BLOCKS: 2}),
-            ("gen 5, 2 CTAs/SM, 3 raw, 4 rows", {nat.OPT_STREAM5_BLOCKS: 2, nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 4}),
-            ("gen 5, 3 raw, 2 rows", {nat.OPT_STREAM5_RAW: 3, nat.OPT_STREAM5_ROWS: 2}),
             ("gen 5, chunk 128", {nat.OPT_SEQ_CHUNK: 128}),
-            ("gen 5, 4 CTAs/SM (64-register build only)", {nat.OPT_STREAM5_BLOCKS: 4}),
             ("tile kernel + wrap scan", {nat.OPT_POLY_KERNEL: 5}), ("stream kernel gen 4 again", {nat.OPT_STREAM_GEN: 4}),
             ("gen 5, fp64 only", {nat.OPT_FP32_FILTER: 0}),
             ("seq1 + wrap scan", {nat.OPT_POLY_KERNEL: 4})]

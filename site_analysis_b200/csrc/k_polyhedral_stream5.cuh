@@ -50,7 +50,12 @@
 #define SAB_S5_MAXRAW 4
 #define SAB_S5_MAXROWS 8
 #define SAB_CNT_FLAGGED 11        // counters[]: frames handed to k_polyhedral_flagged
+#ifndef SAB_S5_KT
 #define SAB_S5_KT 3               // register-resident producer tasks per thread
+#endif
+#ifndef SAB_S5_PREFETCH_ALL
+#define SAB_S5_PREFETCH_ALL 0      // 1: every lane prefetches its cell record every frame (not only after a failed first test)
+#endif
 #define SAB_S5_DELTA22 2.384185791015625e-7f      // 2^-22: every staged coordinate is within this of its float64 value
 
 struct SabStream5Tables {
@@ -195,22 +200,66 @@ __device__ __forceinline__ int sab_cell_of_f4(const float4 x, int G)
     return (c0 * G + c1) * G + c2;
 }
 
-// one coordinate of a framework atom: wrapped float value, tube flag
-__device__ __forceinline__ float sab_s5_wrap_fw(double r, float anc, float delta_t, int &bad)
+// one framework atom: wrapped float position, tube flag.  W = rint(raw - anchor) wherever the frame is inside the tube.
+__device__ __forceinline__ float4 sab_s5_wrap_fw(double r0, double r1, double r2, float a0, float a1, float a2, float delta_t, int &bad)
 {
-    const float rf = (float)r, t = rf - anc, w = sab_rintf_magic(t);   // W = rint(raw - anchor) wherever the frame is inside the tube
-    bad |= !(fabsf(t - w) <= delta_t) | !(fabsf(rf) < 4.f);            // NaN-safe; |x| >= 4 voids the error budget
-    return rf - w;
+    const float f0 = (float)r0, f1 = (float)r1, f2 = (float)r2;
+    const float t0 = f0 - a0, t1 = f1 - a1, t2 = f2 - a2;
+    const float w0 = sab_rintf_magic(t0), w1 = sab_rintf_magic(t1), w2 = sab_rintf_magic(t2);
+    const float e = fmaxf(fmaxf(fabsf(t0 - w0), fabsf(t1 - w1)), fabsf(t2 - w2));
+    const float big = fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fabsf(f2));
+    bad |= !(e <= delta_t) | !(big < 4.f);                             // NaN-safe; |x| >= 4 voids the error budget
+    return make_float4(f0 - w0, f1 - w1, f2 - w2, 0.f);
 }
-// one coordinate of a mobile atom: x - floor(x) (atom.py:104) to within 2^-23
-__device__ __forceinline__ float sab_s5_wrap_mobile(double x)
+// one mobile atom: x - floor(x) (atom.py:104) to within 2^-23; `far` is raised when a coordinate is too large for float
+__device__ __forceinline__ float4 sab_s5_wrap_mobile(double x0, double x1, double x2, int &far)
 {
-    const float xf = (float)x;
-    if (fabsf(xf) < 4.f) { const float e = xf - sab_rintf_magic(xf); return e < 0.f ? e + 1.f : e; }
-    double e = x - floor(x);                                           // far from the cell: reduce in float64 first
-    return (float)e;
+    const float f0 = (float)x0, f1 = (float)x1, f2 = (float)x2;
+    far |= !(fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fabsf(f2)) < 4.f);
+    float e0 = f0 - sab_rintf_magic(f0), e1 = f1 - sab_rintf_magic(f1), e2 = f2 - sab_rintf_magic(f2);
+    e0 = e0 < 0.f ? e0 + 1.f : e0; e1 = e1 < 0.f ? e1 + 1.f : e1; e2 = e2 < 0.f ? e2 + 1.f : e2;
+    return make_float4(e0, e1, e2, 0.f);
+}
+__device__ __noinline__ float4 sab_s5_wrap_mobile_far(const double *x)     // far from the cell: reduce in float64 first
+{
+    return make_float4((float)(x[0] - floor(x[0])), (float)(x[1] - floor(x[1])), (float)(x[2] - floor(x[2])), 0.f);
 }
 
+// ---- synchronisation helpers on 32-bit shared addresses (computed once per thread, outside the frame loop) ----------
+__device__ __forceinline__ unsigned sab_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sab_mbar_wait_a(unsigned a, unsigned parity)
+{
+    for (;;) {
+        unsigned ok;
+#if SAB_S5_SLEEP_NS > 0
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(SAB_S5_SLEEP_NS);
+#else
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(SAB_STREAM_SUSPEND_NS) : "memory");
+        if (ok) break;
+#endif
+    }
+}
+__device__ __forceinline__ void sab_mbar_arrive_a(unsigned a)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ float4 sab_lds128(unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sab_sts128(unsigned a, const float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Row layout (float4 units): [0] {flag, -, -, -} | [1 .. M] framework atoms | [M + 1 .. M + A] mobile atoms | [M + A + 1] spare.
+// Site records hold BYTE offsets of the vertex entries from the start of the row (16 * (1 + framework index)).
 template <bool ONE_GROUP, bool REC_SMEM>
 __global__ void __launch_bounds__(SAB_S5_MAXTHREADS, SAB_S5_MINBLOCKS)
 k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, int64_t chunk, int n_atoms, int n_mobile,
@@ -227,12 +276,14 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
     int2 *last = reinterpret_cast<int2 *>(s_rec + (REC_SMEM ? n_sites : 0));                 // [A] (!ONE_GROUP)
     int *s_mobcol = reinterpret_cast<int *>(last + (ONE_GROUP ? 0 : n_mobile));              // [A] 3 * structure index
     __shared__ __align__(8) uint64_t raw_full[SAB_S5_MAXRAW], row_full[SAB_S5_MAXROWS], row_empty[SAB_S5_MAXROWS];
-    __shared__ int pbad[4], rowflag[SAB_S5_MAXROWS];
+    __shared__ int pbad[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_prod_thr = C.n_prod * 32, n_cons = (blockDim.x >> 5) - C.n_prod, n_cons_thr = n_cons * 32;
     const int RS = C.n_raw, ROWS = C.n_rows;
     const int64_t n_chunks = (n_frames + chunk - 1) / chunk;
+    const unsigned row_bytes = 16u * (unsigned)C.stride4;
+    const unsigned rows_s = sab_saddr(rows), a_full0 = sab_saddr(&row_full[0]), a_empty0 = sab_saddr(&row_empty[0]);
 
     // ---- one-time setup (all threads) ----------------------------------------------------------------------
     for (int t = tid; t < C.n_task; t += blockDim.x) s_task[t] = C.task[t];
@@ -241,7 +292,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
     const uint2 *recs = REC_SMEM ? s_rec : C.rec;
     if (tid == 0) {
         for (int i = 0; i < SAB_S5_MAXRAW; i++) sab_mbar_init(&raw_full[i], 1);
-        for (int i = 0; i < SAB_S5_MAXROWS; i++) { sab_mbar_init(&row_full[i], C.n_prod); sab_mbar_init(&row_empty[i], n_cons); rowflag[i] = 0; }
+        for (int i = 0; i < SAB_S5_MAXROWS; i++) { sab_mbar_init(&row_full[i], C.n_prod); sab_mbar_init(&row_empty[i], n_cons); }
         for (int i = 0; i < 4; i++) pbad[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -251,6 +302,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
         // =========================================== producers ===========================================
         const int pt = tid;
         const unsigned frame_bytes = (unsigned)((size_t)n3 * 8);
+        const unsigned a_raw0 = sab_saddr(&raw_full[0]);
         auto issue = [&](int64_t f, int slot) {                 // thread 0 only: raw frame f -> raw slot
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             sab_mbar_expect_tx(&raw_full[slot], frame_bytes);
@@ -258,21 +310,26 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
         };
         // register-resident tasks: thread pt owns framework atoms pt + k n_prod_thr and the same mobile atoms.  A task that
         // does not exist repeats task 0 / atom 0 (any tube violation it reports is a real one) and writes the spare float4
-        // at the end of the row.
+        // at the end of the row.  r_col / r_mcol: element offset of the atom's x in a raw frame; r_dst / r_mdst: byte offset in a row.
         int r_col[SAB_S5_KT], r_mcol[SAB_S5_KT];
+        unsigned r_dst[SAB_S5_KT], r_mdst[SAB_S5_KT];
         float r_anc[SAB_S5_KT][3];
+        const unsigned spare = 16u * (unsigned)(C.stride4 - 1);
 #pragma unroll
         for (int k = 0; k < SAB_S5_KT; k++) {
             const int t = pt + k * n_prod_thr;
             const bool ok = C.reg_tasks && t < C.n_task, okm = C.reg_tasks && t < n_mobile;
             const float4 tk = s_task[ok ? t : 0];
-            r_col[k] = ok ? __float_as_int(tk.x) : ~__float_as_int(tk.x);     // < 0: no row entry of its own
+            r_col[k] = __float_as_int(tk.x);
             r_anc[k][0] = tk.y; r_anc[k][1] = tk.z; r_anc[k][2] = tk.w;
-            r_mcol[k] = okm ? s_mobcol[t] : ~s_mobcol[0];
+            r_dst[k] = ok ? 16u * (unsigned)(1 + t) : spare;
+            r_mcol[k] = s_mobcol[okm ? t : 0];
+            r_mdst[k] = okm ? 16u * (unsigned)(1 + C.n_task + t) : spare;
         }
         unsigned it = 0;                                        // frames processed by this CTA so far
         int rslot = 0, wslot = 0;                               // ring positions of frame `it`
         unsigned rpar = 0, wpar = 0;                            // phase parities: (it / RS) & 1, (it / ROWS) & 1
+        unsigned row_s = rows_s;                                // shared address of row slot wslot
         for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
             const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
             sab_bar_producers(n_prod_thr);                      // previous chunk fully converted: raw slots idle
@@ -286,48 +343,44 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
             }
             for (int64_t f = c0; f < c1; f++, it++) {
                 double *raw = rawd + (size_t)rslot * n3;
-                if (C.use_tma) sab_mbar_wait_sleep(&raw_full[rslot], rpar);
+                if (C.use_tma) sab_mbar_wait_a(a_raw0 + 8u * (unsigned)rslot, rpar);
                 else {                                          // frames the copy engine cannot take: plain loads
                     const double *g = frac + (size_t)f * n3;
                     for (int q = pt; q < n3; q += n_prod_thr) raw[q] = g[q];
                     sab_bar_producers(n_prod_thr);
                 }
-                if (it >= (unsigned)ROWS) sab_mbar_wait_sleep(&row_empty[wslot], wpar ^ 1u);
-                float4 *row = rows + (size_t)wslot * C.stride4;
+                if (it >= (unsigned)ROWS) sab_mbar_wait_a(a_empty0 + 8u * (unsigned)wslot, wpar ^ 1u);
                 // ---- framework atoms and mobile atoms -> wrapped float32 positions ---------------------------
                 int bad = 0;
                 if (C.reg_tasks) {                              // every load of the frame is issued before the first use
                     double rr[SAB_S5_KT][3], xx[SAB_S5_KT][3];
 #pragma unroll
                     for (int k = 0; k < SAB_S5_KT; k++) {
-                        const int col = r_col[k] ^ (r_col[k] >> 31), mcol = r_mcol[k] ^ (r_mcol[k] >> 31);   // ~v for the stand-ins
+                        const double *pr = raw + r_col[k], *px = raw + r_mcol[k];
 #pragma unroll
-                        for (int d = 0; d < 3; d++) { rr[k][d] = raw[col + d]; xx[k][d] = raw[mcol + d]; }
+                        for (int d = 0; d < 3; d++) { rr[k][d] = pr[d]; xx[k][d] = px[d]; }
                     }
-#pragma unroll
-                    for (int k = 0; k < SAB_S5_KT; k++) {
-                        const float f0 = sab_s5_wrap_fw(rr[k][0], r_anc[k][0], C.delta_t, bad);
-                        const float f1 = sab_s5_wrap_fw(rr[k][1], r_anc[k][1], C.delta_t, bad);
-                        const float f2 = sab_s5_wrap_fw(rr[k][2], r_anc[k][2], C.delta_t, bad);
-                        row[r_col[k] >= 0 ? pt + k * n_prod_thr : C.stride4 - 1] = make_float4(f0, f1, f2, 0.f);
-                    }
+                    int far = 0;
 #pragma unroll
                     for (int k = 0; k < SAB_S5_KT; k++)
-                        row[r_mcol[k] >= 0 ? C.n_task + pt + k * n_prod_thr : C.stride4 - 1] =
-                            make_float4(sab_s5_wrap_mobile(xx[k][0]), sab_s5_wrap_mobile(xx[k][1]), sab_s5_wrap_mobile(xx[k][2]), 0.f);
+                        sab_sts128(row_s + r_dst[k], sab_s5_wrap_fw(rr[k][0], rr[k][1], rr[k][2], r_anc[k][0], r_anc[k][1], r_anc[k][2], C.delta_t, bad));
+#pragma unroll
+                    for (int k = 0; k < SAB_S5_KT; k++)
+                        sab_sts128(row_s + r_mdst[k], sab_s5_wrap_mobile(xx[k][0], xx[k][1], xx[k][2], far));
+                    if (far)                                    // unwrapped input far from the cell (rare): float64 reduction
+                        for (int k = 0; k < SAB_S5_KT; k++)
+                            if (r_mdst[k] != spare) sab_sts128(row_s + r_mdst[k], sab_s5_wrap_mobile_far(raw + r_mcol[k]));
                 } else {
                     for (int t = pt; t < C.n_task; t += n_prod_thr) {
                         const float4 tk = s_task[t];
-                        const int col = __float_as_int(tk.x);
-                        const float f0 = sab_s5_wrap_fw(raw[col], tk.y, C.delta_t, bad);
-                        const float f1 = sab_s5_wrap_fw(raw[col + 1], tk.z, C.delta_t, bad);
-                        const float f2 = sab_s5_wrap_fw(raw[col + 2], tk.w, C.delta_t, bad);
-                        row[t] = make_float4(f0, f1, f2, 0.f);
+                        const double *pr = raw + __float_as_int(tk.x);
+                        sab_sts128(row_s + 16u * (unsigned)(1 + t), sab_s5_wrap_fw(pr[0], pr[1], pr[2], tk.y, tk.z, tk.w, C.delta_t, bad));
                     }
                     for (int q = pt; q < n_mobile; q += n_prod_thr) {
-                        const int col = s_mobcol[q];
-                        row[C.n_task + q] = make_float4(sab_s5_wrap_mobile(raw[col]), sab_s5_wrap_mobile(raw[col + 1]),
-                                                        sab_s5_wrap_mobile(raw[col + 2]), 0.f);
+                        const double *px = raw + s_mobcol[q];
+                        int far = 0;
+                        const float4 v = sab_s5_wrap_mobile(px[0], px[1], px[2], far);
+                        sab_sts128(row_s + 16u * (unsigned)(1 + C.n_task + q), far ? sab_s5_wrap_mobile_far(px) : v);
                     }
                 }
                 if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&pbad[it & 3], 1);
@@ -338,7 +391,7 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                 if (pt == 0) {
                     pbad[(it + 2) & 3] = 0;
                     const int flag = tube_bad || (T.legacy_init && legacy_init_frame == f);
-                    rowflag[wslot] = flag;
+                    sab_sts128(row_s, make_float4(__int_as_float(flag), 0.f, 0.f, 0.f));
                     if (flag) {                                 // outside the validity tube (or the legacy first-frame rule):
                         atomicAdd(n_fallback, 1ULL);            // the whole frame goes to the generic pass after this kernel
                         C.flagged[atomicAdd(&counters[SAB_CNT_FLAGGED], 1ULL)] = (long long)f;
@@ -371,9 +424,10 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                     }
                 }
                 __syncwarp();
-                if (lane == 0) sab_mbar_arrive(&row_full[wslot]);
+                if (lane == 0) sab_mbar_arrive_a(a_full0 + 8u * (unsigned)wslot);
                 if (++rslot == RS) { rslot = 0; rpar ^= 1u; }
-                if (++wslot == ROWS) { wslot = 0; wpar ^= 1u; }
+                row_s += row_bytes;
+                if (++wslot == ROWS) { wslot = 0; wpar ^= 1u; row_s = rows_s; }
             }
         }
     } else {
@@ -381,115 +435,142 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
         const int cw = warp - C.n_prod;
         const unsigned FULL = 0xffffffffu;
         const float T1 = C.T1, T0 = C.T0, TD = C.TD;
+        const unsigned x0off = 16u * (unsigned)(1 + C.n_task);      // byte offset of mobile atom 0 in a row
         int wslot = 0; unsigned wpar = 0;
+        unsigned row_s = rows_s;
+        // One atom-frame.  rcx / rcy: {most recent, previous} site as far as certain (-1 = unknown), ofs / ofs2 their records.
+        // Returns the result code; `flag` frames are not written here.
+        auto atom_frame = [&](const unsigned rs, const int a, const bool valid, const int g0, const int64_t f,
+                              int &rcx, int &rcy, SabTet5Off &ofs, SabTet5Off &ofs2) -> int {
+            const char *rowb = reinterpret_cast<const char *>(rows) + (rs - rows_s);
+            const float4 x = sab_lds128(rs + x0off + 16u * (unsigned)(valid ? a : 0));
+            int out = SAB_NONE;
+            bool dirty = false;                                  // rcx changed: its record must be reloaded
+            // a definite site h: Atom.update_recent_site (atom.py:189-192)
+            #define SAB_RECENT_PUSH(h) do { if ((h) != rcx) { rcy = rcx; ofs2 = ofs; rcx = (h); dirty = true; } } while (0)
+            int v = 0;
+#if SAB_S5_PREFETCH_ALL
+            const int mycell = sab_cell_of_f4(x, C.G);
+            if (valid && C.cell_rec) asm volatile("prefetch.global.L1 [%0];" ::"l"(C.cell_rec + (size_t)mycell * 32));
+#endif
+            if (valid && rcx >= 0 && C.use_f32) v = sab_tet5(rowb, ofs, x, T1, T0, TD);
+            if (v == 1) out = rcx;
+            unsigned m = __ballot_sync(FULL, valid && v != 1);
+            if (m != 0u) {                                       // warp-uniform
+#if !SAB_S5_PREFETCH_ALL
+                const int mycell = sab_cell_of_f4(x, C.G);
+                if (valid && v != 1 && C.cell_rec)               // the search's list arrives while the previous site is tested
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(C.cell_rec + (size_t)mycell * 32));
+#endif
+                // most recent site certainly failed: the reference tests the previous one next
+                if (valid && v == 0 && rcx >= 0 && rcy >= 0) {
+                    if (!ONE_GROUP) ofs2 = sab_tet5_unpack(recs[rcy]);
+                    if (sab_tet5(rowb, ofs2, x, T1, T0, TD) == 1) {
+                        out = rcy; const int t = rcx; rcx = rcy; rcy = t; v = 1;
+                        const SabTet5Off to = ofs; ofs = ofs2; ofs2 = to;
+                    }
+                }
+                m = __ballot_sync(FULL, valid && v != 1);
+                while (m) {                                      // warp-uniform: one search per atom that needs it
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 xs = sab_lds128(rs + x0off + 16u * (unsigned)(g0 + src));
+                    const int cell = __shfl_sync(FULL, mycell, src);
+                    int c = 0, h0 = -1;
+                    unsigned und = C.use_f32 ? 0u : 1u;
+                    int b = 0, len = -1;
+                    if (C.cell_rec && C.use_f32) {               // fixed-size cell record: one load for length and entries
+                        const int e = __ldg(C.cell_rec + (size_t)cell * 32 + lane);
+                        const int n = __shfl_sync(FULL, e, 0);
+                        if (n <= 31) {
+                            len = 0;
+                            int vv = 0;
+                            if (lane >= 1 && lane <= n) vv = sab_tet5(rowb, sab_tet5_unpack(recs[e]), xs, T1, T0, TD);
+                            const unsigned m1 = __ballot_sync(FULL, vv == 1);
+                            und |= __ballot_sync(FULL, vv == 2);
+                            if (m1) h0 = __shfl_sync(FULL, e, __ffs(m1) - 1);
+                            c = __popc(m1);
+                        }
+                    }
+                    if (len < 0) { b = __ldg(C.cell_off + cell); len = __ldg(C.cell_off + cell + 1) - b; }   // long list: CSR form
+                    if (C.use_f32)
+                        for (int i0 = 0; i0 < len; i0 += 32) {
+                            const int i = i0 + lane;
+                            int s = 0, vv = 0;
+                            if (i < len) {
+                                s = __ldg(C.cell_sites + b + i);
+                                vv = sab_tet5(rowb, sab_tet5_unpack(recs[s]), xs, T1, T0, TD);
+                            }
+                            unsigned m1 = __ballot_sync(FULL, vv == 1);
+                            und |= __ballot_sync(FULL, vv == 2);
+                            if (m1 && c == 0) h0 = __shfl_sync(FULL, s, __ffs(m1) - 1);
+                            c += __popc(m1);
+                        }
+                    if (lane == src) {
+                        if (und || c > 1) {                      // float32 could not decide, or several sites: exact pass later
+                            out = SAB_DEFERRED; rcx = -1; rcy = -1;
+                            const unsigned long long di = atomicAdd(&counters[9], 1ULL);
+                            if ((long long)di < C.defer_cap) C.defer[di] = (long long)f * n_mobile + a;
+                        } else if (c == 0) out = SAB_NONE;
+                        else { out = h0; SAB_RECENT_PUSH(h0); }
+                    }
+                }
+            }
+            #undef SAB_RECENT_PUSH
+            if (ONE_GROUP) { if (dirty && rcx >= 0) ofs = sab_tet5_unpack(recs[rcx]); }
+            return out;
+        };
         for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
             const int64_t c0 = ch * chunk, c1 = min(c0 + chunk, n_frames);
             if (!ONE_GROUP)
                 for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) if (g0 + lane < n_mobile) last[g0 + lane] = make_int2(-1, -1);   // owner-private
-            int rcx = -1, rcy = -1;                             // {most recent, previous} site as far as certain, -1 = unknown
-            SabTet5Off ofs = {0u, 0u, 0u, 0u}, ofs2 = {0u, 0u, 0u, 0u};   // records of rcx, rcy (ONE_GROUP: carried from frame to frame)
+            int rcx = -1, rcy = -1;
+            SabTet5Off ofs = {0u, 0u, 0u, 0u}, ofs2 = {0u, 0u, 0u, 0u};   // ONE_GROUP: carried from frame to frame in registers
+            const int a1 = cw * 32 + lane;                       // ONE_GROUP: this lane's atom
+            int32_t *resp = result + (size_t)c0 * n_mobile + a1;
+            size_t poff = (size_t)c0 * n_mobile + a1;
             for (int64_t f = c0; f < c1; f++) {
-                sab_mbar_wait_sleep(&row_full[wslot], wpar);
-                const char *rowb = reinterpret_cast<const char *>(rows + (size_t)wslot * C.stride4);
-                const float4 *xrow = reinterpret_cast<const float4 *>(rowb) + C.n_task;
-                const int flag = rowflag[wslot];
-                int32_t *res = result + (size_t)f * n_mobile;
-                for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {
-                    const int a = g0 + lane;
-                    const bool valid = a < n_mobile;
-                    if (!ONE_GROUP) {
+                sab_mbar_wait_a(a_full0 + 8u * (unsigned)wslot, wpar);
+                const int flag = __float_as_int(sab_lds128(row_s).x);
+                if (ONE_GROUP) {
+                    const bool valid = a1 < n_mobile;
+                    if (flag) { rcx = -1; rcy = -1; }            // outside the validity tube: k_polyhedral_flagged writes the row;
+                    else {                                       // the history restarts (any shortcut needs a certain one)
+                        const int out = atom_frame(row_s, a1, valid, cw * 32, f, rcx, rcy, ofs, ofs2);
+                        if (valid) {
+                            *resp = out;
+                            // fused result all-gather: the same row goes to every peer's copy of the full array (posted NVLink stores)
+                            if (C.n_peer) {
+#pragma unroll
+                                for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][poff] = out;   // static indices: the parameter stays in constant memory
+                            }
+                        }
+                    }
+                    resp += n_mobile; poff += n_mobile;
+                } else {
+                    for (int g0 = cw * 32; g0 < n_mobile; g0 += n_cons_thr) {
+                        const int a = g0 + lane;
+                        const bool valid = a < n_mobile;
+                        if (flag) { if (valid) last[a] = make_int2(-1, -1); continue; }
                         const int2 rc = valid ? last[a] : make_int2(-1, -1);
                         rcx = rc.x; rcy = rc.y;
                         if (rcx >= 0) ofs = sab_tet5_unpack(recs[rcx]);
-                    }
-                    const float4 x = xrow[valid ? a : 0];
-                    int out = SAB_NONE;
-                    bool dirty = false;                          // rcx changed: its record must be reloaded
-                    // a definite site h: Atom.update_recent_site (atom.py:189-192)
-                    #define SAB_RECENT_PUSH(h) do { if ((h) != rcx) { rcy = rcx; ofs2 = ofs; rcx = (h); dirty = true; } } while (0)
-                    if (flag) {                                  // outside the validity tube: k_polyhedral_flagged writes the row;
-                        if (rcx >= 0) dirty = true;              // the history restarts (any shortcut below needs a certain one)
-                        rcx = -1; rcy = -1;
-                    } else {
-                        int v = 0;
-                        if (valid && rcx >= 0 && C.use_f32) v = sab_tet5(rowb, ofs, x, T1, T0, TD);
-                        if (v == 1) out = rcx;
-                        unsigned m = __ballot_sync(FULL, valid && v != 1);
-                        if (m == 0u) goto row_done;              // warp-uniform
-                        const int mycell = sab_cell_of_f4(x, C.G);
-                        if (valid && v != 1 && C.cell_rec)       // the search's list arrives while the previous site is tested
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(C.cell_rec + (size_t)mycell * 32));
-                        // most recent site certainly failed: the reference tests the previous one next
-                        if (valid && v == 0 && rcx >= 0 && rcy >= 0) {
-                            if (!ONE_GROUP) ofs2 = sab_tet5_unpack(recs[rcy]);
-                            if (sab_tet5(rowb, ofs2, x, T1, T0, TD) == 1) {
-                                out = rcy; const int t = rcx; rcx = rcy; rcy = t; v = 1;
-                                const SabTet5Off to = ofs; ofs = ofs2; ofs2 = to;
-                            }
-                        }
-                        m = __ballot_sync(FULL, valid && v != 1);
-                        while (m) {                              // warp-uniform: one search per atom that needs it
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const float4 xs = xrow[g0 + src];
-                            const int cell = __shfl_sync(FULL, mycell, src);
-                            int c = 0, h0 = -1;
-                            unsigned und = C.use_f32 ? 0u : 1u;
-                            int b = 0, len = -1;
-                            if (C.cell_rec && C.use_f32) {       // fixed-size cell record: one load for length and entries
-                                const int e = __ldg(C.cell_rec + (size_t)cell * 32 + lane);
-                                const int n = __shfl_sync(FULL, e, 0);
-                                if (n <= 31) {
-                                    len = 0;
-                                    int vv = 0;
-                                    if (lane >= 1 && lane <= n) vv = sab_tet5(rowb, sab_tet5_unpack(recs[e]), xs, T1, T0, TD);
-                                    const unsigned m1 = __ballot_sync(FULL, vv == 1);
-                                    und |= __ballot_sync(FULL, vv == 2);
-                                    if (m1) h0 = __shfl_sync(FULL, e, __ffs(m1) - 1);
-                                    c = __popc(m1);
-                                }
-                            }
-                            if (len < 0) { b = __ldg(C.cell_off + cell); len = __ldg(C.cell_off + cell + 1) - b; }   // long list: CSR form
-                            if (C.use_f32)
-                                for (int i0 = 0; i0 < len; i0 += 32) {
-                                    const int i = i0 + lane;
-                                    int s = 0, vv = 0;
-                                    if (i < len) {
-                                        s = __ldg(C.cell_sites + b + i);
-                                        vv = sab_tet5(rowb, sab_tet5_unpack(recs[s]), xs, T1, T0, TD);
-                                    }
-                                    unsigned m1 = __ballot_sync(FULL, vv == 1);
-                                    und |= __ballot_sync(FULL, vv == 2);
-                                    if (m1 && c == 0) h0 = __shfl_sync(FULL, s, __ffs(m1) - 1);
-                                    c += __popc(m1);
-                                }
-                            if (lane == src) {
-                                if (und || c > 1) {              // float32 could not decide, or several sites: exact pass later
-                                    out = SAB_DEFERRED; rcx = -1; rcy = -1;
-                                    const unsigned long long di = atomicAdd(&counters[9], 1ULL);
-                                    if ((long long)di < C.defer_cap) C.defer[di] = (long long)f * n_mobile + a;
-                                } else if (c == 0) out = SAB_NONE;
-                                else { out = h0; SAB_RECENT_PUSH(h0); }
-                            }
-                        }
-                    }
-                    row_done:
-                    #undef SAB_RECENT_PUSH
-                    if (valid && !flag) {
-                        res[a] = out;
-                        // fused result all-gather: the same row goes to every peer's copy of the full array (posted NVLink stores)
-                        if (C.n_peer) {
+                        const int out = atom_frame(row_s, a, valid, g0, f, rcx, rcy, ofs, ofs2);
+                        if (valid) {
                             const size_t o = (size_t)f * n_mobile + a;
+                            result[o] = out;
+                            if (C.n_peer) {
 #pragma unroll
-                            for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][o] = out;   // static indices: the parameter stays in constant memory
+                                for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][o] = out;
+                            }
+                            last[a] = make_int2(rcx, rcy);
                         }
                     }
-                    if (ONE_GROUP) { if (dirty && rcx >= 0) ofs = sab_tet5_unpack(recs[rcx]); }
-                    else if (valid) last[a] = make_int2(rcx, rcy);
                 }
                 __syncwarp();
-                if (lane == 0) sab_mbar_arrive(&row_empty[wslot]);
-                if (++wslot == ROWS) { wslot = 0; wpar ^= 1u; }
+                if (lane == 0) sab_mbar_arrive_a(a_empty0 + 8u * (unsigned)wslot);
+                row_s += row_bytes;
+                if (++wslot == ROWS) { wslot = 0; wpar ^= 1u; row_s = rows_s; }
             }
         }
     }

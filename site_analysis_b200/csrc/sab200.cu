@@ -372,7 +372,7 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
     e->s5_ok = false;
     if (e->tile_ok && delta <= 0.12) {
         const int m3 = 3 * e->M;
-        bool ok = e->M * 16 <= 65535;                                                            // 16-bit byte offsets into a row
+        bool ok = (e->M + 1) * 16 <= 65535;                                                      // 16-bit byte offsets into a row
         for (int i = 0; i < m3; i++) if ((double)(float)anchor[i] != anchor[i]) ok = false;     // anchors travel as float
         std::vector<float4> task(e->M);
         for (int m = 0; m < e->M && ok; m++) {
@@ -397,8 +397,8 @@ extern "C" int sab_set_cell_lists(sab_engine *e, int G, double delta, const doub
             for (int d = 0; d < 3; d++) { B[d] = P[1][d] - P[0][d]; Cv[d] = P[2][d] - P[0][d]; D[d] = P[3][d] - P[0][d]; }
             const double det = D[0] * (B[1] * Cv[2] - B[2] * Cv[1]) + D[1] * (B[2] * Cv[0] - B[0] * Cv[2]) + D[2] * (B[0] * Cv[1] - B[1] * Cv[0]);
             if (det < 0.0) std::swap(pos[2], pos[3]);                      // positively oriented records: no sign flip in the kernel
-            rec5[s].x = (unsigned)(16 * pos[0]) | ((unsigned)(16 * pos[1]) << 16);
-            rec5[s].y = (unsigned)(16 * pos[2]) | ((unsigned)(16 * pos[3]) << 16);
+            rec5[s].x = (unsigned)(16 * (1 + pos[0])) | ((unsigned)(16 * (1 + pos[1])) << 16);   // entry 0 of a row is its flag
+            rec5[s].y = (unsigned)(16 * (1 + pos[2])) | ((unsigned)(16 * (1 + pos[3])) << 16);
         }
         // reduced separations equal the reference's unwrapped differences only for sites smaller than half a cell
         const double ee = ee_max + 2.0 * delta + 1e-5, ep = 0.5 + 1e-6, d22 = 2.384185791015625e-7;
@@ -701,7 +701,7 @@ static StreamPlan5 plan_stream5(sab_engine *e, const double *d_frac, int64_t F, 
     if (p.n_prod < 1) return p;
     p.one_group = e->A <= p.n_cons * 32 ? 1 : 0;
     const size_t n3 = 3 * (size_t)e->N;
-    p.stride4 = e->M + e->A + 1;                                          // one spare float4 behind the mobile atoms
+    p.stride4 = e->M + e->A + 2;                                          // flag entry in front, one spare float4 behind the mobile atoms
     p.use_tma = ((n3 * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frac) & 15) == 0 && n3 * 8 < (1u << 20)) ? 1 : 0;
     auto smem_for = [&](int n_raw, int n_rows, int rec_smem) {
         return sizeof(double) * (((size_t)n_raw * n3 + 1) & ~(size_t)1) + 16 * (size_t)n_rows * p.stride4 + 16 * (size_t)e->M +
