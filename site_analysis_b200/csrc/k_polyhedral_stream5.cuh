@@ -95,7 +95,7 @@ struct SabStream5Tables {
 // factor and float64 rounding.  Records are stored with det > 0 at the anchor positions (host).
 //
 // Reduced separations.  A row holds WRAPPED positions u = x - rint(x - anchor) of the vertex atoms (any integer
-// image) and x - floor(x) of the mobile atom.  The reference's vertices are raw + (shift - W) (pbc_utils.py:220): the
+// image) and x - rint(x) of the mobile atom.  The reference's vertices are raw + (shift - W) (pbc_utils.py:220): the
 // same positions up to integers, and inside the validity tube (|u - anchor| <= delta for every vertex; the producers
 // flag every other frame) they span less than 0.45 per axis (host check on the anchor geometry + 2 delta).  Hence each
 // true difference B, C, D is the separation of the wrapped positions reduced by its nearest integer, d - rint(d),
@@ -193,10 +193,11 @@ __device__ __forceinline__ int sab_tet5(const char *__restrict__ rowb, const Sab
     return sab_tet5_slow(Bx, By, Bz, Cx, Cy, Cz, Dx, Dy, Dz, Px, Py, Pz, det, lb, lc, ld, la);
 }
 
-__device__ __forceinline__ int sab_cell_of_f4(const float4 x, int G)
+__device__ __forceinline__ int sab_cell_of_f4(const float4 x, int G)      // x in [-1/2, 1/2]: the atom's image in [0, 1) decides
 {
     const float g = (float)G;
-    int c0 = min(G - 1, (int)(x.x * g)), c1 = min(G - 1, (int)(x.y * g)), c2 = min(G - 1, (int)(x.z * g));
+    const float x0 = x.x < 0.f ? x.x + 1.f : x.x, x1 = x.y < 0.f ? x.y + 1.f : x.y, x2 = x.z < 0.f ? x.z + 1.f : x.z;
+    int c0 = min(G - 1, (int)(x0 * g)), c1 = min(G - 1, (int)(x1 * g)), c2 = min(G - 1, (int)(x2 * g));
     return (c0 * G + c1) * G + c2;
 }
 
@@ -211,18 +212,17 @@ __device__ __forceinline__ float4 sab_s5_wrap_fw(double r0, double r1, double r2
     bad |= !(e <= delta_t) | !(big < 4.f);                             // NaN-safe; |x| >= 4 voids the error budget
     return make_float4(f0 - w0, f1 - w1, f2 - w2, 0.f);
 }
-// one mobile atom: x - floor(x) (atom.py:104) to within 2^-23; `far` is raised when a coordinate is too large for float
+// one mobile atom: x - rint(x) in [-1/2, 1/2], i.e. x - floor(x) (atom.py:104) up to an integer, to within 2^-23 (the pre-test
+// only takes reduced separations from it; the cell lookup adds 1 to a negative component); `far`: too large for float
 __device__ __forceinline__ float4 sab_s5_wrap_mobile(double x0, double x1, double x2, int &far)
 {
     const float f0 = (float)x0, f1 = (float)x1, f2 = (float)x2;
     far |= !(fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fabsf(f2)) < 4.f);
-    float e0 = f0 - sab_rintf_magic(f0), e1 = f1 - sab_rintf_magic(f1), e2 = f2 - sab_rintf_magic(f2);
-    e0 = e0 < 0.f ? e0 + 1.f : e0; e1 = e1 < 0.f ? e1 + 1.f : e1; e2 = e2 < 0.f ? e2 + 1.f : e2;
-    return make_float4(e0, e1, e2, 0.f);
+    return make_float4(f0 - sab_rintf_magic(f0), f1 - sab_rintf_magic(f1), f2 - sab_rintf_magic(f2), 0.f);
 }
 __device__ __noinline__ float4 sab_s5_wrap_mobile_far(const double *x)     // far from the cell: reduce in float64 first
 {
-    return make_float4((float)(x[0] - floor(x[0])), (float)(x[1] - floor(x[1])), (float)(x[2] - floor(x[2])), 0.f);
+    return make_float4((float)(x[0] - rint(x[0])), (float)(x[1] - rint(x[1])), (float)(x[2] - rint(x[2])), 0.f);
 }
 
 // ---- synchronisation helpers on 32-bit shared addresses (computed once per thread, outside the frame loop) ----------

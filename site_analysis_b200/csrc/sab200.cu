@@ -708,13 +708,13 @@ static StreamPlan5 plan_stream5(sab_engine *e, const double *d_frac, int64_t F, 
                (rec_smem ? 8 * (size_t)e->S : 0) + (p.one_group ? 0 : 8 * (size_t)e->A) + 4 * (size_t)e->A + 128;
     };
     // shared-memory plan: as many resident CTAs per SM as SAB_S5_MINBLOCKS allows, rings as deep as then fit
-    static const int shapes[][2] = {{3, 4}, {3, 3}, {2, 3}, {2, 2}};        // {raw slots, row slots}, preference order
+    static const int shapes[][2] = {{3, 5}, {3, 4}, {3, 3}, {2, 3}, {2, 2}};   // {raw slots, row slots}, preference order (measured)
     static const int shapes_big[][2] = {{4, 6}, {3, 6}, {3, 4}, {3, 3}, {2, 3}, {2, 2}};
     bool found = false;
     for (int blocks = e->s5_blocks > 0 ? e->s5_blocks : SAB_S5_MINBLOCKS; blocks >= 1 && !found; blocks--) {
         const size_t budget = (size_t)(228 * 1024) / blocks - 1024 - 320;   // 1 KB per CTA is reserved by the system; static barriers
         const int (*sh)[2] = blocks >= 3 ? shapes : shapes_big;
-        const int n_sh = blocks >= 3 ? 4 : 6;
+        const int n_sh = blocks >= 3 ? 5 : 6;
         for (int i = 0; i < n_sh && !found; i++)
             for (int rec = e->stream_rec_smem ? 1 : 0; rec >= 0 && !found; rec--) {      // deeper rings before records in shared memory
                 const int raw = e->s5_raw > 0 ? e->s5_raw : sh[i][0], rows = e->s5_rows > 0 ? e->s5_rows : sh[i][1];
