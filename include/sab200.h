@@ -275,6 +275,20 @@ int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n
  * memory; stream-ordered, no synchronisation.  The assignment kernels fuse this with their argmin / cut-off test and
  * never build the matrix; this entry serves callers that need the matrix (coordination search, index mapping,
  * alignment objective: tools.py:32-111, reference_workflow/structure_aligner.py:105-147). */
+/* ---- polyhedral containment of given points (stand-alone operator) ----------------------------
+ * d_out uint8[n_sites]: 1 when ANY of the site's n_img query points lies inside the site's polyhedron -- the query of
+ * PolyhedralSite.contains_point / contains_atom (polyhedral_site.py:431-520: FaceTopologyCache.update +
+ * _numba_sn_query, :26-123) and, over many sites at once, of PolyhedralSiteCollection.sites_contain_points
+ * (polyhedral_site_collection.py:113-141).  d_vertex double[n_sites][vmax][3] PBC-corrected vertex coordinates
+ * (PolyhedralSite.vertex_coords), d_n_vert int32[n_sites]; d_simplices int32[n_sites][fmax][3] local vertex numbers of
+ * the hull's triangles (Qhull order), d_n_face int32[n_sites]; d_points double[n_sites][n_img][3] (the caller passes
+ * the 8 images x + {0,1}^3 of tools.py:246-279, or its own).  float64, the reference's operation order, no FMA:
+ * centroid as the sequential sum over vertices / n, normal (v0 - v2) x (v1 - v2), reject iff dot != 0 and
+ * sign(dot) != sign(centre dot).  Device memory, stream-ordered, no synchronisation; vmax <= 16. */
+int sab_polyhedra_contain(int device, const double *d_vertex, const int32_t *d_n_vert, int vmax,
+                          const int32_t *d_simplices, const int32_t *d_n_face, int fmax, int n_sites,
+                          const double *d_points, int n_img, uint8_t *d_out, void *stream);
+
 int sab_mic_distances(int device, const double *d_c1, int n, const double *d_c2, int m,
                       const double *d_lattice, double *d_out, void *stream);
 

@@ -27,3 +27,33 @@ k_mic_distances(const double *__restrict__ c1, int n, const double *__restrict__
         out[p] = sqrt(sab_mic_q27(d0, d1, d2, L));
     }
 }
+
+// One thread per site: does any of its query points lie inside its polyhedron?  (PolyhedralSite.contains_point,
+// polyhedral_site.py:431-520; arithmetic of _numba_update_faces :26-81 and _numba_sn_query :83-123.)
+#include "k_polyhedral.cuh"
+__global__ void k_polyhedra_contain(const double *__restrict__ vertex, const int32_t *__restrict__ n_vert, int vmax,
+                                    const int32_t *__restrict__ simplices, const int32_t *__restrict__ n_face, int fmax,
+                                    int n_sites, const double *__restrict__ points, int n_img, uint8_t *__restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sites) return;
+    double vc[SAB_MAX_VERT][3], cen[3];
+    const int nv = n_vert[s], nf = n_face[s];
+    for (int v = 0; v < nv; v++)
+        for (int d = 0; d < 3; d++) vc[v][d] = vertex[((size_t)s * vmax + v) * 3 + d];
+    for (int d = 0; d < 3; d++) {
+        double sum = 0.0;
+        for (int v = 0; v < nv; v++) sum += vc[v][d];          // 0.0 + v0 + v1 + ... (polyhedral_site.py:46-49)
+        cen[d] = sum / (double)nv;
+    }
+    const int32_t *simp = simplices + (size_t)s * fmax * 3;
+    bool inside = false;
+    for (int i = 0; i < n_img && !inside; i++) {
+        const double *p = points + ((size_t)s * n_img + i) * 3;
+        bool ok = true;
+        for (int j = 0; j < nf && ok; j++)
+            ok = sab_face_accepts(vc[simp[3 * j]], vc[simp[3 * j + 1]], vc[simp[3 * j + 2]], cen, p[0], p[1], p[2]);
+        inside = ok;
+    }
+    out[s] = inside ? 1 : 0;
+}

@@ -1430,6 +1430,21 @@ extern "C" int sab_mic_distances(int device, const double *d_c1, int n, const do
     return SAB_OK;
 }
 
+extern "C" int sab_polyhedra_contain(int device, const double *d_vertex, const int32_t *d_n_vert, int vmax,
+                                     const int32_t *d_simplices, const int32_t *d_n_face, int fmax, int n_sites,
+                                     const double *d_points, int n_img, uint8_t *d_out, void *stream)
+{
+    if (n_sites < 0 || n_img < 0) return fail(SAB_EINVAL, "sab_polyhedra_contain: negative size");
+    if (n_sites == 0) return SAB_OK;
+    if (!d_vertex || !d_n_vert || !d_simplices || !d_n_face || !d_points || !d_out) return fail(SAB_EINVAL, "sab_polyhedra_contain: null argument");
+    if (vmax < 1 || vmax > SAB_MAX_VERT || fmax < 1) return fail(SAB_EINVAL, "sab_polyhedra_contain: 1 <= vmax <= %d and fmax >= 1", SAB_MAX_VERT);
+    CU(cudaSetDevice(device));
+    k_polyhedra_contain<<<(n_sites + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_vertex, d_n_vert, vmax, d_simplices, d_n_face, fmax,
+                                                                                n_sites, d_points, n_img, d_out);
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
+
 // ---------------------------------------------------------------- multi-GPU: result rows stored straight into peer memory
 extern "C" int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *d_peer_slots)
 {

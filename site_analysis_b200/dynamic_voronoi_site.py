@@ -24,6 +24,21 @@ class DynamicVoronoiSite(Site):
         super().reset()
         self._centre_coords = None
 
+    def calculate_centre(self, all_frac_coords: np.ndarray, lattice_matrix: np.ndarray) -> None:
+        """Centre of this site from its reference atoms in one structure (dynamic_voronoi_site.py:88-104):
+        ``mean(correct_pbc(ref_coords, reference_center, lattice)) % 1.0``.  The integer image shifts come from the same
+        numpy calls as the reference's (``_tables.full_pbc_unwrap``); the mean is taken on the GPU by the engine's centre
+        kernel (``sab_dynvor_centres``), the code path whole trajectories use."""
+        import torch
+        from .engine import AssignmentEngine
+        frac = np.ascontiguousarray(all_frac_coords, dtype=np.float64)
+        lat = np.ascontiguousarray(lattice_matrix, dtype=np.float64)
+        eng = AssignmentEngine("dynamic_voronoi", len(frac), [int(self.reference_indices[0])],
+                               slots=[list(self.reference_indices)], reference_centres=[self.reference_center])
+        eng._init_pbc(frac, lat)
+        d = torch.from_numpy(frac[None]).to(torch.device("cuda", eng.device))
+        self._centre_coords = eng.dynvor_centres(d)[0, 0].cpu().numpy()
+
     @property
     def centre(self) -> np.ndarray:
         if self._centre_coords is None:

@@ -36,6 +36,8 @@ class PolyhedralSite(Site):
         self._face_topology_cache: FaceTopology | None = None
         self._pbc_image_shifts: np.ndarray | None = None
         self._pbc_cached_raw_frac: np.ndarray | None = None
+        self._pending_frac_coords: np.ndarray | None = None
+        self._pending_lattice_matrix: np.ndarray | None = None
         self.reference_center = reference_center
 
     def __repr__(self) -> str:
@@ -78,8 +80,50 @@ class PolyhedralSite(Site):
     def get_vertex_species(self, species: list[str]) -> list[str]:
         return [species[i] for i in self.vertex_indices]
 
-    def contains_point(self, x, **kwargs) -> bool:
-        raise NotImplementedError("use PolyhedralSiteCollection.assign_site_occupations (GPU path)")
+    def notify_structure_changed(self, all_frac_coords: np.ndarray, lattice_matrix: np.ndarray) -> None:
+        """Mark the vertex coordinates stale; they are re-derived when the site is next queried
+        (polyhedral_site.py:322-338)."""
+        self._pending_frac_coords = all_frac_coords
+        self._pending_lattice_matrix = lattice_matrix
+
+    def _query_ready(self):
+        """Vertex coordinates and face topology for a query, as ``contains_point`` prepares them
+        (polyhedral_site.py:459-471): pending coordinates applied, topology hulled once and kept."""
+        if self._pending_frac_coords is not None and self._pending_lattice_matrix is not None:
+            frac, lat = self._pending_frac_coords, self._pending_lattice_matrix
+            self._pending_frac_coords = self._pending_lattice_matrix = None
+            self.assign_vertex_coords(frac, lat)
+        if self.vertex_coords is None:
+            raise RuntimeError(f"no vertex coordinates set for polyhedral_site {self.index}")
+        if self._face_topology_cache is None:
+            from . import _tables as tab
+            try:
+                self._face_topology_cache = FaceTopology(tab.hull_simplices(self.vertex_coords, self.index))
+            except RuntimeError as exc:
+                raise RuntimeError(f"Degenerate vertex geometry for polyhedral_site {self.index} "
+                                   f"(vertices {self.vertex_indices})") from exc.__cause__
+        return self.vertex_coords, self._face_topology_cache.face_simplices
+
+    def contains_point(self, x: np.ndarray, *, algo: str | None = None, pbc_images: np.ndarray | None = None) -> bool:
+        """Is the point (or any of ``pbc_images``) inside this polyhedron?  Reference polyhedral_site.py:431-485; the
+        face-plane test runs on the GPU (``sab_polyhedra_contain``, float64, the reference's operation order).  Whole
+        trajectories go through ``PolyhedralSiteCollection`` instead -- this is the single-point query."""
+        if algo is not None:
+            import warnings
+            warnings.warn("The 'algo' parameter is deprecated and will be removed in a future version. The best available "
+                          "containment algorithm is now selected automatically.", DeprecationWarning, stacklevel=2)
+        from .distances import polyhedra_contain, x_pbc
+        vc, simp = self._query_ready()
+        images = np.asarray(pbc_images, dtype=np.float64).reshape(-1, 3) if pbc_images is not None else x_pbc(x)
+        return bool(polyhedra_contain([vc], [simp], [images])[0])
+
+    def contains_atom(self, atom, *, algo: str | None = None, pbc_images: np.ndarray | None = None) -> bool:
+        """polyhedral_site.py:497-520."""
+        if algo is not None:
+            import warnings
+            warnings.warn("The 'algo' parameter is deprecated and will be removed in a future version. The best available "
+                          "containment algorithm is now selected automatically.", DeprecationWarning, stacklevel=2)
+        return self.contains_point(atom.frac_coords, pbc_images=pbc_images)
 
     def as_dict(self) -> dict:
         d = super().as_dict()

@@ -295,6 +295,15 @@ class PolyhedralSiteCollection(PriorityAssignmentMixin, SiteCollection):
         self._engine = None          # primed caches are gone: rebuild from the (reset) sites
 
     def sites_contain_points(self, points, all_frac_coords, lattice_matrix) -> bool:
+        """True if every point lies inside its corresponding site (polyhedral_site_collection.py:113-141): all sites in
+        ONE GPU query (``sab_polyhedra_contain``), after each site's vertex coordinates were brought up to date exactly as
+        the reference's lazy ``notify_structure_changed`` -> ``contains_point`` sequence does."""
         if len(points) != len(self.sites):
             raise ValueError(f"Expected {len(self.sites)} points (one per site), got {len(points)}")
-        raise NotImplementedError("sites_contain_points is outside the accelerated path")
+        from .distances import polyhedra_contain, x_pbc
+        vcs, simps = [], []
+        for s in self.sites:
+            s.notify_structure_changed(all_frac_coords, lattice_matrix)
+            vc, simp = s._query_ready()
+            vcs.append(vc); simps.append(simp)
+        return bool(polyhedra_contain(vcs, simps, [x_pbc(p) for p in points]).all())

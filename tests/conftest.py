@@ -21,8 +21,8 @@ def pytest_configure(config):
 
 def golden_names(prefix=""):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(str(GOLDEN / "*.npz")))
-    # frames_* are raw trajectories; folds_* / distances_* / workflow_* belong to test_folds / test_distances / test_workflow
-    return [n for n in names if not n.startswith(("frames_", "folds_", "distances_", "workflow_")) and n.startswith(prefix)]
+    # frames_* are raw trajectories; folds_* / distances_* / workflow_* / queries_* belong to test_folds / test_distances / test_workflow / test_site_queries
+    return [n for n in names if not n.startswith(("frames_", "folds_", "distances_", "workflow_", "queries_")) and n.startswith(prefix)]
 
 
 @pytest.fixture(scope="session")
