@@ -275,6 +275,27 @@ int sab_fold_result(int device, const int32_t *d_result, int64_t n_frames, int n
  * memory; stream-ordered, no synchronisation.  The assignment kernels fuse this with their argmin / cut-off test and
  * never build the matrix; this entry serves callers that need the matrix (coordination search, index mapping,
  * alignment objective: tools.py:32-111, reference_workflow/structure_aligner.py:105-147). */
+/* ---- exact replay of the reference's lazily updated per-site caches (polyhedral sites) -------
+ * The frame-parallel kernels are identical to the reference while their guards hold.  When a
+ * framework step >= 0.3 invalidates a site's PBC-shift cache (pbc_utils.py:216) or the unwrapped excursion reaches 0.3,
+ * the reference's answer depends on WHEN each site was last queried (polyhedral_site.py:322-416); sab_assign_lazy
+ * replays that literally on the device: frames in order, one cache per site with the frame stamp of its last query,
+ * the priority walk of site_collection.py:113-182 one query at a time, Counters updated in atom order
+ * (csrc/k_polyhedral_lazy.cuh).  It returns final site list positions (-1 = None; no spill codes) and advances the
+ * history arrays (same layout as sab_resolve) itself.
+ * sab_lazy_set_state: per-site caches as the reference holds them BEFORE the first frame: shift int32[S][vmax][3] and
+ * cached_raw double[S][vmax][3] where has_shift[s] (sites primed by the builder, site_factory.py:248-257), reference
+ * centres double[S][3] where has_ref_centre[s].  sab_lazy_get_state reads the caches back (any pointer may be NULL;
+ * stats int64[4] = queries, incremental updates, full corrections, invalidations).
+ * On SAB_EOVERFLOW (Counter row wider than tr_width) the caller restores the per-site state and retries wider. */
+int sab_lazy_set_state(sab_engine *e, const int32_t *shift, const double *cached_raw, const uint8_t *has_shift,
+                       const uint8_t *has_ref_centre, const double *ref_centre);
+int sab_lazy_get_state(sab_engine *e, int32_t *shift, double *cached_raw, uint8_t *has_shift, double *vertex_coords,
+                       int64_t *stats);
+int sab_assign_lazy(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride, int64_t n_frames,
+                    int32_t *d_result, void *stream, int32_t *recent, int32_t *prev, int32_t *tr_n, int32_t *tr_key,
+                    int64_t *tr_cnt, int tr_width, int append);
+
 /* ---- polyhedral containment of given points (stand-alone operator) ----------------------------
  * d_out uint8[n_sites]: 1 when ANY of the site's n_img query points lies inside the site's polyhedron -- the query of
  * PolyhedralSite.contains_point / contains_atom (polyhedral_site.py:431-520: FaceTopologyCache.update +

@@ -78,6 +78,29 @@ def full_pbc_unwrap(raw: np.ndarray, reference_centre, lattice: np.ndarray) -> n
     return _SHIFTS27[np.argmin(dist, axis=1)]
 
 
+def unwrap_margins(raw: np.ndarray, reference_centre, lattice: np.ndarray) -> tuple[float, float]:
+    """How robust the image choice of :func:`full_pbc_unwrap` is (guard G2 of the engine).
+
+    With a reference centre: (half the smallest gap between the best and the second-best image distance over the
+    vertices, Cartesian; inf).  Legacy rule: (inf; the smallest distance, in fractional units, of the rule's inputs from
+    its thresholds -- the spread from 0.5 (halved: both ends may move) and every coordinate of a spread axis from 0.5)."""
+    raw = np.asarray(raw, dtype=np.float64)
+    if reference_centre is None:
+        m = np.inf
+        for d in range(3):
+            spread = raw[:, d].max() - raw[:, d].min()
+            m = min(m, abs(spread - 0.5) / 2.0)
+            if spread > 0.5:
+                m = min(m, float(np.abs(raw[:, d] - 0.5).min()))
+        return np.inf, float(m)
+    n = len(raw)
+    images = raw[:, None, :] + _SHIFTS27[None, :, :]
+    cart = images.reshape(n * 27, 3) @ lattice
+    centre_cart = np.asarray(reference_centre, dtype=np.float64) @ lattice
+    dist = np.sort(np.linalg.norm(cart - centre_cart, axis=1).reshape(n, 27), axis=1)
+    return float((dist[:, 1] - dist[:, 0]).min() / 2.0), np.inf
+
+
 def unwrapped_vertices(raw: np.ndarray, shifts: np.ndarray, non_negative: bool = True) -> np.ndarray:
     """raw + shifts, then the per-axis non-negative offset (pbc_utils.py:102-104 / :218-229)."""
     out = raw + shifts

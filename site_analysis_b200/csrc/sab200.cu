@@ -25,6 +25,7 @@
 #include "k_polyhedral_stream5.cuh"
 #include "k_resolve.cuh"
 #include "k_resolve_fast.cuh"
+#include "k_polyhedral_lazy.cuh"
 #include "k_spherical.cuh"
 #include "k_wrap.cuh"
 
@@ -116,6 +117,10 @@ struct sab_engine {
     int stream_gen = 0;                    // SAB_OPT_STREAM_GEN: 0 automatic (5 when its tables exist), 4 = previous generation
     int s5_rows = 0, s5_raw = 0, s5_blocks = 0;   // SAB_OPT_STREAM5_ROWS / _RAW / _BLOCKS (0 = automatic)
     size_t s5_occ_key = 0; int s5_per_sm = 0;
+    // exact replay of the reference's lazily updated per-site caches (k_polyhedral_lazy.cuh)
+    int32_t *d_lz_shift = nullptr, *d_lz_has = nullptr, *d_lz_lock = nullptr; double *d_lz_cached = nullptr, *d_lz_vc = nullptr, *d_lz_rc = nullptr;
+    long long *d_lz_stamp = nullptr; uint8_t *d_lz_has_rc = nullptr; unsigned long long *d_lz_stats = nullptr; bool lazy_set = false;
+    long long lazy_frames = 0;
     int n_peer = 0; int32_t *peer[SAB_MAX_PEERS] = {nullptr};   // sab_set_result_peers
     bool peers_written = false;            // the last sab_assign_device stored its rows into the peers as well
     size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
@@ -155,7 +160,8 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_legacy_init, e->d_rank, e->d_rank_pos, e->d_neigh_off, e->d_neigh, e->d_lookup, e->d_counters,
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec,
-                    e->d_s5_task, e->d_s5_rec, e->d_s5_cellrec};
+                    e->d_s5_task, e->d_s5_rec, e->d_s5_cellrec, e->d_lz_shift, e->d_lz_has, e->d_lz_lock, e->d_lz_cached,
+                    e->d_lz_vc, e->d_lz_rc, e->d_lz_stamp, e->d_lz_has_rc, e->d_lz_stats};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
@@ -1261,6 +1267,103 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     }
     cudaFree(H.recent); cudaFree(H.prev); cudaFree(H.tr_n); cudaFree(H.tr_key); cudaFree(H.tr_cnt); cudaFree(d_over);
     if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);
+    return SAB_OK;
+}
+
+// ---------------------------------------------------------------- exact replay of the lazily updated per-site caches
+extern "C" int sab_lazy_set_state(sab_engine *e, const int32_t *shift, const double *cached_raw, const uint8_t *has_shift,
+                                  const uint8_t *has_ref_centre, const double *ref_centre)
+{
+    if (!e || !shift || !cached_raw || !has_shift || !has_ref_centre || !ref_centre) return fail(SAB_EINVAL, "sab_lazy_set_state: null argument");
+    if (e->kind != SAB_POLYHEDRAL || !e->d_simp) return fail(SAB_ESTATE, "sab_lazy_set_state: polyhedra not set");
+    CU(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->S * e->smax * 3;
+    std::vector<int32_t> has(e->S);
+    for (int s = 0; s < e->S; s++) has[s] = has_shift[s] ? 1 : 0;
+    std::vector<long long> stamp(e->S, -1LL);
+    std::vector<int32_t> zero(e->S, 0);
+    std::vector<double> vc(n, 0.0);
+    unsigned long long st0[4] = {0, 0, 0, 0};
+    CU(upload(&e->d_lz_shift, shift, n)); CU(upload(&e->d_lz_cached, cached_raw, n)); CU(upload(&e->d_lz_has, has.data(), has.size()));
+    CU(upload(&e->d_lz_stamp, stamp.data(), stamp.size())); CU(upload(&e->d_lz_lock, zero.data(), zero.size()));
+    CU(upload(&e->d_lz_vc, vc.data(), n)); CU(upload(&e->d_lz_has_rc, has_ref_centre, (size_t)e->S));
+    CU(upload(&e->d_lz_rc, ref_centre, (size_t)3 * e->S)); CU(upload(&e->d_lz_stats, st0, (size_t)4));
+    e->lazy_set = true; e->lazy_frames = 0;
+    return SAB_OK;
+}
+
+extern "C" int sab_lazy_get_state(sab_engine *e, int32_t *shift, double *cached_raw, uint8_t *has_shift, double *vertex_coords, int64_t *stats)
+{
+    if (!e || !e->lazy_set) return fail(SAB_ESTATE, "sab_lazy_get_state: lazy state not set");
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    const size_t n = (size_t)e->S * e->smax * 3;
+    if (shift) CU(cudaMemcpy(shift, e->d_lz_shift, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (cached_raw) CU(cudaMemcpy(cached_raw, e->d_lz_cached, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (vertex_coords) CU(cudaMemcpy(vertex_coords, e->d_lz_vc, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (has_shift) {
+        std::vector<int32_t> has(e->S);
+        CU(cudaMemcpy(has.data(), e->d_lz_has, sizeof(int32_t) * e->S, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < e->S; s++) has_shift[s] = (uint8_t)(has[s] != 0);
+    }
+    if (stats) {
+        unsigned long long st[4];
+        CU(cudaMemcpy(st, e->d_lz_stats, sizeof st, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 4; i++) stats[i] = (int64_t)st[i];
+    }
+    return SAB_OK;
+}
+
+extern "C" int sab_assign_lazy(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride, int64_t n_frames,
+                               int32_t *d_result, void *stream, int32_t *recent, int32_t *prev, int32_t *tr_n, int32_t *tr_key,
+                               int64_t *tr_cnt, int tr_width, int append)
+{
+    if (!e || !d_frac || !d_lattice || !d_result || !recent || !prev || !tr_n || !tr_key || !tr_cnt || tr_width <= 0)
+        return fail(SAB_EINVAL, "sab_assign_lazy: null argument");
+    if (!e->lazy_set) return fail(SAB_ESTATE, "sab_assign_lazy: call sab_lazy_set_state first");
+    if (lattice_stride != 0 && lattice_stride != 9) return fail(SAB_EINVAL, "lattice_stride must be 0 or 9");
+    if (n_frames <= 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    struct Tmp {                         // device copies of the history, released on every exit path
+        void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Tmp() { for (void *q : p) if (q) cudaFree(q); }
+    } tmp;
+    SabHistory H{};
+    H.K = tr_width;
+    const size_t nk = (size_t)e->S * tr_width;
+    CU(cudaMalloc(&tmp.p[0], sizeof(int32_t) * 2 * e->A)); CU(cudaMalloc(&tmp.p[1], sizeof(int32_t) * e->A));
+    CU(cudaMalloc(&tmp.p[2], sizeof(int32_t) * e->S)); CU(cudaMalloc(&tmp.p[3], sizeof(int32_t) * nk));
+    CU(cudaMalloc(&tmp.p[4], sizeof(long long) * nk)); CU(cudaMalloc(&tmp.p[5], sizeof(int)));
+    H.recent = (int32_t *)tmp.p[0]; H.prev = (int32_t *)tmp.p[1]; H.tr_n = (int32_t *)tmp.p[2]; H.tr_key = (int32_t *)tmp.p[3];
+    H.tr_cnt = (long long *)tmp.p[4];
+    int *d_over = (int *)tmp.p[5];
+    CU(cudaMemcpyAsync(H.recent, recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.prev, prev, sizeof(int32_t) * e->A, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.tr_n, tr_n, sizeof(int32_t) * e->S, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.tr_key, tr_key, sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(H.tr_cnt, tr_cnt, sizeof(long long) * nk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
+    std::vector<int32_t> simp32;          // the kernel reads the uint8 simplices of sab_set_polyhedra
+    SabLazy Z{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_nface, e->d_simp, e->d_lz_has_rc, e->d_lz_rc, e->d_lz_shift,
+              e->d_lz_cached, e->d_lz_has, e->d_lz_stamp, e->d_lz_lock, e->d_lz_vc, e->d_lz_stats};
+    SabPriorityTables P{e->d_rank, e->d_rank_pos, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
+    const size_t smem = sizeof(double) * 24 * (size_t)e->A + sizeof(int) * (size_t)e->A + 16;
+    CU(cudaFuncSetAttribute(k_polyhedral_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_polyhedral_lazy<<<1, 256, smem, st>>>(d_frac, d_lattice, lattice_stride, n_frames, e->lazy_frames, e->N, e->A, e->d_mobile, e->S,
+                                            Z, P, H, append ? 1 : 0, d_result, d_over);
+    e->launches++;
+    CU(cudaGetLastError());
+    int over = 0;
+    CU(cudaMemcpyAsync(recent, H.recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(prev, H.prev, sizeof(int32_t) * e->A, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tr_n, H.tr_n, sizeof(int32_t) * e->S, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tr_key, H.tr_key, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tr_cnt, H.tr_cnt, sizeof(long long) * nk, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);     // state untouched by the caller: retry wider
+    e->lazy_frames += n_frames;
     return SAB_OK;
 }
 

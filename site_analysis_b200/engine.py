@@ -177,6 +177,15 @@ class AssignmentEngine:
             self._n_slot, self._slot_atom = self._padded(self.slots)
         self._pbc_ready = False
         self.frames_done = 0
+        # polyhedral sites: exact replay of the reference's lazily updated per-site caches (csrc/k_polyhedral_lazy.cuh).
+        # exact_lazy = True uses it from the first frame on, False never; None (default): it serves engines that are fed
+        # frame by frame (first call shorter than LAZY_AUTO_FRAMES: the reference's own append_timestep loop), and it takes
+        # over when a guard of the frame-parallel formulation fails in a batch that starts from the initial state
+        # (DESIGN.md section 4).
+        self.exact_lazy = None
+        self._lazy_mode = False
+        self._g2_cart_margin = np.inf          # guard G2: how far an unprimed vertex may move before its image choice can change
+        self._g2_frac_margin = np.inf
         self.reset_history()
         self.last_info: dict = {}
         # exact-pruning tables of the tetrahedral kernel (built lazily from the first sizeable batch)
@@ -227,6 +236,7 @@ class AssignmentEngine:
         (trajectory.py:364-373, polyhedral_site.py:264-279, dynamic_voronoi_site_collection.py:197-201)."""
         self.reset_history()
         self._pbc_ready = False
+        self._lazy_mode = False
         if self.k in (nat.POLYHEDRAL, nat.DYNAMIC_VORONOI):   # anchors belong to the PBC state; Voronoi lists are static
             self._cells = None
             if self.k == nat.DYNAMIC_VORONOI:
@@ -266,6 +276,7 @@ class AssignmentEngine:
         smax = self._slot_atom.shape[1]
         slot_shift = np.zeros((S, smax, 3), dtype=np.int32)
         legacy = np.zeros(S, dtype=np.uint8)
+        self._g2_cart_margin, self._g2_frac_margin = np.inf, np.inf
         lo = {}
         for s in range(S):
             atoms = self.slots[s]
@@ -286,6 +297,10 @@ class AssignmentEngine:
                 slot_shift[s, :len(atoms)] = tab.full_pbc_unwrap(r, rc, lat0)
                 if rc is None:
                     legacy[s] = 1
+                if self.k == nat.POLYHEDRAL:                    # guard G2 margins of this lazily initialised site
+                    cart, frac_m = tab.unwrap_margins(r, rc, lat0)
+                    self._g2_cart_margin = min(self._g2_cart_margin, cart)
+                    self._g2_frac_margin = min(self._g2_frac_margin, frac_m)
         if self.k == nat.POLYHEDRAL:
             n_face = np.zeros(S, dtype=np.int32)
             faces = []
@@ -316,6 +331,7 @@ class AssignmentEngine:
         self._lat0 = np.asarray(lat0, dtype=np.float64)
         nat.check(self.L.sab_set_pbc_state(self.h, nat.ptr(self.slot_shift), nat.ptr(prev_raw), nat.ptr(wraps),
                                            nat.ptr(np.ascontiguousarray(exc))))
+        self._legacy_flags = legacy
         if legacy.any():
             nat.check(self.L.sab_set_legacy_init(self.h, nat.ptr(legacy), 0))
         else:
@@ -456,7 +472,21 @@ class AssignmentEngine:
         if self.k != nat.POLYHEDRAL:
             return
         if span_bits is not None and float(np.array([span_bits], dtype=np.int64).view(np.float64)[0]) < EXCURSION_LIMIT:
-            return                                        # the device-side maximum already clears guard G1
+            # the device-side maximum already clears guard G1; guard G2: sites without cached shifts took the full unwrap at
+            # the engine's first frame, the reference takes it at the site's first QUERY -- the same image choice as long as
+            # no vertex moved further than half the margin between its best and second-best image (legacy rule: than its
+            # distance from the rule's thresholds)
+            span = float(np.array([span_bits], dtype=np.int64).view(np.float64)[0])
+            if np.isfinite(self._g2_cart_margin) or np.isfinite(self._g2_frac_margin):
+                cart = span * float(np.abs(self._lat0).sum()) * 1.01
+                if cart >= self._g2_cart_margin or span >= self._g2_frac_margin:
+                    msg = (f"unwrapped framework excursion {span:.3f}: a site without cached PBC shifts could choose another "
+                           "periodic image at its first query than at the first frame (guard G2)")
+                    if self.strict:
+                        raise GuardError(msg)
+                    import warnings
+                    warnings.warn(msg)
+            return
         M = len(self.fw_atoms)
         exc = np.zeros((M, 3, 2))
         nat.check(self.L.sab_get_pbc_state(self.h, None, None, None, nat.ptr(exc)))
@@ -528,7 +558,107 @@ class AssignmentEngine:
         ptrs = (C.c_void_p * max(len(peer_slot_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_slot_ptrs])
         nat.check(self.L.sab_set_result_peers(self.h, len(peer_slot_ptrs), ptrs))
 
+    # ------------------------------------------------------------------ exact replay (polyhedral)
+    def _lazy_start(self):
+        """Hand the per-site caches to the replay kernel as the reference holds them before the first frame."""
+        S, smax = self.S, self._slot_atom.shape[1]
+        shift = np.zeros((S, smax, 3), dtype=np.int32); cached = np.zeros((S, smax, 3)); has = np.zeros(S, dtype=np.uint8)
+        for s, pr in enumerate(self.primed):
+            if pr is not None:
+                n = len(self.slots[s])
+                shift[s, :n] = np.asarray(pr[0]); cached[s, :n] = np.asarray(pr[1]); has[s] = 1
+        has_rc = np.array([c is not None for c in self.ref_centres], dtype=np.uint8)
+        rc = np.array([c if c is not None else np.zeros(3) for c in self.ref_centres], dtype=np.float64).reshape(S, 3)
+        self._upload_priority_tables()
+        nat.check(self.L.sab_lazy_set_state(self.h, nat.ptr(shift), nat.ptr(cached), nat.ptr(has), nat.ptr(has_rc),
+                                            nat.ptr(np.ascontiguousarray(rc))))
+        self._lazy_mode = True
+
+    def _lazy_snapshot(self):
+        S, smax = self.S, self._slot_atom.shape[1]
+        shift = np.zeros((S, smax, 3), dtype=np.int32); cached = np.zeros((S, smax, 3)); has = np.zeros(S, dtype=np.uint8)
+        nat.check(self.L.sab_lazy_get_state(self.h, nat.ptr(shift), nat.ptr(cached), nat.ptr(has), None, None))
+        return shift, cached, has
+
+    def lazy_stats(self) -> dict:
+        st = np.zeros(4, dtype=np.int64)
+        nat.check(self.L.sab_lazy_get_state(self.h, None, None, None, None, nat.ptr(st)))
+        return dict(queries=int(st[0]), incremental=int(st[1]), full=int(st[2]), invalidations=int(st[3]))
+
+    def _assign_device_lazy(self, d_frac, d_lattice, stride, d_result, append):
+        """One batch through k_polyhedral_lazy: final positions and the advanced history, nothing left to resolve or fold."""
+        torch = _torch()
+        F = int(d_frac.shape[0])
+        if not self._pbc_ready:
+            lat0 = (d_lattice[0] if stride else d_lattice).cpu().numpy()
+            self._init_pbc(d_frac[0].cpu().numpy(), lat0)          # site tables + face topology (hulled from the first frame, G3)
+        if not self._lazy_mode:
+            self._lazy_start()
+        self.sync_history()
+        stream = torch.cuda.current_stream(d_frac.device).cuda_stream
+        width = max(16, 2 * max((len(t) for t in self.transitions), default=0))
+        has_rc = np.array([c is not None for c in self.ref_centres], dtype=np.uint8)
+        rc = np.ascontiguousarray(np.array([c if c is not None else np.zeros(3) for c in self.ref_centres], dtype=np.float64).reshape(self.S, 3))
+        while True:
+            tr_n = np.zeros(self.S, dtype=np.int32)
+            tr_key = np.zeros((self.S, width), dtype=np.int32)
+            tr_cnt = np.zeros((self.S, width), dtype=np.int64)
+            for s, t in enumerate(self.transitions):
+                tr_n[s] = len(t)
+                if t:
+                    tr_key[s, :len(t)] = list(t.keys()); tr_cnt[s, :len(t)] = list(t.values())
+            recent, prev = self.recent.copy(), self.prev.copy()
+            snap = self._lazy_snapshot()
+            code = self.L.sab_assign_lazy(self.h, d_frac.data_ptr(), d_lattice.data_ptr(), stride, F, d_result.data_ptr(), stream,
+                                          nat.ptr(recent), nat.ptr(prev), nat.ptr(tr_n), nat.ptr(tr_key), nat.ptr(tr_cnt), width,
+                                          1 if append else 0)
+            if code == 3 and width < 4 * self.S:               # SAB_EOVERFLOW: a Counter row outgrew the table; redo wider
+                nat.check(self.L.sab_lazy_set_state(self.h, nat.ptr(snap[0]), nat.ptr(snap[1]), nat.ptr(snap[2]), nat.ptr(has_rc), nat.ptr(rc)))
+                width *= 2
+                continue
+            nat.check(code)
+            break
+        self.recent, self.prev = recent, prev
+        self.transitions = [dict(zip(map(int, tr_key[s, :tr_n[s]]), map(int, tr_cnt[s, :tr_n[s]]))) for s in range(self.S)]
+        self.frames_done += F
+        self.last_info = dict(ambiguous=0, full27=0, launches=1, reinits=0, assign_ns=0, wrap_ns=0, deferred=0, scan_redo=0,
+                              peers_written=0, lazy=1)
+        self._last_pending = []
+        return d_result
+
     def assign_device(self, d_frac, d_lattice, *, append: bool = True, defer_resolve: bool = False, out=None):
+        """Assign a device-resident batch (see :meth:`_assign_device_fast` for the arguments).
+
+        Polyhedral sites: when a guard of the frame-parallel formulation fails (a framework step >= 0.3 invalidates a
+        site's cache; the unwrapped excursion reaches 0.3; an unprimed site could pick another image) in a batch that
+        starts from the engine's initial state, the batch is redone by the exact replay kernel
+        (csrc/k_polyhedral_lazy.cuh) and the engine stays on it.  A violation in a LATER batch cannot be repaired (when each
+        site was last queried during the earlier batches is not known) and raises ``GuardError``; set
+        ``exact_lazy = True`` before the first frame to stream such trajectories exactly."""
+        if self.k != nat.POLYHEDRAL:
+            return self._assign_device_fast(d_frac, d_lattice, append=append, defer_resolve=defer_resolve, out=out)
+        torch = _torch()
+        F = int(d_frac.shape[0])
+        auto = self.exact_lazy is None and self.frames_done == 0 and 0 < F < self.LAZY_AUTO_FRAMES and not defer_resolve
+        if (self.exact_lazy or self._lazy_mode or auto) and F > 0:
+            d_lattice = d_lattice.contiguous()
+            d_result = out if out is not None else torch.empty((F, self.A), dtype=torch.int32, device=d_frac.device)
+            return self._assign_device_lazy(d_frac, d_lattice, 9 if d_lattice.dim() == 3 else 0, d_result, append)
+        start = (self.frames_done, len(self._pending), self.recent.copy(), self.prev.copy(), [dict(t) for t in self.transitions])
+        try:
+            return self._assign_device_fast(d_frac, d_lattice, append=append, defer_resolve=defer_resolve, out=out)
+        except GuardError:
+            if start[0] != 0 or not self.strict or defer_resolve or self.exact_lazy is False:
+                raise
+        # redo from the initial state with the exact replay
+        self.frames_done = 0
+        del self._pending[start[1]:]
+        self.recent, self.prev, self.transitions = start[2], start[3], start[4]
+        d_lattice = d_lattice.contiguous()
+        d_result = out if out is not None else torch.empty((F, self.A), dtype=torch.int32, device=d_frac.device)
+        return self._assign_device_lazy(d_frac, d_lattice, 9 if d_lattice.dim() == 3 else 0, d_result, append)
+
+    def _assign_device_fast(self, d_frac, d_lattice, *, append: bool = True, defer_resolve: bool = False, out=None):
         """Assign a device-resident batch.  ``d_frac`` (F, N, 3) float64 cuda tensor, ``d_lattice`` (3, 3)
         or (F, 3, 3).  Returns an (F, A) int32 cuda tensor of site list positions (-1 = None).
 
@@ -634,22 +764,77 @@ class AssignmentEngine:
             return int(max(nf * self.A // 8, 1) + 1024)
         return 16
 
+    PIPELINE_MIN_FRAMES = 2048      # host batches from this size go through the pipelined C-ABI call (sab_assign_host)
+    LAZY_AUTO_FRAMES = 64           # polyhedral engines whose FIRST call is shorter than this stay on the exact replay kernel
+
+    def _snapshot_pbc(self):
+        if self.slots is None or not self._pbc_ready:
+            return None
+        M = len(self.fw_atoms)
+        sh = np.zeros_like(self.slot_shift)
+        prev_raw = np.zeros((M, 3)); wraps = np.zeros((M, 3), dtype=np.int32); exc = np.zeros((M, 3, 2))
+        nat.check(self.L.sab_get_pbc_state(self.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
+        return sh, prev_raw, wraps, exc, self.frames_done, len(self._pending)
+
+    def _restore_pbc(self, snap):
+        if snap is None:
+            return
+        sh, prev_raw, wraps, exc, done, n_pending = snap
+        nat.check(self.L.sab_set_pbc_state(self.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
+        if done == 0 and getattr(self, "_legacy_flags", None) is not None and self._legacy_flags.any():
+            nat.check(self.L.sab_set_legacy_init(self.h, nat.ptr(self._legacy_flags), 0))     # the first frame is still ahead
+        self.frames_done = done
+        del self._pending[n_pending:]
+
     def assign(self, frac: np.ndarray, lattice: np.ndarray, *, append: bool = True, chunk_frames: int = 32768) -> np.ndarray:
-        """Assign a host trajectory (F, N, 3): staging -> device -> (F, A) int32 numpy."""
+        """Assign a host trajectory (F, N, 3): staging -> device -> (F, A) int32 numpy.
+
+        Long batches take the pipelined host-buffer call of the C ABI (``sab_assign_host``: chunked, H2D copies overlapped
+        with the kernels; pinned input -- e.g. from ``io.read_xdatcar(pinned=True)`` -- is copied asynchronously).  A batch that
+        call cannot finish (atom-frames inside several sites need the priority resolver; a framework step >= 0.3 needs the
+        re-initialising path) is redone from the saved PBC state by the chunked path below, with identical results."""
         torch = _torch()
         frac = np.ascontiguousarray(frac, dtype=np.float64)
         lattice = np.ascontiguousarray(lattice, dtype=np.float64)
         F = frac.shape[0]
+        call_start = (self.frames_done, len(self._pending), self.recent.copy(), self.prev.copy(),
+                      [dict(t) for t in self.transitions] if self.k == nat.POLYHEDRAL and self.frames_done == 0 else None)
+        fast_ok = not (self.k == nat.POLYHEDRAL and (self.exact_lazy or self._lazy_mode or
+                                                     (self.exact_lazy is None and self.frames_done == 0 and F < self.LAZY_AUTO_FRAMES)))
+        if fast_ok and append and F >= self.PIPELINE_MIN_FRAMES and self.k != nat.SPHERICAL:
+            if self.slots is not None and not self._pbc_ready:
+                self._init_pbc(frac[0], lattice if lattice.ndim == 2 else lattice[0])
+            snap = self._snapshot_pbc()
+            try:
+                return self.assign_host_pipelined(frac, lattice)
+            except (nat.NativeError, GuardError):
+                if self.slots is not None and snap is None:
+                    raise
+                self._restore_pbc(snap)
         out = np.empty((F, self.A), dtype=np.int32)
         dev = torch.device("cuda", self.device)
-        for f0 in range(0, F, chunk_frames):
-            f1 = min(F, f0 + chunk_frames)
-            d_frac = torch.from_numpy(frac[f0:f1]).to(dev)
-            lat = lattice if lattice.ndim == 2 else lattice[f0:f1]
-            d_lat = torch.from_numpy(np.ascontiguousarray(lat)).to(dev)
-            out[f0:f1] = self.assign_device(d_frac, d_lat, append=append).cpu().numpy()
-            for idx, start, n in self._last_pending:      # history folds lazily from the host copy
-                self._pending[idx] = (out[f0 + start:f0 + start + n], self._pending[idx][1])
+
+        def chunks():
+            for f0 in range(0, F, chunk_frames):
+                f1 = min(F, f0 + chunk_frames)
+                d_frac = torch.from_numpy(frac[f0:f1]).to(dev)
+                lat = lattice if lattice.ndim == 2 else lattice[f0:f1]
+                d_lat = torch.from_numpy(np.ascontiguousarray(lat)).to(dev)
+                out[f0:f1] = self.assign_device(d_frac, d_lat, append=append).cpu().numpy()
+                for idx, start, n in self._last_pending:      # history folds lazily from the host copy
+                    self._pending[idx] = (out[f0 + start:f0 + start + n], self._pending[idx][1])
+        try:
+            chunks()
+        except GuardError:
+            # a guard failed in a later chunk of a call that started from the initial state: the exact replay redoes the call
+            if self.k != nat.POLYHEDRAL or call_start[0] != 0 or not self.strict or self._lazy_mode or self.exact_lazy is False:
+                raise
+            self.frames_done = 0
+            del self._pending[call_start[1]:]
+            self.recent, self.prev = call_start[2], call_start[3]
+            self.transitions = call_start[4]
+            self._lazy_start()
+            chunks()
         return out
 
     def assign_host_pipelined(self, frac: np.ndarray, lattice: np.ndarray, out: np.ndarray | None = None,

@@ -47,10 +47,12 @@ class SiteCollection:
             self._site_lookup[site.index] = site
         self._pos = {s.index: i for i, s in enumerate(sites)}
         self._index_of_pos = np.array([s.index for s in sites], dtype=np.int32)
+        self._identity_index = bool(np.array_equal(self._index_of_pos, np.arange(len(sites))))   # Site.index == list position
         self._engine: AssignmentEngine | None = None
         self._engine_key = None
         self._current = None            # (frac (N,3), lattice (3,3)) of the last analysed structure
         self.strict = True
+        self.exact_lazy = None          # polyhedral sites: None = automatic, True = always the exact replay kernel (engine.py)
         self.use_cells = True           # exact spatial pruning (False: exhaustive kernels only; for cross-checks)
         self.rank_table = None          # optional override of the distance-rank table (testing)
         self.engine_options: dict[int, int] = {}   # sab_set_option(key, value) pairs applied to the engine
@@ -136,6 +138,7 @@ class SiteCollection:
             self._engine = AssignmentEngine(self._kind, n_atoms, [a.index for a in atoms], strict=self.strict,
                                             rank_table=self.rank_table, **self._engine_kwargs())
             self._engine.use_cells = self.use_cells
+            self._engine.exact_lazy = self.exact_lazy
             for k, v in self.engine_options.items():
                 self._engine.set_option(k, v)
             self._engine_key = key
@@ -196,6 +199,8 @@ class SiteCollection:
                 w = frac[f, mobile] % 1.0
                 for a in np.nonzero(rows[f] >= 0)[0]:
                     self.sites[rows[f, a]].points.append(w[a])
+        if self._identity_index:                                # the usual case: nothing to translate
+            return rows
         return np.where(rows >= 0, self._index_of_pos[np.clip(rows, 0, None)], -1).astype(np.int32)
 
     def _after_batch(self, eng, atoms, frac, rows) -> None:
