@@ -215,6 +215,11 @@ int sab_assign_host(sab_engine *e, const double *h_frac, const double *h_lattice
                     int lattice_stride, int64_t n_frames, int32_t *h_result,
                     int64_t chunk_frames, int64_t *info);
 
+/* Optional device mirror of the rows the next sab_assign_host calls return: row f of the call also lands in
+ * d_full[f * n_mobile ...] (device memory of at least n_frames * n_mobile int32), so that a caller that goes on working
+ * on the GPU (the history fold, sab_fold_result) need not upload the result again.  NULL switches it off. */
+int sab_set_result_mirror(sab_engine *e, int32_t *d_full);
+
 /* ---- priority resolver --------------------------------------------------------------
  * Replays PriorityAssignmentMixin._get_priority_sites (site_collection.py:113-182),
  * SiteCollection.update_occupation (:279-310) and Atom.update_recent_site (atom.py:181-192)
@@ -312,6 +317,10 @@ int sab_polyhedra_contain(int device, const double *d_vertex, const int32_t *d_n
 
 int sab_mic_distances(int device, const double *d_c1, int n, const double *d_c2, int m,
                       const double *d_lattice, double *d_out, void *stream);
+
+/* Measured FP64 arithmetic peak of the device in TFLOP/s, tflops[4] = {DADD only, DMUL only, DMUL + DADD pairs, DFMA counted
+ * as 2}: the roofline denominator of the kernels whose float64 decisions must not use FMA. */
+int sab_measure_fp64_peak(int device, double *tflops);
 
 /* Multi-GPU, frames sharded over ranks: the reference's atoms_trajectory (trajectory.py:375-383) is the concatenation
  * of the shards' rows.  Instead of an all-gather AFTER the kernels, the stream kernel stores every result row it

@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "k_nearest.cuh"
@@ -86,6 +90,8 @@ struct sab_engine {
     unsigned long long *d_counters = nullptr;
     // host-path staging
     void *stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
+    int32_t *d_mirror = nullptr;           // sab_set_result_mirror: device copy of the rows sab_assign_host returns
+    void *h_res_stage[2] = {nullptr, nullptr}; size_t h_res_stage_bytes = 0;   // pinned staging of results bound for pageable memory
     void *ws = nullptr; size_t ws_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t ev_free[2] = {nullptr, nullptr};
@@ -164,6 +170,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->d_lz_vc, e->d_lz_rc, e->d_lz_stamp, e->d_lz_has_rc, e->d_lz_stats};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    for (int i = 0; i < 2; i++) if (e->h_res_stage[i]) cudaFreeHost(e->h_res_stage[i]);
     for (int i = 0; i < 3; i++) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
     for (int i = 0; i < 2; i++) {
         if (e->streams[i]) cudaStreamDestroy(e->streams[i]);
@@ -1130,6 +1137,50 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
     int64_t tot_info[12] = {0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0};
     int status = SAB_OK;
     int64_t n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    // Results bound for PAGEABLE host memory (a fresh numpy array): cudaMemcpyAsync would stage them synchronously and stall
+    // the pipeline, so they go to pinned staging first and a helper thread copies them out while the next chunks compute.
+    bool out_pinned = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, h_result) == cudaSuccess) out_pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+        cudaGetLastError();
+    }
+    if (!out_pinned && e->h_res_stage_bytes < res_b * (size_t)chunk_frames) {
+        for (int i = 0; i < 2; i++) { if (e->h_res_stage[i]) cudaFreeHost(e->h_res_stage[i]); e->h_res_stage[i] = nullptr; }
+        for (int i = 0; i < 2; i++) CU(cudaMallocHost(&e->h_res_stage[i], res_b * (size_t)chunk_frames));
+        e->h_res_stage_bytes = res_b * (size_t)chunk_frames;
+    }
+    struct Job { int b; int64_t f0, nf; };
+    std::mutex mu; std::condition_variable cv; std::deque<Job> jobs; bool quit = false; int busy[2] = {0, 0};
+    cudaEvent_t ev_res[2] = {nullptr, nullptr};
+    std::thread copier;
+    if (!out_pinned) {
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&ev_res[i], cudaEventDisableTiming));
+        const int dev = e->device;
+        copier = std::thread([&, dev]() {
+            cudaSetDevice(dev);
+            for (;;) {
+                Job j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return quit || !jobs.empty(); });
+                    if (jobs.empty()) return;
+                    j = jobs.front(); jobs.pop_front();
+                }
+                cudaEventSynchronize(ev_res[j.b]);
+                memcpy(h_result + (size_t)j.f0 * e->A, e->h_res_stage[j.b], res_b * (size_t)j.nf);
+                { std::lock_guard<std::mutex> lk(mu); busy[j.b] = 0; }
+                cv.notify_all();
+            }
+        });
+    }
+    auto finish_copier = [&]() {
+        if (!copier.joinable()) return;
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        copier.join();
+        for (int i = 0; i < 2; i++) if (ev_res[i]) cudaEventDestroy(ev_res[i]);
+    };
     auto issue_copy = [&](int64_t k) -> cudaError_t {
         int b = (int)(k & 1);
         int64_t f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
@@ -1145,13 +1196,13 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         if (er != cudaSuccess) return er;
         return cudaEventRecord(ev_copied[b], s_copy);
     };
-    CU(issue_copy(0));
-    for (int64_t k = 0; k < n_chunks && status == SAB_OK; k++) {
+    cudaError_t cerr = issue_copy(0);
+    for (int64_t k = 0; k < n_chunks && status == SAB_OK && cerr == cudaSuccess; k++) {
         int b = (int)(k & 1);
         int64_t f0 = k * chunk_frames, nf = std::min(chunk_frames, n_frames - f0);
         char *base = (char *)e->stage[b];
-        if (k + 1 < n_chunks) CU(issue_copy(k + 1));
-        CU(cudaStreamWaitEvent(s_comp, ev_copied[b], 0));
+        if (k + 1 < n_chunks && (cerr = issue_copy(k + 1)) != cudaSuccess) break;
+        if ((cerr = cudaStreamWaitEvent(s_comp, ev_copied[b], 0)) != cudaSuccess) break;
         int64_t ci[12];
         status = sab_assign_device(e, (const double *)base, (const double *)(base + o_lat), lattice_stride, nf,
                                    (int32_t *)(base + o_res), (int32_t *)(base + o_spill), (int64_t)spill_elems,
@@ -1159,17 +1210,36 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
         if (status != SAB_OK) break;
         if (ci[0] > 0) { status = fail(SAB_ESTATE, "sab_assign_host: %lld atom-frames are contained by several sites; "
                                        "use sab_assign_device + sab_resolve", (long long)ci[0]); break; }
-        CU(cudaMemcpyAsync(h_result + (size_t)f0 * e->A, base + o_res, res_b * nf, cudaMemcpyDeviceToHost, s_comp));
-        CU(cudaEventRecord(ev_done[b], s_comp));
+        if (e->d_mirror && (cerr = cudaMemcpyAsync(e->d_mirror + (size_t)f0 * e->A, base + o_res, res_b * nf, cudaMemcpyDeviceToDevice, s_comp)) != cudaSuccess) break;
+        if (out_pinned) {
+            if ((cerr = cudaMemcpyAsync(h_result + (size_t)f0 * e->A, base + o_res, res_b * nf, cudaMemcpyDeviceToHost, s_comp)) != cudaSuccess) break;
+        } else {
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return busy[b] == 0; }); busy[b] = 1; }   // staging b copied out
+            if ((cerr = cudaMemcpyAsync(e->h_res_stage[b], base + o_res, res_b * nf, cudaMemcpyDeviceToHost, s_comp)) != cudaSuccess) break;
+            if ((cerr = cudaEventRecord(ev_res[b], s_comp)) != cudaSuccess) break;
+            { std::lock_guard<std::mutex> lk(mu); jobs.push_back(Job{b, f0, nf}); }
+            cv.notify_all();
+        }
+        if ((cerr = cudaEventRecord(ev_done[b], s_comp)) != cudaSuccess) break;
         tot_info[0] += ci[0]; tot_info[1] += ci[1]; tot_info[4] += ci[4]; tot_info[5] += ci[5];
         tot_info[6] += ci[6]; tot_info[7] += ci[7]; tot_info[9] += ci[9];
         tot_info[8] = std::max(tot_info[8], ci[8]);
         if (ci[3] >= 0 && tot_info[3] < 0) tot_info[3] = f0 + ci[3];
     }
     cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_copy);
+    finish_copier();
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_copied[i]); cudaEventDestroy(ev_done[i]); }
     for (int i = 0; i < 12; i++) info[i] = tot_info[i];
+    if (status == SAB_OK && cerr != cudaSuccess)
+        return fail(SAB_ECUDA, "sab_assign_host: %s", cudaGetErrorString(cerr));
     return status;
+}
+
+extern "C" int sab_set_result_mirror(sab_engine *e, int32_t *d_full)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_result_mirror: null engine");
+    e->d_mirror = d_full;
+    return SAB_OK;
 }
 
 // ---------------------------------------------------------------- priority resolver
@@ -1544,6 +1614,59 @@ extern "C" int sab_polyhedra_contain(int device, const double *d_vertex, const i
     CU(cudaSetDevice(device));
     k_polyhedra_contain<<<(n_sites + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_vertex, d_n_vert, vmax, d_simplices, d_n_face, fmax,
                                                                                 n_sites, d_points, n_img, d_out);
+    CU(cudaGetLastError());
+    return SAB_OK;
+}
+
+// ---------------------------------------------------------------- measured FP64 issue peak without FMA (roofline denominator)
+// mode 0: dependent-free DADD streams, 1: DMUL streams, 2: DMUL + DADD pairs (what -fmad=false code issues), 3: DFMA (context)
+template <int MODE> __global__ void k_fp64_peak(double *out, int iters, double seed)
+{
+    double a[8], b = seed + 1e-9 * threadIdx.x, c = 1.0 - 1e-9 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = seed + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (MODE == 0) a[i] = __dadd_rn(a[i], b);
+            else if (MODE == 1) a[i] = __dmul_rn(a[i], c);
+            else if (MODE == 2) a[i] = __dadd_rn(__dmul_rn(a[i], c), b);
+            else a[i] = __fma_rn(a[i], c, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 12345.678) out[0] = s;            // never true: keeps the arithmetic alive
+}
+
+extern "C" int sab_measure_fp64_peak(int device, double *tflops /* [4]: DADD, DMUL, DMUL+DADD, DFMA (2 flop) */)
+{
+    if (!tflops) return fail(SAB_EINVAL, "sab_measure_fp64_peak: null argument");
+    CU(cudaSetDevice(device));
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = 20000, grid = sm * 8, block = 256;
+    for (int mode = 0; mode < 4; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            if (mode == 0) k_fp64_peak<0><<<grid, block>>>(d, iters, 1.0);
+            else if (mode == 1) k_fp64_peak<1><<<grid, block>>>(d, iters, 1.0);
+            else if (mode == 2) k_fp64_peak<2><<<grid, block>>>(d, iters, 1.0);
+            else k_fp64_peak<3><<<grid, block>>>(d, iters, 1.0);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double ops = (double)grid * block * 8.0 * iters * (mode >= 2 ? 2.0 : 1.0);
+        tflops[mode] = ops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     CU(cudaGetLastError());
     return SAB_OK;
 }

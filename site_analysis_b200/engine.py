@@ -86,16 +86,21 @@ def fold_history(recent: np.ndarray, prev: np.ndarray, transitions: list, rows: 
 DEVICE_FOLD_MIN = 1 << 15     # atom-frames per batch from which the history is folded on the GPU
 
 
-def fold_history_device(recent: np.ndarray, prev: np.ndarray, transitions: list, rows, n_sites: int) -> None:
+def fold_history_device(recent: np.ndarray, prev: np.ndarray, transitions, rows, n_sites: int) -> None:
     """:func:`fold_history` (``append=True``) with the O(F A) part on the GPU: ``sab_fold_result`` (csrc/k_fold.cuh)
     returns the transition pairs in first-occurrence order and each atom's last / last-different site; only O(A + pairs)
-    work is left for the host.  ``rows`` (F, A) int32 positions, CUDA tensor or numpy array."""
+    work is left for the host.  ``rows`` (F, A) int32 positions, CUDA tensor or numpy array.  ``transitions``: the list of
+    per-site dicts, or an :class:`AssignmentEngine` (then the pairs are merged into its array store without touching
+    any dict)."""
     from .folds import fold_rows
-    out = fold_rows(rows, n_sites, prev=prev, want_pairs=True, want_recent=True)
+    out = fold_rows(rows, n_sites, prev=prev, want_pairs=True, want_recent=True, want_runs=False)
     src, dst, cnt, _ = out["pairs"]
-    for a, b, c in zip(src.tolist(), dst.tolist(), cnt.tolist()):      # sorted by first occurrence: Counter insertion order
-        d = transitions[a]
-        d[b] = d.get(b, 0) + c
+    if hasattr(transitions, "_tr_add_pairs"):
+        transitions._tr_add_pairs(src, dst, cnt)
+    else:
+        for a, b, c in zip(src.tolist(), dst.tolist(), cnt.tolist()):  # sorted by first occurrence: Counter insertion order
+            d = transitions[a]
+            d[b] = d.get(b, 0) + c
     last_v, other_v = out["recent"]
     any_assigned, has_other = last_v >= 0, other_v >= 0
     old0, old1 = recent[:, 0].copy(), recent[:, 1].copy()
@@ -225,6 +230,41 @@ class AssignmentEngine:
         nat.check(self.L.sab_set_option(self.h, int(key), int(value)))
 
     # ------------------------------------------------------------------ history (host)
+    # Site.transitions of all sites (site.py:71): per-site dicts {destination position: count} in Counter insertion order.
+    # Long batches are folded on the GPU into (source, destination, count) arrays; the dicts are built from them only when
+    # somebody asks (the priority resolver, the Python objects), so streaming batches never pay for S Python dicts.
+    @property
+    def transitions(self) -> list:
+        if self._tr_dicts is None:
+            src, dst, cnt = self._tr_arrays
+            order = np.argsort(src, kind="stable")               # per source, insertion order kept
+            bounds = np.searchsorted(src[order], np.arange(self.S + 1))
+            d_l, c_l = dst[order].tolist(), cnt[order].tolist()
+            self._tr_dicts = [dict(zip(d_l[a:b], c_l[a:b])) if b > a else {} for a, b in zip(bounds[:-1].tolist(), bounds[1:].tolist())]
+            self._tr_arrays = None                               # the caller may edit the dicts: they are authoritative now
+        return self._tr_dicts
+
+    @transitions.setter
+    def transitions(self, value) -> None:
+        self._tr_dicts, self._tr_arrays = value, None
+
+    def _tr_add_pairs(self, src, dst, cnt) -> None:
+        """Merge transition pairs (in first-occurrence order) into the array store."""
+        if self._tr_arrays is None:
+            s0 = np.fromiter((s for s, t in enumerate(self._tr_dicts) for _ in t), dtype=np.int64)
+            d0 = np.fromiter((k for t in self._tr_dicts for k in t), dtype=np.int64)
+            c0 = np.fromiter((v for t in self._tr_dicts for v in t.values()), dtype=np.int64)
+        else:
+            s0, d0, c0 = self._tr_arrays
+        s1 = np.concatenate([s0, np.asarray(src, dtype=np.int64)]); d1 = np.concatenate([d0, np.asarray(dst, dtype=np.int64)])
+        c1 = np.concatenate([c0, np.asarray(cnt, dtype=np.int64)])
+        _, first, inv = np.unique(s1 * self.S + d1, return_index=True, return_inverse=True)
+        total = np.zeros(len(first), dtype=np.int64)
+        np.add.at(total, inv, c1)
+        order = np.argsort(first, kind="stable")                 # insertion order = first occurrence
+        self._tr_arrays = (s1[first[order]], d1[first[order]], total[order])
+        self._tr_dicts = None
+
     def reset_history(self):
         self.recent = -np.ones((self.A, 2), dtype=np.int32)
         self.prev = np.full(self.A, -2, dtype=np.int32)
@@ -256,7 +296,7 @@ class AssignmentEngine:
                 continue
             rows, append = item
             if append and rows.shape[0] * rows.shape[1] >= DEVICE_FOLD_MIN:
-                fold_history_device(self.recent, self.prev, self.transitions, rows, self.S)
+                fold_history_device(self.recent, self.prev, self, rows, self.S)
                 continue
             if not isinstance(rows, np.ndarray):
                 rows = rows.cpu().numpy()
@@ -873,15 +913,24 @@ class AssignmentEngine:
                 self._build_dynvor_lists(d_s, lat0)
                 del d_s
         info = np.zeros(12, dtype=np.int64)
-        nat.check(self.L.sab_assign_host(self.h, frac.ctypes.data, nat.ptr(lattice), 9 if lattice.ndim == 3 else 0,
-                                         F, out.ctypes.data, chunk_frames, nat.ptr(info)))
+        d_mirror = None
+        if F * self.A >= DEVICE_FOLD_MIN:                 # the history fold runs on the GPU: keep a device copy of the rows
+            torch = _torch()
+            d_mirror = torch.empty((F, self.A), dtype=torch.int32, device=torch.device("cuda", self.device))
+            nat.check(self.L.sab_set_result_mirror(self.h, d_mirror.data_ptr()))
+        try:
+            nat.check(self.L.sab_assign_host(self.h, frac.ctypes.data, nat.ptr(lattice), 9 if lattice.ndim == 3 else 0,
+                                             F, out.ctypes.data, chunk_frames, nat.ptr(info)))
+        finally:
+            if d_mirror is not None:
+                nat.check(self.L.sab_set_result_mirror(self.h, None))
         if info[3] >= 0:
             raise GuardError(f"frame {int(info[3])}: a framework step >= 0.3 fractional units needs the re-initialising "
                              "path; use AssignmentEngine.assign")
         self._check_excursion(int(info[8]))
         if self._cells is not None and info[4] > max(1, F // 50):
             self._cells_stale = True
-        self._pending.append((out, True))
+        self._pending.append((out if d_mirror is None else d_mirror, True))
         self.frames_done += F
         self.last_info = dict(ambiguous=0, full27=int(info[4]), launches=int(info[5]), reinits=0,
                               assign_ns=int(info[6]), wrap_ns=int(info[7]), deferred=int(info[9]))

@@ -26,7 +26,7 @@ def _next_pow2(n: int) -> int:
 
 
 def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: int | None = None,
-              want_recent: bool = False):
+              want_recent: bool = False, want_runs: bool = True):
     """Fold a result array on the GPU.
 
     Args:
@@ -101,7 +101,7 @@ def fold_rows(rows, n_sites: int, prev=None, want_pairs: bool = True, device: in
         else:
             raise nat.NativeError(L.sab_last_error().decode())
         R, P = int(info[0]), int(info[1])
-        runs = tuple(t[:R].cpu().numpy() for t in (r_site, r_atom, r_start, r_len))
+        runs = tuple(t[:R].cpu().numpy() for t in (r_site, r_atom, r_start, r_len)) if want_runs else None   # the history fold needs no runs on the host
         pairs = None
         if want_pairs:
             src, dst, cnt, first = (t[:P].cpu().numpy() for t in (p_src, p_dst, p_cnt, p_first))

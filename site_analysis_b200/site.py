@@ -27,7 +27,23 @@ class Site:
         self._lazy_blocks: list = []                 # pending (results (F, A), atom_index (A,)) pairs
         self._points: list[np.ndarray] = []
         self._lazy_points: list = []                 # pending (BlockFolds with .frac, site position) pairs of long batches
-        self.transitions: Counter = Counter()
+        self._transitions: Counter = Counter()
+        self._lazy_transitions = None                # (collection, state token): the Counter lives in the GPU engine's store
+
+    @property
+    def transitions(self) -> Counter:
+        """Counter {destination Site.index: count} in insertion order (reference site.py:71, site_collection.py:300-302).
+        After a GPU batch it is built from the engine's folded store on first access."""
+        if self._lazy_transitions is not None:
+            collection, token = self._lazy_transitions
+            self._lazy_transitions = None
+            self._transitions = collection._site_transitions(self, token)
+        return self._transitions
+
+    @transitions.setter
+    def transitions(self, value) -> None:
+        self._lazy_transitions = None
+        self._transitions = value
 
     @property
     def trajectory(self) -> list[list[int]]:

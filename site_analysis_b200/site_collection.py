@@ -50,6 +50,7 @@ class SiteCollection:
         self._identity_index = bool(np.array_equal(self._index_of_pos, np.arange(len(sites))))   # Site.index == list position
         self._engine: AssignmentEngine | None = None
         self._engine_key = None
+        self._tr_token = None           # (engine, tag) of the state whose Site.transitions are parked in the engine's store
         self._current = None            # (frac (N,3), lattice (3,3)) of the last analysed structure
         self.strict = True
         self.exact_lazy = None          # polyhedral sites: None = automatic, True = always the exact replay kernel (engine.py)
@@ -160,7 +161,11 @@ class SiteCollection:
             eng.recent[a, 1] = self._to_pos(r[1], "atom history")
             last = atom._last_trajectory_entry()
             eng.prev[a] = last if last < 0 else self._to_pos(last, "atom trajectory")
-        eng.transitions = [{self._to_pos(k, "transition"): int(v) for k, v in s.transitions.items()} for s in self.sites]
+        # Site.transitions: untouched since this collection parked them in the engine's store (lazy) -> nothing to pull
+        token = self._tr_token
+        if token is None or token[0] is not eng or any(getattr(s, "_lazy_transitions", None) is None or s._lazy_transitions[1] is not token
+                                                        for s in self.sites):
+            eng.transitions = [{self._to_pos(k, "transition"): int(v) for k, v in s.transitions.items()} for s in self.sites]
 
     def _push_state(self, eng: AssignmentEngine, atoms, last_row: np.ndarray, last_frac: np.ndarray) -> None:
         eng.sync_history()
@@ -175,10 +180,22 @@ class SiteCollection:
                 self.sites[p].contains_atoms.append(atom.index)
             r0, r1 = int(eng.recent[a, 0]), int(eng.recent[a, 1])
             atom._recent_sites = [None if r0 < 0 else int(idx[r0]), None if r1 < 0 else int(idx[r1])]
+        # Site.transitions stay in the engine's store; each site builds its Counter on first access (_site_transitions)
+        token = self._tr_token = (eng, object())
         for s, site in enumerate(self.sites):
-            t = eng.transitions[s]
-            if t or site.transitions:
-                site.transitions = Counter({int(idx[k]): v for k, v in t.items()})
+            if isinstance(site, Site):
+                site._lazy_transitions = (self, token)
+            else:                                               # a site object of the reference package: plain attribute
+                t = eng.transitions[s]
+                if t or site.transitions:
+                    site.transitions = Counter({int(idx[k]): v for k, v in t.items()})
+
+    def _site_transitions(self, site, token) -> Counter:
+        """The Counter of one site from the engine's store (called by the lazy ``Site.transitions``)."""
+        eng = token[0]
+        t = eng.transitions[self._pos[site.index]]
+        idx = self._index_of_pos
+        return Counter({int(idx[k]): v for k, v in t.items()})
 
     def _run(self, atoms, frac, lattice, append) -> np.ndarray:
         frac = np.ascontiguousarray(frac, dtype=np.float64)

@@ -172,6 +172,16 @@ class Trajectory:
         if F == 0:
             return rows
         atom_index = np.array([a.index for a in self.atoms])
+        foreign = [o for o in list(self.atoms) + list(self.sites) if not hasattr(o, "_lazy_blocks")]
+        if foreign:                                             # objects of the reference package itself: plain lists
+            for a, atom in enumerate(self.atoms):
+                atom.trajectory.extend(None if v < 0 else int(v) for v in rows[:, a].tolist())
+            index_of = [a.index for a in self.atoms]
+            for site in self.sites:
+                hit = rows == site.index
+                site.trajectory.extend([[index_of[a] for a in np.nonzero(r)[0]] for r in hit])
+            self.timesteps.extend(range(1, F + 1) if timesteps is None else timesteps)
+            return rows
         for a, atom in enumerate(self.atoms):
             atom._lazy_blocks.append(rows[:, a])
         # one shared, lazily GPU-folded form of the batch answers every site's trajectory / residence times

@@ -414,7 +414,7 @@ def test_device_history_fold_host_logic(monkeypatch):
     import folds_oracle as fo
     from site_analysis_b200 import engine, folds
 
-    def fake_fold_rows(rows, n_sites, prev=None, want_pairs=True, device=None, want_recent=False):
+    def fake_fold_rows(rows, n_sites, prev=None, want_pairs=True, device=None, want_recent=False, want_runs=True):
         rows = np.asarray(rows)
         tr = fo.transitions(rows, prev)
         first = {}
