@@ -220,6 +220,16 @@ int sab_assign_host(sab_engine *e, const double *h_frac, const double *h_lattice
  * on the GPU (the history fold, sab_fold_result) need not upload the result again.  NULL switches it off. */
 int sab_set_result_mirror(sab_engine *e, int32_t *d_full);
 
+/* Lazy distance ranking (large S): sab_set_priority_tables(e, NULL, lookup, ...) declares that a ranking exists without
+ * uploading the dense S x (S - 1) table of site_collection.py:90-111.  The resolver then ranks the few candidates of an
+ * ambiguous atom-frame by their fractional minimum-image distance to the anchor (numpy's operation order); only when two
+ * candidates are exactly equidistant does the order depend on np.argsort's implementation: the anchor is reported by
+ * sab_rank_missing (returns the number of distinct anchors, writes up to `capacity`, clears the list), the caller computes
+ * those rows with the reference's own numpy call, hands them over with sab_add_rank_rows (rows int32[n_rows][S-1], ranked
+ * order) and redoes the batch.  Cached rows persist for the engine's lifetime. */
+int sab_add_rank_rows(sab_engine *e, int n_rows, const int32_t *anchors, const int32_t *rows);
+int sab_rank_missing(sab_engine *e, int32_t *anchors, int capacity);
+
 /* ---- priority resolver --------------------------------------------------------------
  * Replays PriorityAssignmentMixin._get_priority_sites (site_collection.py:113-182),
  * SiteCollection.update_occupation (:279-310) and Atom.update_recent_site (atom.py:181-192)

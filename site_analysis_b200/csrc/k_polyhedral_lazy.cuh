@@ -264,9 +264,34 @@ k_polyhedral_lazy(const double *__restrict__ frac, const double *__restrict__ la
                         for (int i = 0; i < nk; i++) if (key[i] == d) return true;
                         return false;
                     };
-                    if (cur < 0 && P.rank) {                    // :167-171 the anchor's distance-ranked row
-                        const int32_t *rk = P.rank + (size_t)anchor * (n_sites - 1);
+                    const int slot = (!P.rank && P.row_slot) ? P.row_slot[anchor] : -1;
+                    if (cur < 0 && P.ranked && (P.rank || slot >= 0)) {   // :167-171 the anchor's distance-ranked row
+                        const int32_t *rk = P.rank ? P.rank + (size_t)anchor * (n_sites - 1) : P.row_fwd + (size_t)slot * n_sites;
                         for (int i = 0; i < n_sites - 1 && cur < 0; i++) { const int d = rk[i]; if (!tested(d) && SAB_TRY(d)) cur = d; }
+                    } else if (cur < 0 && P.ranked) {
+                        // no cached row: walk the sites by increasing distance to the anchor (numpy's arithmetic, sab_rank_key);
+                        // equal distances are ordered by the sort implementation of the reference's np.argsort -- reported as
+                        // missing, the host supplies the true row and the batch is redone
+                        double last_k = -1.0; int last_s = -1;
+                        for (int step = 0; step < n_sites - 1 && cur < 0; step++) {
+                            double bk = INFINITY; int bs = INT_MAX;
+                            for (int s2 = lane; s2 < n_sites; s2 += 32) {
+                                if (s2 == anchor) continue;
+                                bool ex;
+                                const double k = sab_rank_key(P, anchor, s2, n_sites, ex);
+                                const bool after = k > last_k || (k == last_k && s2 > last_s);
+                                if (after && (k < bk || (k == bk && s2 < bs))) { bk = k; bs = s2; }
+                            }
+                            for (int o = 16; o; o >>= 1) {
+                                const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                                if (ok < bk || (ok == bk && os < bs)) { bk = ok; bs = os; }
+                            }
+                            if (bs == INT_MAX) break;
+                            if (bk == last_k && lane == 0) sab_rank_missing(P, anchor);
+                            last_k = bk; last_s = bs;
+                            if (!tested(bs) && SAB_TRY(bs)) cur = bs;
+                        }
                     } else if (cur < 0) {                       // :172-179 face-sharing neighbours, then list order
                         const int n0 = P.neigh_off ? P.neigh_off[anchor] : 0, n1 = P.neigh_off ? P.neigh_off[anchor + 1] : 0;
                         for (int i = n0; i < n1 && cur < 0; i++) { const int d = P.neigh[i]; if (!tested(d) && SAB_TRY(d)) cur = d; }

@@ -22,12 +22,55 @@
 #include "sab_device.cuh"
 
 struct SabPriorityTables {
-    const int32_t *rank;        // [S][S-1] or null
-    const int32_t *rank_pos;    // [S][S] inverse: position of site j in anchor i's row (built at upload)
+    const int32_t *rank;        // [S][S-1] dense distance-ranked rows, or null
+    const int32_t *rank_pos;    // [S][S] dense inverse: position of site j in anchor i's row (built at upload), or null
     const double *lookup;       // [S][3] or null
     const int32_t *neigh_off;   // [S+1] or null
     const int32_t *neigh;
+    // lazy ranking (large S): no dense table.  The rank of a candidate is its fractional minimum-image distance to the
+    // anchor, computed here with numpy's own operation order (site_collection.py:100-107); only when two candidates TIE
+    // does the order depend on the sort implementation -- then the anchor's true row (computed by the host with the
+    // reference's np.argsort call) is needed: cached inverse rows, and a list of anchors still missing.
+    int ranked;                 // a distance ranking exists (reference centres known for every site)
+    const int32_t *row_slot;    // [S] slot of the anchor's cached inverse row, -1 = not cached; null with dense tables
+    const int32_t *row_pos;     // [slots][S] inverse rows (position of every site; the anchor itself: INT_MAX)
+    const int32_t *row_fwd;     // [slots][S] the rows themselves (S - 1 entries used)
+    int32_t *missing;           // anchors whose row was needed (the decision taken without it is provisional)
+    int *n_missing;
+    int missing_cap;
 };
+
+// Sort key of candidate c in anchor's ranked row: the exact position when the row is known, else the distance itself.
+__device__ __forceinline__ double sab_rank_key(const SabPriorityTables &P, int anchor, int c, int n_sites, bool &exact)
+{
+    if (P.rank_pos) { exact = true; return (double)P.rank_pos[(size_t)anchor * n_sites + c]; }
+    const int slot = P.row_slot ? P.row_slot[anchor] : -1;
+    if (slot >= 0) { exact = true; return (double)P.row_pos[(size_t)slot * n_sites + c]; }
+    exact = false;
+    double d0 = P.lookup[3 * c] - P.lookup[3 * anchor], d1 = P.lookup[3 * c + 1] - P.lookup[3 * anchor + 1], d2 = P.lookup[3 * c + 2] - P.lookup[3 * anchor + 2];
+    d0 -= rint(d0); d1 -= rint(d1); d2 -= rint(d2);             // delta -= np.round(delta)
+    return sqrt((d0 * d0 + d1 * d1) + d2 * d2);                  // np.linalg.norm(delta, axis=1)
+}
+__device__ __forceinline__ void sab_rank_missing(const SabPriorityTables &P, int anchor)
+{
+    if (!P.missing) return;
+    const int i = atomicAdd(P.n_missing, 1);
+    if (i < P.missing_cap) P.missing[i] = anchor;
+}
+// The member of c[0..n) that comes first in anchor's ranked row (serial; ties without the row: lowest position, reported).
+__device__ __forceinline__ int sab_rank_first(const SabPriorityTables &P, int anchor, const int32_t *c, int n, int n_sites)
+{
+    double bk = INFINITY; int bs = -1; bool tie = false, exact = true;
+    for (int i = 0; i < n; i++) {
+        bool ex;
+        const double k = sab_rank_key(P, anchor, c[i], n_sites, ex);
+        exact = ex;
+        if (k < bk) { bk = k; bs = c[i]; tie = false; }
+        else if (k == bk) { tie = true; if (c[i] < bs) bs = c[i]; }
+    }
+    if (tie && !exact) sab_rank_missing(P, anchor);
+    return bs;
+}
 
 struct SabHistory {
     int32_t *recent;            // [A][2]
@@ -85,15 +128,11 @@ __device__ int sab_resolve_with_counters(const int32_t *c, int n, int r0, const 
             if (cn[i] > bc && sab_in_list(c, n, key[i])) { bc = cn[i]; bi = key[i]; }
         if (bi >= 0) return bi;
     }
-    if (P.rank) {                           // site_collection.py:167-171: first member of C in the anchor's ranked row
-        int bestpos = INT_MAX, bests = -1;
-        for (int i = 0; i < n; i++) {
-            const int pos = P.rank_pos[(size_t)anchor * n_sites + c[i]];
-            if (pos < bestpos) { bestpos = pos; bests = c[i]; }
-        }
+    if (P.ranked) {                         // site_collection.py:167-171: first member of C in the anchor's ranked row
+        const int bests = sab_rank_first(P, anchor, c, n, n_sites);
         if (bests >= 0) return bests;
     }
-    if (P.neigh_off) {                      // :172-176 face-sharing neighbours in list order
+    if (P.neigh_off && !P.ranked) {         // :172-176 face-sharing neighbours in list order
         for (int i = P.neigh_off[anchor]; i < P.neigh_off[anchor + 1]; i++)
             if (sab_in_list(c, n, P.neigh[i])) return P.neigh[i];
     }

@@ -66,15 +66,11 @@ __device__ int sab_resolve_with_counters_smem(const int32_t *c, int n, int r0, c
             if (cn[i] > bc && sab_in_list(c, n, key[i])) { bc = cn[i]; bi = key[i]; }
         if (bi >= 0) return bi;
     }
-    if (P.rank) {                           // site_collection.py:167-171: first member of C in the anchor's ranked row
-        int bestpos = INT_MAX, bests = -1;
-        for (int i = 0; i < n; i++) {
-            const int pos = P.rank_pos[(size_t)anchor * n_sites + c[i]];
-            if (pos < bestpos) { bestpos = pos; bests = c[i]; }
-        }
+    if (P.ranked) {                         // site_collection.py:167-171: first member of C in the anchor's ranked row
+        const int bests = sab_rank_first(P, anchor, c, n, n_sites);
         if (bests >= 0) return bests;
     }
-    if (P.neigh_off)
+    if (P.neigh_off && !P.ranked)
         for (int i = P.neigh_off[anchor]; i < P.neigh_off[anchor + 1]; i++)
             if (sab_in_list(c, n, P.neigh[i])) return P.neigh[i];
     int best = c[0];
@@ -102,8 +98,9 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     constexpr int PC = 12;                           // candidates kept in registers / published per reader
     int *rd_n = flag + n_mobile;                     // [A] published readers: list length
     int *rd_c = rd_n + n_mobile;                     // [A][PC] candidates
-    int *rd_p = rd_c + (size_t)n_mobile * PC;        // [A][PC] their positions in the anchor's distance-ranked row
-    int *row_mark = rd_p + (size_t)n_mobile * PC;    // [S] frame stamp: a reader of this frame consults this Counter row
+    double *rd_p = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(rd_c + (size_t)n_mobile * PC) + 7) & ~(uintptr_t)7);   // [A][PC] their sort keys in the anchor's ranked row (8-byte aligned)
+    int *rd_x = reinterpret_cast<int *>(rd_p + (size_t)n_mobile * PC);   // [A] the keys are exact row positions (not distances)
+    int *row_mark = rd_x + n_mobile;                 // [S] frame stamp: a reader of this frame consults this Counter row
     int *ord_list = row_mark + n_sites;              // [A] atoms left for the ordered section (unsorted)
     __shared__ int reader_unknown_row, ord_n;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
@@ -159,18 +156,20 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 else if (in1) cur = r1;
                 else {
                     fl = 3; my_need = 1;
-                    if (!(one_each && cn[0] <= PC && r0 >= 0 && P.rank_pos)) reader_unknown_row = 1;
-                    if (one_each && cn[0] <= PC && r0 >= 0 && P.rank_pos) {
+                    if (!(one_each && cn[0] <= PC && r0 >= 0 && P.ranked)) reader_unknown_row = 1;
+                    if (one_each && cn[0] <= PC && r0 >= 0 && P.ranked) {
                         row_mark[r0] = (int)(f + 1);
                         // anchor = recent[0] is known: publish the candidates and their rank positions now
                         // (one global load each, in parallel over all readers of the frame)
                         fl = 4;
                         rd_n[a] = cn[0];
 #pragma unroll
+                        bool ex = true;
                         for (int i = 0; i < PC; i++) {
                             rd_c[a * PC + i] = (i < cn[0]) ? cc[0][i] : -1;
-                            rd_p[a * PC + i] = (i < cn[0]) ? __ldg(P.rank_pos + (size_t)r0 * n_sites + cc[0][i]) : INT_MAX;
+                            rd_p[a * PC + i] = (i < cn[0]) ? sab_rank_key(P, r0, cc[0][i], n_sites, ex) : INFINITY;
                         }
+                        rd_x[a] = ex ? 1 : 0;
                     }
                 }
             }
@@ -245,13 +244,19 @@ k_resolve_fast(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                         const int ci = (lane < n) ? rd_c[a * PC + lane] : -1;
                         int cnt = -1, ins = INT_MAX;
                         if (ci >= 0) { int i = sab_row_find(H, anchor, ci); if (i >= 0) { cnt = H.tr_cnt[(size_t)anchor * K + i]; ins = i; } }
-                        int pos = (lane < n) ? rd_p[a * PC + lane] : INT_MAX;
-                        int bcnt = cnt, bins = ins, bsite = ci, bpos = pos, psite = ci;
+                        const double pos = (lane < n) ? rd_p[a * PC + lane] : INFINITY;
+                        int bcnt = cnt, bins = ins, bsite = ci, psite = (lane < n) ? ci : INT_MAX;
+                        double bpos = pos;
                         for (int o = 16; o; o >>= 1) {
                             int oc = __shfl_xor_sync(0xffffffffu, bcnt, o), oi = __shfl_xor_sync(0xffffffffu, bins, o), os = __shfl_xor_sync(0xffffffffu, bsite, o);
                             if (oc > bcnt || (oc == bcnt && oi < bins)) { bcnt = oc; bins = oi; bsite = os; }
-                            int op = __shfl_xor_sync(0xffffffffu, bpos, o), ops = __shfl_xor_sync(0xffffffffu, psite, o);
-                            if (op < bpos) { bpos = op; psite = ops; }
+                            const double op = __shfl_xor_sync(0xffffffffu, bpos, o);
+                            const int ops = __shfl_xor_sync(0xffffffffu, psite, o);
+                            if (op < bpos || (op == bpos && ops < psite)) { bpos = op; psite = ops; }
+                        }
+                        if (bcnt < 0 && !rd_x[a]) {      // distance keys: two candidates at the same distance need the anchor's true row
+                            const unsigned tied = __ballot_sync(0xffffffffu, lane < n && pos == bpos);
+                            if (__popc(tied) > 1 && lane == 0) sab_rank_missing(P, anchor);
                         }
                         cur = (bcnt >= 0) ? bsite : psite;
                     } else if (flag[a] == 3) {

@@ -67,6 +67,7 @@ template <class T> static cudaError_t upload(T **dst, const T *src, size_t n)
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
 }
 
+#define SAB_MISSING_CAP 4096     // anchors the resolver can report as "row needed" per run
 enum { CNT_AMBIGUOUS = 0, CNT_SPILL = 1, CNT_OVERFLOW = 2, CNT_FIRST_BAD = 3, CNT_FULL27 = 4, CNT_SPAN = 8, CNT_N = 12 };
 
 struct sab_engine {
@@ -86,6 +87,9 @@ struct sab_engine {
     uint8_t *d_legacy_init = nullptr; int64_t legacy_init_frame = -1;
     // priority tables
     int32_t *d_rank = nullptr, *d_rank_pos = nullptr, *d_neigh_off = nullptr, *d_neigh = nullptr; double *d_lookup = nullptr;
+    // lazy ranking: cached rows of single anchors (sab_add_rank_rows), anchors reported missing by the last resolver run
+    int ranked = 0; std::vector<int32_t> row_slot_h; int n_row_slots = 0, row_slot_cap = 0;
+    int32_t *d_row_slot = nullptr, *d_row_pos = nullptr, *d_row_fwd = nullptr, *d_missing = nullptr; int *d_n_missing = nullptr;
     // counters
     unsigned long long *d_counters = nullptr;
     // host-path staging
@@ -167,7 +171,8 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec,
                     e->d_s5_task, e->d_s5_rec, e->d_s5_cellrec, e->d_lz_shift, e->d_lz_has, e->d_lz_lock, e->d_lz_cached,
-                    e->d_lz_vc, e->d_lz_rc, e->d_lz_stamp, e->d_lz_has_rc, e->d_lz_stats};
+                    e->d_lz_vc, e->d_lz_rc, e->d_lz_stamp, e->d_lz_has_rc, e->d_lz_stats, e->d_row_slot, e->d_row_pos, e->d_row_fwd,
+                    e->d_missing, e->d_n_missing};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int i = 0; i < 2; i++) if (e->h_res_stage[i]) cudaFreeHost(e->h_res_stage[i]);
@@ -1260,11 +1265,91 @@ extern "C" int sab_set_priority_tables(sab_engine *e, const int32_t *rank, const
         CU(upload(&e->d_rank_pos, pos.data(), pos.size()));
     }
     if (lookup) CU(upload(&e->d_lookup, lookup, (size_t)3 * e->S));
+    e->ranked = lookup ? 1 : 0;                 // a distance ranking exists; without `rank` its rows are supplied lazily
+    if (!rank) {
+        if (e->d_rank) { g_alloc_bytes.erase(e->d_rank); cudaFree(e->d_rank); e->d_rank = nullptr; }
+        if (e->d_rank_pos) { g_alloc_bytes.erase(e->d_rank_pos); cudaFree(e->d_rank_pos); e->d_rank_pos = nullptr; }
+    }
+    if (lookup && !e->d_missing) {
+        CU(cudaMalloc((void **)&e->d_missing, sizeof(int32_t) * SAB_MISSING_CAP));
+        CU(cudaMalloc((void **)&e->d_n_missing, sizeof(int)));
+        CU(cudaMemset(e->d_n_missing, 0, sizeof(int)));
+        e->row_slot_h.assign(e->S, -1);
+        CU(upload(&e->d_row_slot, e->row_slot_h.data(), e->row_slot_h.size()));
+    }
     if (neigh_off) {
         CU(upload(&e->d_neigh_off, neigh_off, (size_t)e->S + 1));
         CU(upload(&e->d_neigh, neigh, (size_t)std::max(neigh_off[e->S], 1)));
     }
     return SAB_OK;
+}
+
+static SabPriorityTables priority_tables(sab_engine *e)
+{
+    SabPriorityTables P{};
+    P.rank = e->d_rank; P.rank_pos = e->d_rank_pos; P.lookup = e->d_lookup;
+    P.neigh_off = e->ranked ? nullptr : e->d_neigh_off; P.neigh = e->d_neigh;
+    P.ranked = e->ranked;
+    P.row_slot = e->d_rank_pos ? nullptr : e->d_row_slot; P.row_pos = e->d_row_pos; P.row_fwd = e->d_row_fwd;
+    P.missing = e->d_missing; P.n_missing = e->d_n_missing; P.missing_cap = SAB_MISSING_CAP;
+    return P;
+}
+
+extern "C" int sab_add_rank_rows(sab_engine *e, int n_rows, const int32_t *anchors, const int32_t *rows)
+{
+    if (!e || n_rows < 0 || (n_rows > 0 && (!anchors || !rows))) return fail(SAB_EINVAL, "sab_add_rank_rows: bad arguments");
+    if (!e->ranked || !e->d_row_slot) return fail(SAB_ESTATE, "sab_add_rank_rows: no lazy ranking (sab_set_priority_tables with lookup, without rank)");
+    if (n_rows == 0) return SAB_OK;
+    CU(cudaSetDevice(e->device));
+    const size_t S = (size_t)e->S;
+    if (e->n_row_slots + n_rows > e->row_slot_cap) {             // grow the row cache
+        const int cap = std::max(2 * e->row_slot_cap, e->n_row_slots + n_rows + 16);
+        int32_t *np = nullptr, *nf = nullptr;
+        CU(cudaMalloc((void **)&np, sizeof(int32_t) * S * cap));
+        CU(cudaMalloc((void **)&nf, sizeof(int32_t) * S * cap));
+        if (e->n_row_slots) {
+            CU(cudaMemcpy(np, e->d_row_pos, sizeof(int32_t) * S * e->n_row_slots, cudaMemcpyDeviceToDevice));
+            CU(cudaMemcpy(nf, e->d_row_fwd, sizeof(int32_t) * S * e->n_row_slots, cudaMemcpyDeviceToDevice));
+        }
+        if (e->d_row_pos) cudaFree(e->d_row_pos);
+        if (e->d_row_fwd) cudaFree(e->d_row_fwd);
+        e->d_row_pos = np; e->d_row_fwd = nf; e->row_slot_cap = cap;
+    }
+    std::vector<int32_t> pos(S), fwd(S, 0);
+    for (int r = 0; r < n_rows; r++) {
+        const int a = anchors[r];
+        if (a < 0 || a >= e->S) return fail(SAB_EINVAL, "sab_add_rank_rows: anchor out of range");
+        if (e->row_slot_h[a] >= 0) continue;
+        std::fill(pos.begin(), pos.end(), INT_MAX);
+        for (size_t j = 0; j + 1 < S; j++) {
+            const int32_t t = rows[(size_t)r * (S - 1) + j];
+            if (t < 0 || t >= e->S) return fail(SAB_EINVAL, "rank row entry out of range");
+            pos[t] = (int32_t)j; fwd[j] = t;
+        }
+        const int slot = e->n_row_slots++;
+        CU(cudaMemcpy(e->d_row_pos + S * slot, pos.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->d_row_fwd + S * slot, fwd.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice));   // stride S, S - 1 used
+        e->row_slot_h[a] = slot;
+    }
+    CU(cudaMemcpy(e->d_row_slot, e->row_slot_h.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    return SAB_OK;
+}
+
+extern "C" int sab_rank_missing(sab_engine *e, int32_t *anchors, int capacity)
+{
+    if (!e || capacity < 0 || (capacity > 0 && !anchors)) return -1;
+    if (!e->d_n_missing) return 0;
+    cudaSetDevice(e->device);
+    int n = 0;
+    if (cudaMemcpy(&n, e->d_n_missing, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    n = std::min(n, SAB_MISSING_CAP);
+    std::vector<int32_t> h(std::max(n, 1));
+    if (n && cudaMemcpy(h.data(), e->d_missing, sizeof(int32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    std::sort(h.begin(), h.begin() + n);
+    n = (int)(std::unique(h.begin(), h.begin() + n) - h.begin());
+    for (int i = 0; i < std::min(n, capacity); i++) anchors[i] = h[i];
+    cudaMemset(e->d_n_missing, 0, sizeof(int));
+    return n;
 }
 
 extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames, int32_t *d_result,
@@ -1292,7 +1377,7 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     CU(cudaMemcpyAsync(H.tr_key, tr_key, sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(H.tr_cnt, tr_cnt, sizeof(long long) * nk, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
-    SabPriorityTables P{e->d_rank, e->d_rank_pos, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
+    SabPriorityTables P = priority_tables(e);
     int block = std::min(1024, ((e->A + 31) / 32) * 32);
     for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
     CU(cudaEventRecord(e->ev_t[0], st));
@@ -1301,13 +1386,13 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     for (int s2 = 0; s2 < e->S; s2++) max_n = std::max(max_n, (int)tr_n[s2]);
     int smem_cap = 0;
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
-    long long fixed = sizeof(int) * ((long long)e->A * (7 + 2 * 12) + 2LL * e->S) + 1024;
+    long long fixed = sizeof(int) * ((long long)e->A * (9 + 3 * 12) + 2LL * e->S) + 1024;
     // rows of tr_width keys must fit in shared memory untruncated; the host starts narrow and widens on
     // overflow, which eventually selects the global-memory kernel
     long long fit = ((long long)smem_cap - fixed) / (8LL * e->S);
     int k_fit = tr_width;
     if (tr_width <= fit && max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr) {
-        size_t smem = sizeof(int) * ((size_t)e->A * (7 + 2 * 12) + 2 * (size_t)e->S + 2 * (size_t)e->S * k_fit);
+        size_t smem = sizeof(int) * ((size_t)e->A * (9 + 3 * 12) + 2 * (size_t)e->S + 2 * (size_t)e->S * k_fit) + 16;
         if (block <= 256) {
             CU(cudaFuncSetAttribute(k_resolve_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_resolve_fast<256><<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
@@ -1417,7 +1502,7 @@ extern "C" int sab_assign_lazy(sab_engine *e, const double *d_frac, const double
     std::vector<int32_t> simp32;          // the kernel reads the uint8 simplices of sab_set_polyhedra
     SabLazy Z{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_nface, e->d_simp, e->d_lz_has_rc, e->d_lz_rc, e->d_lz_shift,
               e->d_lz_cached, e->d_lz_has, e->d_lz_stamp, e->d_lz_lock, e->d_lz_vc, e->d_lz_stats};
-    SabPriorityTables P{e->d_rank, e->d_rank_pos, e->d_lookup, e->d_rank ? nullptr : e->d_neigh_off, e->d_neigh};
+    SabPriorityTables P = priority_tables(e);
     const size_t smem = sizeof(double) * 24 * (size_t)e->A + sizeof(int) * (size_t)e->A + 16;
     CU(cudaFuncSetAttribute(k_polyhedral_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     k_polyhedral_lazy<<<1, 256, smem, st>>>(d_frac, d_lattice, lattice_stride, n_frames, e->lazy_frames, e->N, e->A, e->d_mobile, e->S,

@@ -144,6 +144,7 @@ class AssignmentEngine:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.strict = strict
         self.rank_table = None if rank_table is None else np.ascontiguousarray(rank_table, dtype=np.int32)
+        self.rank_dense_max = 2048      # above this many sites the distance ranking is lazy (no S x S tables)
         self._priority_uploaded = False
         self.slots = None
         if self.k in (nat.SPHERICAL, nat.VORONOI):
@@ -550,14 +551,41 @@ class AssignmentEngine:
             lookup = self.centres
         elif self.k == nat.POLYHEDRAL and all(c is not None for c in self.ref_centres):
             lookup = np.ascontiguousarray(np.array(self.ref_centres, dtype=np.float64))
+        self._lazy_rank = False
         if lookup is not None:
-            rank = self.rank_table if self.rank_table is not None else tab.distance_rank_table(lookup)
-            self.rank_table = np.ascontiguousarray(rank, dtype=np.int32)
+            # small systems (or a table handed in): the dense S x (S - 1) table of site_collection.py:90-111.  Large ones:
+            # lazy ranking -- candidates are ranked by distance on the device, true rows only for anchors with tied candidates
+            if self.rank_table is not None or self.S <= self.rank_dense_max:
+                rank = self.rank_table if self.rank_table is not None else tab.distance_rank_table(lookup)
+                self.rank_table = np.ascontiguousarray(rank, dtype=np.int32)
+            else:
+                self._lazy_rank = True
+                self._lookup = np.ascontiguousarray(lookup, dtype=np.float64)
         elif self.k == nat.POLYHEDRAL:
             off, flat = tab.face_sharing_neighbours(self.slots)
-        nat.check(self.L.sab_set_priority_tables(self.h, nat.ptr(self.rank_table) if lookup is not None else None,
+        nat.check(self.L.sab_set_priority_tables(self.h, nat.ptr(self.rank_table) if (lookup is not None and not self._lazy_rank) else None,
                                                  nat.ptr(lookup), nat.ptr(off), nat.ptr(flat)))
         self._priority_uploaded = True
+
+    def _supply_missing_rank_rows(self) -> int:
+        """Lazy ranking: rows of the anchors the last resolver / replay run reported (tied candidates), computed with the
+        reference's own numpy calls (site_collection.py:100-107) and cached on the device.  Returns how many were added."""
+        if not getattr(self, "_lazy_rank", False):
+            return 0
+        buf = np.zeros(4096, dtype=np.int32)
+        n = int(self.L.sab_rank_missing(self.h, nat.ptr(buf), len(buf)))
+        if n <= 0:
+            return 0
+        anchors = np.ascontiguousarray(buf[:min(n, len(buf))])
+        rows = np.empty((len(anchors), self.S - 1), dtype=np.int32)
+        for r, i in enumerate(anchors):
+            delta = self._lookup - self._lookup[i]
+            delta -= np.round(delta)
+            order = np.argsort(np.linalg.norm(delta, axis=1))
+            rows[r] = order[order != i]
+        nat.check(self.L.sab_add_rank_rows(self.h, len(anchors), nat.ptr(anchors), nat.ptr(rows)))
+        self.rank_rows_cached = getattr(self, "rank_rows_cached", 0) + len(anchors)
+        return len(anchors)
 
     def _resolve(self, d_frac, F, d_result, d_spill, stream, append):
         self.sync_history()
@@ -584,6 +612,9 @@ class AssignmentEngine:
                 width *= 2
                 continue
             nat.check(code)
+            if self._supply_missing_rank_rows():          # lazy ranking: a tie needed an anchor's true row -- redo with it
+                d_result.copy_(d_backup)
+                continue
             break
         self.recent = recent
         if append:
@@ -657,6 +688,9 @@ class AssignmentEngine:
                 width *= 2
                 continue
             nat.check(code)
+            if self._supply_missing_rank_rows():                # lazy ranking: redo the batch with the true rows of the tied anchors
+                nat.check(self.L.sab_lazy_set_state(self.h, nat.ptr(snap[0]), nat.ptr(snap[1]), nat.ptr(snap[2]), nat.ptr(has_rc), nat.ptr(rc)))
+                continue
             break
         self.recent, self.prev = recent, prev
         self.transitions = [dict(zip(map(int, tr_key[s, :tr_n[s]]), map(int, tr_cnt[s, :tr_n[s]]))) for s in range(self.S)]

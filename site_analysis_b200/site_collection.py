@@ -56,6 +56,7 @@ class SiteCollection:
         self.exact_lazy = None          # polyhedral sites: None = automatic, True = always the exact replay kernel (engine.py)
         self.use_cells = True           # exact spatial pruning (False: exhaustive kernels only; for cross-checks)
         self.rank_table = None          # optional override of the distance-rank table (testing)
+        self.rank_dense_max = None      # sites up to which the dense S x (S - 1) rank table is built (None: engine default)
         self.engine_options: dict[int, int] = {}   # sab_set_option(key, value) pairs applied to the engine
 
     # -- reference API ---------------------------------------------------------------------
@@ -140,6 +141,8 @@ class SiteCollection:
                                             rank_table=self.rank_table, **self._engine_kwargs())
             self._engine.use_cells = self.use_cells
             self._engine.exact_lazy = self.exact_lazy
+            if self.rank_dense_max is not None:
+                self._engine.rank_dense_max = self.rank_dense_max
             for k, v in self.engine_options.items():
                 self._engine.set_option(k, v)
             self._engine_key = key

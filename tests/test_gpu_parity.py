@@ -463,3 +463,48 @@ def test_slow_drift_beyond_the_excursion_guard_is_replayed_exactly():
         eng.exact_lazy = lazy
         got = eng.assign_device(torch.from_numpy(frac).cuda(), torch.from_numpy(lat).cuda()).cpu().numpy()
         assert eng._lazy_mode and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["argyrodite_0p_spherical", "fuzz_spherical_0", "fuzz_spherical_1", "fuzz_spherical_2", "fuzz_spherical_3",
+                                  "simple_cubic_spherical", "fuzz_polyhedral_0", "fuzz_polyhedral_4", "fuzz_polyhedral_9"])
+def test_lazy_distance_ranking_equals_the_dense_table(oracle_mod, name):
+    """No S x (S - 1) rank table (site_collection.py:90-111) on the device: candidates are ranked by their distance to the
+    anchor in the kernel, and only anchors whose candidates TIE get their true row (np.argsort of the reference) from the
+    host.  Same rows, Counters (with insertion order) and recent sites as the reference; far fewer rows than sites."""
+    case = oracle_mod.load_case(name)
+    t = trajectory_from_case(case, use_case_rank=False)
+    t.site_collection.rank_dense_max = 0
+    if "polyhedral" in name:
+        t.site_collection.exact_lazy = True        # the replay kernel walks whole ranked rows: by distance, row by row on demand
+    rows = t.trajectory_from_arrays(case["frac"], case["lattice"])
+    eng = t.site_collection._engine
+    assert np.array_equal(rows, case["atoms_traj"])
+    got_tr, want_tr = transitions_of(t), oracle_mod.transitions_from_case(case)
+    assert got_tr == want_tr
+    for k in got_tr:
+        assert list(got_tr[k]) == list(want_tr[k])
+    if getattr(eng, "_priority_uploaded", False):
+        assert eng._lazy_rank and eng.rank_table is None
+        assert getattr(eng, "rank_rows_cached", 0) <= len(t.sites)
+        print(name, "rows supplied for", getattr(eng, "rank_rows_cached", 0), "of", len(t.sites), "anchors")
+
+
+def test_large_overlapping_sphere_system_needs_no_dense_rank_table(oracle_mod):
+    """8,448 overlapping spheres (4x4x4 argyrodite, r = 1.5 A, A = 1536).  The dense rank table
+    and its inverse would take 2 x 285 MB; the lazy ranking supplies rows only for anchors whose candidates tie.  Results
+    must equal the sequential oracle (which uses the reference's full table)."""
+    from site_analysis_b200 import AssignmentEngine, synthetic as syn
+    g = syn.argyrodite_geometry(4)
+    frac, lat = syn.argyrodite_trajectory(g, 64, device="cuda", seed=5)
+    eng = AssignmentEngine("spherical", g.n_atoms, g.mobile_idx, centres=g.site_centres, rcut=1.5)
+    got = eng.assign_device(frac, lat).cpu().numpy()
+    eng.sync_history()
+    assert eng.last_info["ambiguous"] > 50000 and eng._lazy_rank and eng.rank_table is None
+    rows_cached = getattr(eng, "rank_rows_cached", 0)
+    table_bytes = rows_cached * 2 * 4 * len(g.site_centres) + 24 * len(g.site_centres)
+    assert table_bytes < 100e6, (rows_cached, table_bytes)
+    o = oracle_mod.SiteOracle("spherical", g.mobile_idx, centres=g.site_centres, rcut=1.5)
+    want = o.run(frac.cpu().numpy(), lat.cpu().numpy(), positions=True)
+    assert np.array_equal(got, want)
+    assert {s: t for s, t in enumerate(eng.transitions) if t} == o.transitions()       # site_index of this oracle = list positions
+    print(f"S = 8448: {eng.last_info['ambiguous']} ambiguous atom-frames, {rows_cached} rank rows supplied ({table_bytes / 1e6:.1f} MB of tables)")
