@@ -168,6 +168,8 @@ int sab_scan_excursion(sab_engine *e, const double *d_frac, int64_t n_frames, vo
 #define SAB_OPT_STREAM5_ROWS 11    /* generation 5: row slots of the ring, 2..8 (0 = automatic) */
 #define SAB_OPT_STREAM5_RAW 12     /* generation 5: raw-frame slots of the ring, 2..4 (0 = automatic) */
 #define SAB_OPT_STREAM5_BLOCKS 13  /* generation 5: resident CTAs per SM the shared-memory plan aims for, 1..8 (0 = automatic) */
+#define SAB_OPT_RESOLVER 15        /* priority resolver (sab_resolve): 0 (default) = speculative chunks of frames (k_resolve_spec.cuh), 1 = one
+                                    * barrier per frame (k_resolve_fast.cuh), 2 = global-memory history (k_resolve.cuh); identical results */
 int sab_set_option(sab_engine *e, int key, int64_t value);
 
 /* ---- the hot path -------------------------------------------------------------------- */

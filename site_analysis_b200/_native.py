@@ -33,6 +33,7 @@ OPT_STREAM_GEN = 10
 OPT_STREAM5_ROWS = 11
 OPT_STREAM5_RAW = 12
 OPT_STREAM5_BLOCKS = 13
+OPT_RESOLVER = 15
 
 # every symbol include/sab200.h declares (tests/test_host_logic.py checks the header against this)
 SYMBOLS = [

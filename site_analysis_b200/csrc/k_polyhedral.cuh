@@ -148,7 +148,7 @@ __global__ void k_polyhedral_assign_exhaustive(const double *__restrict__ frac, 
             else if (c == 1) out = h[0];
             else {
                 atomicAdd(&counters[0], 1ULL);
-                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(c));
                 if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) {
                     counters[2] = 1ULL;
                     out = SAB_NONE;

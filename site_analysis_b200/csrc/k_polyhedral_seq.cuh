@@ -63,7 +63,7 @@ __device__ __noinline__ int sab_exhaustive_atom(const double *__restrict__ frame
         if (c == 0) return SAB_NONE;
         if (c == 1) return first;
         atomicAdd(&counters[0], 1ULL);
-        off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+        off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(c));
         if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; return SAB_NONE; }
         spill[off] = c;
     }
@@ -228,7 +228,7 @@ k_polyhedral_assign_seq(const double *__restrict__ frac, int64_t n_frames, int c
                 else {
                     la = -1;                                      // several sites: the resolver decides
                     atomicAdd(&counters[0], 1ULL);
-                    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+                    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(c));
                     if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; out = SAB_NONE; }
                     else {
                         spill[off] = c;

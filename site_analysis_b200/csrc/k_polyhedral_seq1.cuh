@@ -191,7 +191,7 @@ k_polyhedral_assign_seq1(const double *__restrict__ frac, int64_t n_frames, int 
                 else {
                     last[a] = -1;                                // several sites: the resolver decides; history uncertain
                     atomicAdd(&counters[0], 1ULL);
-                    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+                    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(c));
                     if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; out = SAB_NONE; }
                     else {
                         spill[off] = c;

@@ -187,7 +187,7 @@ __device__ __noinline__ int sab_tile_spill(int c, int *h, int32_t *__restrict__ 
                                            unsigned long long *__restrict__ counters)
 {
     atomicAdd(&counters[0], 1ULL);
-    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(c + 1));
+    unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(c));
     if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { counters[2] = 1ULL; return SAB_NONE; }
     spill[off] = c;
     for (int i = 1; i < c; i++) { int v = h[i], j = i; while (j > 0 && h[j - 1] > v) { h[j] = h[j - 1]; j--; } h[j] = v; }
@@ -455,7 +455,7 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
         else if (c == 1) out = first;
         else {
             unsigned long long off = 0;
-            if (lane == 0) { atomicAdd(&counters[0], 1ULL); off = atomicAdd(&counters[1], (unsigned long long)(c + 1)); }
+            if (lane == 0) { atomicAdd(&counters[0], 1ULL); off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(c)); }
             off = __shfl_sync(0xffffffffu, off, 0);
             if ((long long)(off + c + 1) > spill_capacity || off + c + 1 >= 0x7ffffff0ULL) { if (lane == 0) counters[2] = 1ULL; out = SAB_NONE; }
             else {

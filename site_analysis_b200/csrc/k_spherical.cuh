@@ -62,7 +62,7 @@ __global__ void k_spherical_assign(const double *__restrict__ frac, const double
             else if (cnt == 1) out = keep[0];
             else {
                 atomicAdd(&counters[0], 1ULL);
-                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(cnt + 1));
+                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(cnt));
                 if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
                     counters[2] = 1ULL;
                     out = SAB_NONE;
@@ -155,7 +155,7 @@ __global__ void k_spherical_assign_cells(const double *__restrict__ frac, const 
             else if (cnt == 1) out = keep[0];
             else {
                 atomicAdd(&counters[0], 1ULL);
-                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)(cnt + 1));
+                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(cnt));
                 if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
                     counters[2] = 1ULL;
                     out = SAB_NONE;

@@ -29,6 +29,7 @@
 #include "k_polyhedral_stream5.cuh"
 #include "k_resolve.cuh"
 #include "k_resolve_fast.cuh"
+#include "k_resolve_spec.cuh"
 #include "k_polyhedral_lazy.cuh"
 #include "k_spherical.cuh"
 #include "k_wrap.cuh"
@@ -123,6 +124,8 @@ struct sab_engine {
     bool force_scan = false;               // the stream kernel's chain check failed: this batch runs on the scan kernels
     // generation-5 stream kernel (k_polyhedral_stream5.cuh): vertex-image rows, derived in sab_set_cell_lists
     bool s5_ok = false; float4 *d_s5_task = nullptr;
+    int resolver = 0;                                     // SAB_OPT_RESOLVER: 0 = speculative chunks, 1 = per-frame (shared memory), 2 = global memory
+    int64_t resolve_ns = 0; int resolve_kind = 0;         // device time of all sab_resolve kernels so far; kernel of the last call
     uint2 *d_s5_rec = nullptr; uint16_t *d_s5_cellrec = nullptr; float s5_T1 = 0.f, s5_T0 = 0.f, s5_TD = 0.f;
     int stream_gen = 0;                    // SAB_OPT_STREAM_GEN: 0 automatic (5 when its tables exist), 4 = previous generation
     int s5_rows = 0, s5_raw = 0, s5_blocks = 0;   // SAB_OPT_STREAM5_ROWS / _RAW / _BLOCKS (0 = automatic)
@@ -511,6 +514,7 @@ extern "C" int sab_set_option(sab_engine *e, int key, int64_t value)
     if (key == SAB_OPT_STREAM_GEN) { e->stream_gen = (int)value; return SAB_OK; }
     if (key == SAB_OPT_STREAM5_ROWS) { if (value < 0 || value > SAB_S5_MAXROWS) return fail(SAB_EINVAL, "row slots: 0..%d", SAB_S5_MAXROWS); e->s5_rows = (int)value; return SAB_OK; }
     if (key == SAB_OPT_STREAM5_RAW) { if (value < 0 || value > SAB_S5_MAXRAW || value == 1) return fail(SAB_EINVAL, "raw slots: 0 or 2..%d", SAB_S5_MAXRAW); e->s5_raw = (int)value; return SAB_OK; }
+    if (key == SAB_OPT_RESOLVER) { if (value < 0 || value > 2) return fail(SAB_EINVAL, "resolver: 0..2"); e->resolver = (int)value; return SAB_OK; }
     if (key == SAB_OPT_STREAM5_BLOCKS) { if (value < 0 || value > 8) return fail(SAB_EINVAL, "CTAs per SM: 0..8"); e->s5_blocks = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_BLOCK) { e->seq_block = (int)value; return SAB_OK; }
     if (key == SAB_OPT_SEQ_CHUNK) { if (value < 1) return fail(SAB_EINVAL, "chunk must be >= 1"); e->seq_chunk = (int)value; return SAB_OK; }
@@ -1361,27 +1365,33 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     if (n_frames <= 0) return SAB_OK;
     CU(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
+    struct Tmp {                         // device copies of the history, released on every exit path
+        void *p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Tmp() { for (void *q : p) if (q) cudaFree(q); }
+    } tmp;
     SabHistory H{};
     H.K = tr_width;
-    int *d_over = nullptr;
     size_t nk = (size_t)e->S * tr_width;
-    CU(cudaMalloc((void **)&H.recent, sizeof(int32_t) * 2 * e->A));
-    CU(cudaMalloc((void **)&H.prev, sizeof(int32_t) * e->A));
-    CU(cudaMalloc((void **)&H.tr_n, sizeof(int32_t) * e->S));
-    CU(cudaMalloc((void **)&H.tr_key, sizeof(int32_t) * nk));
-    CU(cudaMalloc((void **)&H.tr_cnt, sizeof(long long) * nk));
-    CU(cudaMalloc((void **)&d_over, sizeof(int)));
+    CU(cudaMalloc(&tmp.p[0], sizeof(int32_t) * 2 * e->A)); CU(cudaMalloc(&tmp.p[1], sizeof(int32_t) * e->A));
+    CU(cudaMalloc(&tmp.p[2], sizeof(int32_t) * e->S)); CU(cudaMalloc(&tmp.p[3], sizeof(int32_t) * nk));
+    CU(cudaMalloc(&tmp.p[4], sizeof(long long) * nk)); CU(cudaMalloc(&tmp.p[5], sizeof(int)));
+    CU(cudaMalloc(&tmp.p[6], sizeof(SabSpecStats)));
+    H.recent = (int32_t *)tmp.p[0]; H.prev = (int32_t *)tmp.p[1]; H.tr_n = (int32_t *)tmp.p[2];
+    H.tr_key = (int32_t *)tmp.p[3]; H.tr_cnt = (long long *)tmp.p[4];
+    int *d_over = (int *)tmp.p[5];
+    SabSpecStats *d_stats = (SabSpecStats *)tmp.p[6];
     CU(cudaMemcpyAsync(H.recent, recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(H.prev, prev, sizeof(int32_t) * e->A, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(H.tr_n, tr_n, sizeof(int32_t) * e->S, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(H.tr_key, tr_key, sizeof(int32_t) * nk, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(H.tr_cnt, tr_cnt, sizeof(long long) * nk, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(d_stats, 0, sizeof(SabSpecStats), st));
     SabPriorityTables P = priority_tables(e);
     int block = std::min(1024, ((e->A + 31) / 32) * 32);
     for (int i = 0; i < 3; i++) if (!e->ev_t[i]) CU(cudaEventCreate(&e->ev_t[i]));
     CU(cudaEventRecord(e->ev_t[0], st));
-    // shared-memory resolver when the Counter rows fit (K keys per site); else the global-memory one
+    // shared-memory resolvers when the Counter rows fit (K keys per site); else the global-memory one
     int max_n = 0;
     for (int s2 = 0; s2 < e->S; s2++) max_n = std::max(max_n, (int)tr_n[s2]);
     int smem_cap = 0;
@@ -1391,7 +1401,28 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     // overflow, which eventually selects the global-memory kernel
     long long fit = ((long long)smem_cap - fixed) / (8LL * e->S);
     int k_fit = tr_width;
-    if (tr_width <= fit && max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr) {
+    const bool smem_ok = max_n <= tr_width && getenv("SAB_RESOLVE_GLOBAL") == nullptr && e->resolver != 2;
+    // speculative chunks (k_resolve_spec.cuh): one atom per thread, decisions of T frames + logs next to the history
+    int spec_T = 0, spec_NL = 0; size_t spec_smem = 0;
+    if (smem_ok && e->A <= 1024 && e->resolver == 0 && getenv("SAB_RESOLVE_FAST") == nullptr) {
+        int nl = 64; while (nl < e->A * SAB_SPEC_W) nl <<= 1;
+        for (int T = 32; T >= 8 && !spec_T; T >>= 1) {
+            const size_t ints = (size_t)e->A * (3 + (size_t)T + 3 * SAB_SPEC_W + 2 * SAB_SPEC_R + 2) + 2 * (size_t)e->S +
+                                2 * (size_t)e->S * tr_width + 3 * (size_t)nl;
+            if (sizeof(int) * ints + 64 <= (size_t)smem_cap) { spec_T = T; spec_NL = nl; spec_smem = sizeof(int) * ints + 64; }
+        }
+    }
+    int used = 0;                        // 1 speculative, 2 per-frame shared memory, 3 global memory
+    if (spec_T) {
+        if (block <= 256) {
+            CU(cudaFuncSetAttribute(k_resolve_spec<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
+            k_resolve_spec<256><<<1, block, spec_smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, tr_width, spec_T, spec_NL, d_over, d_stats);
+        } else {
+            CU(cudaFuncSetAttribute(k_resolve_spec<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
+            k_resolve_spec<1024><<<1, block, spec_smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, tr_width, spec_T, spec_NL, d_over, d_stats);
+        }
+        used = 1;
+    } else if (smem_ok && tr_width <= fit) {
         size_t smem = sizeof(int) * ((size_t)e->A * (9 + 3 * 12) + 2 * (size_t)e->S + 2 * (size_t)e->S * k_fit) + 16;
         if (block <= 256) {
             CU(cudaFuncSetAttribute(k_resolve_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1400,27 +1431,34 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
             CU(cudaFuncSetAttribute(k_resolve_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_resolve_fast<1024><<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, k_fit, d_over);
         }
+        used = 2;
     } else {
         size_t smem = sizeof(int) * (size_t)e->A;
         CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         k_resolve<<<1, block, smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, d_over);
+        used = 3;
     }
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev_t[1], st));
     int over = 0;
+    SabSpecStats hs{};
     CU(cudaMemcpyAsync(recent, H.recent, sizeof(int32_t) * 2 * e->A, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(prev, H.prev, sizeof(int32_t) * e->A, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(tr_n, H.tr_n, sizeof(int32_t) * e->S, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(tr_key, H.tr_key, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(tr_cnt, H.tr_cnt, sizeof(long long) * nk, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hs, d_stats, sizeof(SabSpecStats), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (const char *dbg = getenv("SAB_DEBUG")) if (dbg[0] == '1') {
+    {
         float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_t[0], e->ev_t[1]);
-        fprintf(stderr, "[sab] resolve: frames=%lld kernel=%.3f ms (%.3f us/frame)\n", (long long)n_frames, ms, 1e3 * ms / (double)n_frames);
+        e->resolve_ns += (int64_t)((double)ms * 1e6);
+        e->resolve_kind = used;
+        if (const char *dbg = getenv("SAB_DEBUG")) if (dbg[0] == '1')
+            fprintf(stderr, "[sab] resolve: kernel %d frames=%lld %.3f ms (%.3f us/frame) width=%d chunk=%d chunks=%llu truncated=%llu exact frames=%llu new keys=%llu\n",
+                    used, (long long)n_frames, ms, 1e3 * ms / (double)n_frames, tr_width, spec_T, hs.chunks, hs.truncated, hs.exact_frames, hs.new_keys);
     }
-    cudaFree(H.recent); cudaFree(H.prev); cudaFree(H.tr_n); cudaFree(H.tr_key); cudaFree(H.tr_cnt); cudaFree(d_over);
     if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);
     return SAB_OK;
 }

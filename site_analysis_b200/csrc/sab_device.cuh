@@ -11,6 +11,9 @@
 
 #define SAB_NONE (-1)
 #define SAB_AMBIGUOUS_BASE (-2)
+// A candidate list in the spill buffer is {n, c_0 .. c_{n-1}} (ascending); records are allocated in multiples of 4 ints so that
+// every list starts on a 16-byte boundary of the (16-byte aligned) buffer: the resolvers fetch them with 128-bit loads.
+#define SAB_SPILL_RECORD(n) ((((n) + 1) + 3) & ~3)
 #define SAB_BBOX_EPS 1e-9      // fractional slack of the exact-pruning bounding boxes
 #define SAB_REL_MARGIN 1e-9    // relative slack of every pruning bound on a distance
 

@@ -833,7 +833,7 @@ class AssignmentEngine:
 
     def _spill_capacity(self, nf: int) -> int:
         if self.k == nat.SPHERICAL:
-            return int(nf * self.A * 4 + 1024)
+            return int(nf * self.A * 8 + 1024)          # records are multiples of 4 ints (SAB_SPILL_RECORD)
         if self.k == nat.POLYHEDRAL:
             return int(max(nf * self.A // 8, 1) + 1024)
         return 16

@@ -508,3 +508,35 @@ def test_large_overlapping_sphere_system_needs_no_dense_rank_table(oracle_mod):
     assert np.array_equal(got, want)
     assert {s: t for s, t in enumerate(eng.transitions) if t} == o.transitions()       # site_index of this oracle = list positions
     print(f"S = 8448: {eng.last_info['ambiguous']} ambiguous atom-frames, {rows_cached} rank rows supplied ({table_bytes / 1e6:.1f} MB of tables)")
+
+
+def test_speculative_resolver_equals_the_per_frame_resolvers_and_the_oracle(oracle_mod):
+    """csrc/k_resolve_spec.cuh settles chunks of frames without a barrier per frame (reads of the shared transition Counters
+    are confirmed afterwards, a conflict truncates the chunk).  It must give exactly what the per-frame resolvers
+    (k_resolve_fast, k_resolve) and the sequential oracle give: rows, Counters WITH insertion order, recent sites -- on
+    overlapping spheres where 98 % of the atom-frames sit in several sites (site_collection.py:113-182), in one batch and
+    in ragged batches (history carried across calls)."""
+    from site_analysis_b200 import AssignmentEngine, _native as nat, synthetic as syn
+    g = syn.argyrodite_geometry(2)
+    F = 3000
+    frac, lat = syn.argyrodite_trajectory(g, F, device="cuda", seed=11)
+    out = {}
+    for label, mode, cuts in (("spec", 0, [F]), ("spec ragged", 0, [1, 7, 40, 1000, F]), ("fast", 1, [F]), ("global", 2, [F])):
+        eng = AssignmentEngine("spherical", g.n_atoms, g.mobile_idx, centres=g.site_centres, rcut=1.5)
+        eng.set_option(nat.OPT_RESOLVER, mode)
+        rows, a = [], 0
+        for b in cuts:
+            rows.append(eng.assign_device(frac[a:b].contiguous(), lat[a:b].contiguous()).cpu().numpy())
+            a = b
+        eng.sync_history()
+        out[label] = (np.concatenate(rows), [list(t.items()) for t in eng.transitions], eng.recent.copy(), eng.prev.copy())
+    ref = out["fast"]
+    assert (ref[0] >= 0).mean() > 0.9
+    for label, got in out.items():
+        assert np.array_equal(got[0], ref[0]), label
+        assert got[1] == ref[1], label                  # keys in insertion order, counts
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3]), label
+    n = 400
+    o = oracle_mod.SiteOracle("spherical", g.mobile_idx, centres=g.site_centres, rcut=1.5)
+    want = o.run(frac[:n].cpu().numpy(), lat[:n].cpu().numpy(), positions=True)
+    assert np.array_equal(out["spec"][0][:n], want)
