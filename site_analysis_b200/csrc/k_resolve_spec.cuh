@@ -12,7 +12,7 @@
 //   phase 1  every thread walks ITS atom through the next T frames on its own, no barrier: decisions that need only the
 //            atom's recent sites are final; a read takes the Counter row as it was at the start of the chunk plus the
 //            atom's OWN writes of this chunk (exact if nobody else wrote that row); every write is logged, not applied;
-//   phase 2  a read is confirmed when all writes of this chunk to its row are the reading atom's own.  The first
+//   phase 2  a read is confirmed when no OTHER atom wrote its row earlier in the chunk ((frame, atom) order).  The first
 //            unconfirmed read (or an atom without history, which needs the warp-wide nearest-centre search, or a full
 //            log) truncates the chunk at its frame t*: frames before t* are exact by construction;
 //   phase 3  the accepted frames are committed: results written, increments of existing Counter keys applied with
@@ -28,9 +28,9 @@
 
 #define SAB_SPEC_W 8            // own writes (site changes) an atom may log per chunk
 #define SAB_SPEC_R 6            // Counter reads an atom may log per chunk
-#define SAB_SPEC_PC 11          // candidates kept in registers per prefetched list: three 128-bit loads {n, c_0 .. c_10}
+#define SAB_SPEC_PC 7           // candidates a lane keeps in registers: two 128-bit loads {n, c_0 .. c_6}; longer lists are read from memory
 
-struct SabSpecStats { unsigned long long chunks, truncated, exact_frames, reads, new_keys; };
+struct SabSpecStats { unsigned long long chunks, truncated, exact_frames, reads, new_keys, cyc_load, cyc_walk, cyc_commit, cyc_exact; };
 
 // Choice among the candidates c[0..n) for an atom whose recent sites both miss: learned destinations of the anchor
 // (Counter row at the start of the chunk + the atom's own logged writes, in order), then the distance-ranked row, then
@@ -72,6 +72,59 @@ __device__ int sab_spec_decide(const int32_t *c, int n, int anchor, int n_sites,
     return best;
 }
 
+// The same choice by a whole warp: lane i holds candidate `cand` (< 0: none), n <= 32.  Every lane looks its candidate up in the
+// anchor's Counter row (+ the atom's own logged writes, walked by all lanes in lockstep), then one reduction picks the
+// learned destination with the highest count (ties: insertion order); without one, the candidates' rank keys are fetched
+// in parallel (one load per lane) and the first of the anchor's ranked row wins (site_collection.py:167-171).
+__device__ int sab_spec_decide_warp(int cand, int anchor, int n_sites, const SabPriorityTables &P, const SabSmemHistory &H,
+                                    const int *wl_src, const int *wl_dst, int nw, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int nk = H.tr_n[anchor];
+    const int *key = H.tr_key + (size_t)anchor * H.K, *cnt = H.tr_cnt + (size_t)anchor * H.K;
+    int k = 0, ins = INT_MAX;
+    if (cand >= 0) for (int j = 0; j < nk; j++) if (key[j] == cand) { k = cnt[j]; ins = j; break; }
+    int created = 0;
+    for (int j = 0; j < nw; j++) {                       // uniform over the warp
+        if (wl_src[j] != anchor) continue;
+        const int d = wl_dst[j];
+        bool fresh = true;
+        for (int q = 0; q < nk && fresh; q++) if (key[q] == d) fresh = false;
+        for (int q = 0; q < j && fresh; q++) if (wl_src[q] == anchor && wl_dst[q] == d) fresh = false;
+        if (cand == d) { k++; if (ins == INT_MAX) ins = nk + created; }
+        if (fresh) created++;
+    }
+    int bk = k, bi = ins, bs = cand;
+    for (int o = 16; o; o >>= 1) {
+        const int ok = __shfl_xor_sync(FULL, bk, o), oi = __shfl_xor_sync(FULL, bi, o), os = __shfl_xor_sync(FULL, bs, o);
+        if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; bs = os; }
+    }
+    if (bk > 0) return bs;
+    if (P.ranked) {
+        bool exact = true;
+        const double pos = cand >= 0 ? sab_rank_key(P, anchor, cand, n_sites, exact) : INFINITY;
+        double bp = pos; int ps = cand >= 0 ? cand : INT_MAX;
+        for (int o = 16; o; o >>= 1) {
+            const double op = __shfl_xor_sync(FULL, bp, o);
+            const int os = __shfl_xor_sync(FULL, ps, o);
+            if (op < bp || (op == bp && os < ps)) { bp = op; ps = os; }
+        }
+        const unsigned tied = __ballot_sync(FULL, cand >= 0 && pos == bp);
+        const unsigned inexact = __ballot_sync(FULL, cand >= 0 && !exact);
+        if (__popc(tied) > 1 && inexact && lane == 0) sab_rank_missing(P, anchor);
+        if (ps != INT_MAX) return ps;
+    }
+    // no ranking (sites without reference centres): face-sharing neighbours in list order, then list order
+    int best = INT_MAX;
+    if (P.neigh_off && !P.ranked)
+        for (int i = P.neigh_off[anchor]; i < P.neigh_off[anchor + 1] && best == INT_MAX; i++)
+            if (__ballot_sync(FULL, cand == P.neigh[i])) best = P.neigh[i];
+    if (best != INT_MAX) return best;
+    int lo = cand >= 0 ? cand : INT_MAX;
+    for (int o = 16; o; o >>= 1) lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+    return lo;
+}
+
 // One transition prev -> cur into the shared-memory Counters (site_collection.py:300-306); single thread.
 __device__ __forceinline__ void sab_spec_add(const SabSmemHistory &H, int pv, int cur, int *overflow)
 {
@@ -109,8 +162,10 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
     int *nl_dst = nl_src + NL;
     int *flag = nl_dst + NL;                             // [A] exact frame: atom needs the ordered walk
     int *cur_s = flag + n_mobile;                        // [A]
+    int *at_nw = cur_s + n_mobile, *at_nr = at_nw + n_mobile, *at_stop = at_nr + n_mobile, *at_amb = at_stop + n_mobile;   // [A] each: phase 1 -> 2 / 3
+    int *at_r0 = at_amb + n_mobile, *at_r1 = at_r0 + n_mobile, *at_pv = at_r1 + n_mobile;                                 // state after the whole chunk
     __shared__ int t_stop, nl_n, any_flag;
-    __shared__ unsigned long long st_loc[5];
+    __shared__ unsigned long long st_loc[9];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const bool mine = tid < n_mobile;
     const int a = tid;
@@ -121,7 +176,7 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
         H.tr_n[s] = n; wcnt[s] = 0;
         for (int i = 0; i < n && i < K; i++) { H.tr_key[(size_t)s * K + i] = G.tr_key[(size_t)s * G.K + i]; H.tr_cnt[(size_t)s * K + i] = (int)G.tr_cnt[(size_t)s * G.K + i]; }
     }
-    if (tid < 5) st_loc[tid] = 0ULL;
+    if (tid < 9) st_loc[tid] = 0ULL;
     __syncthreads();
 
     int64_t c0 = 0;
@@ -130,88 +185,102 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
         if (tid == 0) { t_stop = Te; nl_n = 0; }
         __syncthreads();
         // ------------------------------------------------------------------ phase 0: the chunk's result entries -> shared memory
-        // (coalesced, independent loads; afterwards the address of every candidate list of the chunk is known at once, so the
-        // lists can be fetched several frames ahead -- they are the only global-memory reads left in phase 1)
-        unsigned amb = 0u;                               // bit t: this atom's entry of frame t is ambiguous (commit writes only those)
-        if (mine)
-            for (int t = 0; t < Te; t++) dec[(size_t)t * n_mobile + a] = result[(size_t)(c0 + t) * n_mobile + a];
-        // (each thread reads back only what it wrote itself: no barrier needed)
-        // ------------------------------------------------------------------ phase 1: every atom on its own
-        int nw = 0, nr = 0, my_stop = INT_MAX;
-        int r0 = -1, r1 = -1, pv = -2;
-        if (mine) {
-            r0 = H.recent[2 * a]; r1 = H.recent[2 * a + 1]; pv = H.prev[a];
-            int *my_src = wl_src + a * SAB_SPEC_W, *my_dst = wl_dst + a * SAB_SPEC_W, *my_t = wl_t + a * SAB_SPEC_W;
-            // candidate lists: into L2 eleven frames ahead, into registers three frames ahead (no load depends on the atom's
-            // state).  Three register buffers used round-robin (frame t lives in buffer t mod 3; the loop is unrolled by three
-            // so that no buffer is ever copied); slots behind a list's end are filled with -3, which no site id equals.
-            int er[3], cn[3], cc[3][SAB_SPEC_PC];
-            const int *ent = dec + a;                    // this atom's column of the chunk's entries / decisions
-            auto load_r = [&](int t) -> int { return t < Te ? ent[(size_t)t * n_mobile] : SAB_NONE; };
-            auto load_c = [&](int r, int &n, int *c) {           // records are 16-byte aligned (SAB_SPILL_RECORD): 3 loads, not 12
-                const int4 *p = reinterpret_cast<const int4 *>(spill + ((r <= SAB_AMBIGUOUS_BASE) ? (SAB_AMBIGUOUS_BASE - r) : 0));
-                const int4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+        long long tk0 = clock64();
+        for (int i = tid; i < Te * n_mobile; i += nthr) dec[i] = result[(size_t)c0 * n_mobile + i];       // coalesced
+        __syncthreads();
+        long long tk1 = clock64();
+        // ------------------------------------------------------------------ phase 1: one WARP per atom, one LANE per frame
+        // Lane j holds the entry and the candidate list of frame j.  Whether the atom's most recent site r0 still contains it
+        // is tested for ALL frames of the chunk at once (one ballot); the leading run of "stays" is settled in one step, the
+        // first frame that is not a stay (3 % of the atom-frames) is handled serially by the whole warp with that lane's list
+        // broadcast by shuffles, the state (r0, r1, previous entry) is updated and the remaining frames are tested again.
+        for (int q = tid >> 5; q < n_mobile; q += nthr >> 5) {
+            const int e = lane < Te ? dec[(size_t)lane * n_mobile + q] : SAB_NONE;
+            int n = 0, c[SAB_SPEC_PC];
+            {
+                const int4 *p = reinterpret_cast<const int4 *>(spill + ((e <= SAB_AMBIGUOUS_BASE) ? (SAB_AMBIGUOUS_BASE - e) : 0));
+                int4 q0 = make_int4(0, -3, -3, -3), q1 = make_int4(-3, -3, -3, -3);
+                if (e <= SAB_AMBIGUOUS_BASE) { q0 = __ldg(p); q1 = __ldg(p + 1); }
                 n = q0.x;
                 c[0] = q0.y; c[1] = q0.z; c[2] = q0.w; c[3] = q1.x; c[4] = q1.y; c[5] = q1.z; c[6] = q1.w;
-                c[7] = q2.x; c[8] = q2.y; c[9] = q2.z; c[10] = q2.w;
-            };
-            auto touch_c = [&](int t) {
-                const int r = load_r(t);
-                if (r <= SAB_AMBIGUOUS_BASE) asm volatile("prefetch.global.L2 [%0];" ::"l"(spill + (SAB_AMBIGUOUS_BASE - r)));
-            };
-            for (int t = 3; t < 11; t++) touch_c(t);
 #pragma unroll
-            for (int b = 0; b < 3; b++) { er[b] = load_r(b); load_c(er[b], cn[b], cc[b]); }
-            bool stop_now = false;
-            // one frame, its list in buffer B (a compile-time constant)
-#define SAB_SPEC_STEP(B, t_)                                                                                              \
-            do {                                                                                                          \
-                const int t = (t_);                                                                                       \
-                if (t >= Te) break;                                                                                       \
-                const int r = er[B];                                                                                      \
-                int cur = r;                                                                                              \
-                touch_c(t + 11);                                                                                          \
-                if (r <= SAB_AMBIGUOUS_BASE) {                                                                            \
-                    amb |= 1u << t;                                                                                       \
-                    bool in0 = false, in1 = false;                                                                        \
-                    const int n = cn[B];                                                                                  \
-                    if (n <= SAB_SPEC_PC) {                                                                               \
-                        _Pragma("unroll") for (int i = 0; i < SAB_SPEC_PC; i++) { const int ci = i < n ? cc[B][i] : -3; in0 |= ci == r0; in1 |= ci == r1; } \
-                    } else {                                                                                              \
-                        const int32_t *c = spill + (SAB_AMBIGUOUS_BASE - r) + 1;                                          \
-                        in0 = r0 >= 0 && sab_in_list(c, n, r0);                                                           \
-                        in1 = r1 >= 0 && sab_in_list(c, n, r1);                                                           \
-                    }                                                                                                     \
-                    if (in0) cur = r0;                                                                                    \
-                    else if (in1) cur = r1;                                                                               \
-                    else {                                                                                                \
-                        if (r0 < 0 || nr == SAB_SPEC_R) { my_stop = t; stop_now = true; break; }   /* no history (nearest-centre search) / log full */ \
-                        cur = sab_spec_decide(spill + (SAB_AMBIGUOUS_BASE - r) + 1, n, r0, n_sites, P, H, my_src, my_dst, nw); \
-                        rl_row[a * SAB_SPEC_R + nr] = r0; rl_t[a * SAB_SPEC_R + nr] = t; nr++;                            \
-                    }                                                                                                     \
-                }                                                                                                         \
-                if (cur >= 0 && pv >= 0 && pv != cur) {                                                                   \
-                    if (nw == SAB_SPEC_W) { my_stop = t; stop_now = true; break; }                                        \
-                    my_src[nw] = pv; my_dst[nw] = cur; my_t[nw] = t; nw++;                                                \
-                    atomicAdd(&wcnt[pv], 1);                                                                              \
-                }                                                                                                         \
-                if (cur >= 0 && cur != r0) { r1 = r0; r0 = cur; }                                                         \
-                pv = cur;                                                                                                 \
-                er[B] = load_r(t + 3);                       /* before the decision overwrites nothing it needs: t + 3 > t */ \
-                load_c(er[B], cn[B], cc[B]);                                                                              \
-                dec[(size_t)t * n_mobile + a] = cur;                                                                      \
-            } while (0)
-            for (int t3 = 0; t3 < Te && !stop_now; t3 += 3) {
-                SAB_SPEC_STEP(0, t3);
-                if (stop_now) break;
-                SAB_SPEC_STEP(1, t3 + 1);
-                if (stop_now) break;
-                SAB_SPEC_STEP(2, t3 + 2);
+                for (int i = 0; i < SAB_SPEC_PC; i++) if (i >= n) c[i] = -3;          // no site id equals -3
             }
-#undef SAB_SPEC_STEP
+            const unsigned ambm = __ballot_sync(0xffffffffu, e <= SAB_AMBIGUOUS_BASE);
+            int r0 = H.recent[2 * q], r1 = H.recent[2 * q + 1], pv = H.prev[q];
+            int *my_src = wl_src + q * SAB_SPEC_W, *my_dst = wl_dst + q * SAB_SPEC_W, *my_t = wl_t + q * SAB_SPEC_W;
+            int nw = 0, nr = 0, stop = INT_MAX, t = 0;
+            while (t < Te) {
+                // frames in which the atom certainly stays in r0: r0 is in the (short) list, or the entry IS r0
+                bool stay = false;
+                if (r0 >= 0 && (pv == r0 || pv < 0)) {
+                    if (e <= SAB_AMBIGUOUS_BASE) {
+                        if (n <= SAB_SPEC_PC) {
+#pragma unroll
+                            for (int i = 0; i < SAB_SPEC_PC; i++) stay |= c[i] == r0;
+                        }
+                    } else stay = e == r0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, stay && lane < Te) >> t;
+                const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;
+                if (run > 0) {                           // no transition (the previous entry is r0 or none), no change of the recent sites
+                    if (lane >= t && lane < t + run) dec[(size_t)lane * n_mobile + q] = r0;
+                    pv = r0;
+                    t += run;
+                    if (t >= Te) break;
+                }
+                // ---- frame t, serially (warp-uniform): its entry and list come from lane t
+                const int et = __shfl_sync(0xffffffffu, e, t);
+                int cur = et;
+                if (et <= SAB_AMBIGUOUS_BASE) {
+                    const int nt = __shfl_sync(0xffffffffu, n, t);
+                    bool in0 = false, in1 = false;
+                    int cand = -1;                       // lane i <-> candidate i of frame t
+                    if (nt <= SAB_SPEC_PC) {
+#pragma unroll
+                        for (int i = 0; i < SAB_SPEC_PC; i++) {
+                            const int ci = __shfl_sync(0xffffffffu, c[i], t);
+                            in0 |= ci == r0; in1 |= ci == r1;
+                            if (lane == i) cand = ci;
+                        }
+                        in0 &= r0 >= 0; in1 &= r1 >= 0;
+                    } else {
+                        const int32_t *cl = spill + (SAB_AMBIGUOUS_BASE - et) + 1;
+                        in0 = r0 >= 0 && sab_in_list(cl, nt, r0);
+                        in1 = r1 >= 0 && sab_in_list(cl, nt, r1);
+                        if (lane < nt) cand = cl[lane];
+                    }
+                    if (in0) cur = r0;
+                    else if (in1) cur = r1;
+                    else {
+                        if (r0 < 0 || nr == SAB_SPEC_R) { stop = t; break; }           // no history (nearest-centre search) / log full
+                        if (nt <= 32) cur = sab_spec_decide_warp(cand, r0, n_sites, P, H, my_src, my_dst, nw, lane);
+                        else {
+                            if (lane == 0) cur = sab_spec_decide(spill + (SAB_AMBIGUOUS_BASE - et) + 1, nt, r0, n_sites, P, H, my_src, my_dst, nw);
+                            cur = __shfl_sync(0xffffffffu, cur, 0);
+                        }
+                        if (lane == 0) { rl_row[q * SAB_SPEC_R + nr] = r0; rl_t[q * SAB_SPEC_R + nr] = t; }
+                        nr++;
+                    }
+                }
+                if (cur >= 0 && pv >= 0 && pv != cur) {
+                    if (nw == SAB_SPEC_W) { stop = t; break; }
+                    if (lane == 0) { my_src[nw] = pv; my_dst[nw] = cur; my_t[nw] = t; atomicAdd(&wcnt[pv], 1); }
+                    nw++;
+                    __syncwarp();                        // the log is read by lane 0 in a later sab_spec_decide
+                }
+                if (cur >= 0 && cur != r0) { r1 = r0; r0 = cur; }
+                pv = cur;
+                if (lane == 0) dec[(size_t)t * n_mobile + q] = cur;
+                t++;
+            }
+            if (lane == 0) { at_nw[q] = nw; at_nr[q] = nr; at_stop[q] = stop; at_amb[q] = (int)ambm; at_r0[q] = r0; at_r1[q] = r1; at_pv[q] = pv; }
         }
         __syncthreads();
+        long long tk2 = clock64();
         // ------------------------------------------------------------------ phase 2: confirm the reads
+        const int nw = mine ? at_nw[a] : 0, nr = mine ? at_nr[a] : 0, my_stop = mine ? at_stop[a] : INT_MAX;
+        const unsigned amb = mine ? (unsigned)at_amb[a] : 0u;
         if (mine) {
             int stop = my_stop;
             const int *my_src = wl_src + a * SAB_SPEC_W;
@@ -219,7 +288,17 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                 const int row = rl_row[a * SAB_SPEC_R + i];
                 int own = 0;
                 for (int j = 0; j < nw; j++) own += (my_src[j] == row);
-                if (wcnt[row] != own) { stop = min(stop, rl_t[a * SAB_SPEC_R + i]); break; }   // somebody else wrote this row in the chunk
+                if (wcnt[row] == own) continue;          // every write of the chunk to this row is the atom's own: confirmed
+                // somebody else wrote this row in the chunk: a conflict only if that write comes BEFORE the read in (frame, atom) order
+                const int t_read = rl_t[a * SAB_SPEC_R + i], key_read = t_read * n_mobile + a;
+                bool conflict = false;
+                for (int b = 0; b < n_mobile && !conflict; b++) {
+                    if (b == a) continue;
+                    const int nb = at_nw[b];
+                    for (int j = 0; j < nb; j++)
+                        if (wl_src[b * SAB_SPEC_W + j] == row && wl_t[b * SAB_SPEC_W + j] * n_mobile + b < key_read) { conflict = true; break; }
+                }
+                if (conflict) { stop = min(stop, t_read); break; }
             }
             if (stop < Te) atomicMin(&t_stop, stop);
         }
@@ -229,15 +308,14 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
         if (mine) {
             // the atom's state after the accepted frames: replay its decisions (they need no list)
             int q0 = H.recent[2 * a], q1 = H.recent[2 * a + 1], qp = H.prev[a];
-            if (ts == Te && my_stop == INT_MAX) { q0 = r0; q1 = r1; qp = pv; }
-            else
+            if (ts == Te && my_stop == INT_MAX) { q0 = at_r0[a]; q1 = at_r1[a]; qp = at_pv[a]; }
+            else {
                 for (int t = 0; t < ts; t++) {
                     const int cur = dec[(size_t)t * n_mobile + a];
                     if (cur >= 0 && cur != q0) { q1 = q0; q0 = cur; }
                     qp = cur;
                 }
-            for (int t = 0; t < ts; t++)                 // results (only ambiguous entries change): stores only
-                if (amb >> t & 1u) result[(size_t)(c0 + t) * n_mobile + a] = dec[(size_t)t * n_mobile + a];
+            }
             // own writes of the accepted frames: existing keys are incremented in place (commutes), new keys are listed
             for (int j = 0; j < nw; j++) {
                 const int t = wl_t[a * SAB_SPEC_W + j];
@@ -253,6 +331,10 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
             H.recent[2 * a] = q0; H.recent[2 * a + 1] = q1; H.prev[a] = qp;
         }
         for (int s = tid; s < n_sites; s += nthr) wcnt[s] = 0;
+        for (int i = tid; i < ts * n_mobile; i += nthr) {   // results of the accepted frames (only ambiguous entries change): all threads, stores only
+            const int t = i / n_mobile, q = i - t * n_mobile;
+            if ((unsigned)at_amb[q] >> t & 1u) result[(size_t)c0 * n_mobile + i] = dec[i];
+        }
         __syncthreads();
         // NOTE: sab_row_find above ran against rows that other threads only INCREMENT meanwhile (keys and tr_n are not
         // modified before the barrier), so the classification existing / new is race-free.
@@ -286,6 +368,8 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
         }
         __syncthreads();
         c0 += ts;
+        long long tk3 = clock64();
+        if (tid == 0) { st_loc[5] += (unsigned long long)(tk1 - tk0); st_loc[6] += (unsigned long long)(tk2 - tk1); st_loc[7] += (unsigned long long)(tk3 - tk2); }
         if (ts == Te) continue;
         // ------------------------------------------------------------------ the truncating frame, exactly (as k_resolve)
         {
@@ -340,7 +424,7 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
                     __syncwarp();
                 }
             }
-            if (tid == 0) st_loc[2]++;
+            if (tid == 0) { st_loc[2]++; st_loc[8] += (unsigned long long)(clock64() - tk3); }
             __syncthreads();
             c0 += 1;
         }
@@ -352,5 +436,5 @@ k_resolve_spec(const double *__restrict__ frac, int64_t n_frames, int n_atoms, i
         G.tr_n[s] = n;
         for (int i = 0; i < n; i++) { G.tr_key[(size_t)s * G.K + i] = H.tr_key[(size_t)s * K + i]; G.tr_cnt[(size_t)s * G.K + i] = H.tr_cnt[(size_t)s * K + i]; }
     }
-    if (stats && tid == 0) { stats->chunks = st_loc[0]; stats->truncated = st_loc[1]; stats->exact_frames = st_loc[2]; stats->reads = st_loc[3]; stats->new_keys = st_loc[4]; }
+    if (stats && tid == 0) { stats->chunks = st_loc[0]; stats->truncated = st_loc[1]; stats->exact_frames = st_loc[2]; stats->reads = st_loc[3]; stats->new_keys = st_loc[4]; stats->cyc_load = st_loc[5]; stats->cyc_walk = st_loc[6]; stats->cyc_commit = st_loc[7]; stats->cyc_exact = st_loc[8]; }
 }

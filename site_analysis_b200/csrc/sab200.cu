@@ -1406,21 +1406,16 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
     int spec_T = 0, spec_NL = 0; size_t spec_smem = 0;
     if (smem_ok && e->A <= 1024 && e->resolver == 0 && getenv("SAB_RESOLVE_FAST") == nullptr) {
         int nl = 64; while (nl < e->A * SAB_SPEC_W) nl <<= 1;
-        for (int T = 32; T >= 8 && !spec_T; T >>= 1) {
-            const size_t ints = (size_t)e->A * (3 + (size_t)T + 3 * SAB_SPEC_W + 2 * SAB_SPEC_R + 2) + 2 * (size_t)e->S +
+        for (int T = 32; T >= 32 && !spec_T; T >>= 1) {      // one lane per frame of a chunk
+            const size_t ints = (size_t)e->A * (3 + (size_t)T + 3 * SAB_SPEC_W + 2 * SAB_SPEC_R + 2 + 7) + 2 * (size_t)e->S +
                                 2 * (size_t)e->S * tr_width + 3 * (size_t)nl;
             if (sizeof(int) * ints + 64 <= (size_t)smem_cap) { spec_T = T; spec_NL = nl; spec_smem = sizeof(int) * ints + 64; }
         }
     }
     int used = 0;                        // 1 speculative, 2 per-frame shared memory, 3 global memory
-    if (spec_T) {
-        if (block <= 256) {
-            CU(cudaFuncSetAttribute(k_resolve_spec<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
-            k_resolve_spec<256><<<1, block, spec_smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, tr_width, spec_T, spec_NL, d_over, d_stats);
-        } else {
-            CU(cudaFuncSetAttribute(k_resolve_spec<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
-            k_resolve_spec<1024><<<1, block, spec_smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, tr_width, spec_T, spec_NL, d_over, d_stats);
-        }
+    if (spec_T) {                        // one warp per atom at a time: 32 warps share the atoms (and thread a < A commits atom a)
+        CU(cudaFuncSetAttribute(k_resolve_spec<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
+        k_resolve_spec<1024><<<1, 1024, spec_smem, st>>>(d_frac, n_frames, e->N, e->A, e->d_mobile, e->S, d_result, d_spill, P, H, tr_width, spec_T, spec_NL, d_over, d_stats);
         used = 1;
     } else if (smem_ok && tr_width <= fit) {
         size_t smem = sizeof(int) * ((size_t)e->A * (9 + 3 * 12) + 2 * (size_t)e->S + 2 * (size_t)e->S * k_fit) + 16;
@@ -1456,8 +1451,9 @@ extern "C" int sab_resolve(sab_engine *e, const double *d_frac, int64_t n_frames
         e->resolve_ns += (int64_t)((double)ms * 1e6);
         e->resolve_kind = used;
         if (const char *dbg = getenv("SAB_DEBUG")) if (dbg[0] == '1')
-            fprintf(stderr, "[sab] resolve: kernel %d frames=%lld %.3f ms (%.3f us/frame) width=%d chunk=%d chunks=%llu truncated=%llu exact frames=%llu new keys=%llu\n",
-                    used, (long long)n_frames, ms, 1e3 * ms / (double)n_frames, tr_width, spec_T, hs.chunks, hs.truncated, hs.exact_frames, hs.new_keys);
+            fprintf(stderr, "[sab] resolve: kernel %d frames=%lld %.3f ms (%.3f us/frame) width=%d chunk=%d chunks=%llu truncated=%llu exact frames=%llu new keys=%llu Mcycles: load %.2f walk %.2f commit %.2f exact %.2f\n",
+                    used, (long long)n_frames, ms, 1e3 * ms / (double)n_frames, tr_width, spec_T, hs.chunks, hs.truncated, hs.exact_frames, hs.new_keys,
+                    hs.cyc_load * 1e-6, hs.cyc_walk * 1e-6, hs.cyc_commit * 1e-6, hs.cyc_exact * 1e-6);
     }
     if (over) return fail(SAB_EOVERFLOW, "transition table width %d exceeded", tr_width);
     return SAB_OK;
