@@ -343,6 +343,11 @@ int sab_measure_fp64_peak(int device, double *tflops);
  * kernels other than the tetrahedral stream kernel ignore the peers); n_peers = 0 clears.  The caller orders the
  * peers' reads after this rank's kernels (any collective issued after them on the same stream does). */
 int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *d_peer_slots);
+/* The same through ONE multicast mapping (NVLS; e.g. torch symmetric memory's multicast_ptr): d_multicast_slot = where this
+ * rank's rows start inside the multicast view of the int32[F_total][A] array.  Every row is then stored once with
+ * multimem.st and the NVSwitch replicates it into every rank's copy (this rank's included) -- 1/(N-1) of the NVLink egress of
+ * the unicast form.  NULL clears.  Replaces any peers set with sab_set_result_peers. */
+int sab_set_result_multicast(sab_engine *e, int32_t *d_multicast_slot);
 
 /* ---- XDATCAR text -> arrays (host code) -----------------------------
  * The reference takes Sequence[Structure] (trajectory.py:413-432), which users build with pymatgen's Xdatcar parser;

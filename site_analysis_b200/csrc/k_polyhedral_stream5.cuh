@@ -85,6 +85,7 @@ struct SabStream5Tables {
     double delta_d;               // the validity tube in float64 (>= what delta_t admits)
     int n_peer;
     int32_t *peer[SAB_MAX_PEERS];
+    int peer_mc;                  // peer[0] is a multicast address (one store reaches every rank: multimem.st)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -541,8 +542,11 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                             *resp = out;
                             // fused result all-gather: the same row goes to every peer's copy of the full array (posted NVLink stores)
                             if (C.n_peer) {
+                                if (C.peer_mc) sab_multicast_store(C.peer[0] + poff, out);      // NVLS: the switch replicates the store
+                                else {
 #pragma unroll
-                                for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][poff] = out;   // static indices: the parameter stays in constant memory
+                                    for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][poff] = out;   // static indices: the parameter stays in constant memory
+                                }
                             }
                         }
                     }
@@ -560,8 +564,11 @@ k_polyhedral_assign_stream5(const double *__restrict__ frac, int64_t n_frames, i
                             const size_t o = (size_t)f * n_mobile + a;
                             result[o] = out;
                             if (C.n_peer) {
+                                if (C.peer_mc) sab_multicast_store(C.peer[0] + o, out);
+                                else {
 #pragma unroll
-                                for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][o] = out;
+                                    for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < C.n_peer) C.peer[q][o] = out;
+                                }
                             }
                             last[a] = make_int2(rcx, rcy);
                         }
@@ -594,6 +601,8 @@ __global__ void k_polyhedral_flagged(const double *__restrict__ frac, int n_atom
         const size_t o = (size_t)f * n_mobile + a;
         result[o] = out;
 #pragma unroll
-        for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < peers.n) peers.p[q][o] = out;
+        if (peers.mc) sab_multicast_store(peers.p[0] + o, out);
+        else
+            for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < peers.n) peers.p[q][o] = out;
     }
 }

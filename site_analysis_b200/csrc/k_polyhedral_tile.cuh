@@ -412,7 +412,13 @@ k_polyhedral_assign_tile(const double *__restrict__ frac, int64_t n_frames, int 
 #ifndef SAB_MAX_PEERS
 #define SAB_MAX_PEERS 7
 #endif
-struct SabPeers { int n; int32_t *p[SAB_MAX_PEERS]; };   // other ranks' slots for this rank's result rows (multi-GPU)
+struct SabPeers { int n; int32_t *p[SAB_MAX_PEERS]; int mc; };   // other ranks' slots for this rank's result rows (multi-GPU);
+                                                                 // mc: p[0] is ONE multicast address that reaches every rank
+// One 32-bit store through a multicast mapping (NVLS): the switch replicates it into every rank's copy of the array.
+__device__ __forceinline__ void sab_multicast_store(int32_t *mc_addr, int v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
 
 __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n_frames, int n_atoms, int n_mobile,
                                       const int32_t *__restrict__ mobile, SabPolyTables T, int G,
@@ -421,7 +427,7 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
                                       long long defer_cap, int32_t *__restrict__ result, int32_t *__restrict__ spill,
                                       long long spill_capacity, unsigned long long *__restrict__ counters,
                                       const double *__restrict__ anchor = nullptr,   // wrows == nullptr: W = rint(raw - anchor)
-                                      SabPeers peers = SabPeers{0, {nullptr}})
+                                      SabPeers peers = SabPeers{0, {nullptr}, 0})
 {
     const long long n_def = (long long)counters[9];
     if (n_def == 0) return;
@@ -475,7 +481,9 @@ __global__ void k_polyhedral_deferred(const double *__restrict__ frac, int64_t n
         if (lane == 0) {
             result[idx] = out;
 #pragma unroll
-            for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < peers.n) peers.p[q][idx] = out;
+            if (peers.mc) sab_multicast_store(peers.p[0] + idx, out);
+            else
+                for (int q = 0; q < SAB_MAX_PEERS; q++) if (q < peers.n) peers.p[q][idx] = out;
         }
     }
 }

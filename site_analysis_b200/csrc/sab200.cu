@@ -134,7 +134,7 @@ struct sab_engine {
     int32_t *d_lz_shift = nullptr, *d_lz_has = nullptr, *d_lz_lock = nullptr; double *d_lz_cached = nullptr, *d_lz_vc = nullptr, *d_lz_rc = nullptr;
     long long *d_lz_stamp = nullptr; uint8_t *d_lz_has_rc = nullptr; unsigned long long *d_lz_stats = nullptr; bool lazy_set = false;
     long long lazy_frames = 0;
-    int n_peer = 0; int32_t *peer[SAB_MAX_PEERS] = {nullptr};   // sab_set_result_peers
+    int n_peer = 0; int32_t *peer[SAB_MAX_PEERS] = {nullptr}; int peer_mc = 0;   // sab_set_result_peers / sab_set_result_multicast
     bool peers_written = false;            // the last sab_assign_device stored its rows into the peers as well
     size_t stream_occ_key = 0; int stream_per_sm = 0;     // cached occupancy query of the stream kernel
     unsigned long long *h_pinned = nullptr;               // pinned [2][CNT_N]: counter initialiser | read-back
@@ -681,10 +681,11 @@ static int launch_stream(sab_engine *e, const StreamPlan &p, const double *d_fra
                       (float)e->delta - 4e-7f, e->fp32_filter, w.defer, w.defer_cap, e->d_anchor, e->d_fw_atoms, e->d_prev_raw,
                       e->d_wraps, e->skip_step_check_once ? 1 : 0, p.n_raw, p.n_prod, p.use_tma, w.chunk_exc, e->delta > 0.12 ? 1 : 0,
                       (e->stream_reg_cols && 3 * e->M <= SAB_STREAM_KMAX * 32 * p.n_prod && 3 * e->A <= SAB_STREAM_KMAX * 32 * p.n_prod &&
-                       e->n_used < 65536) ? 1 : 0, e->n_peer, {nullptr}};
-    SabPeers peers{e->n_peer, {nullptr}};
-    for (int q = 0; q < e->n_peer; q++) { C.peer[q] = e->peer[q]; peers.p[q] = e->peer[q]; }
-    e->peers_written = e->n_peer > 0;
+                       e->n_used < 65536) ? 1 : 0, e->peer_mc ? 0 : e->n_peer, {nullptr}};
+    const int n_peer4 = e->peer_mc ? 0 : e->n_peer;          // the previous-generation kernel only knows unicast peers
+    SabPeers peers{n_peer4, {nullptr}, 0};
+    for (int q = 0; q < n_peer4; q++) { C.peer[q] = e->peer[q]; peers.p[q] = e->peer[q]; }
+    e->peers_written = n_peer4 > 0;
     const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
     if (p.rec_smem)
         k_polyhedral_assign_stream<true><<<p.grid, (p.n_prod + p.n_cons) * 32, p.smem, st>>>(d_frac, F, p.chunk, e->N, e->A, e->d_mobile, e->S, T, C,
@@ -778,8 +779,8 @@ static int launch_stream5(sab_engine *e, const StreamPlan5 &p, const double *d_f
     C.anchor = e->d_anchor; C.fw_atoms = e->d_fw_atoms; C.prev_raw = e->d_prev_raw; C.wraps = e->d_wraps;
     C.skip_check_frame0 = e->skip_step_check_once ? 1 : 0;
     C.n_raw = p.n_raw; C.n_rows = p.n_rows; C.n_prod = p.n_prod; C.use_tma = p.use_tma;
-    C.chunk_exc = w.chunk_exc; C.delta_d = e->delta; C.n_peer = e->n_peer;
-    SabPeers peers{e->n_peer, {nullptr}};
+    C.chunk_exc = w.chunk_exc; C.delta_d = e->delta; C.n_peer = e->n_peer; C.peer_mc = e->peer_mc;
+    SabPeers peers{e->n_peer, {nullptr}, e->peer_mc};
     for (int q = 0; q < e->n_peer; q++) { C.peer[q] = e->peer[q]; peers.p[q] = e->peer[q]; }
     e->peers_written = e->n_peer > 0;
     const int64_t n_chunks = (F + p.chunk - 1) / p.chunk;
@@ -1796,7 +1797,18 @@ extern "C" int sab_set_result_peers(sab_engine *e, int n_peers, int32_t *const *
     if (!e || n_peers < 0 || n_peers > SAB_MAX_PEERS || (n_peers > 0 && !d_peer_slots))
         return fail(SAB_EINVAL, "sab_set_result_peers: between 0 and %d peers", SAB_MAX_PEERS);
     e->n_peer = n_peers;
+    e->peer_mc = 0;
     for (int q = 0; q < SAB_MAX_PEERS; q++) e->peer[q] = q < n_peers ? d_peer_slots[q] : nullptr;
+    return SAB_OK;
+}
+
+extern "C" int sab_set_result_multicast(sab_engine *e, int32_t *d_multicast_slot)
+{
+    if (!e) return fail(SAB_EINVAL, "sab_set_result_multicast: null engine");
+    e->n_peer = d_multicast_slot ? 1 : 0;
+    e->peer_mc = d_multicast_slot ? 1 : 0;
+    for (int q = 0; q < SAB_MAX_PEERS; q++) e->peer[q] = nullptr;
+    e->peer[0] = d_multicast_slot;
     return SAB_OK;
 }
 

@@ -134,12 +134,23 @@ class PeerResultBuffers:
         import torch.distributed._symmetric_memory as symm_mem
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.F, self.A = int(n_frames_local), int(n_mobile)
-        self.buffers, self.ptrs = [], []
+        self.buffers, self.ptrs, self.mc_ptrs = [], [], []
+        import os
         for _ in range(2):
             t = symm_mem.empty((self.world * self.F, self.A), dtype=torch.int32, device=device)
             h = symm_mem.rendezvous(t, group)
             self.buffers.append(t)
             self.ptrs.append([int(p) for p in h.buffer_ptrs])
+            mc = 0
+            try:                                  # NVLS multicast view of the same buffers (0 / absent when the fabric has none)
+                # opt-in: measured on 4 B200s the multimem.st form (a strong system-scope store) makes the kernel 10 % slower
+                # than three plain unicast stores (0.663 vs 0.604 ms, profiles/README.md); it saves NVLink egress at larger N
+                if os.environ.get("SAB_MULTICAST") == "1" and self.world > 2:
+                    mc = int(getattr(h, "multicast_ptr", 0) or 0)
+            except Exception:
+                mc = 0
+            self.mc_ptrs.append(mc)
+        self.multicast = all(p != 0 for p in self.mc_ptrs)
         self._handles = None
         self.turn = 0
 
@@ -150,6 +161,7 @@ class PeerResultBuffers:
         full = self.buffers[k]
         slot_bytes = self.rank * self.F * self.A * 4
         peers = [self.ptrs[k][q] + slot_bytes for q in range(self.world) if q != self.rank]
+        self.mc_slot = self.mc_ptrs[k] + slot_bytes if getattr(self, "multicast", False) else 0
         return full, full[self.rank * self.F:(self.rank + 1) * self.F], peers
 
 
@@ -207,9 +219,13 @@ def _carry_by_totals(engine, d_frac_local, group):
         nat.check(engine.L.sab_set_pbc_state(engine.h, nat.ptr(sh), nat.ptr(prev_raw), nat.ptr(wraps), nat.ptr(exc)))
 
 
-def _carry_by_anchor(engine, d_frac_local, group):
+def _carry_by_anchor(engine, d_frac_local, group, halo_frame=None):
     """Polyhedral sites (guard G1 makes it exact, see ``carry_from_halo``): one tiny all-gather of the halo frames,
-    then the carry is set ON THE DEVICE (sab_set_carry_device) -- no pass over the data, no host round trip."""
+    then the carry is set ON THE DEVICE (sab_set_carry_device) -- no pass over the data, no host round trip.
+
+    ``halo_frame``: the frame that precedes this rank's shard, (N, 3) float64 on the shard's device, when the caller has
+    it already (a loader that hands rank r the frames [f0 - 1, f1) gets it for free): then NO collective is issued here.
+    Ignored on rank 0, whose predecessor is the state the engine was initialised with."""
     import torch
     import torch.distributed as dist
     from . import _native as nat
@@ -222,12 +238,16 @@ def _carry_by_anchor(engine, d_frac_local, group):
             fw=torch.as_tensor(engine.fw_atoms.astype(np.int64), device=dev),
             p0=torch.as_tensor(np.ascontiguousarray(p0), device=dev),
             anchor0=torch.as_tensor(np.ascontiguousarray(p0 - w0), device=dev))
-    last_raw = d_frac_local[-1].index_select(0, st["fw"])
-    halos = _all_gather(last_raw, group)
-    halo = st["p0"] if rank == 0 else halos[rank - 1]
+    if halo_frame is not None:
+        halo = st["p0"] if rank == 0 else halo_frame.index_select(0, st["fw"]).contiguous()
+        st["keep"] = (halo,)
+    else:
+        last_raw = d_frac_local[-1].index_select(0, st["fw"])
+        halos = _all_gather(last_raw, group)
+        halo = st["p0"] if rank == 0 else halos[rank - 1]
+        st["keep"] = (halos, last_raw)                       # alive until the stream has consumed them
     nat.check(engine.L.sab_set_carry_device(engine.h, halo.data_ptr(), st["anchor0"].data_ptr(),
                                             torch.cuda.current_stream(dev).cuda_stream))
-    st["keep"] = (halos, last_raw)                           # alive until the stream has consumed them
 
 
 def relay_history(engine, group) -> None:
@@ -258,8 +278,46 @@ def relay_history(engine, group) -> None:
                 engine.transitions = [dict(t) for t in transitions]
 
 
+def exchange_halo_frames(d_frac_local, group):
+    """One-off helper for callers whose loader did not keep the frame before each shard: all-gather of the shards' last
+    frames; returns the (N, 3) frame preceding THIS rank's shard (rank 0: its own last frame, unused).  Input
+    distribution, not part of the per-batch data path: pass the result as ``assign_sharded(halo_frame=...)``."""
+    import torch.distributed as dist
+    last = _all_gather(d_frac_local[-1].contiguous(), group)
+    return last[max(dist.get_rank(group) - 1, 0)].clone()
+
+
+def finish_sharded(engine) -> None:
+    """Evaluate the guard / flag records of every ``assign_sharded(..., deferred_check=True)`` call made so far (one
+    host synchronisation for all of them).  Raises what the immediate form would have raised: ``GuardError`` for a
+    framework excursion >= 0.3 over the sharded trajectory, ``RuntimeError`` when some rank met an atom-frame in several
+    sites or could not store its rows into the peers (such a batch must be redone with ``deferred_check=False``, whose
+    history relay / all-gather fallback handles it)."""
+    from .engine import EXCURSION_LIMIT, GuardError
+    checks, engine._sharded_checks = getattr(engine, "_sharded_checks", []), []
+    engine._barrier_events = []                # ev.synchronize() below covers them: every peer's rows of every batch have arrived
+    pool = getattr(engine, "_pinned_pool", None)
+    for ev, host, guarded, M, fused in checks:
+        ev.synchronize()
+        parts = host.numpy().copy()
+        if pool is not None and len(pool) < 64:
+            pool.append(host)
+        if float(parts[:, -1].max()) > 0:
+            raise RuntimeError("assign_sharded(deferred_check=True): some shard holds atom-frames contained in several sites; "
+                               "the priority order needs the history relay -- redo the batch with deferred_check=False")
+        if fused and float(parts[:, -2].max()) > 0:
+            raise RuntimeError("assign_sharded(deferred_check=True): some rank could not store its rows into the peers "
+                               "(batch redone by the scan kernels); redo the batch with deferred_check=False")
+        if guarded:
+            exc = parts[:, :-2].reshape(parts.shape[0], M, 3, 2)
+            span = float((exc[..., 1].max(axis=0) - exc[..., 0].min(axis=0)).max())
+            if span >= EXCURSION_LIMIT and engine.strict:
+                raise GuardError("a framework atom moved over >= 0.3 fractional units across the sharded trajectory")
+
+
 def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, first_lattice_global, group,
-                   equal_shards: bool = False, async_gather: bool = False, peer_buffers: PeerResultBuffers | None = None):
+                   equal_shards: bool = False, async_gather: bool = False, peer_buffers: PeerResultBuffers | None = None,
+                   halo_frame=None, deferred_check: bool = False, keep_history: bool = False):
     """Assign this rank's contiguous shard with the correct PBC carry and return the FULL
     (F_total, A) int32 result (device tensor) on every rank.
 
@@ -276,7 +334,16 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
       result collective is issued at all (unless some rank reports overlapping sites or a redone batch -- then this call
       falls back to the all-gather below), or
     * by one NCCL all-gather of ``int32[F_local, A]``; ``async_gather=True`` (equal shards) returns ``(full, work)``
-      with it still in flight on its own communicator."""
+      with it still in flight on its own communicator.
+
+    ``halo_frame``: the (N, 3) frame preceding this rank's shard, if the caller has it (``exchange_halo_frames``): the halo
+    all-gather is then skipped.  ``deferred_check=True``: the guard / flag all-gather is still issued on the stream (it is
+    the completion barrier of the peer stores) but its result is copied to pinned host memory asynchronously and examined
+    by ``finish_sharded(engine)`` later -- no host synchronisation per call, so consecutive batches queue back to back.
+    ``keep_history=True``: every rank folds the gathered full result into its engine's history (recent sites, previous
+    entries, transition Counters; device fold) on every call, so that the engines stay usable for a later call that does
+    meet overlapping sites.  Without it a call that leaves no ambiguity drops its history and marks the engine's history
+    stale; a later ambiguous call on a stale engine raises instead of resolving against the wrong Counters."""
     import torch
     import torch.distributed as dist
     from . import _native as nat
@@ -285,15 +352,23 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
     if engine.slots is not None:
         _initial_state(engine, first_frame_global, first_lattice_global)
         if engine.k == nat.POLYHEDRAL:
-            _carry_by_anchor(engine, d_frac_local, group)
+            _carry_by_anchor(engine, d_frac_local, group, halo_frame)
         else:
             _carry_by_totals(engine, d_frac_local, group)
     full = out = None
     if peer_buffers is not None:
         if not equal_shards or int(d_frac_local.shape[0]) != peer_buffers.F:
             raise ValueError("peer_buffers need equal shards of the size they were made for")
+        evs = getattr(engine, "_barrier_events", None)
+        if evs:                                     # deferred barriers on the side stream: this call reuses the array of the call
+            if len(evs) >= 2:                       # before the previous one -- every rank must have finished that batch's kernels
+                torch.cuda.current_stream(dev).wait_event(evs[-2])
+            engine._barrier_events = evs[-2:]
         full, out, peers = peer_buffers.next()
-        engine.set_result_peers(peers)
+        if getattr(peer_buffers, "multicast", False):     # one multimem.st per row; the switch replicates it (N > 2, NVLS present)
+            engine.set_result_multicast(peer_buffers.mc_slot)
+        else:
+            engine.set_result_peers(peers)
     try:
         local = engine.assign_device(d_frac_local, d_lattice_local, defer_resolve=True, out=out)
     finally:
@@ -313,6 +388,46 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
             note[-1] = 1.0
         if not fused:
             note[-2] = 1.0
+        if deferred_check:
+            # Examined later (finish_sharded): no host synchronisation here.  SAB_BARRIER_STREAM=1 additionally moves the
+            # all-gather (with the fused result exchange it is only the completion barrier of the peer stores) to a side
+            # stream behind this batch's kernels, the kernels of batch k + 2 waiting on the device for the barrier of batch k
+            # (what keeps the two alternating result arrays safe).  Measured on 4 B200s (profiles/README.md) it does not pay:
+            # the persistent stream kernel fills every SM, NCCL's kernel runs behind it either way, and short runs end with
+            # a queue of barriers (1.48 vs 1.28 ms per step over 5 steps, 1.19 over 20) -- so it is off by default.
+            world_n = dist.get_world_size(group)
+            shape = (world_n, int(note.numel()))
+            pool = getattr(engine, "_pinned_pool", None)           # page-locked allocation is slow (~0.2 ms): reuse the buffers
+            if pool is None:                                       # first deferred call: a batch of buffers at once
+                pool = engine._pinned_pool = [torch.empty(shape, dtype=note.dtype, pin_memory=True) for _ in range(16)]
+            host = pool.pop() if pool and tuple(pool[-1].shape) == shape else torch.empty(shape, dtype=note.dtype, pin_memory=True)
+            main = torch.cuda.current_stream(dev)
+            side = main
+            import os
+            use_side = peer_buffers is not None and os.environ.get("SAB_BARRIER_STREAM") == "1"
+            if use_side:
+                side = getattr(engine, "_barrier_stream", None)
+                if side is None:
+                    side = engine._barrier_stream = torch.cuda.Stream(device=dev)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                note.record_stream(side)
+            with torch.cuda.stream(side):
+                parts = torch.stack(_all_gather(note, group))      # also orders every peer's row stores before our reads
+                host.copy_(parts, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            if not hasattr(engine, "_sharded_checks"):
+                engine._sharded_checks = []
+            engine._sharded_checks.append((ev, host, guarded, M, fused))
+            if use_side:
+                engine._barrier_events = (getattr(engine, "_barrier_events", None) or []) + [ev]
+            engine._pending = []
+            engine._history_stale = True
+            if peer_buffers is not None:
+                return (full, None) if async_gather else full
+            return gather_assignments(local, _result_group(group) if async_gather else group, equal_shards, async_op=async_gather)
         parts = torch.stack(_all_gather(note, group))              # also orders every peer's row stores before our reads
         parts = parts.cpu().numpy()                                # the one host synchronisation after the kernels (a few KB)
         any_ambiguous, any_unfused, span = float(parts[:, -1].max()), float(parts[:, -2].max()), 0.0
@@ -321,13 +436,30 @@ def assign_sharded(engine, d_frac_local, d_lattice_local, first_frame_global, fi
             span = float((exc[..., 1].max(axis=0) - exc[..., 0].min(axis=0)).max())
         all_fused = fused and not any_unfused and not any_ambiguous
         if any_ambiguous:
+            if getattr(engine, "_history_stale", False):
+                raise RuntimeError("assign_sharded: this batch needs the priority order (atom-frames in several sites) but the "
+                                   "history of earlier sharded batches was dropped; call assign_sharded(keep_history=True) "
+                                   "from the first batch on, or engine.reset() before a new trajectory")
             relay_history(engine, group)                           # resolves `local` in place, shard after shard
         if guarded and span >= EXCURSION_LIMIT and engine.strict:
             raise GuardError("a framework atom moved over >= 0.3 fractional units across the sharded trajectory")
+    folded = bool(any_ambiguous)                                   # relay_history left every engine with the whole history
     engine._pending = []
     if peer_buffers is not None:
-        if all_fused:
-            return (full, None) if async_gather else full
-        dist.all_gather_into_tensor(full, local.clone(), group=group)            # some rank could not fuse: plain all-gather
-        return (full, None) if async_gather else full
-    return gather_assignments(local, _result_group(group) if async_gather else group, equal_shards, async_op=async_gather)
+        if not all_fused:
+            dist.all_gather_into_tensor(full, local.clone(), group=group)        # some rank could not fuse: plain all-gather
+        out_full = full
+    elif async_gather and not keep_history:
+        if not folded:
+            engine._history_stale = True
+        return gather_assignments(local, _result_group(group), equal_shards, async_op=True)
+    else:
+        out_full = gather_assignments(local, group, equal_shards)
+    if not folded:
+        if keep_history:       # every rank folds the WHOLE gathered batch: all engines end with the same history, as after a relay
+            from .engine import fold_history_device
+            torch.cuda.current_stream(dev).synchronize()
+            fold_history_device(engine.recent, engine.prev, engine, out_full, engine.S)
+        else:
+            engine._history_stale = True
+    return (out_full, None) if async_gather else out_full

@@ -278,6 +278,10 @@ class AssignmentEngine:
         self.reset_history()
         self._pbc_ready = False
         self._lazy_mode = False
+        self._initial_pbc = None          # distributed.py: state at the start of the sharded trajectory, device copies of it
+        self._shard_dev = None
+        self._history_stale = False
+        self._sharded_checks = []
         if self.k in (nat.POLYHEDRAL, nat.DYNAMIC_VORONOI):   # anchors belong to the PBC state; Voronoi lists are static
             self._cells = None
             if self.k == nat.DYNAMIC_VORONOI:
@@ -315,6 +319,8 @@ class AssignmentEngine:
         """
         S = self.S
         smax = self._slot_atom.shape[1]
+        self._initial_pbc = None          # cached by distributed._initial_state / _carry_by_anchor: stale from here on
+        self._shard_dev = None
         slot_shift = np.zeros((S, smax, 3), dtype=np.int32)
         legacy = np.zeros(S, dtype=np.uint8)
         self._g2_cart_margin, self._g2_frac_margin = np.inf, np.inf
@@ -628,6 +634,11 @@ class AssignmentEngine:
         array (``sab_set_result_peers``); the tetrahedral stream kernel then stores each row there as well.  ``[]`` clears."""
         ptrs = (C.c_void_p * max(len(peer_slot_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_slot_ptrs])
         nat.check(self.L.sab_set_result_peers(self.h, len(peer_slot_ptrs), ptrs))
+
+    def set_result_multicast(self, multicast_slot_ptr: int) -> None:
+        """Multi-GPU with NVLS: ONE multicast address (int; this rank's slot inside the multicast view of the full result
+        array, ``sab_set_result_multicast``); each row is stored once and the NVSwitch replicates it to every rank.  0 clears."""
+        nat.check(self.L.sab_set_result_multicast(self.h, C.c_void_p(int(multicast_slot_ptr)) if multicast_slot_ptr else None))
 
     # ------------------------------------------------------------------ exact replay (polyhedral)
     def _lazy_start(self):

@@ -49,8 +49,25 @@ def main():
                 torch.cuda.synchronize()
                 assert torch.equal(fused, full), f"fused peer-store result differs from the all-gathered one (turn {turn})"
             fused_note = f"identical to the NCCL all-gather on 3 passes (rows stored by the kernel: {bool(eng.last_info.get('peers_written'))})"
+            # the same with the halo frame distributed up front and the guard / flag record examined later: no halo
+            # collective, no host synchronisation per call
+            halo = sd.exchange_halo_frames(frac[f0:f1], dist.group.WORLD)
+            for turn in range(3):
+                lazy = sd.assign_sharded(eng, frac[f0:f1].contiguous(), lat[f0:f1].contiguous(), frame0, lat0, dist.group.WORLD,
+                                         equal_shards=True, peer_buffers=bufs, halo_frame=halo, deferred_check=True)
+            sd.finish_sharded(eng)
+            torch.cuda.synchronize()
+            assert torch.equal(lazy, full), "halo_frame + deferred_check result differs"
+            fused_note += "; halo_frame + deferred_check: identical on 3 queued passes"
     if rank == 0:
         print(f"multigpu_check: fused peer-store path: {fused_note}")
+    # keep_history: every rank folds the gathered result, so all engines end with the sequential run's history
+    eng_h = AssignmentEngine("polyhedral", geom.n_atoms, geom.mobile_idx, device=local,
+                             **syn.polyhedral_engine_kwargs(geom, frame0, lat0))
+    full_h = sd.assign_sharded(eng_h, frac[f0:f1].contiguous(), lat[f0:f1].contiguous(), frame0, lat0, dist.group.WORLD,
+                               keep_history=True)
+    assert torch.equal(full_h, full)
+    hist = ({s: dict(t) for s, t in enumerate(eng_h.transitions) if t}, eng_h.recent.copy(), eng_h.prev.copy())
     # overlapping spheres: nearly every atom-frame is in several sites, so the priority order -- and with it the history
     # handed from shard to shard (distributed.relay_history) -- decides the result
     eng_s = AssignmentEngine("spherical", geom.n_atoms, geom.mobile_idx, device=local, centres=geom.site_centres, rcut=1.5)
@@ -73,6 +90,11 @@ def main():
         wraps = int((np.abs(np.rint(np.diff(frac[:, geom.n_mobile:].cpu().numpy(), axis=0))) > 0).sum())
         print(f"multigpu_check: world={world} frames={F} framework wrap events={wraps} mismatches vs oracle={mism}")
         ok = ok and mism == 0
+        oh = bench.oracle_for(geom, frame0, lat0)()
+        oh.run(frac.cpu().numpy(), lat.cpu().numpy(), positions=True)
+        tr_h = {k: dict(v) for k, v in oh.transitions().items()} == hist[0]
+        print(f"multigpu_check: keep_history=True: transition Counters of the sharded run equal the sequential oracle's: {tr_h}")
+        ok = ok and tr_h
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -132,3 +132,63 @@ def test_shard_bounds_cover_all_frames():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _halo_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, F = 7, 5
+        frames = torch.arange(world * F * N * 3, dtype=torch.float64).reshape(world * F, N, 3)      # same on every rank
+        mine = frames[rank * F:(rank + 1) * F]
+        halo = sd.exchange_halo_frames(mine, dist.group.WORLD)
+        want = frames[rank * F - 1] if rank > 0 else mine[-1]
+        assert torch.equal(halo, want), rank
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_frames_come_from_the_preceding_shard_world2():
+    """distributed.exchange_halo_frames: rank r gets the last frame of rank r - 1's shard (input distribution of the sharded
+    polyhedral path; with it assign_sharded issues no halo collective per batch)."""
+    mp.spawn(_halo_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+class _DoneEvent:
+    def synchronize(self):
+        pass
+
+
+class _FakeEngine:
+    strict = True
+
+
+def test_deferred_guard_records_raise_what_the_immediate_check_raises():
+    """distributed.finish_sharded: the records assign_sharded(deferred_check=True) leaves behind (per rank: excursion
+    min / max of every framework coordinate, 'rows not stored into the peers' flag, 'ambiguous atom-frames' flag)."""
+    from site_analysis_b200.engine import GuardError
+    M, world = 3, 2
+
+    def record(span=0.1, unfused=0.0, ambiguous=0.0):
+        parts = torch.zeros((world, 6 * M + 2), dtype=torch.float64)
+        exc = parts[:, :-2].reshape(world, M, 3, 2)
+        exc[..., 0] = 0.2
+        exc[..., 1] = 0.25
+        exc[1, 2, 1, 1] = 0.2 + span                          # one coordinate of one rank carries the span
+        parts[0, -2] = unfused
+        parts[1, -1] = ambiguous
+        return (_DoneEvent(), parts, True, M, True)
+
+    e = _FakeEngine()
+    e._sharded_checks = [record(), record(span=0.29)]
+    sd.finish_sharded(e)                                      # within the guard: nothing raised, list consumed
+    assert e._sharded_checks == []
+    e._sharded_checks = [record(span=0.31)]
+    with pytest.raises(GuardError):
+        sd.finish_sharded(e)
+    e._sharded_checks = [record(ambiguous=1.0)]
+    with pytest.raises(RuntimeError, match="several sites"):
+        sd.finish_sharded(e)
+    e._sharded_checks = [record(unfused=1.0)]
+    with pytest.raises(RuntimeError, match="peers"):
+        sd.finish_sharded(e)

@@ -176,3 +176,9 @@ def test_peer_result_buffers_slot_arithmetic():
     full, slot, peers = b.next()
     assert full is b.buffers[1] and peers == [5240, 6240, 8240]
     assert b.next()[0] is b.buffers[0]
+    # NVLS: the multicast view of the same arrays, same slot offset
+    b.multicast, b.mc_ptrs, b.turn = True, [90000, 91000], 0
+    b.next()
+    assert b.mc_slot == 90000 + 240
+    b.next()
+    assert b.mc_slot == 91000 + 240
