@@ -16,7 +16,7 @@
 #define SAB_NEAREST_BATCH 4
 #endif
 #ifndef SAB_NEAREST_MINBLOCKS
-#define SAB_NEAREST_MINBLOCKS 2
+#define SAB_NEAREST_MINBLOCKS 3   // measured (profiles/r2_experiments/ab_nearest.txt): 8.92 -> 8.40 ms on config 3 (2 -> 3 CTAs per SM, 80 registers, cold-path spills)
 #endif
 
 struct SabNearestLists {

@@ -46,23 +46,43 @@ __global__ void k_spherical_assign(const double *__restrict__ frac, const double
         __syncthreads();
         if (threadIdx.x == 0) sab_lattice_load(lattice + (size_t)f * lattice_stride, lat);
         __syncthreads();
-        for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
-            double x[3];
+        // every thread takes part in every pass (valid = it has an atom): whole warps share one spill reservation below
+        for (int a0 = 0; a0 < n_mobile; a0 += blockDim.x) {
+            const int a = a0 + threadIdx.x;
+            const bool valid = a < n_mobile;
+            double x[3] = {0.0, 0.0, 0.0};
+            if (valid) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
+                for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
+            }
             int cnt = 0;
             int keep[SAB_SPH_KEEP];
-            for (int s = 0; s < n_sites; s++)
+            for (int s = 0; s < (valid ? n_sites : 0); s++)
                 if (sab_sphere_contains(sc + 3 * s, x, sr[s], sq[s], lat)) {
                     if (cnt < SAB_SPH_KEEP) keep[cnt] = s;
                     cnt++;
                 }
+            // ONE reservation per warp: 98 % of the atom-frames of the overlapping-sphere benchmark spill, and two atomics
+            // each on the same two counters serialise in L2 (ncu: 67 long-scoreboard stall cycles per issued instruction)
+            const unsigned FULLM = 0xffffffffu;
+            const int lane_w = threadIdx.x & 31;
+            const int need = cnt > 1 ? SAB_SPILL_RECORD(cnt) : 0;
+            int pre = need;                               // inclusive prefix sum over the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULLM, pre, o); if (lane_w >= o) pre += v; }
+            const int warp_total = __shfl_sync(FULLM, pre, 31);
+            const unsigned amb_mask = __ballot_sync(FULLM, cnt > 1);
+            unsigned long long base = 0ULL;
+            if (lane_w == 0 && warp_total > 0) {
+                atomicAdd(&counters[0], (unsigned long long)__popc(amb_mask));
+                base = atomicAdd(&counters[1], (unsigned long long)warp_total);
+            }
+            base = __shfl_sync(FULLM, base, 0);
             int out;
             if (cnt == 0) out = SAB_NONE;
             else if (cnt == 1) out = keep[0];
             else {
-                atomicAdd(&counters[0], 1ULL);
-                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(cnt));
+                const unsigned long long off = base + (unsigned long long)(pre - need);
                 if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
                     counters[2] = 1ULL;
                     out = SAB_NONE;
@@ -78,7 +98,7 @@ __global__ void k_spherical_assign(const double *__restrict__ frac, const double
                     out = SAB_AMBIGUOUS_BASE - (int)off;
                 }
             }
-            result[(size_t)f * n_mobile + a] = out;
+            if (valid) result[(size_t)f * n_mobile + a] = out;
         }
     }
 }
@@ -129,12 +149,17 @@ __global__ void k_spherical_assign_cells(const double *__restrict__ frac, const 
         }
         __syncthreads();
         const bool use_lists = lists_ok != 0;
-        for (int a = threadIdx.x; a < n_mobile; a += blockDim.x) {
-            double x[3];
+        // every thread takes part in every pass (valid = it has an atom) so that whole warps can share one spill reservation
+        for (int a0 = 0; a0 < n_mobile; a0 += blockDim.x) {
+            const int a = a0 + threadIdx.x;
+            const bool valid = a < n_mobile;
+            double x[3] = {0.0, 0.0, 0.0};
+            if (valid) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
-            int b = 0, e = n_sites;
-            if (use_lists) {
+                for (int d = 0; d < 3; d++) x[d] = sab_pymod1(frame[(size_t)mobile[a] * 3 + d]);
+            }
+            int b = 0, e = valid ? n_sites : 0;
+            if (use_lists && valid) {
                 int c0 = min(SL.G - 1, (int)(x[0] * (double)SL.G)), c1 = min(SL.G - 1, (int)(x[1] * (double)SL.G)),
                     c2 = min(SL.G - 1, (int)(x[2] * (double)SL.G));
                 const int cell = (c0 * SL.G + c1) * SL.G + c2;
@@ -150,12 +175,27 @@ __global__ void k_spherical_assign_cells(const double *__restrict__ frac, const 
                     cnt++;
                 }
             }
+            // ONE reservation per warp: 98 % of the atom-frames of the overlapping-sphere benchmark spill, and two atomics
+            // each on the same two counters serialise in L2 (ncu: 67 long-scoreboard stall cycles per issued instruction)
+            const unsigned FULLM = 0xffffffffu;
+            const int lane_w = threadIdx.x & 31;
+            const int need = cnt > 1 ? SAB_SPILL_RECORD(cnt) : 0;
+            int pre = need;                               // inclusive prefix sum over the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULLM, pre, o); if (lane_w >= o) pre += v; }
+            const int warp_total = __shfl_sync(FULLM, pre, 31);
+            const unsigned amb_mask = __ballot_sync(FULLM, cnt > 1);
+            unsigned long long base = 0ULL;
+            if (lane_w == 0 && warp_total > 0) {
+                atomicAdd(&counters[0], (unsigned long long)__popc(amb_mask));
+                base = atomicAdd(&counters[1], (unsigned long long)warp_total);
+            }
+            base = __shfl_sync(FULLM, base, 0);
             int out;
             if (cnt == 0) out = SAB_NONE;
             else if (cnt == 1) out = keep[0];
             else {
-                atomicAdd(&counters[0], 1ULL);
-                unsigned long long off = atomicAdd(&counters[1], (unsigned long long)SAB_SPILL_RECORD(cnt));
+                const unsigned long long off = base + (unsigned long long)(pre - need);
                 if ((long long)(off + cnt + 1) > spill_capacity || off + cnt + 1 >= 0x7ffffff0ULL) {
                     counters[2] = 1ULL;
                     out = SAB_NONE;
@@ -174,7 +214,7 @@ __global__ void k_spherical_assign_cells(const double *__restrict__ frac, const 
                     out = SAB_AMBIGUOUS_BASE - (int)off;
                 }
             }
-            result[(size_t)f * n_mobile + a] = out;
+            if (valid) result[(size_t)f * n_mobile + a] = out;
         }
     }
 }

@@ -143,9 +143,12 @@ class PeerResultBuffers:
             self.ptrs.append([int(p) for p in h.buffer_ptrs])
             mc = 0
             try:                                  # NVLS multicast view of the same buffers (0 / absent when the fabric has none)
-                # opt-in: measured on 4 B200s the multimem.st form (a strong system-scope store) makes the kernel 10 % slower
-                # than three plain unicast stores (0.663 vs 0.604 ms, profiles/README.md); it saves NVLink egress at larger N
-                if os.environ.get("SAB_MULTICAST") == "1" and self.world > 2:
+                # Measured (profiles/README.md): on 4 B200s the multimem.st form (a strong system-scope store) makes the stream
+                # kernel 10 % slower than three plain unicast stores (0.663 vs 0.604 ms); on 8 the seven unicast stores are
+                # NVLink-egress bound (672 MB per rank and step: kernel 1.23 ms against 0.55 ms on one GPU), which is where one
+                # multicast store per row pays.  Default: multicast from 8 ranks on; SAB_MULTICAST=1 / 0 forces it on / off.
+                want = os.environ.get("SAB_MULTICAST")
+                if self.world > 2 and (want == "1" or (want != "0" and self.world >= 8)):
                     mc = int(getattr(h, "multicast_ptr", 0) or 0)
             except Exception:
                 mc = 0

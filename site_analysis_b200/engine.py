@@ -249,6 +249,19 @@ class AssignmentEngine:
     def transitions(self, value) -> None:
         self._tr_dicts, self._tr_arrays = value, None
 
+    def _tr_snapshot(self):
+        """Copy of the transition store in whichever form it is held (no array <-> dict conversion)."""
+        if self._tr_dicts is None:
+            return ("arrays", tuple(x.copy() for x in self._tr_arrays))
+        return ("dicts", [dict(t) for t in self._tr_dicts])
+
+    def _tr_restore(self, snap) -> None:
+        kind, value = snap
+        if kind == "arrays":
+            self._tr_arrays, self._tr_dicts = value, None
+        else:
+            self._tr_dicts, self._tr_arrays = value, None
+
     def _tr_add_pairs(self, src, dst, cnt) -> None:
         """Merge transition pairs (in first-occurrence order) into the array store."""
         if self._tr_arrays is None:
@@ -433,6 +446,13 @@ class AssignmentEngine:
                                             nat.ptr(np.ascontiguousarray(off)), nat.ptr(ent)))
         self._cells = dict(G=G, delta=delta, entries=int(len(ent)), mean_candidates=float(len(ent)) / G ** 3)
         self._cells_stale = False
+
+    def _exhaustive_too_big(self) -> bool:
+        """The exhaustive kernels stage every site in shared memory (24 B per Voronoi / dynamic-Voronoi centre, 40 B per
+        sphere): beyond ~200 KB they cannot launch, so even single-frame calls (the reference's per-frame API) build the
+        cell lists first."""
+        per_site = 40 if self.k == nat.SPHERICAL else 24
+        return self.S * per_site > 200_000
 
     def _build_nearest_lists(self, lattice0):
         """Voronoi: cell lists of the centres that can be nearest anywhere in a cell (``_tables.nearest_cell_lists``)."""
@@ -729,7 +749,10 @@ class AssignmentEngine:
             d_lattice = d_lattice.contiguous()
             d_result = out if out is not None else torch.empty((F, self.A), dtype=torch.int32, device=d_frac.device)
             return self._assign_device_lazy(d_frac, d_lattice, 9 if d_lattice.dim() == 3 else 0, d_result, append)
-        start = (self.frames_done, len(self._pending), self.recent.copy(), self.prev.copy(), [dict(t) for t in self.transitions])
+        # snapshot for the redo below -- only a batch that starts from the initial state can be redone, so later batches
+        # (the streaming case) pay nothing for it
+        start = (self.frames_done, len(self._pending), self.recent.copy(), self.prev.copy(),
+                 self._tr_snapshot() if self.frames_done == 0 else None)
         try:
             return self._assign_device_fast(d_frac, d_lattice, append=append, defer_resolve=defer_resolve, out=out)
         except GuardError:
@@ -738,7 +761,8 @@ class AssignmentEngine:
         # redo from the initial state with the exact replay
         self.frames_done = 0
         del self._pending[start[1]:]
-        self.recent, self.prev, self.transitions = start[2], start[3], start[4]
+        self.recent, self.prev = start[2], start[3]
+        self._tr_restore(start[4])
         d_lattice = d_lattice.contiguous()
         d_result = out if out is not None else torch.empty((F, self.A), dtype=torch.int32, device=d_frac.device)
         return self._assign_device_lazy(d_frac, d_lattice, 9 if d_lattice.dim() == 3 else 0, d_result, append)
@@ -774,11 +798,11 @@ class AssignmentEngine:
         if self.slots is not None and not self._pbc_ready:
             lat0 = (d_lattice[0] if stride else d_lattice).cpu().numpy()
             self._init_pbc(d_frac[0].cpu().numpy(), lat0)
-        if self.k == nat.VORONOI and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+        if self.k == nat.VORONOI and self.use_cells and self._cells is None and (F >= self.cells_min_frames or self._exhaustive_too_big()) and 64 <= self.S <= 65535:
             self._build_nearest_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
-        if self.k == nat.DYNAMIC_VORONOI and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+        if self.k == nat.DYNAMIC_VORONOI and self.use_cells and self._cells is None and (F >= self.cells_min_frames or self._exhaustive_too_big()) and 64 <= self.S <= 65535:
             self._build_dynvor_lists(d_frac, (d_lattice[0] if stride else d_lattice).cpu().numpy())
-        if self.k == nat.SPHERICAL and self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+        if self.k == nat.SPHERICAL and self.use_cells and self._cells is None and (F >= self.cells_min_frames or self._exhaustive_too_big()) and 64 <= self.S <= 65535:
             self._build_sphere_lists((d_lattice[0] if stride else d_lattice).cpu().numpy())
         stream = torch.cuda.current_stream(dev).cuda_stream
         f0 = 0
@@ -883,7 +907,7 @@ class AssignmentEngine:
         lattice = np.ascontiguousarray(lattice, dtype=np.float64)
         F = frac.shape[0]
         call_start = (self.frames_done, len(self._pending), self.recent.copy(), self.prev.copy(),
-                      [dict(t) for t in self.transitions] if self.k == nat.POLYHEDRAL and self.frames_done == 0 else None)
+                      self._tr_snapshot() if self.k == nat.POLYHEDRAL and self.frames_done == 0 else None)
         fast_ok = not (self.k == nat.POLYHEDRAL and (self.exact_lazy or self._lazy_mode or
                                                      (self.exact_lazy is None and self.frames_done == 0 and F < self.LAZY_AUTO_FRAMES)))
         if fast_ok and append and F >= self.PIPELINE_MIN_FRAMES and self.k != nat.SPHERICAL:
@@ -917,7 +941,7 @@ class AssignmentEngine:
             self.frames_done = 0
             del self._pending[call_start[1]:]
             self.recent, self.prev = call_start[2], call_start[3]
-            self.transitions = call_start[4]
+            self._tr_restore(call_start[4])
             self._lazy_start()
             chunks()
         return out
@@ -946,7 +970,7 @@ class AssignmentEngine:
                                     margin=0.65)
             del d_s, d_ws
         lat0 = lattice if lattice.ndim == 2 else lattice[0]
-        if self.use_cells and self._cells is None and F >= self.cells_min_frames and 64 <= self.S <= 65535:
+        if self.use_cells and self._cells is None and (F >= self.cells_min_frames or self._exhaustive_too_big()) and 64 <= self.S <= 65535:
             if self.k == nat.VORONOI:
                 self._build_nearest_lists(lat0)
             elif self.k == nat.SPHERICAL:
