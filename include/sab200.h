@@ -313,6 +313,18 @@ int sab_assign_lazy(sab_engine *e, const double *d_frac, const double *d_lattice
                     int32_t *d_result, void *stream, int32_t *recent, int32_t *prev, int32_t *tr_n, int32_t *tr_key,
                     int64_t *tr_cnt, int tr_width, int append);
 
+/* Face topology at the first query (non-simplicial polyhedra).  The reference hulls a site when it is first QUERIED
+ * (FaceTopologyCache, polyhedral_site.py:138-159, 468-471) and Qhull's triangulation of e.g. a cube's quads depends on the
+ * vertex coordinates of that frame.  sab_lazy_set_open_topology marks the sites whose uploaded triangulation is provisional
+ * (uint8[S], NULL = none) and clears the records; the following sab_assign_lazy calls record, for every open site they query
+ * for the first time, the global frame number and vertex_coords of that query; sab_lazy_get_first_queries reads them back
+ * (first_frame int64[S], -1 = not queried; first_vc double[S][vmax][3]).  The host re-hulls from exactly those coordinates,
+ * uploads changed triangulations with sab_update_face_topology (same layout as sab_set_polyhedra's simplices; nothing else
+ * of the engine is touched), restores the per-site state and redoes the batch until no triangulation changes. */
+int sab_lazy_set_open_topology(sab_engine *e, const uint8_t *open_site);
+int sab_lazy_get_first_queries(sab_engine *e, int64_t *first_frame, double *first_vc);
+int sab_update_face_topology(sab_engine *e, int fmax, const int32_t *n_face, const int32_t *simplices);
+
 /* ---- polyhedral containment of given points (stand-alone operator) ----------------------------
  * d_out uint8[n_sites]: 1 when ANY of the site's n_img query points lies inside the site's polyhedron -- the query of
  * PolyhedralSite.contains_point / contains_atom (polyhedral_site.py:431-520: FaceTopologyCache.update +

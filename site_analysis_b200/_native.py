@@ -42,7 +42,7 @@ SYMBOLS = [
     "sab_set_pbc_state", "sab_get_pbc_state", "sab_set_legacy_init", "sab_set_option",
     "sab_workspace_bytes", "sab_wrap_totals", "sab_assign_device", "sab_commit_pbc", "sab_assign_host", "sab_set_result_mirror",
     "sab_set_priority_tables", "sab_add_rank_rows", "sab_rank_missing", "sab_resolve", "sab_dynvor_centres", "sab_set_cell_lists", "sab_scan_excursion", "sab_set_nearest_lists", "sab_set_dynvor_lists", "sab_set_sphere_lists",
-    "sab_set_carry_device", "sab_get_excursion_device", "sab_fold_workspace_bytes", "sab_fold_result", "sab_mic_distances", "sab_polyhedra_contain", "sab_measure_fp64_peak", "sab_lazy_set_state", "sab_lazy_get_state", "sab_assign_lazy", "sab_set_result_peers", "sab_set_result_multicast", "sab_xdatcar_index", "sab_xdatcar_parse",
+    "sab_set_carry_device", "sab_get_excursion_device", "sab_fold_workspace_bytes", "sab_fold_result", "sab_mic_distances", "sab_polyhedra_contain", "sab_measure_fp64_peak", "sab_lazy_set_state", "sab_lazy_get_state", "sab_assign_lazy", "sab_lazy_set_open_topology", "sab_lazy_get_first_queries", "sab_update_face_topology", "sab_set_result_peers", "sab_set_result_multicast", "sab_xdatcar_index", "sab_xdatcar_parse",
     "sab_parse_double",
 ]
 
@@ -109,6 +109,9 @@ def lib():
         "sab_get_excursion_device": (i32, [vp, vp, vp]),
         "sab_set_result_peers": (i32, [vp, i32, vp]),
         "sab_set_result_multicast": (i32, [vp, vp]),
+        "sab_lazy_set_open_topology": (i32, [vp, vp]),
+        "sab_lazy_get_first_queries": (i32, [vp, vp, vp]),
+        "sab_update_face_topology": (i32, [vp, i32, vp, vp]),
         "sab_xdatcar_index": (i32, [vp, i64, i64, i32, vp, vp, i64, vp]),
         "sab_xdatcar_parse": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, i32]),
         "sab_parse_double": (i32, [C.c_char_p, i64, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

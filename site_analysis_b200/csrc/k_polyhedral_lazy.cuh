@@ -39,6 +39,13 @@ struct SabLazy {
     int32_t *lock;               // [S]
     double *vc;                  // [S][smax][3] vertex_coords of the last query
     unsigned long long *stats;   // [4] queries, incremental updates, full corrections, invalidations
+    // Face topology hulled at the site's FIRST query (polyhedral_site.py:468-471): for non-simplicial polyhedra Qhull's
+    // triangulation depends on the vertex coordinates of that frame.  Sites whose topology is still provisional are
+    // marked open; the kernel records the frame and the vertex coordinates of their first query, the host re-hulls from
+    // exactly those and redoes the batch if a triangulation changed (engine._assign_device_lazy).  All three may be null.
+    const int32_t *open_topo;    // [S] 1 = topology provisional
+    long long *first_frame;      // [S] -1, or the global frame number of the first query in this run
+    double *first_vc;            // [S][smax][3] vertex_coords of that query
 };
 
 // _store_vertex_coords (polyhedral_site.py:377-416) for site s in the current frame, by one warp.
@@ -149,6 +156,15 @@ __device__ bool sab_lazy_query(const SabLazy &Z, int s, long long fs, const doub
         if (got) {
             if (*((volatile long long *)&Z.stamp[s]) != fs) {
                 sab_lazy_store(Z, s, frame, L, lane);
+                if (Z.open_topo && Z.open_topo[s]) {            // provisional topology: keep what the reference hulls from
+                    const long long ff = *((volatile long long *)&Z.first_frame[s]);
+                    if (__shfl_sync(0xffffffffu, ff, 0) < 0) {
+                        const int n3 = 3 * Z.n_slot[s];
+                        for (int i = lane; i < n3; i += 32) Z.first_vc[(size_t)s * Z.smax * 3 + i] = Z.vc[(size_t)s * Z.smax * 3 + i];
+                        __syncwarp();
+                        if (lane == 0) *((volatile long long *)&Z.first_frame[s]) = fs;
+                    }
+                }
                 __threadfence_block();
                 if (lane == 0) *((volatile long long *)&Z.stamp[s]) = fs;
             }

@@ -133,6 +133,7 @@ struct sab_engine {
     // exact replay of the reference's lazily updated per-site caches (k_polyhedral_lazy.cuh)
     int32_t *d_lz_shift = nullptr, *d_lz_has = nullptr, *d_lz_lock = nullptr; double *d_lz_cached = nullptr, *d_lz_vc = nullptr, *d_lz_rc = nullptr;
     long long *d_lz_stamp = nullptr; uint8_t *d_lz_has_rc = nullptr; unsigned long long *d_lz_stats = nullptr; bool lazy_set = false;
+    int32_t *d_lz_open = nullptr; long long *d_lz_first_frame = nullptr; double *d_lz_first_vc = nullptr;   // sab_lazy_set_open_topology
     long long lazy_frames = 0;
     int n_peer = 0; int32_t *peer[SAB_MAX_PEERS] = {nullptr}; int peer_mc = 0;   // sab_set_result_peers / sab_set_result_multicast
     bool peers_written = false;            // the last sab_assign_device stored its rows into the peers as well
@@ -174,7 +175,7 @@ extern "C" void sab_engine_destroy(sab_engine *e)
                     e->stage[0], e->stage[1], e->ws, e->d_rec, e->d_cell_sites, e->d_cell_off, e->d_anchor,
                     e->d_nl_off, e->d_nl_sites, e->d_nl_excl, e->d_nl_anchor, e->d_nl_l0, e->d_tile_vars, e->d_tile_rec,
                     e->d_s5_task, e->d_s5_rec, e->d_s5_cellrec, e->d_lz_shift, e->d_lz_has, e->d_lz_lock, e->d_lz_cached,
-                    e->d_lz_vc, e->d_lz_rc, e->d_lz_stamp, e->d_lz_has_rc, e->d_lz_stats, e->d_row_slot, e->d_row_pos, e->d_row_fwd,
+                    e->d_lz_vc, e->d_lz_rc, e->d_lz_stamp, e->d_lz_has_rc, e->d_lz_stats, e->d_lz_open, e->d_lz_first_frame, e->d_lz_first_vc, e->d_row_slot, e->d_row_pos, e->d_row_fwd,
                     e->d_missing, e->d_n_missing};
     for (void *p : ptrs) if (p) { g_alloc_bytes.erase(p); cudaFree(p); }
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
@@ -1096,12 +1097,11 @@ extern "C" int sab_dynvor_centres(sab_engine *e, const double *d_frac, int64_t n
     run_wrap_pass(e, d_frac, n_frames, w, st, true);
     CU(cudaGetLastError());
     static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    double *d_lat = nullptr;
-    CU(cudaMalloc((void **)&d_lat, sizeof ident));
-    CU(cudaMemcpyAsync(d_lat, ident, sizeof ident, cudaMemcpyHostToDevice, st));
-    rc = launch_assign(e, d_frac, d_lat, 0, n_frames, nullptr, nullptr, 0, w, st, d_centres);
+    struct Tmp { double *p = nullptr; ~Tmp() { if (p) cudaFree(p); } } lat;      // released on every exit path
+    CU(cudaMalloc((void **)&lat.p, sizeof ident));
+    CU(cudaMemcpyAsync(lat.p, ident, sizeof ident, cudaMemcpyHostToDevice, st));
+    rc = launch_assign(e, d_frac, lat.p, 0, n_frames, nullptr, nullptr, 0, w, st, d_centres);
     cudaStreamSynchronize(st);
-    cudaFree(d_lat);
     return rc;
 }
 
@@ -1138,7 +1138,11 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
     // The wrap scan carries state from chunk to chunk through the engine (stream-ordered):
     // chunk k+1's kernels must follow chunk k's commit, so compute is serialised on stream 0
     // while the H2D copy of the next chunk runs on stream 1 (and vice versa).
-    cudaEvent_t ev_copied[2], ev_done[2];
+    struct Events {                                       // destroyed on every exit path (the CU() early returns included)
+        cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+        ~Events() { for (int i = 0; i < 2; i++) { if (copied[i]) cudaEventDestroy(copied[i]); if (done[i]) cudaEventDestroy(done[i]); } }
+    } evs;
+    cudaEvent_t *ev_copied = evs.copied, *ev_done = evs.done;
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
@@ -1238,7 +1242,6 @@ extern "C" int sab_assign_host(sab_engine *e, const double *h_frac, const double
     }
     cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_copy);
     finish_copier();
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_copied[i]); cudaEventDestroy(ev_done[i]); }
     for (int i = 0; i < 12; i++) info[i] = tot_info[i];
     if (status == SAB_OK && cerr != cudaSuccess)
         return fail(SAB_ECUDA, "sab_assign_host: %s", cudaGetErrorString(cerr));
@@ -1504,6 +1507,54 @@ extern "C" int sab_lazy_get_state(sab_engine *e, int32_t *shift, double *cached_
     return SAB_OK;
 }
 
+extern "C" int sab_lazy_set_open_topology(sab_engine *e, const uint8_t *open_site)
+{
+    if (!e || e->kind != SAB_POLYHEDRAL || !e->d_simp) return fail(SAB_ESTATE, "sab_lazy_set_open_topology: polyhedra not set");
+    CU(cudaSetDevice(e->device));
+    std::vector<int32_t> open(e->S, 0);
+    if (open_site) for (int s = 0; s < e->S; s++) open[s] = open_site[s] ? 1 : 0;
+    std::vector<long long> first(e->S, -1LL);
+    std::vector<double> vc((size_t)e->S * e->smax * 3, 0.0);
+    CU(upload(&e->d_lz_open, open.data(), open.size()));
+    CU(upload(&e->d_lz_first_frame, first.data(), first.size()));
+    CU(upload(&e->d_lz_first_vc, vc.data(), vc.size()));
+    return SAB_OK;
+}
+
+extern "C" int sab_lazy_get_first_queries(sab_engine *e, int64_t *first_frame, double *first_vc)
+{
+    if (!e || !first_frame || !first_vc) return fail(SAB_EINVAL, "sab_lazy_get_first_queries: null argument");
+    if (!e->d_lz_first_frame || !e->d_lz_first_vc) return fail(SAB_ESTATE, "sab_lazy_get_first_queries: call sab_lazy_set_open_topology first");
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(first_frame, e->d_lz_first_frame, sizeof(long long) * (size_t)e->S, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(first_vc, e->d_lz_first_vc, sizeof(double) * (size_t)e->S * e->smax * 3, cudaMemcpyDeviceToHost));
+    return SAB_OK;
+}
+
+extern "C" int sab_update_face_topology(sab_engine *e, int fmax, const int32_t *n_face, const int32_t *simplices)
+{
+    if (!e || !n_face || !simplices) return fail(SAB_EINVAL, "sab_update_face_topology: null argument");
+    if (e->kind != SAB_POLYHEDRAL || !e->d_simp) return fail(SAB_ESTATE, "sab_update_face_topology: polyhedra not set");
+    if (fmax <= 0) return fail(SAB_EINVAL, "fmax must be positive");
+    CU(cudaSetDevice(e->device));
+    std::vector<int32_t> nv(e->S);
+    CU(cudaMemcpy(nv.data(), e->d_nslot, sizeof(int32_t) * (size_t)e->S, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> simp((size_t)e->S * fmax * 3, 0);
+    for (int s = 0; s < e->S; s++) {
+        if (n_face[s] < 4 || n_face[s] > fmax) return fail(SAB_EINVAL, "site %d: bad face count %d", s, n_face[s]);
+        for (int j = 0; j < 3 * n_face[s]; j++) {
+            const int v = simplices[(size_t)s * fmax * 3 + j];
+            if (v < 0 || v >= nv[s]) return fail(SAB_EINVAL, "site %d: face vertex %d out of range", s, v);
+            simp[(size_t)s * fmax * 3 + j] = (uint8_t)v;
+        }
+    }
+    e->fmax = fmax;
+    CU(upload(&e->d_nface, n_face, (size_t)e->S));
+    CU(upload(&e->d_simp, simp.data(), simp.size()));
+    return SAB_OK;
+}
+
 extern "C" int sab_assign_lazy(sab_engine *e, const double *d_frac, const double *d_lattice, int lattice_stride, int64_t n_frames,
                                int32_t *d_result, void *stream, int32_t *recent, int32_t *prev, int32_t *tr_n, int32_t *tr_key,
                                int64_t *tr_cnt, int tr_width, int append)
@@ -1536,7 +1587,8 @@ extern "C" int sab_assign_lazy(sab_engine *e, const double *d_frac, const double
     CU(cudaMemsetAsync(d_over, 0, sizeof(int), st));
     std::vector<int32_t> simp32;          // the kernel reads the uint8 simplices of sab_set_polyhedra
     SabLazy Z{e->smax, e->fmax, e->d_nslot, e->d_slot_atom, e->d_nface, e->d_simp, e->d_lz_has_rc, e->d_lz_rc, e->d_lz_shift,
-              e->d_lz_cached, e->d_lz_has, e->d_lz_stamp, e->d_lz_lock, e->d_lz_vc, e->d_lz_stats};
+              e->d_lz_cached, e->d_lz_has, e->d_lz_stamp, e->d_lz_lock, e->d_lz_vc, e->d_lz_stats,
+              e->d_lz_open, e->d_lz_first_frame, e->d_lz_first_vc};
     SabPriorityTables P = priority_tables(e);
     const size_t smem = sizeof(double) * 24 * (size_t)e->A + sizeof(int) * (size_t)e->A + 16;
     CU(cudaFuncSetAttribute(k_polyhedral_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));

@@ -144,6 +144,7 @@ class AssignmentEngine:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.strict = strict
         self.rank_table = None if rank_table is None else np.ascontiguousarray(rank_table, dtype=np.int32)
+        self._open_topology = np.zeros(0, dtype=bool)
         self.rank_dense_max = 2048      # above this many sites the distance ranking is lazy (no S x S tables)
         self._priority_uploaded = False
         self.slots = None
@@ -158,6 +159,13 @@ class AssignmentEngine:
                                  for c in reference_centres])
             self.primed = [None] * self.S if primed is None else list(primed)
             self.simplices = [None] * self.S if simplices is None else list(simplices)
+            # Non-simplicial polyhedra without a cached face topology: the reference hulls a site at its FIRST QUERY
+            # (polyhedral_site.py:468-471) and Qhull's triangulation of e.g. a cube's quads depends on that frame's vertex
+            # coordinates.  Such sites are "open": the exact replay kernel reports the coordinates of their first query and
+            # the host hulls from exactly those (_assign_device_lazy).  Simplicial sites need none of this (every vertex
+            # triple is a face).
+            self._open_topology = np.array([self.simplices[s] is None and len(self.slots[s]) > 4 for s in range(self.S)], dtype=bool) \
+                if self.k == nat.POLYHEDRAL else np.zeros(self.S, dtype=bool)
         h = C.c_void_p()
         nat.check(self.L.sab_engine_create(C.byref(h), self.k, self.device, self.N, self.A,
                                            nat.ptr(self.mobile), self.S))
@@ -687,6 +695,31 @@ class AssignmentEngine:
         nat.check(self.L.sab_lazy_get_state(self.h, None, None, None, None, nat.ptr(st)))
         return dict(queries=int(st[0]), incremental=int(st[1]), full=int(st[2]), invalidations=int(st[3]))
 
+    def _rehull_first_queries(self, topo_pass: int) -> bool:
+        """After a replay attempt: hull every open site that was queried for the first time from the vertex coordinates
+        of that query (what ``FaceTopologyCache.__init__`` does, polyhedral_site.py:138-159).  Returns True -- and uploads
+        the new triangulations -- when one differs from the triangulation the attempt used."""
+        S, smax = self.S, self._slot_atom.shape[1]
+        first_frame = np.zeros(S, dtype=np.int64); first_vc = np.zeros((S, smax, 3))
+        nat.check(self.L.sab_lazy_get_first_queries(self.h, nat.ptr(first_frame), nat.ptr(first_vc)))
+        self._first_queried = (first_frame >= 0) & self._open_topology
+        changed = False
+        for s in np.nonzero(self._first_queried)[0]:
+            n = len(self.slots[s])
+            new = tab.hull_simplices(first_vc[s, :n], s)
+            if not np.array_equal(new, np.asarray(self.simplices[s])):
+                self.simplices[s] = new
+                changed = True
+        if not changed or topo_pass >= 16:
+            return False
+        fmax = max(len(f) for f in self.simplices)
+        n_face = np.array([len(f) for f in self.simplices], dtype=np.int32)
+        simp = np.zeros((S, fmax, 3), dtype=np.int32)
+        for s, f in enumerate(self.simplices):
+            simp[s, :len(f)] = f
+        nat.check(self.L.sab_update_face_topology(self.h, fmax, nat.ptr(n_face), nat.ptr(np.ascontiguousarray(simp))))
+        return True
+
     def _assign_device_lazy(self, d_frac, d_lattice, stride, d_result, append):
         """One batch through k_polyhedral_lazy: final positions and the advanced history, nothing left to resolve or fold."""
         torch = _torch()
@@ -701,6 +734,7 @@ class AssignmentEngine:
         width = max(16, 2 * max((len(t) for t in self.transitions), default=0))
         has_rc = np.array([c is not None for c in self.ref_centres], dtype=np.uint8)
         rc = np.ascontiguousarray(np.array([c if c is not None else np.zeros(3) for c in self.ref_centres], dtype=np.float64).reshape(self.S, 3))
+        topo_pass = 0
         while True:
             tr_n = np.zeros(self.S, dtype=np.int32)
             tr_key = np.zeros((self.S, width), dtype=np.int32)
@@ -711,6 +745,9 @@ class AssignmentEngine:
                     tr_key[s, :len(t)] = list(t.keys()); tr_cnt[s, :len(t)] = list(t.values())
             recent, prev = self.recent.copy(), self.prev.copy()
             snap = self._lazy_snapshot()
+            open_now = self._open_topology.any()
+            if open_now:                                        # clears the first-query records of the previous attempt
+                nat.check(self.L.sab_lazy_set_open_topology(self.h, nat.ptr(np.ascontiguousarray(self._open_topology, dtype=np.uint8))))
             code = self.L.sab_assign_lazy(self.h, d_frac.data_ptr(), d_lattice.data_ptr(), stride, F, d_result.data_ptr(), stream,
                                           nat.ptr(recent), nat.ptr(prev), nat.ptr(tr_n), nat.ptr(tr_key), nat.ptr(tr_cnt), width,
                                           1 if append else 0)
@@ -722,12 +759,21 @@ class AssignmentEngine:
             if self._supply_missing_rank_rows():                # lazy ranking: redo the batch with the true rows of the tied anchors
                 nat.check(self.L.sab_lazy_set_state(self.h, nat.ptr(snap[0]), nat.ptr(snap[1]), nat.ptr(snap[2]), nat.ptr(has_rc), nat.ptr(rc)))
                 continue
+            if open_now and self._rehull_first_queries(topo_pass):
+                # some site's triangulation differs from the one this attempt used: redo the batch with it.  Sites queried
+                # EARLIER than the first wrong one keep their (now confirmed) triangulation, so every pass settles at least
+                # the earliest open site -- the loop ends after at most as many passes as there are first-query frames.
+                topo_pass += 1
+                nat.check(self.L.sab_lazy_set_state(self.h, nat.ptr(snap[0]), nat.ptr(snap[1]), nat.ptr(snap[2]), nat.ptr(has_rc), nat.ptr(rc)))
+                continue
             break
+        if open_now:                                            # first-queried sites own their topology from now on
+            self._open_topology &= ~self._first_queried
         self.recent, self.prev = recent, prev
         self.transitions = [dict(zip(map(int, tr_key[s, :tr_n[s]]), map(int, tr_cnt[s, :tr_n[s]]))) for s in range(self.S)]
         self.frames_done += F
         self.last_info = dict(ambiguous=0, full27=0, launches=1, reinits=0, assign_ns=0, wrap_ns=0, deferred=0, scan_redo=0,
-                              peers_written=0, lazy=1)
+                              peers_written=0, lazy=1, topology_passes=topo_pass)
         self._last_pending = []
         return d_result
 
@@ -745,6 +791,8 @@ class AssignmentEngine:
         torch = _torch()
         F = int(d_frac.shape[0])
         auto = self.exact_lazy is None and self.frames_done == 0 and 0 < F < self.LAZY_AUTO_FRAMES and not defer_resolve
+        if self.exact_lazy is None and self.frames_done == 0 and self._open_topology.any() and not defer_resolve:
+            auto = True                                         # face topology at the first query needs the replay kernel
         if (self.exact_lazy or self._lazy_mode or auto) and F > 0:
             d_lattice = d_lattice.contiguous()
             d_result = out if out is not None else torch.empty((F, self.A), dtype=torch.int32, device=d_frac.device)
@@ -909,7 +957,8 @@ class AssignmentEngine:
         call_start = (self.frames_done, len(self._pending), self.recent.copy(), self.prev.copy(),
                       self._tr_snapshot() if self.k == nat.POLYHEDRAL and self.frames_done == 0 else None)
         fast_ok = not (self.k == nat.POLYHEDRAL and (self.exact_lazy or self._lazy_mode or
-                                                     (self.exact_lazy is None and self.frames_done == 0 and F < self.LAZY_AUTO_FRAMES)))
+                                                     (self.exact_lazy is None and self.frames_done == 0 and
+                                                      (F < self.LAZY_AUTO_FRAMES or self._open_topology.any()))))
         if fast_ok and append and F >= self.PIPELINE_MIN_FRAMES and self.k != nat.SPHERICAL:
             if self.slots is not None and not self._pbc_ready:
                 self._init_pbc(frac[0], lattice if lattice.ndim == 2 else lattice[0])

@@ -311,7 +311,10 @@ class PolyhedralSiteCollection(PriorityAssignmentMixin, SiteCollection):
                     reference_centres=[s.reference_center for s in self.sites], primed=primed, simplices=simp)
 
     def _after_batch(self, eng, atoms, frac, rows) -> None:
+        open_topo = getattr(eng, "_open_topology", None)
         for s, site in enumerate(self.sites):              # topology is permanent once computed
+            if open_topo is not None and len(open_topo) > s and open_topo[s]:
+                continue                                   # never queried so far: the reference has hulled nothing yet either
             if getattr(site, "_face_topology_cache", None) is None and eng.simplices[s] is not None:
                 site._face_topology_cache = FaceTopology(eng.simplices[s])
 
