@@ -220,10 +220,12 @@ def _per_frame_lattice(rng, base, n_frames, eps=2e-3):
                      for _ in range(n_frames)])
 
 
-def fuzz_spherical_voronoi(seed):
+def fuzz_spherical_voronoi(seed, big=False):
+    """``big``: 40 mobile atoms, 60 sites, 400 frames (round 2: the small cases have 6 atoms and 80 frames)."""
     from site_analysis import TrajectoryBuilder
-    rng = np.random.default_rng(seed)
-    n_fw, n_mob, F, S = 5, 6, 80, 14
+    rng = np.random.default_rng(seed + (7000 if big else 0))
+    n_fw, n_mob, F, S = (8, 40, 400, 60) if big else (5, 6, 80, 14)
+    tag = f"big{seed}" if big else f"{seed}"
     species = ["O"] * n_fw + ["Li"] * n_mob
     base = _triclinic(rng)
     lattice = _per_frame_lattice(rng, base, F) if seed % 2 else base
@@ -243,18 +245,18 @@ def fuzz_spherical_voronoi(seed):
         centres = rng.uniform(0, 1, (S, 3))
     st = refcases.structures_from_arrays(species, lattice, frac)
 
-    radii = list(rng.uniform(1.2, 3.2, S))
+    radii = list(rng.uniform(1.2, 2.4 if big else 3.2, S))
     t = (TrajectoryBuilder().with_structure(st[0]).with_mobile_species("Li")
          .with_spherical_sites(centres=centres.tolist(), radii=radii).build())
     case = refcases.run_case(t, species, lattice, frac)
     case["frac"] = frac
-    save(f"fuzz_spherical_{seed}", case)
+    save(f"fuzz_spherical_{tag}", case)
 
     t = (TrajectoryBuilder().with_structure(st[0]).with_mobile_species("Li")
          .with_voronoi_sites(centres=centres.tolist()).build())
     case = refcases.run_case(t, species, lattice, frac)
     case["frac"] = frac
-    save(f"fuzz_voronoi_{seed}", case)
+    save(f"fuzz_voronoi_{tag}", case)
 
 
 def _grid_framework(rng, n, jitter):
@@ -296,7 +298,7 @@ def _tet_sites(n):
     return verts, np.array(centres)
 
 
-def fuzz_polyhedral(seed):
+def fuzz_polyhedral(seed, big=False):
     """Hand-made PolyhedralSite objects (the reference's low-level API) on a jittered grid.
 
     Variants by seed: cubes / tetrahedra; with / without reference centres; primed from the
@@ -307,16 +309,16 @@ def fuzz_polyhedral(seed):
     from site_analysis.polyhedral_site import PolyhedralSite
     from site_analysis.site import Site
     from site_analysis.trajectory import Trajectory
-    rng = np.random.default_rng(seed)
-    n = 3
-    F = 70
+    rng = np.random.default_rng(seed + (7000 if big else 0))
+    n = 4 if big else 3                    # big: 64 cubes / 320 tetrahedra, 24 mobile atoms, 300 frames
+    F = 300 if big else 70
     tets = bool(seed % 2)
     with_rc = (seed // 2) % 2 == 0
     primed = (seed // 4) % 2 == 0
     jump = seed % 5 == 4
     verts, centres = _tet_sites(n) if tets else _cube_sites(n)
     n_fw = n ** 3
-    n_mob = 7
+    n_mob = 24 if big else 7
     species = ["O"] * n_fw + ["Li"] * n_mob
     base = _triclinic(rng, 8.0, 11.0, 12.0)
     lattice = _per_frame_lattice(rng, base, F) if seed % 3 == 0 else base
@@ -349,26 +351,27 @@ def fuzz_polyhedral(seed):
     case["variant"] = np.array(f"tets={tets} rc={with_rc} primed={primed} jump={jump}")
     n_none = int((case["atoms_traj"] < 0).sum())
     print(f"   {case['variant']}: None assignments {n_none}/{case['atoms_traj'].size}")
-    save(f"fuzz_polyhedral_{seed}", case)
+    save(f"fuzz_polyhedral_big{seed}" if big else f"fuzz_polyhedral_{seed}", case)
 
 
-def fuzz_dynvor(seed):
+def fuzz_dynvor(seed, big=False):
     """DynamicVoronoiSite objects with two reference-count groups (R=4 tetrahedra and R=8 cubes)."""
     from site_analysis.atom import Atom
     from site_analysis.dynamic_voronoi_site import DynamicVoronoiSite
     from site_analysis.site import Site
     from site_analysis.trajectory import Trajectory
-    rng = np.random.default_rng(1000 + seed)
-    n, F = 3, 70
+    rng = np.random.default_rng(1000 + seed + (7000 if big else 0))
+    n, F = (4, 300) if big else (3, 70)
     with_rc = seed % 2 == 0
     jump = seed % 3 == 2
     cube_v, cube_c = _cube_sites(n)
     tet_v, tet_c = _tet_sites(n)
-    pick_t = rng.choice(len(tet_v), 20, replace=False)
-    pick_c = rng.choice(len(cube_v), 9, replace=False)
-    defs = [(tet_v[i], tet_c[i]) for i in pick_t[:10]] + [(cube_v[i], cube_c[i]) for i in pick_c] + \
-           [(tet_v[i], tet_c[i]) for i in pick_t[10:]]                     # interleaved groups
-    n_fw, n_mob = n ** 3, 6
+    pick_t = rng.choice(len(tet_v), 60 if big else 20, replace=False)
+    pick_c = rng.choice(len(cube_v), 24 if big else 9, replace=False)
+    half = len(pick_t) // 2
+    defs = [(tet_v[i], tet_c[i]) for i in pick_t[:half]] + [(cube_v[i], cube_c[i]) for i in pick_c] + \
+           [(tet_v[i], tet_c[i]) for i in pick_t[half:]]                   # interleaved groups
+    n_fw, n_mob = n ** 3, (20 if big else 6)
     species = ["O"] * n_fw + ["Li"] * n_mob
     base = _triclinic(rng, 8.0, 11.0, 12.0)
     lattice = _per_frame_lattice(rng, base, F) if seed % 2 else base
@@ -394,7 +397,7 @@ def fuzz_dynvor(seed):
     case["centre_frames"] = np.arange(F)
     case["centres_at"] = np.array(all_centres)
     case["variant"] = np.array(f"rc={with_rc} jump={jump}")
-    save(f"fuzz_dynvor_{seed}", case)
+    save(f"fuzz_dynvor_big{seed}" if big else f"fuzz_dynvor_{seed}", case)
 
 
 CASES = {
@@ -404,6 +407,14 @@ CASES = {
     **{f"fuzz_sphvor_{s}": (lambda s=s: fuzz_spherical_voronoi(s)) for s in range(4)},
     **{f"fuzz_polyhedral_{s}": (lambda s=s: fuzz_polyhedral(s)) for s in range(10)},
     **{f"fuzz_dynvor_{s}": (lambda s=s: fuzz_dynvor(s)) for s in range(4)},
+    # round 2: larger systems ("fuzz fixtures are tiny"): 20-40 mobile atoms, 300-400 frames
+    "fuzzbig_sphvor_1": lambda: fuzz_spherical_voronoi(1, big=True),
+    "fuzzbig_sphvor_3": lambda: fuzz_spherical_voronoi(3, big=True),
+    "fuzzbig_polyhedral_1": lambda: fuzz_polyhedral(1, big=True),     # tetrahedra, reference centres, primed
+    "fuzzbig_polyhedral_4": lambda: fuzz_polyhedral(4, big=True),     # cubes, reference centres, unprimed, a > 0.3 jump
+    "fuzzbig_polyhedral_7": lambda: fuzz_polyhedral(7, big=True),     # tetrahedra, no reference centres, unprimed
+    "fuzzbig_dynvor_1": lambda: fuzz_dynvor(1, big=True),
+    "fuzzbig_dynvor_2": lambda: fuzz_dynvor(2, big=True),             # a 0.38 jump: group re-initialisation
 }
 
 

@@ -65,7 +65,8 @@ def test_per_frame_api_matches_reference_golden(oracle_mod, name):
         assert st_last[s] == [a.index for a in t.atoms if a.in_site == site.index]
 
 
-@pytest.mark.parametrize("name", ["fuzz_voronoi_1", "fuzz_polyhedral_0", "fuzz_dynvor_0", "fuzz_spherical_2"])
+@pytest.mark.parametrize("name", ["fuzz_voronoi_1", "fuzz_polyhedral_0", "fuzz_dynvor_0", "fuzz_spherical_2",
+                                  "fuzz_polyhedral_big1", "fuzz_spherical_big3", "fuzz_dynvor_big2"])
 def test_ragged_batches_equal_one_batch(oracle_mod, name):
     """State carried between calls (PBC wrap counters, history) makes any split equivalent."""
     case = oracle_mod.load_case(name)
@@ -415,7 +416,8 @@ def test_fast_path_is_the_one_that_runs():
 
 
 @pytest.mark.parametrize("name", ["argyrodite_0p_polyhedral", "simple_cubic_polyhedral", "fuzz_polyhedral_0", "fuzz_polyhedral_2",
-                                  "fuzz_polyhedral_3", "fuzz_polyhedral_5", "fuzz_polyhedral_8", "fuzz_polyhedral_9"])
+                                  "fuzz_polyhedral_3", "fuzz_polyhedral_5", "fuzz_polyhedral_8", "fuzz_polyhedral_9",
+                                  "fuzz_polyhedral_big4", "fuzz_polyhedral_big7"])
 def test_exact_replay_kernel_equals_reference_golden(oracle_mod, name):
     """exact_lazy = True: every batch through the literal replay of the reference's per-site lazy caches
     (polyhedral_site.py:322-416) -- same rows, Counters (with insertion order) and recent sites as the reference, for
@@ -543,7 +545,7 @@ def test_speculative_resolver_equals_the_per_frame_resolvers_and_the_oracle(orac
 
 
 @pytest.mark.parametrize("name", ["simple_cubic_polyhedral", "fuzz_polyhedral_0", "fuzz_polyhedral_2", "fuzz_polyhedral_4",
-                                  "fuzz_polyhedral_6", "fuzz_polyhedral_8"])
+                                  "fuzz_polyhedral_6", "fuzz_polyhedral_8", "fuzz_polyhedral_big4"])
 def test_unseeded_cubes_take_their_topology_from_the_first_query(oracle_mod, name):
     """Non-simplicial polyhedra WITHOUT a seeded face topology.  The reference hulls a site at its first query
     (FaceTopologyCache, polyhedral_site.py:138-159, 468-471) and Qhull's triangulation of a cube's quads depends on that

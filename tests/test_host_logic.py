@@ -182,3 +182,43 @@ def test_peer_result_buffers_slot_arithmetic():
     assert b.mc_slot == 90000 + 240
     b.next()
     assert b.mc_slot == 91000 + 240
+
+
+def test_transition_store_keeps_counter_semantics_in_both_forms():
+    """AssignmentEngine's transition store (site.py:71 Counters of all sites): per-site dicts in insertion order <-> the
+    (source, destination, count) arrays the device fold merges into.  Merging pairs in first-occurrence order must give what
+    ``transitions[src][dst] += n`` gives (counts added, NEW keys appended in order), and a snapshot must survive later
+    merges in whichever form it was taken (host logic only: no device is touched)."""
+    from site_analysis_b200.engine import AssignmentEngine
+    e = AssignmentEngine.__new__(AssignmentEngine)
+    e.S = 5
+    e.transitions = [dict() for _ in range(5)]
+    e.transitions[2][4] = 3                                   # edited through the dict view
+    e.transitions[2][0] = 1
+    snap_d = e._tr_snapshot()
+    assert snap_d[0] == "dicts"
+    e._tr_add_pairs(np.array([2, 1, 2, 1]), np.array([0, 3, 1, 0]), np.array([5, 2, 7, 1]))
+    snap_a = e._tr_snapshot()
+    assert snap_a[0] == "arrays"
+    want = [{}, {3: 2, 0: 1}, {4: 3, 0: 6, 1: 7}, {}, {}]
+    assert e.transitions == want and [list(t) for t in e.transitions] == [list(t) for t in want]      # insertion order too
+    e._tr_add_pairs(np.array([2, 4]), np.array([4, 4]), np.array([1, 9]))
+    assert e.transitions[2] == {4: 4, 0: 6, 1: 7} and e.transitions[4] == {4: 9}
+    e._tr_restore(snap_a)
+    assert e.transitions == want
+    e._tr_restore(snap_d)
+    assert e.transitions == [{}, {}, {4: 3, 0: 1}, {}, {}]
+    e.h = None                                                # nothing to destroy
+
+
+def test_exhaustive_kernels_are_not_chosen_beyond_their_shared_memory():
+    """The exhaustive spherical / Voronoi kernels stage every site in shared memory (40 / 24 B per site); single-frame calls on
+    larger site tables must build the cell lists first."""
+    from site_analysis_b200 import _native as nat
+    from site_analysis_b200.engine import AssignmentEngine
+    e = AssignmentEngine.__new__(AssignmentEngine)
+    for kind, S, want in ((nat.SPHERICAL, 5000, False), (nat.SPHERICAL, 5001, True), (nat.VORONOI, 8448, True),
+                          (nat.VORONOI, 8333, False), (nat.DYNAMIC_VORONOI, 576, False)):
+        e.k, e.S = kind, S
+        assert e._exhaustive_too_big() == want, (kind, S)
+    e.h = None
